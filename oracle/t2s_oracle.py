@@ -1,0 +1,302 @@
+"""CPU oracle for the T2S generation hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a plain-tensor (torch fp32, CPU) restatement of the reference algorithm.  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` leg
+may import it; nothing under ``t2ms_b200/`` does (the product path is CUDA only and fails loudly
+when the extension is missing).
+
+Parity pinning: the reference (Bill9125/T2MS) ships no tests and no golden vectors, so
+this oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF run in the build container:
+``oracle/make_golden.py`` imports the unmodified reference modules from /root/reference (with two
+import shims for the absent third-party ``timm==1.0.11`` Attention/Mlp and ``matplotlib``) and
+writes ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks every function below against
+those fixtures.
+
+Third-party arithmetic restated here: ``timm.models.vision_transformer.Attention`` and ``Mlp``
+(timm==1.0.11, requirements.txt:9), called from model/denoiser/transformer.py:104-105,116-117.
+
+All ``file:line`` citations are relative to the reference repo root.  Weights are passed as a plain
+``dict[str, Tensor]`` using the reference's state-dict key names.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+# ----------------------------------------------------------------------------------------------
+# DiT denoiser (model/denoiser/transformer.py)
+# ----------------------------------------------------------------------------------------------
+
+D_MODEL = 128      # transformer.py:97,135
+N_HEADS = 4        # transformer.py:104
+N_LAYERS = 4       # transformer.py:149
+LAT_C = 64         # latent channels  (self.W, transformer.py:134)
+LAT_P = 30         # latent positions (self.H, transformer.py:133)
+N_TOK = 480        # (30/2)*(64/2), transformer.py:136
+
+
+def modulate(x, shift, scale):
+    """transformer.py:7-8"""
+    return x * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1)
+
+
+def sinusoidal_pos_embed(num_positions: int, d_model: int) -> torch.Tensor:
+    """transformer.py:14-23 -> (1, num_positions, d_model)"""
+    position = torch.arange(num_positions).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * -(math.log(10000.0) / d_model)).unsqueeze(0)
+    pe = torch.zeros(num_positions, d_model)
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe.unsqueeze(0)
+
+
+def time_embedding(t: torch.Tensor, dim: int = D_MODEL) -> torch.Tensor:
+    """TimeEmbedding.forward, transformer.py:30-40.  t: (B,) float32 or int64 -> (B, dim)."""
+    t = t * 100.0
+    t = t.unsqueeze(-1)
+    freqs = torch.pow(10000, torch.linspace(0, 1, dim // 2)).to(t.device)
+    sin_emb = torch.sin(t[:, None] / freqs)
+    cos_emb = torch.cos(t[:, None] / freqs)
+    return torch.cat([sin_emb, cos_emb], dim=-1).squeeze(1)
+
+
+def attention(sd: SD, pre: str, x: torch.Tensor) -> torch.Tensor:
+    """timm==1.0.11 Attention.forward (qkv_bias=True, no qk-norm, no dropout), call site
+    transformer.py:116.  softmax(q k^T / sqrt(d_head)) v, heads re-concatenated, then proj."""
+    B, N, C = x.shape
+    hd = C // N_HEADS
+    qkv = F.linear(x, sd[pre + "attn.qkv.weight"], sd[pre + "attn.qkv.bias"])
+    qkv = qkv.reshape(B, N, 3, N_HEADS, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv.unbind(0)
+    att = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    att = att.softmax(dim=-1)
+    o = (att @ v).transpose(1, 2).reshape(B, N, C)
+    return F.linear(o, sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"])
+
+
+def mlp(sd: SD, pre: str, x: torch.Tensor) -> torch.Tensor:
+    """timm==1.0.11 Mlp.forward with act=GELU(tanh), drop=0, call site transformer.py:117."""
+    x = F.linear(x, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"])
+    x = F.gelu(x, approximate="tanh")
+    return F.linear(x, sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"])
+
+
+def dit_layer(sd: SD, l: int, x: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+    """Transformerlayer.forward, transformer.py:114-124 (norms: :102-103, eps 1e-6, no affine)."""
+    pre = f"layers.{l}."
+    ada = F.linear(F.silu(c), sd[pre + "adaLN_modulation.1.weight"], sd[pre + "adaLN_modulation.1.bias"])
+    sh1, sc1, g1, sh2, sc2, g2 = ada.chunk(6, dim=1)
+    x = x + g1.unsqueeze(1) * attention(sd, pre, modulate(F.layer_norm(x, (D_MODEL,), eps=1e-6), sh1, sc1))
+    x = x + g2.unsqueeze(1) * mlp(sd, pre, modulate(F.layer_norm(x, (D_MODEL,), eps=1e-6), sh2, sc2))
+    return x
+
+
+def dit_embed(sd: SD, inp: torch.Tensor) -> torch.Tensor:
+    """Patchify + embed, transformer.py:166-172.  inp (B,64,30) -> (B,480,128)."""
+    x = inp.permute(0, 2, 1).unsqueeze(1)                      # (B,1,30,64)
+    x = F.conv2d(x, sd["conv.weight"], sd["conv.bias"], stride=2)   # (B,4,15,32)
+    x = x.permute(0, 2, 3, 1)
+    x = x.reshape(x.size(0), N_TOK, x.size(3))
+    x = F.linear(x, sd["patch_emb.weight"], sd["patch_emb.bias"])
+    return x + sd["pos_embed"]
+
+
+def dit_unembed(sd: SD, x: torch.Tensor) -> torch.Tensor:
+    """Final LN + projection + unpatchify, transformer.py:182-190.  (B,480,128) -> (B,64,30)."""
+    x = F.layer_norm(x, (D_MODEL,), sd["ln.weight"], sd["ln.bias"], eps=1e-5)
+    x = F.linear(x, sd["linear_emb_to_patch.weight"], sd["linear_emb_to_patch.bias"])
+    B = x.size(0)
+    x = x.view(B, LAT_P // 2, LAT_C // 2, 1, 2, 2)
+    x = x.permute(0, 3, 1, 2, 4, 5).permute(0, 1, 2, 4, 3, 5)
+    x = x.reshape(B, 1, LAT_P, LAT_C).squeeze(1)
+    return x.permute(0, 2, 1)
+
+
+def dit_forward(sd: SD, inp: torch.Tensor, t: torch.Tensor, text: Optional[torch.Tensor],
+                return_hidden: bool = False):
+    """Transformer.forward, transformer.py:158-193."""
+    x = dit_embed(sd, inp)
+    c = time_embedding(t)
+    if text is not None:
+        c = c + text                                           # transformer.py:176-178
+    hidden = [x]
+    for l in range(N_LAYERS):
+        x = dit_layer(sd, l, x, c)
+        hidden.append(x)
+    out = dit_unembed(sd, x)
+    return (out, hidden) if return_hidden else out
+
+
+# ----------------------------------------------------------------------------------------------
+# Rectified flow (model/backbone/rectified_flow.py) and DDPM (model/backbone/DDPM.py)
+# ----------------------------------------------------------------------------------------------
+
+def rf_euler(x_t, v, dt):
+    """RectifiedFlow.euler, rectified_flow.py:5-7"""
+    return x_t + v * dt
+
+
+def rf_create_flow(x_1, t, x_0):
+    """RectifiedFlow.create_flow, rectified_flow.py:8-12, with the noise x_0 supplied."""
+    t = t[:, None, None]
+    return t * x_1 + (1 - t) * x_0
+
+
+def mse(a, b):
+    """rectified_flow.py:13-16 / DDPM.py:37-38"""
+    return F.mse_loss(a, b)
+
+
+def ddpm_schedule(total_steps: int):
+    """DDPM.__init__, DDPM.py:11-18 -> (beta, alpha, alpha_bar)"""
+    beta = torch.linspace(0.0001, 0.02, total_steps)
+    alpha = 1 - beta
+    alpha_bar = torch.cumprod(alpha, dim=0)
+    return beta, alpha, alpha_bar
+
+
+def _gather(consts, t):
+    """DDPM.py:7-9"""
+    return consts.gather(-1, t).reshape(-1, 1, 1)
+
+
+def ddpm_q_sample(x0, t, eps, sched):
+    """DDPM.q_xt_x0 + q_sample, DDPM.py:19-27"""
+    _, _, alpha_bar = sched
+    mean = _gather(alpha_bar, t) ** 0.5 * x0
+    var = 1 - _gather(alpha_bar, t)
+    return mean + (var ** 0.5) * eps
+
+
+def ddpm_p_sample(xt, eps_pred, t, noise, sched):
+    """DDPM.p_sample, DDPM.py:28-36, with the per-step Gaussian ``noise`` supplied
+    (the reference draws torch.randn inside, DDPM.py:35; noise is added at t == 0 too)."""
+    beta, alpha, alpha_bar = sched
+    ab = _gather(alpha_bar, t)
+    a = _gather(alpha, t)
+    eps_coef = (1 - a) / (1 - ab) ** .5
+    mean = 1 / (a ** 0.5) * (xt - eps_coef * eps_pred)
+    var = _gather(beta, t)
+    return mean + (var ** .5) * noise
+
+
+# ----------------------------------------------------------------------------------------------
+# LA-VAE (model/pretrained/vqvae.py)
+# ----------------------------------------------------------------------------------------------
+
+def _residual_stack(sd: SD, pre: str, x: torch.Tensor, n_layers: int = 2) -> torch.Tensor:
+    """ResidualStack.forward vqvae.py:30-33 over Residual.forward vqvae.py:21-22.
+    nn.ReLU(True) as the first op of _block mutates x in place before the add, so each layer
+    returns relu(x) + conv1(relu(conv3(relu(x))))."""
+    for i in range(n_layers):
+        r = F.relu(x)
+        y = F.conv1d(r, sd[f"{pre}_residual_stack._layers.{i}._block.1.weight"], None, padding=1)
+        y = F.relu(y)
+        y = F.conv1d(y, sd[f"{pre}_residual_stack._layers.{i}._block.3.weight"], None)
+        x = r + y
+    return F.relu(x)
+
+
+def vae_encode(sd: SD, x: torch.Tensor, pre: str = "encoder.") -> Tuple[torch.Tensor, torch.Tensor]:
+    """Encoder.forward, vqvae.py:57-71.  x (B,L) -> z (B,64,30), before (B,64,L/4)."""
+    x = x.view(x.shape[0], 1, x.shape[-1])
+    x = F.relu(F.conv1d(x, sd[pre + "_conv_1.weight"], sd[pre + "_conv_1.bias"], stride=2, padding=1))
+    x = F.relu(F.conv1d(x, sd[pre + "_conv_2.weight"], sd[pre + "_conv_2.bias"], stride=2, padding=1))
+    x = F.conv1d(x, sd[pre + "_conv_3.weight"], sd[pre + "_conv_3.bias"], padding=1)
+    x = _residual_stack(sd, pre, x)
+    before = F.conv1d(x, sd[pre + "_pre_vq_conv.weight"], sd[pre + "_pre_vq_conv.bias"])
+    z = F.interpolate(before, size=30, mode="linear", align_corners=True)
+    return z, before
+
+
+def vae_decode(sd: SD, z: torch.Tensor, length: int, pre: str = "decoder.") -> Tuple[torch.Tensor, torch.Tensor]:
+    """Decoder.forward, vqvae.py:97-105.  z (B,64,30) -> series (B,L) [torch.squeeze'd], after (B,64,L/4)."""
+    x = F.interpolate(z, size=int(length / 4), mode="linear", align_corners=True)
+    after = x
+    x = F.conv1d(x, sd[pre + "_conv_1.weight"], sd[pre + "_conv_1.bias"], padding=1)
+    x = _residual_stack(sd, pre, x)
+    x = F.relu(F.conv_transpose1d(x, sd[pre + "_conv_trans_1.weight"], sd[pre + "_conv_trans_1.bias"], stride=2, padding=1))
+    x = F.conv_transpose1d(x, sd[pre + "_conv_trans_2.weight"], sd[pre + "_conv_trans_2.bias"], stride=2, padding=1)
+    return torch.squeeze(x), after
+
+
+# ----------------------------------------------------------------------------------------------
+# Sampling loops (infer.py:75-95) and the training step (train.py:66-87)
+# ----------------------------------------------------------------------------------------------
+
+def rf_timesteps(steps: int, batch: int) -> torch.Tensor:
+    """infer.py:78 — t_j = round(full(j/steps) * steps) / steps, float32, (steps, batch)."""
+    return torch.stack([torch.round(torch.full((batch,), j * 1.0 / steps) * steps) / steps for j in range(steps)])
+
+
+@torch.no_grad()
+def rf_sample(dit: SD, vae: Optional[SD], noise: torch.Tensor, emb: torch.Tensor, steps: int,
+              cfg_scale: float, length: Optional[int] = None, return_velocities: bool = False):
+    """infer.py:75-82 (+ :95 decode when ``vae`` and ``length`` are given); the initial latent
+    ``noise`` replaces randn_like (infer.py:75).  Returns (latent, series|None[, velocities])."""
+    x_t = noise.clone()
+    vel = []
+    for j in range(steps):
+        t = torch.round(torch.full((x_t.shape[0],), j * 1.0 / steps) * steps) / steps
+        u = dit_forward(dit, x_t, t, None)
+        c = dit_forward(dit, x_t, t, emb)
+        pred = u + cfg_scale * (c - u)
+        if return_velocities:
+            vel.append(pred)
+        x_t = rf_euler(x_t, pred, 1.0 / steps)
+    series = vae_decode(vae, x_t, length)[0] if (vae is not None and length) else None
+    return (x_t, series, vel) if return_velocities else (x_t, series)
+
+
+@torch.no_grad()
+def ddpm_sample(dit: SD, vae: Optional[SD], noise: torch.Tensor, emb: torch.Tensor, steps: int,
+                cfg_scale: float, step_noise: torch.Tensor, length: Optional[int] = None,
+                return_eps: bool = False):
+    """infer.py:83-88 (+ :95).  ``step_noise`` (steps,B,64,30) replaces the torch.randn drawn inside
+    DDPM.p_sample (DDPM.py:35)."""
+    sched = ddpm_schedule(steps)
+    x_t = noise.clone()
+    eps_l = []
+    for j in range(steps):
+        t = torch.full((x_t.size(0),), math.floor(steps - 1 - j), dtype=torch.long)
+        u = dit_forward(dit, x_t, t, None)
+        c = dit_forward(dit, x_t, t, emb)
+        pred = u + cfg_scale * (c - u)
+        if return_eps:
+            eps_l.append(pred)
+        x_t = ddpm_p_sample(x_t, pred, t, step_noise[j], sched)
+    series = vae_decode(vae, x_t, length)[0] if (vae is not None and length) else None
+    return (x_t, series, eps_l) if return_eps else (x_t, series)
+
+
+TRAINABLE_EXCLUDE = ("pos_embed", "unpatch.", "encoder.")
+
+
+def train_step_grads(dit: SD, x_t: torch.Tensor, t: torch.Tensor, emb: Optional[torch.Tensor],
+                     target: torch.Tensor):
+    """One forward/backward of train.py:83-85: pred = model(x_t,t,emb|None); loss = mse(pred,target).
+    Returns (loss, {name: grad}) for every parameter that receives a gradient."""
+    names = [k for k in dit if not k.startswith(TRAINABLE_EXCLUDE)]
+    leaf = {k: dit[k].detach().clone().requires_grad_(True) for k in names}
+    sd = dict(dit)
+    sd.update(leaf)
+    loss = mse(dit_forward(sd, x_t, t, emb), target)
+    grads = torch.autograd.grad(loss, [leaf[k] for k in names])
+    return loss.detach(), dict(zip(names, grads))
+
+
+def adamw_step(p, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-8, wd=0.0):
+    """torch.optim.AdamW single-tensor update as configured at train.py:37 (lr 1e-4, wd 0)."""
+    p = p * (1 - lr * wd)
+    m = beta1 * m + (1 - beta1) * g
+    v = beta2 * v + (1 - beta2) * g * g
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    denom = (v.sqrt() / math.sqrt(bc2)) + eps
+    p = p - (lr / bc1) * m / denom
+    return p, m, v

@@ -1,0 +1,134 @@
+"""The CPU oracle (oracle/t2s_oracle.py) against outputs of the unmodified reference
+(tests/golden/*.npz, written by oracle/make_golden.py)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import T, load_golden
+from oracle import t2s_oracle as O
+from t2ms_b200 import synth
+
+
+def close(a, b, atol, rtol=0.0):
+    a = torch.as_tensor(a).double()
+    b = torch.as_tensor(b).double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs().max().item()
+    assert err <= atol + rtol * b.abs().max().item(), f"max-abs err {err}"
+
+
+def test_weights_reproduce():
+    g = load_golden("dit_forward.npz")
+    sd = synth.make_dit_state(int(g["dit_seed"]), bias_std=float(g["bias_std"]))
+    assert synth.state_checksum(sd) == str(g["dit_checksum"])
+    v = load_golden("vae.npz")
+    assert synth.state_checksum(synth.make_vae_state(int(v["vae_seed"]))) == str(v["vae_checksum"])
+    assert len(sd) == 55
+    assert torch.equal(O.sinusoidal_pos_embed(480, 128), sd["pos_embed"])
+
+
+def test_time_embedding():
+    g = load_golden("dit_forward.npz")
+    close(O.time_embedding(T(g["t_float"])), g["temb_float"], 1e-6)
+    close(O.time_embedding(T(g["t_int"])), g["temb_int"], 1e-6)
+
+
+def test_dit_forward():
+    g = load_golden("dit_forward.npz")
+    sd = synth.make_dit_state(int(g["dit_seed"]), bias_std=float(g["bias_std"]))
+    x, emb = T(g["x"]), T(g["emb"])
+    with torch.no_grad():
+        out, hid = O.dit_forward(sd, x, T(g["t_float"]), emb, return_hidden=True)
+        close(out, g["cond_float"], 2e-5)
+        close(O.dit_forward(sd, x, T(g["t_float"]), None), g["uncond_float"], 2e-5)
+        close(O.dit_forward(sd, x, T(g["t_int"]), emb), g["cond_int"], 2e-5)
+        tok = g["hidden_tok"].tolist()
+        for l in range(4):
+            close(hid[l + 1][:, tok, :], g["hidden"][l], 2e-5)
+
+
+@pytest.mark.parametrize("L", [24, 48, 96])
+def test_vae(L):
+    g = load_golden("vae.npz")
+    sd = synth.make_vae_state(int(g["vae_seed"]))
+    with torch.no_grad():
+        z, before = O.vae_encode(sd, T(g[f"series_{L}"]))
+        close(z, g[f"z_{L}"], 1e-5)
+        close(before, g[f"before_{L}"], 1e-5)
+        rec, after = O.vae_decode(sd, T(g[f"z_{L}"]), L)
+        close(rec, g[f"rec_{L}"], 1e-5)
+        close(after, g[f"after_{L}"], 1e-5)
+        close(O.vae_decode(sd, T(g["zlat"]), L)[0], g[f"dec_noise_{L}"], 1e-5)
+    if L == 48:
+        r1 = O.vae_decode(sd, T(g["zlat"])[:1], 48)[0]
+        assert r1.shape == (48,)          # torch.squeeze drops the batch dim at B == 1 (vqvae.py:105)
+        close(r1, g["dec_b1_48"], 1e-5)
+
+
+def test_backbone():
+    g = load_golden("backbone.npz")
+    x1, t, x0, eps, ti = (T(g[k]) for k in ("x1", "t", "x0", "eps", "ti"))
+    close(O.rf_create_flow(x1, t, x0), g["x_t"], 1e-7)
+    close(O.rf_euler(x1, eps, 0.01), g["euler"], 1e-7)
+    close(O.mse(x1, eps), g["rf_loss"], 1e-6)
+    sched = O.ddpm_schedule(1000)
+    for a, k in zip(sched, ("beta", "alpha", "alpha_bar")):
+        assert np.array_equal(a.numpy(), g[k])
+    close(O.ddpm_q_sample(x1, ti, eps, sched), g["q_sample"], 1e-6)
+    close(O.ddpm_p_sample(x1, eps, ti, T(g["p_noise"]), sched), g["p_sample"], 1e-5)
+    assert abs(sched[2][-1].item() - 4.04e-5) < 1e-6
+
+
+def test_sampling_loops():
+    g = load_golden("sampling.npz")
+    dit = synth.make_dit_state(int(g["dit_seed"]), bias_std=float(g["bias_std"]))
+    vae = synth.make_vae_state(int(g["vae_seed"]))
+    assert synth.state_checksum(dit) == str(g["dit_checksum"])
+    emb = T(g["emb"])
+    for steps, L in ((4, 24), (6, 48), (5, 96)):
+        k = f"rf_{steps}_{L}_"
+        lat, ser, vel = O.rf_sample(dit, vae, T(g[k + "noise"]), emb, steps, float(g[k + "cfg"]), L,
+                                    return_velocities=True)
+        close(torch.stack(vel), g[k + "vel"], 2e-4)
+        close(lat, g[k + "latent"], 2e-4)
+        close(ser, g[k + "series"], 2e-4)
+    steps, L = int(g["ddpm_steps"]), int(g["ddpm_L"])
+    lat, ser, eps = O.ddpm_sample(dit, vae, T(g["ddpm_noise"]), emb, steps, float(g["ddpm_cfg"]),
+                                  T(g["ddpm_step_noise"]), L, return_eps=True)
+    close(torch.stack(eps), g["ddpm_eps"], 1e-6, rtol=1e-4)
+    close(lat, g["ddpm_latent"], 1e-6, rtol=1e-4)
+    close(ser, g["ddpm_series"], 1e-6, rtol=1e-4)
+
+
+def test_rf_timesteps_match_infer_formula():
+    tt = O.rf_timesteps(100, 2)
+    for j in (0, 1, 33, 99):
+        ref = torch.round(torch.full((2,), j * 1.0 / 100) * 100) / 100
+        assert torch.equal(tt[j], ref)
+
+
+def test_train_step():
+    g = load_golden("train.npz")
+    dit = synth.make_dit_state(int(g["dit_seed"]), bias_std=float(g["bias_std"]))
+    vae = synth.make_vae_state(int(g["vae_seed"]))
+    assert synth.state_checksum(dit) == str(g["dit_checksum"])
+    series, emb, x0, t = (T(g[k]) for k in ("series", "emb", "x0", "t"))
+    with torch.no_grad():
+        x1, _ = O.vae_encode(vae, series)
+    close(x1, g["x1"], 1e-5)
+    x_t = O.rf_create_flow(x1, t, x0)
+    loss, grads = O.train_step_grads(dit, x_t, t, emb, x1 - x0)
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * max(1.0, abs(float(g["loss"])))
+    names = [str(n)[len("grad_norm/"):] for n in g["names"]]
+    assert sorted(names) == sorted(grads.keys())          # 48 tensors receive a gradient
+    assert sum(v.numel() for v in grads.values()) == 925592
+    for n, ref in zip(names, g["norms"]):
+        assert abs(grads[n].norm().item() - ref) <= 1e-4 * max(ref, 1e-3), n
+    for k in g.files:
+        if k.startswith("grad/"):
+            n = k[len("grad/"):]
+            close(grads[n].reshape(-1)[:256], g[k], 1e-7, rtol=2e-4)
+            p, m, v = O.adamw_step(dit[n], grads[n], torch.zeros_like(dit[n]), torch.zeros_like(dit[n]), 1, 1e-4)
+            close(p.reshape(-1)[:256], g["param_after/" + n], 2e-7)
