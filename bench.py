@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the T2S generation hot path (BASELINE.json metric: sampled series/sec, length 96,
+rectified flow, classifier-free guidance, LA-VAE decode).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input: `--batch` series generated
+from text embeddings with `--rf-steps` guided denoising steps + decode (BASELINE config 2: batch 1024,
+length 96, 100 steps, cfg 7).  N > 1 (torchrun, one rank per GPU): every rank generates its own
+`--batch` series (weak scaling) and the step ends with the final all_gather of the series.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "t2s_dit_rf_sampled_series_per_sec"
+UNIT = "series/s"
+FLOP_FWD = 976_960_512                 # per DiT forward per sequence
+FLOP_ATTN_LAYER = 2 * 58_982_400       # QK^T + PV per sequence per block
+FLOP_TOKEN_MID = 15_728_640 + 31_457_280 + 31_457_280 + 47_185_920   # proj + fc1 + fc2 + next-block QKV
+FLOP_DECODE_96 = 15_360_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="series per GPU per step")
+    ap.add_argument("--length", type=int, default=96)
+    ap.add_argument("--rf-steps", type=int, default=100)
+    ap.add_argument("--cfg", type=float, default=7.0)
+    ap.add_argument("--backbone", default="flowmatching", choices=["flowmatching", "ddpm"])
+    ap.add_argument("--chunk", type=int, default=0, help="samples per launch wave (0 = whole batch)")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="series in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1399.4))), "hbm": float(d.get("hbm_gbs", 6546.2)),
+                "src": "measured (MEASURED_PEAKS.json, bf16/fp16 dense sustained)"}
+    return {"tflops": 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(a, n_series: int, repeats: int = 1):
+    """The oracle port of the reference loop (infer.py:75-95) on the host cores; returns (series/s, seconds, threads)."""
+    from oracle import t2s_oracle as O
+    from t2ms_b200 import synth
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    dsd, vsd = synth.make_dit_state(0), synth.make_vae_state(1)
+    emb, noise = synth.make_text_embeddings(n_series), synth.make_noise(n_series)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        if a.backbone == "flowmatching":
+            O.rf_sample(dsd, vsd, noise, emb, a.rf_steps, a.cfg, a.length)
+        else:
+            O.ddpm_sample(dsd, vsd, noise, emb, a.rf_steps, a.cfg, synth.make_step_noise(a.rf_steps, n_series), a.length)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_series / best, best, threads
+
+
+def workload_name(a):
+    kind = "rectified-flow" if a.backbone == "flowmatching" else "DDPM"
+    return (f"T2S-DiT {kind} sampling length {a.length} with CFG {a.cfg:g}, batch {a.batch}/GPU, {a.rf_steps} steps, "
+            f"LA-VAE decode (BASELINE config 2)")
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    n = a.cpu_sample
+    times = []
+    for i in range(a.warmup + a.steps):
+        v, dt, threads = cpu_reference_run(a, n)
+        if i >= a.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = n * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": workload_name(a), "sample": f"{n} series per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n} series x {a.rf_steps} guided steps + decode per step, oracle port (torch fp32 CPU)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def kernel_breakdown(smp, dit, vae, a, dev):
+    """Per-kernel device time at the bench workload size, CUDA events on the launching stream."""
+    import ctypes as C
+    from t2ms_b200 import _lib
+    from t2ms_b200.denoiser import _aligned
+    lib = _lib.load()
+    nseq = 2 * (a.chunk or a.batch)
+    pk = dit.packed()
+    ws = dit.workspace(nseq, dev)
+    wp = _aligned(ws)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    x = torch.randn(nseq // 2, 64, 30, device=dev)
+    emb = torch.randn(nseq // 2, 128, device=dev)
+    t100 = torch.full((1,), 37.0, device=dev)
+    out = torch.empty(nseq, 64, 30, device=dev)
+    series = torch.empty(nseq // 2, a.length, device=dev)
+    calls = {
+        "cond": lambda: lib.t2s_dit_cond(pk.ref, t100.data_ptr(), 0, emb.data_ptr(), 1, nseq, wp, st),
+        "embed_qkv": lambda: lib.t2s_dit_embed_qkv(pk.ref, x.data_ptr(), 1, nseq, wp, st),
+        "attention": lambda: lib.t2s_dit_attention(nseq, wp, st),
+        "token_mid": lambda: lib.t2s_dit_block_post(pk.ref, 1, nseq, wp, st),
+        "token_final": lambda: lib.t2s_dit_final(pk.ref, out.data_ptr(), nseq, wp, st),
+        "vae_decode": lambda: vae.decoder.decode_into(x, a.length, series, None),
+    }
+    res = {}
+    for name, fn in calls.items():
+        for _ in range(3):
+            fn()
+        reps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        res[name] = e0.elapsed_time(e1) / reps
+    return res, nseq
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    import torch.distributed as dist
+    from t2ms_b200 import T2SSampler, Transformer, synth, vqvae
+    from t2ms_b200.compat import VAE_ARGS
+    from t2ms_b200.sampler import gather_series
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dit = Transformer()
+    dit.load_state_dict(synth.make_dit_state(0))
+    dit = dit.to(dev).eval()
+    vae = vqvae(VAE_ARGS)
+    vae.load_state_dict(synth.make_vae_state(1))
+    vae = vae.to(dev).eval()
+    smp = T2SSampler(dit, vae)
+    B = a.batch
+    gen = torch.Generator().manual_seed(1234 + rank)
+    emb_host = torch.nn.functional.normalize(torch.randn(B, 128, generator=gen), dim=-1).pin_memory()
+    out_host = torch.empty(B, a.length, dtype=torch.float32).pin_memory()
+    emb_dev = emb_host.to(dev)
+    noise = torch.randn(B, 64, 30, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    kw = dict(steps=a.rf_steps, cfg_scale=a.cfg, backbone=a.backbone, chunk=a.chunk or None)
+
+    def step_device():
+        flush.zero_()                                                   # L2 flush between timed iterations
+        s = smp.sample(emb_dev, a.length, noise=noise, **kw)
+        return gather_series(s, B * world) if world > 1 else s
+
+    def step_e2e():
+        flush.zero_()
+        s = smp.sample_host(emb_host, a.length, out_host=out_host, **kw)
+        return s
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_device, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+
+    value = world * B * a.steps / (ms / 1e3)
+    e2e = world * B * a.steps / (ms_e2e / 1e3)
+    line = None
+    if rank == 0:
+        pk = peaks()
+        kb, nseq = kernel_breakdown(smp, dit, vae, a, dev)
+        n_chunks = 1 if not a.chunk else -(-B // a.chunk)
+        step_kernel_ms = a.rf_steps * (kb["cond"] + kb["embed_qkv"] + 4 * kb["attention"] + 3 * kb["token_mid"] + kb["token_final"]) * n_chunks
+        shares = {k: round(a.rf_steps * n_chunks * v * {"attention": 4, "token_mid": 3}.get(k, 1) / step_kernel_ms, 4)
+                  for k, v in kb.items() if k != "vae_decode"}
+        dom = max(("attention", "token_mid"), key=lambda k: shares[k])
+        flop = (FLOP_ATTN_LAYER if dom == "attention" else FLOP_TOKEN_MID) * nseq
+        achieved = flop / (kb[dom] * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate (10-bit mantissa = tf32 operand precision); residual, LayerNorm, softmax, update in f32",
+            "data": "synthetic (random-init weights seed 0/1, unit-norm 128-d text embeddings, Gaussian initial latents)",
+            "config": {"workload": workload_name(a), "batch_per_gpu": B, "length": a.length, "denoise_steps": a.rf_steps,
+                       "cfg_scale": a.cfg, "backbone": a.backbone, "parallelism": f"batch-shard x{world}, final all_gather",
+                       "l2": "256 MiB flush write between timed iterations; per-step working set (1.5 GB scratch) exceeds the 126 MB L2"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": emb_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
+                    "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": a.steps * (a.rf_steps * 10 * n_chunks + 1),
+            "clocks": clocks,
+            "tflops_algorithmic": world * B * a.steps * (2 * a.rf_steps * FLOP_FWD + FLOP_DECODE_96) / (ms / 1e3) / 1e12,
+            "roofline": {"bound": "tensor", "kernel": "attn_kernel" if dom == "attention" else "token_kernel<MID>",
+                         "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+                         "traffic": None, "peak_source": pk["src"], "flop_per_launch": flop, "launch_ms": kb[dom]},
+            "kernel_ms": {k: round(v, 4) for k, v in kb.items()},
+            "kernel_share_of_step": shares,
+        }
+        if not a.no_cpu_baseline:
+            v, dt, threads = cpu_reference_run(a, a.cpu_sample)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{a.cpu_sample} series x {a.rf_steps} guided steps + decode in {dt:.1f} s, oracle port (torch fp32 CPU)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,15 @@
+"""t2ms_b200 — B200-native (sm_100a) implementation of the T2S generation hot path.
+
+Public surface mirrors the reference modules used by infer.py / train.py:
+``Transformer`` (model/denoiser/transformer.py), ``RectifiedFlow`` / ``DDPM`` (model/backbone),
+``vqvae`` / ``Encoder`` / ``Decoder`` (model/pretrained/vqvae.py), plus ``T2SSampler`` which runs the
+whole guided sampling loop + decode in one enqueue.
+"""
+from .backbone import DDPM, RectifiedFlow
+from .denoiser import Transformer, Transformerlayer, TimeEmbedding
+from .lavae import Decoder, Encoder, vqvae
+from .sampler import T2SSampler, gather_series, shard_range
+
+__all__ = ["Transformer", "Transformerlayer", "TimeEmbedding", "RectifiedFlow", "DDPM", "vqvae", "Encoder", "Decoder",
+           "T2SSampler", "gather_series", "shard_range"]
+__version__ = "0.1.0"

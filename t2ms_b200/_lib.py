@@ -1,0 +1,88 @@
+"""ctypes binding of the C ABI declared in include/t2s_b200.h.
+
+The product path is CUDA only: if the shared library is missing this raises, there is no CPU or
+PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libt2s_b200.so")
+
+EXPORTS = [
+    "t2s_version", "t2s_last_error", "t2s_init", "t2s_dit_workspace_bytes", "t2s_dit_workspace_offsets",
+    "t2s_dit_forward", "t2s_sample", "t2s_vae_decode", "t2s_vae_encode",
+    "t2s_dit_cond", "t2s_dit_embed_qkv", "t2s_dit_attention", "t2s_dit_block_post", "t2s_dit_final",
+]
+
+P = C.c_void_p
+
+
+class DitWeights(C.Structure):
+    _fields_ = [("w_qkv", P * 4), ("w_post", P * 4), ("b_qkv", P * 4), ("b_proj", P * 4), ("b_fc1", P * 4),
+                ("b_fc2", P * 4), ("w_ada_t", P), ("b_ada", P), ("w_embed", P), ("b_embed", P), ("pos", P),
+                ("w_final", P), ("b_final", P), ("freqs", P)]
+
+
+class VaeDecWeights(C.Structure):
+    _fields_ = [("conv1_w", P), ("conv1_b", P), ("res_w3", P * 2), ("res_w1", P * 2), ("ct1_w", P), ("ct1_b", P),
+                ("ct2_w", P), ("ct2_b", P)]
+
+
+class VaeEncWeights(C.Structure):
+    _fields_ = [("conv1_w", P), ("conv1_b", P), ("conv2_w", P), ("conv2_b", P), ("conv3_w", P), ("conv3_b", P),
+                ("res_w3", P * 2), ("res_w1", P * 2), ("pre_w", P), ("pre_b", P)]
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libt2s_b200.so (built by t2ms_b200.build / __graft_entry__.build)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m t2ms_b200.build` "
+                "(t2ms_b200 has no CPU / PyTorch fallback)")
+        lib = C.CDLL(LIB_PATH)
+        i, f, sz = C.c_int, C.c_float, C.c_size_t
+        lib.t2s_version.restype = i
+        lib.t2s_last_error.restype = C.c_char_p
+        lib.t2s_init.restype = i
+        lib.t2s_dit_workspace_bytes.restype = sz
+        lib.t2s_dit_workspace_bytes.argtypes = [i]
+        lib.t2s_dit_workspace_offsets.restype = None
+        lib.t2s_dit_workspace_offsets.argtypes = [i, C.POINTER(sz * 4)]
+        lib.t2s_dit_forward.restype = i
+        lib.t2s_dit_forward.argtypes = [C.POINTER(DitWeights), P, P, P, P, i, P, sz, P]
+        lib.t2s_sample.restype = i
+        lib.t2s_sample.argtypes = [C.POINTER(DitWeights), i, P, P, P, C.POINTER(f), P, P, i, i, f, P, sz, P]
+        lib.t2s_vae_decode.restype = i
+        lib.t2s_vae_decode.argtypes = [C.POINTER(VaeDecWeights), P, P, P, i, i, P]
+        lib.t2s_vae_encode.restype = i
+        lib.t2s_vae_encode.argtypes = [C.POINTER(VaeEncWeights), P, P, P, i, i, P]
+        lib.t2s_dit_cond.restype = i
+        lib.t2s_dit_cond.argtypes = [C.POINTER(DitWeights), P, i, P, i, i, P, P]
+        lib.t2s_dit_embed_qkv.restype = i
+        lib.t2s_dit_embed_qkv.argtypes = [C.POINTER(DitWeights), P, i, i, P, P]
+        lib.t2s_dit_attention.restype = i
+        lib.t2s_dit_attention.argtypes = [i, P, P]
+        lib.t2s_dit_block_post.restype = i
+        lib.t2s_dit_block_post.argtypes = [C.POINTER(DitWeights), i, i, P, P]
+        lib.t2s_dit_final.restype = i
+        lib.t2s_dit_final.argtypes = [C.POINTER(DitWeights), P, i, P, P]
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str = "t2s") -> None:
+    if rc != 0:
+        msg = load().t2s_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

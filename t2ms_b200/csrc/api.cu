@@ -1,0 +1,254 @@
+// C ABI of the T2S B200 hot path: host-side launch logic (see include/t2s_b200.h).
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/t2s_b200.h"
+#include "dit_kernels.cuh"
+#include "vae_kernels.cuh"
+
+using namespace t2s;
+
+static_assert(sizeof(DitWeights) == sizeof(t2s_dit_weights), "DitWeights must mirror t2s_dit_weights");
+static_assert(sizeof(VaeDecWeights) == sizeof(t2s_vae_dec_weights), "VaeDecWeights must mirror t2s_vae_dec_weights");
+static_assert(sizeof(VaeEncWeights) == sizeof(t2s_vae_enc_weights), "VaeEncWeights must mirror t2s_vae_enc_weights");
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+#define CUDA_OK(expr)                                                                   \
+    do {                                                                                \
+        cudaError_t e_ = (expr);                                                        \
+        if (e_ != cudaSuccess) return fail(T2S_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr int MAX_DEV = 64;
+bool g_inited[MAX_DEV] = {};
+
+int ensure_init() {
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEV) return fail(T2S_EINVAL, "device index out of range%s%s");
+    if (g_inited[dev]) return T2S_OK;
+    int major = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return fail(T2S_EARCH, "t2s_b200 is built for sm_100a only%s%s");
+    CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_EMBED>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    const int dec = VAE_DEC_SMEM_FLOATS * 4, enc = VAE_ENC_SMEM_FLOATS * 4;
+    CUDA_OK(cudaFuncSetAttribute(vae_decode_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec));
+    CUDA_OK(cudaFuncSetAttribute(vae_decode_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec));
+    CUDA_OK(cudaFuncSetAttribute(vae_decode_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec));
+    CUDA_OK(cudaFuncSetAttribute(vae_encode_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc));
+    CUDA_OK(cudaFuncSetAttribute(vae_encode_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc));
+    CUDA_OK(cudaFuncSetAttribute(vae_encode_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc));
+    g_inited[dev] = true;
+    return T2S_OK;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct Workspace {
+    float* h; __half* qkv; __half* o; float* mod;
+};
+void ws_offsets(int nseq, size_t off[4], size_t* total) {
+    size_t p = 0;
+    off[0] = p; p = align256(p + (size_t)nseq * NTOK * D * 4);
+    off[1] = p; p = align256(p + (size_t)nseq * NTOK * 3 * D * 2);
+    off[2] = p; p = align256(p + (size_t)nseq * NTOK * D * 2);
+    off[3] = p; p = align256(p + (size_t)nseq * NLAYER * MOD * 4);
+    if (total) *total = p;
+}
+Workspace ws_view(void* base, int nseq) {
+    size_t off[4];
+    ws_offsets(nseq, off, nullptr);
+    char* b = static_cast<char*>(base);
+    return Workspace{reinterpret_cast<float*>(b + off[0]), reinterpret_cast<__half*>(b + off[1]),
+                     reinterpret_cast<__half*>(b + off[2]), reinterpret_cast<float*>(b + off[3])};
+}
+
+int check_ws(const void* ws, size_t bytes, int nseq) {
+    if (ws == nullptr) return fail(T2S_EINVAL, "workspace is NULL%s%s");
+    if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(T2S_EINVAL, "workspace must be 256-byte aligned%s%s");
+    if (bytes < t2s_dit_workspace_bytes(nseq)) return fail(T2S_EWORKSPACE, "workspace too small%s%s");
+    return T2S_OK;
+}
+
+TokArgs base_args(const t2s_dit_weights* w, const Workspace& ws, int nseq) {
+    TokArgs a;
+    memset(&a, 0, sizeof(a));
+    memcpy(&a.w, w, sizeof(DitWeights));
+    a.h = ws.h; a.qkv = ws.qkv; a.o = ws.o; a.mod = ws.mod; a.nseq = nseq;
+    return a;
+}
+
+int launch_cond(const t2s_dit_weights* w, const float* t100, int t_stride, const float* emb, int emb_shift, int cfg_pairs,
+                int nseq, const Workspace& ws, cudaStream_t st) {
+    dim3 grid((nseq + 7) / 8, NLAYER);
+    cond_kernel<<<grid, 256, 0, st>>>(ws.mod, t100, t_stride, emb, emb_shift, cfg_pairs, w->freqs, w->w_ada_t, w->b_ada, nseq);
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+int launch_embed(const t2s_dit_weights* w, const float* x, int x_shift, int nseq, const Workspace& ws, cudaStream_t st) {
+    TokArgs a = base_args(w, ws, nseq);
+    a.x = x; a.x_shift = x_shift;
+    token_kernel<TOK_EMBED><<<((nseq + 1) / 2) * TILES_PER_PAIR, 256, TOK_SMEM_BYTES, st>>>(a);
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+int launch_attn(int nseq, const Workspace& ws, cudaStream_t st) {
+    attn_kernel<<<nseq * NHEAD, ATT_THREADS, ATT_SMEM_BYTES, st>>>(ws.qkv, ws.o);
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+int launch_mid(const t2s_dit_weights* w, int layer, int nseq, const Workspace& ws, cudaStream_t st) {
+    TokArgs a = base_args(w, ws, nseq);
+    a.layer = layer;
+    token_kernel<TOK_MID><<<((nseq + 1) / 2) * TILES_PER_PAIR, 256, TOK_SMEM_BYTES, st>>>(a);
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+int launch_final(const t2s_dit_weights* w, int nseq, const Workspace& ws, int out_mode, float* out, float* x_upd,
+                 const float* noise, float cfg, float c1, float c2, float c3, cudaStream_t st) {
+    TokArgs a = base_args(w, ws, nseq);
+    a.layer = NLAYER - 1;
+    a.out_mode = out_mode; a.out = out; a.x_upd = x_upd; a.noise = noise;
+    a.cfg = cfg; a.c1 = c1; a.c2 = c2; a.c3 = c3;
+    token_kernel<TOK_FINAL><<<((nseq + 1) / 2) * TILES_PER_PAIR, 256, TOK_SMEM_BYTES, st>>>(a);
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+
+#define TRY(expr)                 \
+    do {                          \
+        int rc_ = (expr);         \
+        if (rc_ != T2S_OK) return rc_; \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int t2s_version(void) { return 100; }
+const char* t2s_last_error(void) { return g_err; }
+int t2s_init(void) { return ensure_init(); }
+
+size_t t2s_dit_workspace_bytes(int nseq) {
+    size_t off[4], total = 0;
+    ws_offsets(nseq > 0 ? nseq : 0, off, &total);
+    return total;
+}
+void t2s_dit_workspace_offsets(int nseq, size_t offsets[4]) { ws_offsets(nseq, offsets, nullptr); }
+
+int t2s_dit_cond(const t2s_dit_weights* w, const float* t100, int t_stride, const float* emb, int cfg_pairs, int nseq,
+                 void* workspace, t2s_stream_t stream) {
+    if (!w || !t100 || nseq <= 0 || !workspace) return fail(T2S_EINVAL, "t2s_dit_cond: bad argument%s%s");
+    TRY(ensure_init());
+    return launch_cond(w, t100, t_stride, emb, cfg_pairs ? 1 : 0, cfg_pairs, nseq, ws_view(workspace, nseq), (cudaStream_t)stream);
+}
+int t2s_dit_embed_qkv(const t2s_dit_weights* w, const float* x, int x_shared, int nseq, void* workspace, t2s_stream_t stream) {
+    if (!w || !x || nseq <= 0 || !workspace) return fail(T2S_EINVAL, "t2s_dit_embed_qkv: bad argument%s%s");
+    TRY(ensure_init());
+    return launch_embed(w, x, x_shared ? 1 : 0, nseq, ws_view(workspace, nseq), (cudaStream_t)stream);
+}
+int t2s_dit_attention(int nseq, void* workspace, t2s_stream_t stream) {
+    if (nseq <= 0 || !workspace) return fail(T2S_EINVAL, "t2s_dit_attention: bad argument%s%s");
+    TRY(ensure_init());
+    return launch_attn(nseq, ws_view(workspace, nseq), (cudaStream_t)stream);
+}
+int t2s_dit_block_post(const t2s_dit_weights* w, int layer, int nseq, void* workspace, t2s_stream_t stream) {
+    if (!w || layer < 0 || layer >= NLAYER - 1 || nseq <= 0 || !workspace)
+        return fail(T2S_EINVAL, "t2s_dit_block_post: bad argument (layer must be 0..2)%s%s");
+    TRY(ensure_init());
+    return launch_mid(w, layer, nseq, ws_view(workspace, nseq), (cudaStream_t)stream);
+}
+int t2s_dit_final(const t2s_dit_weights* w, float* out, int nseq, void* workspace, t2s_stream_t stream) {
+    if (!w || !out || nseq <= 0 || !workspace) return fail(T2S_EINVAL, "t2s_dit_final: bad argument%s%s");
+    TRY(ensure_init());
+    return launch_final(w, nseq, ws_view(workspace, nseq), OUT_FWD, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, (cudaStream_t)stream);
+}
+
+int t2s_dit_forward(const t2s_dit_weights* w, const float* x, const float* t100, const float* emb, float* out, int nseq,
+                    void* workspace, size_t workspace_bytes, t2s_stream_t stream) {
+    if (!w || !x || !t100 || !out || nseq <= 0) return fail(T2S_EINVAL, "t2s_dit_forward: bad argument%s%s");
+    TRY(check_ws(workspace, workspace_bytes, nseq));
+    TRY(ensure_init());
+    cudaStream_t st = (cudaStream_t)stream;
+    const Workspace ws = ws_view(workspace, nseq);
+    TRY(launch_cond(w, t100, 1, emb, 0, 0, nseq, ws, st));
+    TRY(launch_embed(w, x, 0, nseq, ws, st));
+    for (int l = 0; l < NLAYER; ++l) {
+        TRY(launch_attn(nseq, ws, st));
+        if (l < NLAYER - 1) TRY(launch_mid(w, l, nseq, ws, st));
+    }
+    return launch_final(w, nseq, ws, OUT_FWD, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, st);
+}
+
+int t2s_sample(const t2s_dit_weights* w, int kind, float* x, const float* emb, const float* t100, const float* coef,
+               const float* step_noise, float* pred_trace, int batch, int steps, float cfg_scale, void* workspace,
+               size_t workspace_bytes, t2s_stream_t stream) {
+    if (!w || !x || !emb || !t100 || !coef || batch <= 0 || steps <= 0 || (kind != 0 && kind != 1))
+        return fail(T2S_EINVAL, "t2s_sample: bad argument%s%s");
+    if (kind == 1 && !step_noise) return fail(T2S_EINVAL, "t2s_sample: DDPM needs step_noise%s%s");
+    const int nseq = 2 * batch;
+    TRY(check_ws(workspace, workspace_bytes, nseq));
+    TRY(ensure_init());
+    cudaStream_t st = (cudaStream_t)stream;
+    const Workspace ws = ws_view(workspace, nseq);
+    const size_t lat = (size_t)batch * LAT;
+    for (int j = 0; j < steps; ++j) {
+        TRY(launch_cond(w, t100 + j, 0, emb, 1, 1, nseq, ws, st));
+        TRY(launch_embed(w, x, 1, nseq, ws, st));
+        for (int l = 0; l < NLAYER; ++l) {
+            TRY(launch_attn(nseq, ws, st));
+            if (l < NLAYER - 1) TRY(launch_mid(w, l, nseq, ws, st));
+        }
+        TRY(launch_final(w, nseq, ws, kind == 0 ? OUT_RF : OUT_DDPM, pred_trace ? pred_trace + j * lat : nullptr, x,
+                         kind == 1 ? step_noise + j * lat : nullptr, cfg_scale, coef[3 * j], coef[3 * j + 1], coef[3 * j + 2], st));
+    }
+    return T2S_OK;
+}
+
+int t2s_vae_decode(const t2s_vae_dec_weights* w, const float* z, float* series, float* after, int batch, int length,
+                   t2s_stream_t stream) {
+    if (!w || !z || !series || batch <= 0) return fail(T2S_EINVAL, "t2s_vae_decode: bad argument%s%s");
+    TRY(ensure_init());
+    VaeDecWeights dw;
+    memcpy(&dw, w, sizeof(dw));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int smem = VAE_DEC_SMEM_FLOATS * 4;
+    switch (length) {
+        case 24: vae_decode_kernel<6><<<batch, 256, smem, st>>>(dw, z, series, after); break;
+        case 48: vae_decode_kernel<12><<<batch, 256, smem, st>>>(dw, z, series, after); break;
+        case 96: vae_decode_kernel<24><<<batch, 256, smem, st>>>(dw, z, series, after); break;
+        default: return fail(T2S_EINVAL, "t2s_vae_decode: length must be 24, 48 or 96%s%s");
+    }
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+
+int t2s_vae_encode(const t2s_vae_enc_weights* w, const float* x, float* z, float* before, int batch, int length,
+                   t2s_stream_t stream) {
+    if (!w || !x || !z || batch <= 0) return fail(T2S_EINVAL, "t2s_vae_encode: bad argument%s%s");
+    TRY(ensure_init());
+    VaeEncWeights ew;
+    memcpy(&ew, w, sizeof(ew));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int smem = VAE_ENC_SMEM_FLOATS * 4;
+    switch (length) {
+        case 24: vae_encode_kernel<6><<<batch, 256, smem, st>>>(ew, x, z, before); break;
+        case 48: vae_encode_kernel<12><<<batch, 256, smem, st>>>(ew, x, z, before); break;
+        case 96: vae_encode_kernel<24><<<batch, 256, smem, st>>>(ew, x, z, before); break;
+        default: return fail(T2S_EINVAL, "t2s_vae_encode: length must be 24, 48 or 96%s%s");
+    }
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+
+}  // extern "C"

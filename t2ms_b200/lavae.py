@@ -1,0 +1,179 @@
+"""LA-VAE with the reference module interface (model/pretrained/vqvae.py, core.py).
+
+``vqvae(args).encoder(x) -> (z, before)`` and ``.decoder(z, length) -> (squeeze(series), after)`` keep
+the reference's names, shapes and state-dict keys; both forwards are single fused sm_100a kernels
+(t2s_vae_encode / t2s_vae_decode in include/t2s_b200.h).  CUDA only.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+
+import torch
+import torch.nn as nn
+from torch.optim.lr_scheduler import CosineAnnealingLR, LinearLR, SequentialLR
+
+from . import _lib
+from .packing import PackedVaeDecoder, PackedVaeEncoder
+
+LENGTHS = (24, 48, 96)
+
+
+class BaseModel(nn.Module, ABC):
+    """model/pretrained/core.py:8-20"""
+
+    def __init__(self):
+        super().__init__()
+
+    @abstractmethod
+    def shared_eval(self, batch, optimizer, scheduler, mode):
+        pass
+
+    def configure_optimizers(self, lr=1e-3):
+        optimizer = torch.optim.AdamW(self.parameters(), lr=lr, weight_decay=1e-2)
+        scheduler1 = LinearLR(optimizer, start_factor=0.1, total_iters=1000)
+        scheduler2 = CosineAnnealingLR(optimizer, T_max=400 - 1000, eta_min=1e-6)
+        scheduler = SequentialLR(optimizer, schedulers=[scheduler1, scheduler2], milestones=[1000])
+        return optimizer, scheduler
+
+
+class Residual(nn.Module):
+    """model/pretrained/vqvae.py:7-22 (parameters only; the in-place-ReLU semantics live in the kernel)."""
+
+    def __init__(self, in_channels, num_hiddens, num_residual_hiddens):
+        super().__init__()
+        self._block = nn.Sequential(
+            nn.ReLU(True),
+            nn.Conv1d(in_channels, num_residual_hiddens, kernel_size=3, stride=1, padding=1, bias=False),
+            nn.ReLU(True),
+            nn.Conv1d(num_residual_hiddens, num_hiddens, kernel_size=1, stride=1, bias=False))
+
+
+class ResidualStack(nn.Module):
+    """model/pretrained/vqvae.py:24-33"""
+
+    def __init__(self, in_channels, num_hiddens, num_residual_layers, num_residual_hiddens):
+        super().__init__()
+        self._num_residual_layers = num_residual_layers
+        self._layers = nn.ModuleList([Residual(in_channels, num_hiddens, num_residual_hiddens)
+                                      for _ in range(num_residual_layers)])
+
+
+class _PackedMixin:
+    _packer = None
+
+    def _packed_weights(self):
+        params = list(self.named_parameters())
+        dev = params[0][1].device
+        if dev.type != "cuda":
+            raise RuntimeError(f"t2ms_b200 {type(self).__name__} runs on CUDA (sm_100a) only (no CPU fallback)")
+        key = (str(dev), tuple(p._version for _, p in params), tuple(p.data_ptr() for _, p in params))
+        if getattr(self, "_pk", None) is None or self._pk_key != key:
+            with torch.no_grad():
+                self._pk = type(self)._packer({n: p for n, p in params}, dev)
+            self._pk_key = key
+        return self._pk
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st.pop("_pk", None)
+        st.pop("_pk_key", None)
+        return st
+
+
+def _check_arch(num_hiddens, num_residual_layers, num_residual_hiddens, embedding_dim):
+    if (num_hiddens, num_residual_layers, num_residual_hiddens, embedding_dim) != (128, 2, 256, 64):
+        raise ValueError("t2ms_b200 LA-VAE kernels are specialised for block_hidden_size=128, num_residual_layers=2, "
+                         "res_hidden_size=256, embedding_dim=64 (pretrained_lavae_unified.py:119-122)")
+
+
+class Encoder(_PackedMixin, nn.Module):
+    """model/pretrained/vqvae.py:36-71"""
+    _packer = PackedVaeEncoder
+
+    def __init__(self, in_channels, num_hiddens, num_residual_layers, num_residual_hiddens, embedding_dim):
+        super().__init__()
+        if in_channels != 1:
+            raise ValueError("univariate series only (in_channels=1)")
+        _check_arch(num_hiddens, num_residual_layers, num_residual_hiddens, embedding_dim)
+        self._conv_1 = nn.Conv1d(in_channels, num_hiddens // 2, kernel_size=4, stride=2, padding=1)
+        self._conv_2 = nn.Conv1d(num_hiddens // 2, num_hiddens, kernel_size=4, stride=2, padding=1)
+        self._conv_3 = nn.Conv1d(num_hiddens, num_hiddens, kernel_size=3, stride=1, padding=1)
+        self._residual_stack = ResidualStack(num_hiddens, num_hiddens, num_residual_layers, num_residual_hiddens)
+        self._pre_vq_conv = nn.Conv1d(num_hiddens, embedding_dim, kernel_size=1, stride=1)
+
+    def forward(self, inputs):
+        if not inputs.is_cuda:
+            raise RuntimeError("t2ms_b200 Encoder.forward needs CUDA tensors (no CPU fallback)")
+        B, L = inputs.shape[0], inputs.shape[-1]
+        if L not in LENGTHS:
+            raise ValueError(f"series length must be one of {LENGTHS}, got {L}")
+        x = inputs.detach().reshape(B, L).to(torch.float32).contiguous()
+        z = torch.empty(B, 64, 30, device=x.device, dtype=torch.float32)
+        before = torch.empty(B, 64, L // 4, device=x.device, dtype=torch.float32)
+        pk = self._packed_weights()
+        with torch.cuda.device(x.device):
+            rc = _lib.load().t2s_vae_encode(pk.ref, x.data_ptr(), z.data_ptr(), before.data_ptr(), B, L,
+                                            torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "t2s_vae_encode")
+        return z, before
+
+
+class Decoder(_PackedMixin, nn.Module):
+    """model/pretrained/vqvae.py:74-105"""
+    _packer = PackedVaeDecoder
+
+    def __init__(self, in_channels, num_hiddens, num_residual_layers, num_residual_hiddens):
+        super().__init__()
+        _check_arch(num_hiddens, num_residual_layers, num_residual_hiddens, in_channels)
+        self._conv_1 = nn.Conv1d(in_channels, num_hiddens, kernel_size=3, stride=1, padding=1)
+        self._residual_stack = ResidualStack(num_hiddens, num_hiddens, num_residual_layers, num_residual_hiddens)
+        self._conv_trans_1 = nn.ConvTranspose1d(num_hiddens, num_hiddens // 2, kernel_size=4, stride=2, padding=1)
+        self._conv_trans_2 = nn.ConvTranspose1d(num_hiddens // 2, 1, kernel_size=4, stride=2, padding=1)
+
+    def decode_into(self, z: torch.Tensor, length: int, series: torch.Tensor, after=None):
+        pk = self._packed_weights()
+        with torch.cuda.device(z.device):
+            rc = _lib.load().t2s_vae_decode(pk.ref, z.data_ptr(), series.data_ptr(), after.data_ptr() if after is not None else None,
+                                            z.shape[0], int(length), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "t2s_vae_decode")
+
+    def forward(self, inputs, length):
+        if not inputs.is_cuda:
+            raise RuntimeError("t2ms_b200 Decoder.forward needs CUDA tensors (no CPU fallback)")
+        length = int(length)
+        if length not in LENGTHS:
+            raise ValueError(f"series length must be one of {LENGTHS}, got {length}")
+        z = inputs.detach().to(torch.float32).contiguous()
+        assert z.shape[1:] == (64, 30), f"latent must be (B,64,30), got {tuple(z.shape)}"
+        B = z.shape[0]
+        series = torch.empty(B, 1, length, device=z.device, dtype=torch.float32)
+        after = torch.empty(B, 64, length // 4, device=z.device, dtype=torch.float32)
+        self.decode_into(z, length, series, after)
+        return torch.squeeze(series), after          # vqvae.py:105 (drops the batch dim at B == 1)
+
+
+class vqvae(BaseModel):
+    """model/pretrained/vqvae.py:108-142"""
+
+    def __init__(self, args):
+        super().__init__()
+        self.encoder = Encoder(1, args.block_hidden_size, args.num_residual_layers, args.res_hidden_size, args.embedding_dim)
+        self.decoder = Decoder(args.embedding_dim, args.block_hidden_size, args.num_residual_layers, args.res_hidden_size)
+
+    def shared_eval(self, batch, optimizer, mode):
+        """vqvae.py:118-135.  Only the frozen forward is on the generation path (train.py:31-33);
+        LA-VAE training is outside the scope of this package."""
+        if mode == "train":
+            raise NotImplementedError("LA-VAE training is out of scope for t2ms_b200 (frozen in the T2S path)")
+        import torch.nn.functional as F
+        with torch.no_grad():
+            z, before = self.encoder(batch)
+            data_recon, after = self.decoder(z, length=batch.shape[-1])
+            recon_error = F.mse_loss(data_recon, batch)
+            cross_loss = F.mse_loss(before, after)
+            loss = recon_error + cross_loss
+        return loss, recon_error, data_recon, z
+
+    def forward(self, x):
+        raise NotImplementedError("vqvae.forward is broken in the reference (vqvae.py:137-142 passes a tuple "
+                                  "to the decoder) and unused; call .encoder / .decoder")

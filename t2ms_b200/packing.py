@@ -1,0 +1,129 @@
+"""Host-side weight packing: reference state-dict tensors -> the device layouts the kernels read.
+
+Layouts are documented in include/t2s_b200.h and DESIGN.md.  Everything here runs once per weight
+update (module construction, load_state_dict, optimizer step), never inside the sampling loop.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict
+
+import torch
+
+from . import _lib
+
+D = 128
+
+
+def swizzle_stage(w: torch.Tensor) -> torch.Tensor:
+    """[N][K] weight (nn.Linear layout: row n = output feature, K contiguous) -> fp16 smem image.
+
+    Row n holds K/8 16-byte chunks; logical chunk c is stored at physical chunk c ^ (n & 7), which
+    makes every ldmatrix 8x8 read bank-conflict-free (t2ms_b200/csrc/dit_kernels.cuh: warp_gemm_*).
+    """
+    n, k = w.shape
+    assert k % 64 == 0
+    w16 = w.detach().to(torch.float16).reshape(n, k // 8, 8)
+    pc = torch.arange(k // 8, device=w.device).unsqueeze(0)                 # physical chunk
+    src = pc ^ (torch.arange(n, device=w.device).unsqueeze(1) & 7)          # logical chunk stored there
+    out = torch.gather(w16, 1, src.unsqueeze(-1).expand(n, k // 8, 8))
+    return out.reshape(-1).contiguous()
+
+
+def _ptr(t: torch.Tensor) -> int:
+    return t.data_ptr()
+
+
+class PackedDit:
+    """Device-resident packed DiT weights + the ctypes struct handed to the C ABI."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], device: torch.device):
+        f32 = dict(device=device, dtype=torch.float32)
+        g = lambda k: sd[k].detach().to(**f32)
+        keep = []
+        st = _lib.DitWeights()
+        for l in range(4):
+            p = f"layers.{l}."
+            wq = g(p + "attn.qkv.weight")                                           # [384][128]
+            qkv = torch.cat([swizzle_stage(wq[i * D:(i + 1) * D]) for i in range(3)])
+            w1, w2 = g(p + "mlp.fc1.weight"), g(p + "mlp.fc2.weight")               # [256][128], [128][256]
+            post = [swizzle_stage(g(p + "attn.proj.weight"))]
+            for c in range(4):
+                post.append(swizzle_stage(w1[c * 64:(c + 1) * 64]))                 # [64][128]  16 KB
+                post.append(swizzle_stage(w2[:, c * 64:(c + 1) * 64].contiguous()))  # [128][64]  16 KB
+            post = torch.cat(post)
+            assert qkv.numel() * 2 == 3 * 32768 and post.numel() * 2 == 5 * 32768
+            bq, bp = g(p + "attn.qkv.bias").contiguous(), g(p + "attn.proj.bias").contiguous()
+            b1, b2 = g(p + "mlp.fc1.bias").contiguous(), g(p + "mlp.fc2.bias").contiguous()
+            keep += [qkv, post, bq, bp, b1, b2]
+            st.w_qkv[l], st.w_post[l] = _ptr(qkv), _ptr(post)
+            st.b_qkv[l], st.b_proj[l], st.b_fc1[l], st.b_fc2[l] = _ptr(bq), _ptr(bp), _ptr(b1), _ptr(b2)
+        w_ada_t = torch.stack([g(f"layers.{l}.adaLN_modulation.1.weight").t().contiguous() for l in range(4)]).contiguous()
+        b_ada = torch.stack([g(f"layers.{l}.adaLN_modulation.1.bias") for l in range(4)]).contiguous()
+        wpe, wc = g("patch_emb.weight"), g("conv.weight").reshape(4, 4)              # conv [oc][p*2+q]
+        w_embed = (wpe @ wc).contiguous()                                            # [128][4]
+        b_embed = (wpe @ g("conv.bias") + g("patch_emb.bias")).contiguous()
+        pos = g("pos_embed").reshape(480, D).contiguous()
+        wl = g("linear_emb_to_patch.weight")
+        w_final = (wl * g("ln.weight").unsqueeze(0)).contiguous()                    # [4][128]
+        b_final = (wl @ g("ln.bias") + g("linear_emb_to_patch.bias")).contiguous()
+        freqs = torch.pow(10000, torch.linspace(0, 1, D // 2)).to(**f32).contiguous()  # transformer.py:34
+        keep += [w_ada_t, b_ada, w_embed, b_embed, pos, w_final, b_final, freqs]
+        st.w_ada_t, st.b_ada, st.w_embed, st.b_embed = _ptr(w_ada_t), _ptr(b_ada), _ptr(w_embed), _ptr(b_embed)
+        st.pos, st.w_final, st.b_final, st.freqs = _ptr(pos), _ptr(w_final), _ptr(b_final), _ptr(freqs)
+        self.struct = st
+        self.ref = C.byref(st)
+        self._keep = keep
+        self.device = device
+
+
+def _conv_w(w):      # Conv1d weight [oc][ic][k] -> [ic][k][oc]
+    return w.permute(1, 2, 0).contiguous()
+
+
+def _convT_w(w):     # ConvTranspose1d weight [ic][oc][k] -> [ic][k][oc]
+    return w.permute(0, 2, 1).contiguous()
+
+
+class PackedVaeDecoder:
+    def __init__(self, sd: Dict[str, torch.Tensor], device: torch.device, prefix: str = ""):
+        g = lambda k: sd[prefix + k].detach().to(device=device, dtype=torch.float32)
+        st = _lib.VaeDecWeights()
+        t = {
+            "conv1_w": _conv_w(g("_conv_1.weight")), "conv1_b": g("_conv_1.bias").contiguous(),
+            "ct1_w": _convT_w(g("_conv_trans_1.weight")), "ct1_b": g("_conv_trans_1.bias").contiguous(),
+            "ct2_w": g("_conv_trans_2.weight").reshape(64, 4).contiguous(), "ct2_b": g("_conv_trans_2.bias").contiguous(),
+        }
+        assert t["conv1_w"].shape == (64, 3, 128) and t["ct1_w"].shape == (128, 4, 64), \
+            "LA-VAE kernels are built for block_hidden_size=128, res_hidden_size=256, embedding_dim=64"
+        for k, v in t.items():
+            setattr(st, k, _ptr(v))
+        for i in range(2):
+            w3 = _conv_w(g(f"_residual_stack._layers.{i}._block.1.weight"))
+            w1 = g(f"_residual_stack._layers.{i}._block.3.weight").reshape(128, 256).t().contiguous()
+            assert w3.shape == (128, 3, 256)
+            t[f"w3{i}"], t[f"w1{i}"] = w3, w1
+            st.res_w3[i], st.res_w1[i] = _ptr(w3), _ptr(w1)
+        self.struct, self.ref, self._keep, self.device = st, C.byref(st), t, device
+
+
+class PackedVaeEncoder:
+    def __init__(self, sd: Dict[str, torch.Tensor], device: torch.device, prefix: str = ""):
+        g = lambda k: sd[prefix + k].detach().to(device=device, dtype=torch.float32)
+        st = _lib.VaeEncWeights()
+        t = {
+            "conv1_w": _conv_w(g("_conv_1.weight")), "conv1_b": g("_conv_1.bias").contiguous(),
+            "conv2_w": _conv_w(g("_conv_2.weight")), "conv2_b": g("_conv_2.bias").contiguous(),
+            "conv3_w": _conv_w(g("_conv_3.weight")), "conv3_b": g("_conv_3.bias").contiguous(),
+            "pre_w": g("_pre_vq_conv.weight").reshape(64, 128).t().contiguous(), "pre_b": g("_pre_vq_conv.bias").contiguous(),
+        }
+        assert t["conv1_w"].shape == (1, 4, 64) and t["conv2_w"].shape == (64, 4, 128) and t["conv3_w"].shape == (128, 3, 128), \
+            "LA-VAE kernels are built for block_hidden_size=128, res_hidden_size=256, embedding_dim=64"
+        for k, v in t.items():
+            setattr(st, k, _ptr(v))
+        for i in range(2):
+            w3 = _conv_w(g(f"_residual_stack._layers.{i}._block.1.weight"))
+            w1 = g(f"_residual_stack._layers.{i}._block.3.weight").reshape(128, 256).t().contiguous()
+            t[f"w3{i}"], t[f"w1{i}"] = w3, w1
+            st.res_w3[i], st.res_w1[i] = _ptr(w3), _ptr(w1)
+        self.struct, self.ref, self._keep, self.device = st, C.byref(st), t, device

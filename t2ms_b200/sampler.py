@@ -1,0 +1,136 @@
+"""Fused classifier-free-guided sampling: the whole loop of infer.py:75-95 in one call.
+
+``T2SSampler.sample`` enqueues, on the current CUDA stream and without any host synchronisation,
+``steps`` x {conditioning, patch-embed+QKV, 4 x (attention, fused token block)} where the last block
+kernel also applies the guidance mix and the Euler (rectified flow) or ancestral (DDPM) update in
+place, followed by the LA-VAE decode.  Samples are independent, so multi-GPU sampling shards the
+batch across ranks with no collective inside the loop and one final all_gather (``gather_series``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from .backbone import DDPM, RectifiedFlow
+from .denoiser import Transformer, _aligned
+
+KIND = {"flowmatching": 0, "rf": 0, "rectified_flow": 0, "ddpm": 1}
+
+
+class T2SSampler:
+    def __init__(self, dit: Transformer, vae=None):
+        self.dit = dit
+        self.decoder = getattr(vae, "decoder", vae)
+        self._tables = {}
+
+    def _table(self, kind: int, steps: int, device) -> Tuple[torch.Tensor, C.Array]:
+        key = (kind, steps, str(device))
+        if key not in self._tables:
+            if kind == 0:
+                t = RectifiedFlow.timesteps(steps)
+                coef = RectifiedFlow.coefficients(steps)
+            else:
+                t = DDPM.timesteps(steps)
+                coef = DDPM.coefficients(steps)
+            t100 = (t * 100.0).to(torch.float32).to(device)             # TimeEmbedding, transformer.py:31
+            flat = coef.reshape(-1).tolist()
+            self._tables[key] = (t100, (C.c_float * len(flat))(*flat))
+        return self._tables[key]
+
+    @torch.no_grad()
+    def sample_latent(self, emb: torch.Tensor, steps: int = 100, cfg_scale: float = 7.0, backbone: str = "flowmatching",
+                      noise: Optional[torch.Tensor] = None, step_noise: Optional[torch.Tensor] = None,
+                      generator: Optional[torch.Generator] = None, trace: bool = False, chunk: Optional[int] = None):
+        """emb (B,128) CUDA -> final latent (B,64,30) [, per-step guided predictions (steps,B,64,30)]."""
+        if not emb.is_cuda:
+            raise RuntimeError("T2SSampler needs CUDA tensors (no CPU fallback); use sample_host for host buffers")
+        lib = _lib.load()
+        kind = KIND[backbone]
+        dev = emb.device
+        B = emb.shape[0]
+        emb = emb.detach().to(torch.float32).contiguous()
+        if noise is None:
+            x = torch.randn(B, 64, 30, device=dev, dtype=torch.float32, generator=generator)   # infer.py:75
+        else:
+            x = noise.detach().to(device=dev, dtype=torch.float32).clone().contiguous()
+        if kind == 1:
+            if step_noise is None:                                                         # DDPM.py:35
+                step_noise = torch.randn(steps, B, 64, 30, device=dev, dtype=torch.float32, generator=generator)
+            step_noise = step_noise.detach().to(device=dev, dtype=torch.float32).contiguous()
+            assert step_noise.shape == (steps, B, 64, 30)
+        tr = torch.empty(steps, B, 64, 30, device=dev, dtype=torch.float32) if trace else None
+        t100, coef = self._table(kind, steps, dev)
+        pk = self.dit.packed()
+        chunk = B if not chunk else min(int(chunk), B)
+        ws = self.dit.workspace(2 * chunk, dev)
+        nbytes = lib.t2s_dit_workspace_bytes(2 * chunk)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            for b0 in range(0, B, chunk):
+                nb = min(chunk, B - b0)
+                sn = tr_c = None
+                if kind == 1:
+                    sn = step_noise[:, b0:b0 + nb].contiguous() if nb != B else step_noise
+                if trace:
+                    tr_c = tr if nb == B else torch.empty(steps, nb, 64, 30, device=dev, dtype=torch.float32)
+                rc = lib.t2s_sample(pk.ref, kind, x[b0:b0 + nb].data_ptr(), emb[b0:b0 + nb].data_ptr(), t100.data_ptr(), coef,
+                                    sn.data_ptr() if sn is not None else None, tr_c.data_ptr() if tr_c is not None else None,
+                                    nb, steps, float(cfg_scale), _aligned(ws), nbytes, stream)
+                _lib.check(rc, "t2s_sample")
+                if trace and nb != B:
+                    tr[:, b0:b0 + nb] = tr_c
+        return (x, tr) if trace else x
+
+    @torch.no_grad()
+    def sample(self, emb: torch.Tensor, length: int, steps: int = 100, cfg_scale: float = 7.0,
+               backbone: str = "flowmatching", noise=None, step_noise=None, generator=None, chunk=None,
+               return_latent: bool = False):
+        """Text embeddings (B,128) -> generated series (B,length) fp32 (infer.py:75-95)."""
+        if self.decoder is None:
+            raise RuntimeError("T2SSampler was built without an LA-VAE decoder")
+        z = self.sample_latent(emb, steps, cfg_scale, backbone, noise, step_noise, generator, False, chunk)
+        series = torch.empty(z.shape[0], int(length), device=z.device, dtype=torch.float32)
+        self.decoder.decode_into(z, int(length), series, None)
+        return (series, z) if return_latent else series
+
+    @torch.no_grad()
+    def sample_host(self, emb_host: torch.Tensor, length: int, out_host: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
+        """End-to-end call with HOST buffers: H2D copy of the (pinned) text embeddings, the fused loop,
+        D2H copy of the series.  Returns the host tensor after synchronising the stream."""
+        dev = next(self.dit.parameters()).device
+        emb = emb_host.to(dev, non_blocking=True)
+        series = self.sample(emb, length, **kw)
+        if out_host is None:
+            out_host = torch.empty(series.shape, dtype=torch.float32, pin_memory=True)
+        out_host.copy_(series, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out_host
+
+
+# ---------------------------------------------------------------------------------------- multi-GPU
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous batch shard [lo, hi) of rank `rank`; sizes differ by at most one."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_series(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
+    """The only collective of multi-GPU sampling: all_gather of the per-rank series
+    (np.concatenate at infer.py:112-113).  Works with NCCL (CUDA) and gloo (CPU tests)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    rank = dist.get_rank(group)
+    sizes = [shard_range(total, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros(width, *local.shape[1:], dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    assert sizes[rank][1] - sizes[rank][0] == local.shape[0]
+    return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)

@@ -1,0 +1,77 @@
+"""Helpers shared by the -m gpu parity tests: drive single kernels through the C ABI and view the workspace."""
+import ctypes as C
+
+import torch
+
+from t2ms_b200 import _lib, synth
+from t2ms_b200.compat import VAE_ARGS
+from t2ms_b200.denoiser import Transformer, _aligned
+from t2ms_b200.lavae import vqvae
+
+DEV = "cuda:0"
+
+
+def make_dit(seed, bias_std=0.02):
+    sd = synth.make_dit_state(seed, bias_std=bias_std)
+    m = Transformer()
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).eval(), sd
+
+
+def make_vae(seed):
+    sd = synth.make_vae_state(seed)
+    m = vqvae(VAE_ARGS)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).eval(), sd
+
+
+def rel_l2(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def max_abs(a, b):
+    return (a.detach().double().cpu() - b.detach().double().cpu()).abs().max().item()
+
+
+class Workspace:
+    """Typed views of the DiT scratch buffer (layout: t2s_dit_workspace_offsets)."""
+
+    def __init__(self, model, nseq):
+        lib = _lib.load()
+        self.nseq = nseq
+        self.buf = model.workspace(nseq, torch.device(DEV))
+        self.ptr = _aligned(self.buf)
+        self.nbytes = lib.t2s_dit_workspace_bytes(nseq)
+        off = (C.c_size_t * 4)()
+        lib.t2s_dit_workspace_offsets(nseq, C.byref(off))
+        self.off = list(off)
+        self.base = self.ptr - self.buf.data_ptr()
+
+    def _view(self, i, nbytes, dtype, shape):
+        s = self.base + self.off[i]
+        return self.buf[s:s + nbytes].view(dtype).view(shape)
+
+    def h(self):
+        return self._view(0, self.nseq * 480 * 128 * 4, torch.float32, (self.nseq, 480, 128))
+
+    def qkv(self):
+        """-> (nseq, 3, 4 heads, 480, 32) fp32, de-swizzled."""
+        raw = self._view(1, self.nseq * 480 * 384 * 2, torch.float16, (self.nseq, 4, 3, 480, 4, 8))
+        tok = torch.arange(480, device=raw.device)
+        pc = torch.arange(4, device=raw.device)
+        src = pc.unsqueeze(0) ^ ((tok.unsqueeze(1) >> 1) & 3)            # logical chunk c lives at physical c ^ s
+        idx = src.view(1, 1, 1, 480, 4, 1).expand(self.nseq, 4, 3, 480, 4, 8)
+        logical = torch.gather(raw, 4, idx)                               # logical[c] = raw[c ^ s]
+        return logical.reshape(self.nseq, 4, 3, 480, 32).permute(0, 2, 1, 3, 4).float()
+
+    def o(self):
+        return self._view(2, self.nseq * 480 * 128 * 2, torch.float16, (self.nseq, 480, 128)).float()
+
+    def mod(self):
+        return self._view(3, self.nseq * 4 * 768 * 4, torch.float32, (self.nseq, 4, 768))
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream

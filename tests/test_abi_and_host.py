@@ -1,0 +1,191 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol include/t2s_b200.h declares;
+host logic (packing layouts, coefficient tables, sharding, module interfaces) behaves like the reference."""
+import ctypes
+import math
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, T, load_golden
+from oracle import t2s_oracle as O
+from t2ms_b200 import DDPM, RectifiedFlow, Transformer, _lib, synth, vqvae
+from t2ms_b200.compat import VAE_ARGS
+from t2ms_b200.packing import swizzle_stage
+from t2ms_b200.sampler import gather_series, shard_range
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from t2ms_b200.build import build
+    build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "t2s_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(t2s_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/t2s_b200.h but not exported"
+    assert sorted(declared) == sorted(_lib.EXPORTS)
+    assert lib.t2s_version() == 100
+
+
+def test_workspace_sizes(lib):
+    off = (ctypes.c_size_t * 4)()
+    lib.t2s_dit_workspace_offsets(2048, ctypes.byref(off))
+    off = list(off)
+    assert off[0] == 0 and off[1] == 2048 * 480 * 128 * 4 and all(o % 256 == 0 for o in off)
+    assert lib.t2s_dit_workspace_bytes(2048) >= off[3] + 2048 * 4 * 768 * 4
+    assert lib.t2s_dit_workspace_bytes(1) < lib.t2s_dit_workspace_bytes(2)
+
+
+def test_bad_arguments_return_error_codes(lib):
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    assert lib.t2s_dit_forward(None, None, None, None, None, 0, None, 0, None) == -1
+    assert b"bad argument" in lib.t2s_last_error()
+    assert lib.t2s_sample(None, 0, None, None, None, None, None, None, 1, 1, 7.0, None, 0, None) == -1
+    assert lib.t2s_vae_decode(None, None, None, None, 1, 96, None) == -1
+
+
+def test_no_cpu_fallback():
+    m = Transformer()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(input=torch.zeros(1, 64, 30), t=torch.zeros(1), text_input=None)
+    v = vqvae(VAE_ARGS)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        v.decoder(torch.zeros(1, 64, 30), length=24)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        v.encoder(torch.zeros(1, 24))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "t2ms_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_swizzle_stage_layout():
+    w = torch.arange(128 * 128, dtype=torch.float32).reshape(128, 128) % 2048      # exact in fp16
+    img = swizzle_stage(w).reshape(128, 16, 8)
+    for n in (0, 1, 7, 8, 77, 127):
+        for c in (0, 3, 9, 15):
+            assert torch.equal(img[n, c ^ (n & 7)].float(), w[n, c * 8:(c + 1) * 8])
+    w2 = torch.arange(128 * 64, dtype=torch.float32).reshape(128, 64) % 2048
+    img2 = swizzle_stage(w2).reshape(128, 8, 8)
+    assert torch.equal(img2[5, 2 ^ 5].float(), w2[5, 16:24])
+
+
+def test_module_interfaces_match_reference_state_dict():
+    sd = synth.make_dit_state(3)
+    m = Transformer()
+    assert sorted(m.state_dict().keys()) == sorted(sd.keys())
+    for k, v in m.state_dict().items():
+        assert v.shape == sd[k].shape, k
+    m.load_state_dict(sd, strict=True)
+    assert not m.pos_embed.requires_grad
+    assert sum(p.numel() for p in m.parameters() if p.requires_grad) == 946265
+    # default init: adaLN zero, biases zero (transformer.py:194-204)
+    m2 = Transformer()
+    assert float(m2.layers[0].adaLN_modulation[-1].weight.abs().sum()) == 0.0
+    assert float(m2.layers[2].attn.qkv.bias.abs().sum()) == 0.0
+    v = vqvae(VAE_ARGS)
+    vsd = synth.make_vae_state(4)
+    assert sorted(v.state_dict().keys()) == sorted(vsd.keys())
+    assert sum(p.numel() for p in v.parameters()) == 672833
+    # attaching the frozen encoder like train.py:30-33 / infer.py:47
+    m.encoder = v.encoder
+    names = [n for n, _ in m.named_parameters()]
+    assert sum("encoder" in n for n in names) == 12
+    assert len(m.state_dict()) == 67
+    with pytest.raises(ValueError):
+        vqvae(type(VAE_ARGS)(block_hidden_size=64, num_residual_layers=2, res_hidden_size=256, embedding_dim=64))
+
+
+def test_backbone_classes_match_reference_golden():
+    g = load_golden("backbone.npz")
+    x1, t, eps, ti = (T(g[k]) for k in ("x1", "t", "eps", "ti"))
+    rf, dd = RectifiedFlow(), DDPM(1000, "cpu")
+    torch.manual_seed(77)
+    x_t, x_0 = rf.create_flow(x1, t)
+    assert torch.equal(x_0, T(g["x0"])) and torch.allclose(x_t, T(g["x_t"]), atol=1e-7)
+    assert torch.allclose(rf.euler(x1, eps, 0.01), T(g["euler"]), atol=1e-7)
+    assert abs(float(rf.loss(x1, eps)) - float(g["rf_loss"])) < 1e-6
+    for a, k in ((dd.beta, "beta"), (dd.alpha, "alpha"), (dd.alpha_bar, "alpha_bar")):
+        assert np.array_equal(a.numpy(), g[k])
+    q, _ = dd.q_sample(x1, ti, eps)
+    assert torch.allclose(q, T(g["q_sample"]), atol=1e-6)
+
+
+def test_sampler_tables_match_oracle_formulas():
+    for steps in (4, 10, 100):
+        tt = RectifiedFlow.timesteps(steps)
+        assert torch.equal(tt, O.rf_timesteps(steps, 1)[:, 0])
+        c = RectifiedFlow.coefficients(steps)
+        assert c[0, 0].item() == np.float32(1.0 / steps) and float(c[:, 1:].abs().sum()) == 0
+    steps = 50
+    t = DDPM.timesteps(steps)
+    assert t.tolist() == [math.floor(steps - 1 - j) for j in range(steps)]
+    coef = DDPM.coefficients(steps)
+    sched = O.ddpm_schedule(steps)
+    x, e, n = torch.randn(3, 64, 30), torch.randn(3, 64, 30), torch.randn(3, 64, 30)
+    for j in (0, 7, 49):
+        tj = torch.full((3,), int(t[j]), dtype=torch.long)
+        ref = O.ddpm_p_sample(x, e, tj, n, sched)
+        mine = coef[j, 0] * (x - coef[j, 1] * e) + coef[j, 2] * n
+        assert torch.allclose(mine, ref, atol=1e-6, rtol=1e-6)
+
+
+def test_shard_range_partitions():
+    for total in (1, 7, 512, 1024, 1025):
+        for world in (1, 2, 4, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from t2ms_b200.sampler import gather_series, shard_range
+dist.init_process_group("gloo", init_method="env://")
+rank, world = dist.get_rank(), dist.get_world_size()
+total = 7
+full = torch.arange(total * 5, dtype=torch.float32).reshape(total, 5)
+lo, hi = shard_range(total, rank, world)
+out = gather_series(full[lo:hi].clone(), total)
+assert torch.equal(out, full), (rank, out)
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_gather_series_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_compat_aliases():
+    from t2ms_b200 import compat
+    compat.install()
+    from model.denoiser.transformer import Transformer as RT
+    from model.backbone.DDPM import DDPM as RD
+    from model.pretrained.vqvae import vqvae as RV
+    assert RT is Transformer and RD is DDPM and RV is vqvae
+    v = compat.convert_reference_vae(synth.make_vae_state(5))
+    assert isinstance(v, vqvae)

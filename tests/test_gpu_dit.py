@@ -1,0 +1,168 @@
+"""GPU parity of the DiT denoiser kernels against the CPU oracle and the reference golden vectors.
+
+Tolerances (BASELINE.json north_star): per-forward velocity / epsilon within 2e-3 relative (L2) with
+fp16-operand / fp32-accumulate tensor-core math; fp32-only stages (conditioning, patch embedding)
+within 1e-5.
+"""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import ROOT, T, load_golden
+from oracle import t2s_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_FWD = 2e-3
+
+
+def _dump(name, obj):
+    d = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, name), "w") as f:
+        json.dump(obj, f, indent=1)
+
+
+def _oracle_stages(sd, x, t, emb):
+    st = {}
+    h = O.dit_embed(sd, x)
+    c = O.time_embedding(t)
+    if emb is not None:
+        c = c + emb
+    st["h0"] = h
+    st["mod"] = torch.stack([F.linear(F.silu(c), sd[f"layers.{l}.adaLN_modulation.1.weight"],
+                                      sd[f"layers.{l}.adaLN_modulation.1.bias"]) for l in range(4)], dim=1)
+    B = x.shape[0]
+    for l in range(4):
+        pre = f"layers.{l}."
+        sh1, sc1, g1, sh2, sc2, g2 = st["mod"][:, l].chunk(6, dim=1)
+        a = O.modulate(F.layer_norm(h, (128,), eps=1e-6), sh1, sc1)
+        qkv = F.linear(a, sd[pre + "attn.qkv.weight"], sd[pre + "attn.qkv.bias"])
+        st[f"qkv{l}"] = qkv.reshape(B, 480, 3, 4, 32).permute(0, 2, 3, 1, 4)          # (B,3,4,480,32)
+        q, k, v = st[f"qkv{l}"].unbind(1)
+        att = ((q * 32 ** -0.5) @ k.transpose(-2, -1)).softmax(-1)
+        st[f"o{l}"] = (att @ v).transpose(1, 2).reshape(B, 480, 128)
+        h = O.dit_layer(sd, l, h, c)
+        st[f"h{l + 1}"] = h
+    st["out"] = O.dit_unembed(sd, h)
+    return st
+
+
+@pytest.mark.parametrize("cond", [True, False])
+def test_stagewise(cond):
+    """Every kernel of one forward, checked where it writes: modulation, h0, q|k|v, attention output,
+    residual stream after each block, final projection."""
+    from gpu_util import DEV, Workspace, make_dit, max_abs, rel_l2, stream
+    from t2ms_b200 import _lib, synth
+    lib = _lib.load()
+    model, sd = make_dit(31, bias_std=0.05)
+    B = 3                                              # odd: exercises the half-empty last pair tile
+    x = synth.make_noise(B, seed=32)
+    emb = synth.make_text_embeddings(B, seed=33) if cond else None
+    t = torch.tensor([0.0, 0.41, 1.0])
+    with torch.no_grad():
+        ref = _oracle_stages(sd, x, t, emb)
+    xd, t100 = x.to(DEV), (t * 100.0).to(DEV)
+    embd = emb.to(DEV) if cond else None
+    pk = model.packed()
+    ws = Workspace(model, B)
+    err = {}
+    chk = lambda rc: _lib.check(rc, "stage")
+    chk(lib.t2s_dit_cond(pk.ref, t100.data_ptr(), 1, embd.data_ptr() if cond else None, 0, B, ws.ptr, stream()))
+    torch.cuda.synchronize()
+    err["mod"] = max_abs(ws.mod(), ref["mod"])
+    chk(lib.t2s_dit_embed_qkv(pk.ref, xd.data_ptr(), 0, B, ws.ptr, stream()))
+    torch.cuda.synchronize()
+    err["h0"] = max_abs(ws.h(), ref["h0"])
+    for l in range(4):
+        qkv_gpu = ws.qkv().clone()
+        err[f"qkv{l}"] = rel_l2(qkv_gpu, ref[f"qkv{l}"])
+        chk(lib.t2s_dit_attention(B, ws.ptr, stream()))
+        torch.cuda.synchronize()
+        q, k, v = qkv_gpu.cpu().unbind(1)
+        o_self = (((q * 32 ** -0.5) @ k.transpose(-2, -1)).softmax(-1) @ v).transpose(1, 2).reshape(B, 480, 128)
+        err[f"attn{l}_vs_own_qkv"] = rel_l2(ws.o(), o_self)
+        err[f"o{l}"] = rel_l2(ws.o(), ref[f"o{l}"])
+        if l < 3:
+            chk(lib.t2s_dit_block_post(pk.ref, l, B, ws.ptr, stream()))
+            torch.cuda.synchronize()
+            err[f"h{l + 1}"] = rel_l2(ws.h(), ref[f"h{l + 1}"])
+    out = torch.empty(B, 64, 30, device=DEV)
+    chk(lib.t2s_dit_final(pk.ref, out.data_ptr(), B, ws.ptr, stream()))
+    torch.cuda.synchronize()
+    err["out"] = rel_l2(out, ref["out"])
+    print("stage errors:", json.dumps(err, indent=1))
+    _dump(f"stage_errors_cond{int(cond)}.json", err)
+    assert err["mod"] < 2e-5 and err["h0"] < 1e-5
+    for k_, v_ in err.items():
+        if k_ not in ("mod", "h0"):
+            assert v_ < TOL_FWD, (k_, v_)
+
+
+@pytest.mark.parametrize("B", [1, 2, 5, 16])
+def test_forward_matches_oracle(B):
+    from gpu_util import DEV, make_dit, rel_l2
+    from t2ms_b200 import synth
+    model, sd = make_dit(41, bias_std=0.02)
+    x = synth.make_noise(B, seed=42)
+    emb = synth.make_text_embeddings(B, seed=43)
+    t = torch.linspace(0, 1, B)
+    with torch.no_grad():
+        ref_c = O.dit_forward(sd, x, t, emb)
+        ref_u = O.dit_forward(sd, x, t, None)
+        out_c = model(input=x.to(DEV), t=t.to(DEV), text_input=emb.to(DEV))
+        out_u = model(input=x.to(DEV), t=t.to(DEV), text_input=None)
+    assert out_c.shape == (B, 64, 30)
+    e_c, e_u = rel_l2(out_c, ref_c), rel_l2(out_u, ref_u)
+    print(f"B={B} rel-L2 cond {e_c:.2e} uncond {e_u:.2e}")
+    assert e_c < TOL_FWD and e_u < TOL_FWD
+    # guidance amplifies the error of (c - u): check the mixed prediction too (infer.py:81)
+    mix = out_u + 7.0 * (out_c - out_u)
+    mix_ref = ref_u + 7.0 * (ref_c - ref_u)
+    e_m = rel_l2(mix, mix_ref)
+    print(f"B={B} rel-L2 cfg-7 mix {e_m:.2e}")
+    assert e_m < TOL_FWD
+
+
+def test_forward_matches_reference_golden():
+    from gpu_util import DEV, make_dit, rel_l2
+    g = load_golden("dit_forward.npz")
+    model, sd = make_dit(int(g["dit_seed"]), bias_std=float(g["bias_std"]))
+    x, emb = T(g["x"]).to(DEV), T(g["emb"]).to(DEV)
+    with torch.no_grad():
+        e1 = rel_l2(model(input=x, t=T(g["t_float"]).to(DEV), text_input=emb), T(g["cond_float"]))
+        e2 = rel_l2(model(input=x, t=T(g["t_float"]).to(DEV), text_input=None), T(g["uncond_float"]))
+        e3 = rel_l2(model(input=x, t=T(g["t_int"]).to(DEV), text_input=emb), T(g["cond_int"]))   # int64 DDPM timesteps
+    print(f"golden rel-L2: {e1:.2e} {e2:.2e} {e3:.2e}")
+    assert max(e1, e2, e3) < TOL_FWD
+
+
+def test_reference_default_init_is_identity_blocks():
+    """With the reference's zero-initialised adaLN (transformer.py:202-204) cond == uncond exactly."""
+    from gpu_util import DEV
+    from t2ms_b200 import Transformer, synth
+    torch.manual_seed(0)
+    m = Transformer().to(DEV).eval()
+    x = synth.make_noise(2, seed=1).to(DEV)
+    t = torch.tensor([0.2, 0.7], device=DEV)
+    emb = synth.make_text_embeddings(2).to(DEV)
+    with torch.no_grad():
+        a = m(input=x, t=t, text_input=emb)
+        b = m(input=x, t=t, text_input=None)
+    assert torch.equal(a, b)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = O.dit_forward(sd, x.cpu(), t.cpu(), None)
+    assert (a.cpu() - ref).abs().max().item() < 1e-4
+
+
+def test_errors_are_loud():
+    from gpu_util import DEV, make_dit
+    model, _ = make_dit(1)
+    with pytest.raises(RuntimeError):
+        model(input=torch.zeros(1, 64, 30), t=torch.zeros(1), text_input=None)       # CPU tensor: no fallback
+    with pytest.raises(AssertionError):
+        model(input=torch.zeros(1, 30, 64, device=DEV), t=torch.zeros(1, device=DEV), text_input=None)

@@ -1,0 +1,139 @@
+"""GPU parity of the fused sampling loops + LA-VAE against the oracle and the reference golden vectors.
+
+Tolerances (BASELINE.json north_star): per-step guided velocity / epsilon within 2e-3 relative (L2),
+final generated series within 1e-2 max-abs; LA-VAE (fp32) within 1e-5 relative to the output scale.
+"""
+import pytest
+import torch
+
+from conftest import T, load_golden
+from oracle import t2s_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_STEP = 2e-3
+TOL_SERIES = 1e-2
+
+
+@pytest.mark.parametrize("L", [24, 48, 96])
+def test_vae_matches_reference_golden(L):
+    from gpu_util import DEV, make_vae, max_abs
+    g = load_golden("vae.npz")
+    vae, sd = make_vae(int(g["vae_seed"]))
+    with torch.no_grad():
+        z, before = vae.encoder(T(g[f"series_{L}"]).to(DEV))
+        assert z.shape == (3, 64, 30) and before.shape == (3, 64, L // 4)
+        assert max_abs(z, T(g[f"z_{L}"])) < 1e-5 and max_abs(before, T(g[f"before_{L}"])) < 1e-5
+        rec, after = vae.decoder(T(g[f"z_{L}"]).to(DEV), length=L)
+        assert rec.shape == (3, L)
+        assert max_abs(rec, T(g[f"rec_{L}"])) < 1e-5 and max_abs(after, T(g[f"after_{L}"])) < 1e-5
+        rec2, _ = vae.decoder(T(g["zlat"]).to(DEV), length=L)
+        assert max_abs(rec2, T(g[f"dec_noise_{L}"])) < 2e-5
+        if L == 48:
+            r1, _ = vae.decoder(T(g["zlat"])[:1].to(DEV), length=48)
+            assert r1.shape == (48,)                       # torch.squeeze at B == 1 (vqvae.py:105)
+            assert max_abs(r1, T(g["dec_b1_48"])) < 2e-5
+
+
+def test_vae_large_batch_vs_oracle():
+    from gpu_util import DEV, make_vae, max_abs
+    from t2ms_b200 import synth
+    vae, sd = make_vae(7)
+    z = synth.make_noise(257, seed=8)
+    with torch.no_grad():
+        for L in (24, 96):
+            ref, ref_after = O.vae_decode(sd, z, L)
+            out, after = vae.decoder(z.to(DEV), length=L)
+            assert max_abs(out, ref) < 2e-5 and max_abs(after, ref_after) < 1e-5
+        s = synth.make_series(130, 96, seed=9)
+        zr, br = O.vae_encode(sd, s)
+        zo, bo = vae.encoder(s.to(DEV))
+        assert max_abs(zo, zr) < 1e-5 and max_abs(bo, br) < 1e-5
+
+
+def test_rf_sampling_matches_reference_golden():
+    from gpu_util import DEV, make_dit, make_vae, max_abs, rel_l2
+    from t2ms_b200 import T2SSampler
+    g = load_golden("sampling.npz")
+    dit, _ = make_dit(int(g["dit_seed"]), bias_std=float(g["bias_std"]))
+    vae, _ = make_vae(int(g["vae_seed"]))
+    smp = T2SSampler(dit, vae)
+    emb = T(g["emb"]).to(DEV)
+    for steps, L in ((4, 24), (6, 48), (5, 96)):
+        k = f"rf_{steps}_{L}_"
+        noise = T(g[k + "noise"]).to(DEV)
+        lat, trace = smp.sample_latent(emb, steps=steps, cfg_scale=float(g[k + "cfg"]), noise=noise, trace=True)
+        ser = smp.sample(emb, L, steps=steps, cfg_scale=float(g[k + "cfg"]), noise=noise)
+        vel = T(g[k + "vel"])
+        per_step = [rel_l2(trace[j], vel[j]) for j in range(steps)]
+        print(k, "per-step rel-L2", ["%.2e" % e for e in per_step], "series max-abs %.2e" % max_abs(ser, T(g[k + "series"])))
+        assert max(per_step) < TOL_STEP
+        assert max_abs(lat, T(g[k + "latent"])) < TOL_SERIES
+        assert ser.shape == (2, L) and max_abs(ser, T(g[k + "series"])) < TOL_SERIES
+        assert torch.equal(noise, T(g[k + "noise"]).to(DEV))          # the caller's noise tensor is not modified
+
+
+def test_ddpm_sampling_matches_reference_golden():
+    from gpu_util import DEV, make_dit, make_vae, max_abs, rel_l2
+    from t2ms_b200 import T2SSampler
+    g = load_golden("sampling.npz")
+    dit, _ = make_dit(int(g["dit_seed"]), bias_std=float(g["bias_std"]))
+    vae, _ = make_vae(int(g["vae_seed"]))
+    smp = T2SSampler(dit, vae)
+    steps, L, cfg = int(g["ddpm_steps"]), int(g["ddpm_L"]), float(g["ddpm_cfg"])
+    emb = T(g["emb"]).to(DEV)
+    lat, trace = smp.sample_latent(emb, steps=steps, cfg_scale=cfg, backbone="ddpm", noise=T(g["ddpm_noise"]).to(DEV),
+                                   step_noise=T(g["ddpm_step_noise"]).to(DEV), trace=True)
+    eps = T(g["ddpm_eps"])
+    per_step = [rel_l2(trace[j], eps[j]) for j in range(steps)]
+    print("ddpm per-step rel-L2", ["%.2e" % e for e in per_step])
+    assert max(per_step) < TOL_STEP
+    ref_lat = T(g["ddpm_latent"])
+    assert rel_l2(lat, ref_lat) < TOL_STEP
+    ser = smp.sample(emb, L, steps=steps, cfg_scale=cfg, backbone="ddpm", noise=T(g["ddpm_noise"]).to(DEV),
+                     step_noise=T(g["ddpm_step_noise"]).to(DEV))
+    scale = max(1.0, T(g["ddpm_series"]).abs().max().item())
+    assert max_abs(ser, T(g["ddpm_series"])) < TOL_SERIES * scale
+
+
+def test_rf_sampling_vs_oracle_config1():
+    """BASELINE config 1: RF, length 24, batch 8 (reference CPU case), 10 steps for test time."""
+    from gpu_util import DEV, make_dit, make_vae, max_abs, rel_l2
+    from t2ms_b200 import T2SSampler, synth
+    dit, dsd = make_dit(51)
+    vae, vsd = make_vae(52)
+    B, steps = 8, 10
+    emb, noise = synth.make_text_embeddings(B, 53), synth.make_noise(B, 54)
+    lat_ref, ser_ref, vel_ref = O.rf_sample(dsd, vsd,
+                                            noise, emb, steps, 7.0, 24, return_velocities=True)
+    smp = T2SSampler(dit, vae)
+    lat, trace = smp.sample_latent(emb.to(DEV), steps=steps, cfg_scale=7.0, noise=noise.to(DEV), trace=True)
+    ser = smp.sample(emb.to(DEV), 24, steps=steps, cfg_scale=7.0, noise=noise.to(DEV))
+    per_step = [rel_l2(trace[j], vel_ref[j]) for j in range(steps)]
+    print("config1 per-step rel-L2", ["%.2e" % e for e in per_step], "series max-abs %.2e" % max_abs(ser, ser_ref))
+    assert max(per_step) < TOL_STEP
+    assert max_abs(ser, ser_ref) < TOL_SERIES
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (B=1024, L=96) through size-independent properties: samples are independent,
+    so any sub-batch / chunking reproduces the same series bit-for-bit; duplicates of one prompt+noise
+    produce identical rows; and a small slice matches the oracle."""
+    from gpu_util import DEV, make_dit, make_vae, max_abs
+    from t2ms_b200 import T2SSampler, synth
+    dit, dsd = make_dit(61)
+    vae, vsd = make_vae(62)
+    B, steps = 1024, 3
+    emb, noise = synth.make_text_embeddings(B, 63).to(DEV), synth.make_noise(B, 64).to(DEV)
+    emb[1000:] = emb[0]
+    noise[1000:] = noise[0]
+    smp = T2SSampler(dit, vae)
+    full = smp.sample(emb, 96, steps=steps, noise=noise)
+    assert full.shape == (B, 96) and torch.isfinite(full).all()
+    assert all(torch.equal(full[i], full[0]) for i in range(1000, B))
+    chunked = smp.sample(emb, 96, steps=steps, noise=noise, chunk=37)
+    assert torch.equal(full, chunked)
+    sub = smp.sample(emb[500:507], 96, steps=steps, noise=noise[500:507])
+    assert torch.equal(full[500:507], sub)
+    _, ser_ref = O.rf_sample(dsd, vsd, noise[:4].cpu(), emb[:4].cpu(), steps, 7.0, 96)
+    assert max_abs(full[:4], ser_ref) < TOL_SERIES
