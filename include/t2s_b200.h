@@ -29,8 +29,10 @@ enum {
 /* DiT weights, packed by the host (t2ms_b200/packing.py) from the reference state dict
  * (model/denoiser/transformer.py:127-154; key names in SURVEY.md §8b).  All device pointers. */
 typedef struct {
-    const void* w_qkv[4];   /* fp16, 3 stages x [128 n][128 k]: q | k | v of layers.{l}.attn.qkv.weight, chunk-swizzled */
-    const void* w_post[4];  /* fp16, 5 stages x 32 KB: attn.proj, then 4 x { mlp.fc1 rows c*64.. | mlp.fc2 cols c*64.. } */
+    /* fp16 weight stages, each a [128 n][128 k] operand image in the tcgen05 no-swizzle K-major canonical layout:
+     * element (n,k) at byte (k/8)*2048 + (n/8)*128 + (n%8)*16 + (k%8)*2 */
+    const void* w_qkv[4];   /* 3 stages: q | k | v rows of layers.{l}.attn.qkv.weight */
+    const void* w_post[4];  /* 5 stages: attn.proj | mlp.fc1 rows 0..127 | rows 128..255 | mlp.fc2 cols 0..127 | cols 128..255 */
     const float* b_qkv[4];  /* [384] */
     const float* b_proj[4]; /* [128] */
     const float* b_fc1[4];  /* [256] */
@@ -39,7 +41,7 @@ typedef struct {
     const float* b_ada;     /* [4][768] */
     const float* w_embed;   /* [128][4]  patch_emb.weight @ conv.weight.view(4,4) */
     const float* b_embed;   /* [128]     patch_emb.weight @ conv.bias + patch_emb.bias */
-    const float* pos;       /* [480][128] pos_embed */
+    const float* pos;       /* [8 tiles][32 col chunks][64 rows][4] pos_embed in the residual tile layout */
     const float* w_final;   /* [4][128]  linear_emb_to_patch.weight * ln.weight */
     const float* b_final;   /* [4]       linear_emb_to_patch.weight @ ln.bias + linear_emb_to_patch.bias */
     const float* freqs;     /* [64]      10000 ** linspace(0,1,64)   (TimeEmbedding, transformer.py:34) */
@@ -76,7 +78,8 @@ const char* t2s_last_error(void);
 /* Sets kernel attributes for the current device; call once per device before stream capture. */
 int t2s_init(void);
 
-/* Bytes of scratch for `nseq` sequences (residual stream, q|k|v, attention output, modulation). */
+/* Bytes of scratch for `nseq` sequences (residual stream, q|k|v, attention output, modulation).
+ * Contents need no initialisation; rows of partially filled tiles are never read back. */
 size_t t2s_dit_workspace_bytes(int nseq);
 
 /* Transformer.forward (model/denoiser/transformer.py:158-193).

@@ -59,9 +59,10 @@ struct Workspace {
 };
 void ws_offsets(int nseq, size_t off[4], size_t* total) {
     size_t p = 0;
-    off[0] = p; p = align256(p + (size_t)nseq * NTOK * D * 4);
-    off[1] = p; p = align256(p + (size_t)nseq * NTOK * 3 * D * 2);
-    off[2] = p; p = align256(p + (size_t)nseq * NTOK * D * 2);
+    const size_t ntile = (size_t)((nseq + 1) / 2) * TILES_PER_PAIR;           // pair tiles of 128 rows
+    off[0] = p; p = align256(p + ntile * TILE_ROWS * D * 4);                   // residual stream tiles, fp32
+    off[1] = p; p = align256(p + (size_t)nseq * NTOK * 3 * D * 2);             // q|k|v, fp16
+    off[2] = p; p = align256(p + ntile * TILE_ROWS * D * 2);                   // attention-output tiles, fp16
     off[3] = p; p = align256(p + (size_t)nseq * NLAYER * MOD * 4);
     if (total) *total = p;
 }
@@ -98,7 +99,7 @@ int launch_cond(const t2s_dit_weights* w, const float* t100, int t_stride, const
 int launch_embed(const t2s_dit_weights* w, const float* x, int x_shift, int nseq, const Workspace& ws, cudaStream_t st) {
     TokArgs a = base_args(w, ws, nseq);
     a.x = x; a.x_shift = x_shift;
-    token_kernel<TOK_EMBED><<<((nseq + 1) / 2) * TILES_PER_PAIR, 256, TOK_SMEM_BYTES, st>>>(a);
+    token_kernel<TOK_EMBED><<<((nseq + 1) / 2) * TILES_PER_PAIR, TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
@@ -110,7 +111,7 @@ int launch_attn(int nseq, const Workspace& ws, cudaStream_t st) {
 int launch_mid(const t2s_dit_weights* w, int layer, int nseq, const Workspace& ws, cudaStream_t st) {
     TokArgs a = base_args(w, ws, nseq);
     a.layer = layer;
-    token_kernel<TOK_MID><<<((nseq + 1) / 2) * TILES_PER_PAIR, 256, TOK_SMEM_BYTES, st>>>(a);
+    token_kernel<TOK_MID><<<((nseq + 1) / 2) * TILES_PER_PAIR, TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
@@ -120,7 +121,7 @@ int launch_final(const t2s_dit_weights* w, int nseq, const Workspace& ws, int ou
     a.layer = NLAYER - 1;
     a.out_mode = out_mode; a.out = out; a.x_upd = x_upd; a.noise = noise;
     a.cfg = cfg; a.c1 = c1; a.c2 = c2; a.c3 = c3;
-    token_kernel<TOK_FINAL><<<((nseq + 1) / 2) * TILES_PER_PAIR, 256, TOK_SMEM_BYTES, st>>>(a);
+    token_kernel<TOK_FINAL><<<((nseq + 1) / 2) * TILES_PER_PAIR, TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }

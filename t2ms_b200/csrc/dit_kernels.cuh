@@ -26,7 +26,7 @@ struct DitWeights {                 // device pointers; mirrors t2s_dit_weights 
     const float* b_ada;             // [4][768]
     const float* w_embed;           // [128][4]   patch_emb.weight @ conv.weight  (folded)
     const float* b_embed;           // [128]      patch_emb.weight @ conv.bias + patch_emb.bias
-    const float* pos;               // [480][128]
+    const float* pos;               // [8 tiles][32 col chunks][64 rows][4]  pos_embed in the residual tile layout
     const float* w_final;           // [4][128]   linear_emb_to_patch.weight * ln.weight
     const float* b_final;           // [4]        linear_emb_to_patch.weight @ ln.bias + bias
     const float* freqs;             // [64]       10000 ** linspace(0,1,64)
@@ -39,9 +39,9 @@ struct TokArgs {
     DitWeights w;
     const float* x;        // latents [(nseq >> x_shift)][64][30]
     int x_shift;           // 1 when the two sequences of a pair share one latent (CFG), else 0
-    float* h;              // residual stream  [nseq][480][128] fp32
+    float* h;              // residual stream, tiled: [npair][8 tiles][32 col chunks][128 rows][4] fp32
     __half* qkv;           // [nseq][4 heads][3][480][32] fp16, 16B chunks XOR-swizzled by (tok>>1)&3
-    const __half* o;       // attention output [nseq][480][128] fp16
+    const __half* o;       // attention output, tiled A-operand images: [npair][8 tiles][16 K chunks][16 row groups][8][8] fp16
     const float* mod;      // adaLN modulation [nseq][4][768] fp32
     int nseq;
     int layer;             // block whose post-attention half runs here (MID / FINAL)
@@ -102,398 +102,381 @@ __global__ void __launch_bounds__(256) cond_kernel(float* __restrict__ mod, cons
     }
 }
 
-// =================================================================================== warp GEMM helpers
-// acc[NB n8-blocks][4] += A(16 rows x 16*KS) . W^T, A in registers (mma A fragments), W stage in smem as
-// [n][k] fp16 rows of ROWB bytes with 16B chunks XOR-swizzled by (n & 7).
-template <int NB, int KS, int ROWB>
-__device__ __forceinline__ void warp_gemm_rega(float (&acc)[NB][4], const uint32_t (&a)[KS][4], uint32_t wbase, int lane) {
-    const int l7 = lane & 7;
-    const int kc = (lane >> 3) & 1;
-    const uint32_t lane_base = wbase + (uint32_t)(l7 + ((lane >> 4) << 3)) * ROWB;
+// =================================================================================== token block (tcgen05)
+// One CTA = one pair tile (128 rows = 60 tokens x {sequence 2p, sequence 2p+1}, 4+4 padding rows).
+// Everything that is local to a token runs here for one DiT block boundary:
+//   MID  (block l):  x += gate_msa*proj(o) ; a2 = mod(LN2(x)) ; x += gate_mlp*fc2(GELU(fc1(a2))) ; store x ;
+//                    a' = mod(LN1(x)) of block l+1 ; q|k|v = a' Wqkv^T + b   (transformer.py:114-117, timm Attention/Mlp)
+//   EMBED:           x = patch-embed + pos ; a' of block 0 ; q|k|v
+//   FINAL (block 3): ... ; final LN + Linear(128->4) + unpatchify + CFG mix + Euler/DDPM update
+// Warp roles (192 threads): warps 0-3 = epilogue, one thread per tile row (= TMEM lane), the residual row
+// lives in 128 registers; warp 4 = producer (bulk async copies of 32 KB weight stages and of the
+// attention-output tile, completion on mbarriers); warp 5 = MMA issuer (one lane issues
+// tcgen05.mma.kind::f16 128x128x16, accumulators in TMEM, completion via tcgen05.commit).
+// The seven GEMM chunks of a tile (proj | fc1 a,b | fc2 K-halves | q,k,v), each 128x128x128, rotate over
+// three 128-column TMEM regions so that the MMA of chunk i+1 overlaps the epilogue of chunk i.
+constexpr int TC_THREADS = 192;
+constexpr int TC_NSTAGE = 3;
+constexpr int TC_SM_A = 0;                                       // 32 KB A operand: o tile / a2 / hidden-b / a'
+constexpr int TC_SM_HA = STAGE_BYTES;                            // 32 KB A operand: hidden-a
+constexpr int TC_SM_W = 2 * STAGE_BYTES;                         // weight ring
+constexpr int TC_SM_VEC = TC_SM_W + TC_NSTAGE * STAGE_BYTES;     // per-tile vectors (fp32)
+constexpr int V_MOD = 0;        // [2 branches][768]  adaLN chunk of block l
+constexpr int V_MODN = 1536;    // [2][256]           shift_msa | scale_msa of the next block
+constexpr int V_BPROJ = 2048, V_B1 = 2176, V_B2 = 2432, V_BQKV = 2560;
+constexpr int V_WEMB = 2944;    // [128][4]
+constexpr int V_BEMB = 3456;    // [128]
+constexpr int V_WFIN = 3584;    // [4][128]
+constexpr int V_BFIN = 4096;    // [4]
+constexpr int V_END = 4104;
+constexpr int TC_SM_VB = TC_SM_VEC + V_END * 4;                  // [128][4] fp32 final-projection exchange
+constexpr int TC_SM_BAR = TC_SM_VB + TILE_ROWS * 4 * 4;
+constexpr int TC_SM_TMEM = TC_SM_BAR + 32 * 8;
+constexpr int TOK_SMEM_BYTES = TC_SM_TMEM + 16;
+enum { B_WFULL = 0, B_WEMPTY = 3, B_OFULL = 6, B_A2 = 7, B_HA = 8, B_HB = 9, B_A3 = 10, B_ACC = 11 /* ..17 */, B_COUNT = 18 };
+constexpr uint32_t TC_IDESC = umma_idesc_f16(128, 128);
+constexpr uint32_t KCH = 2048;   // byte stride between K chunks (16 row groups x 128 B) in a [128][128] operand image
+
+// one 128x128x128 GEMM chunk: 8 x tcgen05.mma (K = 16 each); operands in the canonical no-swizzle K-major image
+__device__ __forceinline__ void tc_gemm(uint32_t a_smem, uint32_t w_smem, uint32_t d_tmem, bool accumulate) {
 #pragma unroll
-    for (int kk = 0; kk < KS; ++kk) {
-        const uint32_t koff = (uint32_t)(((2 * kk + kc) ^ l7) << 4);
+    for (int k = 0; k < 8; ++k)
+        umma_f16(d_tmem, umma_desc(a_smem + k * 2 * KCH, KCH, 128), umma_desc(w_smem + k * 2 * KCH, KCH, 128), TC_IDESC,
+                 (accumulate || k > 0) ? 1u : 0u);
+}
+
+// thread-per-row LayerNorm (no affine) + modulate, packed to fp16 and stored as the A operand image.
+__device__ __forceinline__ void ln_mod_store(const float (&h)[D], const float* __restrict__ shift, const float* __restrict__ scale,
+                                             float eps, uint8_t* abuf, int r) {
+    float s = 0.f;
 #pragma unroll
-        for (int jj = 0; jj < NB / 2; ++jj) {
-            uint32_t b0, b1, b2, b3;
-            ldmatrix_x4(b0, b1, b2, b3, lane_base + jj * 16 * ROWB + koff);
-            mma_f16(acc[2 * jj], a[kk][0], a[kk][1], a[kk][2], a[kk][3], b0, b1);
-            mma_f16(acc[2 * jj + 1], a[kk][0], a[kk][1], a[kk][2], a[kk][3], b2, b3);
+    for (int c = 0; c < D; ++c) s += h[c];
+    const float mean = s * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < D; ++c) { const float d = h[c] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(q * (1.f / D) + eps);
+#pragma unroll
+    for (int c8 = 0; c8 < 16; ++c8) {
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; j += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(scale + c8 * 8 + j);
+            const float4 sh = *reinterpret_cast<const float4*>(shift + c8 * 8 + j);
+            y[j + 0] = fmaf((h[c8 * 8 + j + 0] - mean) * rstd, 1.f + sc.x, sh.x);
+            y[j + 1] = fmaf((h[c8 * 8 + j + 1] - mean) * rstd, 1.f + sc.y, sh.y);
+            y[j + 2] = fmaf((h[c8 * 8 + j + 2] - mean) * rstd, 1.f + sc.z, sh.z);
+            y[j + 3] = fmaf((h[c8 * 8 + j + 3] - mean) * rstd, 1.f + sc.w, sh.w);
+        }
+        *reinterpret_cast<uint4*>(abuf + c8 * KCH + r * 16) =
+            make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7]));
+    }
+}
+
+// x += gate * (acc + bias) over the 128 columns of a TMEM region
+__device__ __forceinline__ void residual_update(float (&h)[D], uint32_t taddr, const float* __restrict__ gate,
+                                                const float* __restrict__ bias) {
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+        float v[32];
+        tmem_ld32(taddr + cb * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 g4 = *reinterpret_cast<const float4*>(gate + cb * 32 + j);
+            const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 32 + j);
+            h[cb * 32 + j + 0] = fmaf(g4.x, v[j + 0] + b4.x, h[cb * 32 + j + 0]);
+            h[cb * 32 + j + 1] = fmaf(g4.y, v[j + 1] + b4.y, h[cb * 32 + j + 1]);
+            h[cb * 32 + j + 2] = fmaf(g4.z, v[j + 2] + b4.z, h[cb * 32 + j + 2]);
+            h[cb * 32 + j + 3] = fmaf(g4.w, v[j + 3] + b4.w, h[cb * 32 + j + 3]);
         }
     }
 }
 
-// Same with A read from a swizzled smem tile [rows][128 fp16] (256 B rows, chunk ^ (row & 7)).
-template <int NB>
-__device__ __forceinline__ void warp_gemm_smema(float (&acc)[NB][4], uint32_t abase, int row0, uint32_t wbase, int lane) {
-    const int l7 = lane & 7;
-    const int kc = (lane >> 3) & 1;
-    const uint32_t lane_base = wbase + (uint32_t)(l7 + ((lane >> 4) << 3)) * 256;
-    const int arow = row0 + (lane & 15);
-    const uint32_t a_lane = abase + arow * 256;
-    const int a7 = arow & 7, ah = lane >> 4;
+// hidden = GELU_tanh(acc + b1) packed to fp16 into an A operand image (timm Mlp, transformer.py:99,105)
+__device__ __forceinline__ void gelu_store(uint32_t taddr, const float* __restrict__ bias, uint8_t* abuf, int r) {
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-        uint32_t a0, a1, a2, a3;
-        ldmatrix_x4(a0, a1, a2, a3, a_lane + (uint32_t)(((2 * kk + ah) ^ a7) << 4));
-        const uint32_t koff = (uint32_t)(((2 * kk + kc) ^ l7) << 4);
+    for (int cb = 0; cb < 4; ++cb) {
+        float v[32];
+        tmem_ld32(taddr + cb * 32, v);
+        tmem_wait_ld();
 #pragma unroll
-        for (int jj = 0; jj < NB / 2; ++jj) {
-            uint32_t b0, b1, b2, b3;
-            ldmatrix_x4(b0, b1, b2, b3, lane_base + jj * 16 * 256 + koff);
-            mma_f16(acc[2 * jj], a0, a1, a2, a3, b0, b1);
-            mma_f16(acc[2 * jj + 1], a0, a1, a2, a3, b2, b3);
+        for (int c8 = 0; c8 < 4; ++c8) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + cb * 32 + c8 * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + cb * 32 + c8 * 8 + 4);
+            const float* x = v + c8 * 8;
+            *reinterpret_cast<uint4*>(abuf + (cb * 4 + c8) * KCH + r * 16) =
+                make_uint4(pack_h2(gelu_tanh(x[0] + b0.x), gelu_tanh(x[1] + b0.y)), pack_h2(gelu_tanh(x[2] + b0.z), gelu_tanh(x[3] + b0.w)),
+                           pack_h2(gelu_tanh(x[4] + b1.x), gelu_tanh(x[5] + b1.y)), pack_h2(gelu_tanh(x[6] + b1.z), gelu_tanh(x[7] + b1.w)));
         }
     }
 }
 
-// LayerNorm (no affine) over the 128 features of the two rows a thread quad holds in accumulator
-// layout, then modulate x*(1+scale)+shift (transformer.py:7-8,102-103,116-117) and repack as fp16
-// mma A fragments for the next GEMM.  Row statistics: warp-shuffle reduction over the quad.
-__device__ __forceinline__ void ln_mod_afrag(const float (&x)[16][4], uint32_t (&a)[8][4], const float* __restrict__ shift,
-                                             const float* __restrict__ scale, float eps, int t) {
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { s0 += x[j][0] + x[j][1]; s1 += x[j][2] + x[j][3]; }
-    const float m0 = quad_sum(s0) * (1.f / D), m1 = quad_sum(s1) * (1.f / D);
-    float v0 = 0.f, v1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        float d;
-        d = x[j][0] - m0; v0 = fmaf(d, d, v0);
-        d = x[j][1] - m0; v0 = fmaf(d, d, v0);
-        d = x[j][2] - m1; v1 = fmaf(d, d, v1);
-        d = x[j][3] - m1; v1 = fmaf(d, d, v1);
-    }
-    const float r0 = rsqrtf(quad_sum(v0) * (1.f / D) + eps), r1 = rsqrtf(quad_sum(v1) * (1.f / D) + eps);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int f = 8 * j + 2 * t;
-        const float2 sc = *reinterpret_cast<const float2*>(scale + f);
-        const float2 sh = *reinterpret_cast<const float2*>(shift + f);
-        const float y00 = fmaf((x[j][0] - m0) * r0, 1.f + sc.x, sh.x);
-        const float y01 = fmaf((x[j][1] - m0) * r0, 1.f + sc.y, sh.y);
-        const float y10 = fmaf((x[j][2] - m1) * r1, 1.f + sc.x, sh.x);
-        const float y11 = fmaf((x[j][3] - m1) * r1, 1.f + sc.y, sh.y);
-        a[j >> 1][(j & 1) * 2 + 0] = pack_h2(y00, y01);
-        a[j >> 1][(j & 1) * 2 + 1] = pack_h2(y10, y11);
-    }
-}
-
-// Weight-stage ring: 2 x 32 KB smem buffers filled by bulk async copies (TMA engine, UBLKCP),
-// completion on mbarriers; the consumer side is the whole CTA (a __syncthreads releases a buffer).
-struct StageRing {
-    uint32_t buf, bar;                // smem addresses: 2 buffers, 2 mbarriers
-    const char* src_a; int n_a;       // first n_a stages come from src_a, the rest from src_b
-    const char* src_b; int n_total;
-    __device__ __forceinline__ const char* stage_src(int s) const {
-        return s < n_a ? src_a + (size_t)s * STAGE_BYTES : src_b + (size_t)(s - n_a) * STAGE_BYTES;
-    }
-    __device__ __forceinline__ void issue(int s) const {     // one thread
-        const uint32_t b = bar + (s & 1) * 8;
-        mbar_expect_tx(b, STAGE_BYTES);
-        bulk_g2s(buf + (s & 1) * STAGE_BYTES, stage_src(s), STAGE_BYTES, b);
-    }
-    __device__ __forceinline__ uint32_t wait(int s) const {  // all threads; returns the stage's smem address
-        mbar_wait(bar + (s & 1) * 8, (s >> 1) & 1);
-        return buf + (s & 1) * STAGE_BYTES;
-    }
-    __device__ __forceinline__ void release(int s, int tid) const {  // all threads
-        __syncthreads();
-        if (tid == 0 && s + 2 < n_total) issue(s + 2);
-    }
-};
-
-// LN1+modulate of block `l` -> QKV GEMM (3 stages starting at ring stage s0) -> q|k|v stored fp16 in the
-// attention kernel's smem image layout.
-__device__ __forceinline__ void qkv_phase(const float (&hreg)[16][4], const TokArgs& p, const StageRing& ring, int s0, int l,
-                                          int seq, bool v0, bool v1, int tok0, int tok1, int lane, int tid) {
-    const int t = lane & 3;
-    const float* mod = p.mod + ((size_t)seq * NLAYER + l) * MOD;
-    uint32_t a[8][4];
-    ln_mod_afrag(hreg, a, mod /*shift_msa*/, mod + D /*scale_msa*/, 1e-6f, t);
-    const float* bq = p.w.b_qkv[l];
-#pragma unroll 1
-    for (int which = 0; which < 3; ++which) {
-        const uint32_t wb = ring.wait(s0 + which);
-        float acc[16][4];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-        warp_gemm_rega<16, 8, 256>(acc, a, wb, lane);
-        ring.release(s0 + which, tid);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int f = 8 * j + 2 * t, head = j >> 2, chunk = j & 3;
-            const float2 b = *reinterpret_cast<const float2*>(bq + which * D + f);
-            __half* base = p.qkv + (((size_t)seq * NHEAD + head) * 3 + which) * (NTOK * HD) + 2 * t;
-            if (v0) *reinterpret_cast<uint32_t*>(base + tok0 * HD + ((chunk ^ ((tok0 >> 1) & 3)) << 3)) =
-                        pack_h2(acc[j][0] + b.x, acc[j][1] + b.y);
-            if (v1) *reinterpret_cast<uint32_t*>(base + tok1 * HD + ((chunk ^ ((tok1 >> 1) & 3)) << 3)) =
-                        pack_h2(acc[j][2] + b.x, acc[j][3] + b.y);
-        }
-    }
-}
-
-// smem carve-up of token_kernel
-constexpr int TOK_SMEM_W = 0;                                   // 2 x 32 KB weight stages
-constexpr int TOK_SMEM_O = 2 * STAGE_BYTES;                     // attention-output tile, fp16 [128][128] swizzled
-constexpr int HS_LD = 136;                                      // fp32 row stride of the h tile (bank-conflict-free float2)
-constexpr int TOK_SMEM_H = TOK_SMEM_O + TILE_ROWS * D * 2;      // residual tile fp32 [128][136]
-constexpr int TOK_SMEM_BAR = TOK_SMEM_H + TILE_ROWS * HS_LD * 4;
-constexpr int TOK_SMEM_V = TOK_SMEM_BAR + 64;                   // [128][4] fp32 final projection exchange
-constexpr int TOK_SMEM_BYTES = TOK_SMEM_V + TILE_ROWS * 4 * 4;
-
-// grid = npair * 8 tiles, block = 256 (8 warps x 16 rows)
+// grid = npair * 8 tiles, block = 192
 template <int MODE>
-__global__ void __launch_bounds__(256, 1) token_kernel(const TokArgs p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pair = blockIdx.x / TILES_PER_PAIR, tt = blockIdx.x % TILES_PER_PAIR;
-    const uint32_t s_base = smem_u32(smem);
+    const uint32_t sb = smem_u32(smem);
+    const uint32_t bar0 = sb + TC_SM_BAR;
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    float* vec = reinterpret_cast<float*>(smem + TC_SM_VEC);
+    const int l = p.layer;                                         // block whose second half runs here (MID / FINAL)
+    const int ln = (MODE == TOK_EMBED) ? 0 : l + 1;                // block whose QKV is produced here (EMBED / MID)
+    constexpr int N_STAGES = (MODE == TOK_EMBED) ? 3 : (MODE == TOK_MID ? 8 : 5);
 
-    // rows owned by this thread: r0 = warp*16 + g and r0 + 8 (same sequence: branch = warp >> 2)
-    const int branch = warp >> 2;
-    const int seq = 2 * pair + branch;
-    const bool seq_ok = seq < p.nseq;
-    const int tl0 = (warp & 3) * 16 + g, tl1 = tl0 + 8;
-    const bool v0 = seq_ok && tl0 < TILE_TOK, v1 = seq_ok && tl1 < TILE_TOK;
-    const int tok0 = tt * TILE_TOK + tl0, tok1 = tt * TILE_TOK + tl1;
-    const int seq_c = seq_ok ? seq : 0;                           // clamped for address formation
-    const int l = p.layer;
-
-    StageRing ring;
-    ring.buf = s_base + TOK_SMEM_W;
-    ring.bar = s_base + TOK_SMEM_BAR;
-    if (MODE == TOK_EMBED) {
-        ring.src_a = reinterpret_cast<const char*>(p.w.w_qkv[0]); ring.n_a = 3; ring.src_b = nullptr; ring.n_total = 3;
-    } else if (MODE == TOK_MID) {
-        ring.src_a = reinterpret_cast<const char*>(p.w.w_post[l]); ring.n_a = 5;
-        ring.src_b = reinterpret_cast<const char*>(p.w.w_qkv[l + 1]); ring.n_total = 8;
-    } else {
-        ring.src_a = reinterpret_cast<const char*>(p.w.w_post[l]); ring.n_a = 5; ring.src_b = nullptr; ring.n_total = 5;
-    }
     if (tid == 0) {
-        mbar_init(ring.bar, 1);
-        mbar_init(ring.bar + 8, 1);
+        for (int i = 0; i < 7; ++i) mbar_init(BAR(i), 1);
+        for (int i = B_A2; i <= B_A3; ++i) mbar_init(BAR(i), 128);
+        for (int i = B_ACC; i < B_COUNT; ++i) mbar_init(BAR(i), 1);
         mbar_fence_init();
-        ring.issue(0);
-        ring.issue(1);
     }
-
-    float hreg[16][4];   // residual rows in accumulator layout: [j][0..1] row r0, [j][2..3] row r0+8, cols 8j+2t,+1
-
-    if (MODE == TOK_EMBED) {
-        // ---- patchify + patch_emb + pos_embed (transformer.py:166-172), conv folded into the Linear
-        float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* xs = p.x + (size_t)(seq_c >> p.x_shift) * LAT;
-        if (v0) {
-            const int i = tok0 >> 5, j = tok0 & 31;
-#pragma unroll
-            for (int pq = 0; pq < 4; ++pq) xa[pq] = xs[(2 * j + (pq & 1)) * LATP + 2 * i + (pq >> 1)];
+    if (warp == 4) tmem_alloc(sb + TC_SM_TMEM, 512);
+    // stage the per-tile vectors
+    {
+        const int sq0 = min(2 * pair, p.nseq - 1), sq1 = min(2 * pair + 1, p.nseq - 1);
+        if (MODE != TOK_EMBED) {
+            for (int i = tid; i < 2 * MOD; i += TC_THREADS)
+                vec[V_MOD + i] = p.mod[((size_t)(i < MOD ? sq0 : sq1) * NLAYER + l) * MOD + (i < MOD ? i : i - MOD)];
+            for (int i = tid; i < D; i += TC_THREADS) { vec[V_BPROJ + i] = p.w.b_proj[l][i]; vec[V_B2 + i] = p.w.b_fc2[l][i]; }
+            for (int i = tid; i < DMLP; i += TC_THREADS) vec[V_B1 + i] = p.w.b_fc1[l][i];
         }
-        if (v1) {
-            const int i = tok1 >> 5, j = tok1 & 31;
-#pragma unroll
-            for (int pq = 0; pq < 4; ++pq) xb[pq] = xs[(2 * j + (pq & 1)) * LATP + 2 * i + (pq >> 1)];
+        if (MODE != TOK_FINAL) {
+            for (int i = tid; i < 512; i += TC_THREADS)
+                vec[V_MODN + i] = p.mod[((size_t)(i < 256 ? sq0 : sq1) * NLAYER + ln) * MOD + (i & 255)];
+            for (int i = tid; i < 3 * D; i += TC_THREADS) vec[V_BQKV + i] = p.w.b_qkv[ln][i];
         }
-        float* hg = p.h + (size_t)seq_c * NTOK * D;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int f = 8 * j + 2 * t;
-            const float4 wa = *reinterpret_cast<const float4*>(p.w.w_embed + f * 4);
-            const float4 wb = *reinterpret_cast<const float4*>(p.w.w_embed + f * 4 + 4);
-            const float2 be = *reinterpret_cast<const float2*>(p.w.b_embed + f);
-            float2 h0 = make_float2(0.f, 0.f), h1 = make_float2(0.f, 0.f);
-            if (v0) {
-                const float2 pe = *reinterpret_cast<const float2*>(p.w.pos + tok0 * D + f);
-                h0.x = wa.x * xa[0] + wa.y * xa[1] + wa.z * xa[2] + wa.w * xa[3] + be.x + pe.x;
-                h0.y = wb.x * xa[0] + wb.y * xa[1] + wb.z * xa[2] + wb.w * xa[3] + be.y + pe.y;
-                *reinterpret_cast<float2*>(hg + tok0 * D + f) = h0;
+        if (MODE == TOK_EMBED) {
+            for (int i = tid; i < 4 * D; i += TC_THREADS) vec[V_WEMB + i] = p.w.w_embed[i];
+            for (int i = tid; i < D; i += TC_THREADS) vec[V_BEMB + i] = p.w.b_embed[i];
+        }
+        if (MODE == TOK_FINAL) {
+            for (int i = tid; i < 4 * D; i += TC_THREADS) vec[V_WFIN + i] = p.w.w_final[i];
+            if (tid < 4) vec[V_BFIN + tid] = p.w.b_final[tid];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + TC_SM_TMEM);
+    const size_t tile = (size_t)pair * TILES_PER_PAIR + tt;
+
+    if (warp == 4) {
+        // ================================================================= producer
+        if (lane == 0) {
+            if (MODE != TOK_EMBED) {
+                mbar_expect_tx(BAR(B_OFULL), STAGE_BYTES);
+                bulk_g2s(sb + TC_SM_A, reinterpret_cast<const char*>(p.o) + tile * STAGE_BYTES, STAGE_BYTES, BAR(B_OFULL));
             }
-            if (v1) {
-                const float2 pe = *reinterpret_cast<const float2*>(p.w.pos + tok1 * D + f);
-                h1.x = wa.x * xb[0] + wa.y * xb[1] + wa.z * xb[2] + wa.w * xb[3] + be.x + pe.x;
-                h1.y = wb.x * xb[0] + wb.y * xb[1] + wb.z * xb[2] + wb.w * xb[3] + be.y + pe.y;
-                *reinterpret_cast<float2*>(hg + tok1 * D + f) = h1;
-            }
-            hreg[j][0] = h0.x; hreg[j][1] = h0.y; hreg[j][2] = h1.x; hreg[j][3] = h1.y;
-        }
-        __syncthreads();    // mbarrier init visible to all waiters
-        qkv_phase(hreg, p, ring, 0, 0, seq_c, v0, v1, tok0, tok1, lane, tid);
-        return;
-    }
-
-    // ---- MID / FINAL: stage the attention-output tile (fp16) and the residual tile (fp32) in smem
-    {
-        const uint32_t so = s_base + TOK_SMEM_O;
-        for (int q = tid; q < TILE_ROWS * 16; q += 256) {
-            const int r = q >> 4, c = q & 15, sq = 2 * pair + (r >> 6), tl = r & 63;
-            const uint32_t dst = so + r * 256 + ((c ^ (r & 7)) << 4);
-            if (tl < TILE_TOK && sq < p.nseq)
-                cp_async16(dst, p.o + ((size_t)sq * NTOK + tt * TILE_TOK + tl) * D + c * 8);
-            else
-                *reinterpret_cast<uint4*>(smem + TOK_SMEM_O + r * 256 + ((c ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-        }
-        const uint32_t sh = s_base + TOK_SMEM_H;
-        for (int q = tid; q < TILE_ROWS * 32; q += 256) {
-            const int r = q >> 5, c = q & 31, sq = 2 * pair + (r >> 6), tl = r & 63;
-            if (tl < TILE_TOK && sq < p.nseq)
-                cp_async16(sh + (r * HS_LD + c * 4) * 4, p.h + ((size_t)sq * NTOK + tt * TILE_TOK + tl) * D + c * 4);
-            else
-                *reinterpret_cast<float4*>(smem + TOK_SMEM_H + (r * HS_LD + c * 4) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        cp_async_commit();
-        cp_async_wait_all();
-        __syncthreads();
-    }
-    float* hs = reinterpret_cast<float*>(smem + TOK_SMEM_H);
-    const int r0 = warp * 16 + g, r1 = r0 + 8;
-    const float* mod = p.mod + ((size_t)seq_c * NLAYER + l) * MOD;
-
-    // ---- attention out-projection + gate + residual   x = x + gate_msa * proj(o)   (transformer.py:116)
-    {
-        const uint32_t wb = ring.wait(0);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) hreg[j][0] = hreg[j][1] = hreg[j][2] = hreg[j][3] = 0.f;
-        warp_gemm_smema<16>(hreg, s_base + TOK_SMEM_O, warp * 16, wb, lane);
-        ring.release(0, tid);
-        const float* gate = mod + 2 * D;
-        const float* bp = p.w.b_proj[l];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int f = 8 * j + 2 * t;
-            const float2 gv = *reinterpret_cast<const float2*>(gate + f);
-            const float2 bv = *reinterpret_cast<const float2*>(bp + f);
-            float2 h0 = *reinterpret_cast<float2*>(hs + r0 * HS_LD + f);
-            float2 h1 = *reinterpret_cast<float2*>(hs + r1 * HS_LD + f);
-            h0.x = fmaf(gv.x, hreg[j][0] + bv.x, h0.x);
-            h0.y = fmaf(gv.y, hreg[j][1] + bv.y, h0.y);
-            h1.x = fmaf(gv.x, hreg[j][2] + bv.x, h1.x);
-            h1.y = fmaf(gv.y, hreg[j][3] + bv.y, h1.y);
-            *reinterpret_cast<float2*>(hs + r0 * HS_LD + f) = h0;
-            *reinterpret_cast<float2*>(hs + r1 * HS_LD + f) = h1;
-            hreg[j][0] = h0.x; hreg[j][1] = h0.y; hreg[j][2] = h1.x; hreg[j][3] = h1.y;
-        }
-    }
-    // ---- MLP: x = x + gate_mlp * fc2(GELU(fc1(modulate(LN2(x)))))   (transformer.py:117), hidden in 4 chunks of 64
-    {
-        uint32_t a2[8][4];
-        ln_mod_afrag(hreg, a2, mod + 3 * D, mod + 4 * D, 1e-6f, t);
-        float acc2[16][4];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc2[j][0] = acc2[j][1] = acc2[j][2] = acc2[j][3] = 0.f;
-        const float* b1 = p.w.b_fc1[l];
+            const char* src_a = reinterpret_cast<const char*>(MODE == TOK_EMBED ? p.w.w_qkv[0] : p.w.w_post[l]);
+            const char* src_b = reinterpret_cast<const char*>(MODE == TOK_MID ? p.w.w_qkv[l + 1] : nullptr);
+            constexpr int N_A = (MODE == TOK_EMBED) ? 3 : 5;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            const uint32_t wb = ring.wait(1 + c);
-            float acc1[8][4];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc1[j][0] = acc1[j][1] = acc1[j][2] = acc1[j][3] = 0.f;
-            warp_gemm_rega<8, 8, 256>(acc1, a2, wb, lane);
-            uint32_t hf[4][4];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float2 b = *reinterpret_cast<const float2*>(b1 + c * 64 + 8 * j + 2 * t);
-                hf[j >> 1][(j & 1) * 2 + 0] = pack_h2(gelu_tanh(acc1[j][0] + b.x), gelu_tanh(acc1[j][1] + b.y));
-                hf[j >> 1][(j & 1) * 2 + 1] = pack_h2(gelu_tanh(acc1[j][2] + b.x), gelu_tanh(acc1[j][3] + b.y));
-            }
-            warp_gemm_rega<16, 4, 128>(acc2, hf, wb + 16384, lane);
-            ring.release(1 + c, tid);
-        }
-        const float* gate = mod + 5 * D;
-        const float* b2 = p.w.b_fc2[l];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int f = 8 * j + 2 * t;
-            const float2 gv = *reinterpret_cast<const float2*>(gate + f);
-            const float2 bv = *reinterpret_cast<const float2*>(b2 + f);
-            const float2 h0 = *reinterpret_cast<const float2*>(hs + r0 * HS_LD + f);
-            const float2 h1 = *reinterpret_cast<const float2*>(hs + r1 * HS_LD + f);
-            hreg[j][0] = fmaf(gv.x, acc2[j][0] + bv.x, h0.x);
-            hreg[j][1] = fmaf(gv.y, acc2[j][1] + bv.y, h0.y);
-            hreg[j][2] = fmaf(gv.x, acc2[j][2] + bv.x, h1.x);
-            hreg[j][3] = fmaf(gv.y, acc2[j][3] + bv.y, h1.y);
-        }
-    }
-
-    if (MODE == TOK_MID) {
-        float* hg = p.h + (size_t)seq_c * NTOK * D;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int f = 8 * j + 2 * t;
-            if (v0) *reinterpret_cast<float2*>(hg + tok0 * D + f) = make_float2(hreg[j][0], hreg[j][1]);
-            if (v1) *reinterpret_cast<float2*>(hg + tok1 * D + f) = make_float2(hreg[j][2], hreg[j][3]);
-        }
-        qkv_phase(hreg, p, ring, 5, l + 1, seq_c, v0, v1, tok0, tok1, lane, tid);
-        return;
-    }
-
-    // ---- FINAL: LN(eps 1e-5, affine folded) + Linear(128->4) + unpatchify (transformer.py:182-190)
-    {
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { s0 += hreg[j][0] + hreg[j][1]; s1 += hreg[j][2] + hreg[j][3]; }
-        const float m0 = quad_sum(s0) * (1.f / D), m1 = quad_sum(s1) * (1.f / D);
-        float q0 = 0.f, q1 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            float d;
-            d = hreg[j][0] - m0; q0 = fmaf(d, d, q0);
-            d = hreg[j][1] - m0; q0 = fmaf(d, d, q0);
-            d = hreg[j][2] - m1; q1 = fmaf(d, d, q1);
-            d = hreg[j][3] - m1; q1 = fmaf(d, d, q1);
-        }
-        const float rs0 = rsqrtf(quad_sum(q0) * (1.f / D) + 1e-5f), rs1 = rsqrtf(quad_sum(q1) * (1.f / D) + 1e-5f);
-        float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int f = 8 * j + 2 * t;
-            const float y00 = (hreg[j][0] - m0) * rs0, y01 = (hreg[j][1] - m0) * rs0;
-            const float y10 = (hreg[j][2] - m1) * rs1, y11 = (hreg[j][3] - m1) * rs1;
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                const float2 w = *reinterpret_cast<const float2*>(p.w.w_final + c4 * D + f);
-                d0[c4] = fmaf(y00, w.x, fmaf(y01, w.y, d0[c4]));
-                d1[c4] = fmaf(y10, w.x, fmaf(y11, w.y, d1[c4]));
+            for (int s = 0; s < N_STAGES; ++s) {
+                const int slot = s % TC_NSTAGE, use = s / TC_NSTAGE;
+                if (use > 0) mbar_wait(BAR(B_WEMPTY + slot), (use - 1) & 1);
+                mbar_expect_tx(BAR(B_WFULL + slot), STAGE_BYTES);
+                bulk_g2s(sb + TC_SM_W + slot * STAGE_BYTES, s < N_A ? src_a + (size_t)s * STAGE_BYTES : src_b + (size_t)(s - N_A) * STAGE_BYTES,
+                         STAGE_BYTES, BAR(B_WFULL + slot));
             }
         }
-        float* vb = reinterpret_cast<float*>(smem + TOK_SMEM_V);
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-            const float e0 = quad_sum(d0[c4]) + p.w.b_final[c4];
-            const float e1 = quad_sum(d1[c4]) + p.w.b_final[c4];
-            if (t == c4) { vb[r0 * 4 + c4] = e0; vb[r1 * 4 + c4] = e1; }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ================================================================= MMA issuer
+        if (lane == 0) {
+            int s = 0;
+            auto chunk = [&](uint32_t a_smem, uint32_t d_col, bool accumulate, int acc_bar) {
+                const int slot = s % TC_NSTAGE;
+                mbar_wait(BAR(B_WFULL + slot), (s / TC_NSTAGE) & 1);
+                tc_fence_after();
+                tc_gemm(a_smem, sb + TC_SM_W + slot * STAGE_BYTES, tmem + d_col, accumulate);
+                umma_commit(BAR(B_WEMPTY + slot));
+                if (acc_bar >= 0) umma_commit(BAR(B_ACC + acc_bar));
+                ++s;
+            };
+            if (MODE != TOK_EMBED) {
+                mbar_wait(BAR(B_OFULL), 0);
+                chunk(sb + TC_SM_A, 0, false, 0);                       // proj            -> R0
+                mbar_wait(BAR(B_A2), 0);
+                chunk(sb + TC_SM_A, 128, false, 1);                     // fc1 cols 0..127   -> R1
+                chunk(sb + TC_SM_A, 256, false, 2);                     // fc1 cols 128..255 -> R2
+                mbar_wait(BAR(B_HA), 0);
+                chunk(sb + TC_SM_HA, 0, false, -1);                     // fc2, K half 0   -> R0
+                mbar_wait(BAR(B_HB), 0);
+                chunk(sb + TC_SM_A, 0, true, 3);                        // fc2, K half 1   -> R0
+            }
+            if (MODE != TOK_FINAL) {
+                mbar_wait(BAR(B_A3), 0);
+                chunk(sb + TC_SM_A, 128, false, 4);                     // q -> R1
+                chunk(sb + TC_SM_A, 256, false, 5);                     // k -> R2
+                chunk(sb + TC_SM_A, 0, false, 6);                       // v -> R0
+            }
         }
-        __syncthreads();
-        if (p.out_mode == OUT_FWD) {
-            for (int idx = tid; idx < 2 * TILE_TOK * 4; idx += 256) {
-                const int br = idx / (TILE_TOK * 4), rem = idx - br * (TILE_TOK * 4), tl = rem >> 2, c4 = rem & 3;
-                const int sq = 2 * pair + br;
-                if (sq < p.nseq) {
-                    const int n = tt * TILE_TOK + tl, i = n >> 5, jx = n & 31;
-                    p.out[(size_t)sq * LAT + (2 * jx + (c4 & 1)) * LATP + 2 * i + (c4 >> 1)] = vb[(br * 64 + tl) * 4 + c4];
+        __syncwarp();
+    } else {
+        // ================================================================= epilogue: thread r <-> tile row r <-> TMEM lane r
+        const int r = tid;
+        const int branch = r >> 6, tl = r & 63;
+        const int seq = 2 * pair + branch;
+        const bool valid = tl < TILE_TOK && seq < p.nseq;
+        const int tok = tt * TILE_TOK + tl;
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const float* modb = vec + V_MOD + branch * MOD;
+        float* htile = p.h + tile * (TILE_ROWS * D);                    // [32 col chunks][128 rows][4]
+        float h[D];
+        if (MODE == TOK_EMBED) {
+            // patchify + patch_emb + pos_embed (transformer.py:166-172), conv folded into the Linear
+            float xv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (valid) {
+                const float* xs = p.x + (size_t)(seq >> p.x_shift) * LAT;
+                const int i = tok >> 5, j = tok & 31;
+#pragma unroll
+                for (int pq = 0; pq < 4; ++pq) xv[pq] = xs[(2 * j + (pq & 1)) * LATP + 2 * i + (pq >> 1)];
+            }
+            const float* pos = p.w.pos + ((size_t)tt * 32 * 64 + tl) * 4;   // [8 tiles][32 chunks][64 rows][4]
+#pragma unroll
+            for (int c4 = 0; c4 < 32; ++c4) {
+                float4 pe = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) pe = *reinterpret_cast<const float4*>(pos + c4 * 64 * 4);
+                const float pev[4] = {pe.x, pe.y, pe.z, pe.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(vec + V_WEMB + (c4 * 4 + e) * 4);
+                    h[c4 * 4 + e] = valid ? (w4.x * xv[0] + w4.y * xv[1] + w4.z * xv[2] + w4.w * xv[3] + vec[V_BEMB + c4 * 4 + e] + pev[e]) : 0.f;
                 }
             }
-        } else if (tid < TILE_TOK * 4) {
-            // classifier-free guidance mix (infer.py:81/:87) + Euler (rectified_flow.py:5-7) or
-            // DDPM ancestral update (DDPM.py:28-36), latent updated in place
-            const int tl = tid >> 2, c4 = tid & 3;
-            const int n = tt * TILE_TOK + tl, i = n >> 5, jx = n & 31;
-            const size_t xi = (size_t)pair * LAT + (2 * jx + (c4 & 1)) * LATP + 2 * i + (c4 >> 1);
-            const float u = vb[tl * 4 + c4], c = vb[(64 + tl) * 4 + c4];
-            const float pred = u + p.cfg * (c - u);
-            if (p.out != nullptr) p.out[xi] = pred;
-            const float xo = p.x_upd[xi];
-            float xn;
-            if (p.out_mode == OUT_RF) {
-                xn = xo + pred * p.c1;
-            } else {
-                const float mean = p.c1 * (xo - p.c2 * pred);
-                xn = mean + p.c3 * p.noise[xi];
+        } else {
+#pragma unroll
+            for (int c4 = 0; c4 < 32; ++c4) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) v = *reinterpret_cast<const float4*>(htile + (c4 * TILE_ROWS + r) * 4);
+                h[c4 * 4 + 0] = v.x; h[c4 * 4 + 1] = v.y; h[c4 * 4 + 2] = v.z; h[c4 * 4 + 3] = v.w;
             }
-            p.x_upd[xi] = xn;
+            // x = x + gate_msa * (o Wproj^T + b)        (transformer.py:116)
+            mbar_wait(BAR(B_ACC + 0), 0);
+            tc_fence_after();
+            residual_update(h, trow + 0, modb + 2 * D, vec + V_BPROJ);
+            ln_mod_store(h, modb + 3 * D, modb + 4 * D, 1e-6f, smem + TC_SM_A, r);
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(BAR(B_A2));
+            // hidden = GELU(fc1)                         (transformer.py:117)
+            mbar_wait(BAR(B_ACC + 1), 0);
+            tc_fence_after();
+            gelu_store(trow + 128, vec + V_B1, smem + TC_SM_HA, r);
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(BAR(B_HA));
+            mbar_wait(BAR(B_ACC + 2), 0);
+            tc_fence_after();
+            gelu_store(trow + 256, vec + V_B1 + D, smem + TC_SM_A, r);
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(BAR(B_HB));
+            // x = x + gate_mlp * (hidden W2^T + b)
+            mbar_wait(BAR(B_ACC + 3), 0);
+            tc_fence_after();
+            residual_update(h, trow + 0, modb + 5 * D, vec + V_B2);
+        }
+
+        if (MODE != TOK_FINAL) {
+            if (valid) {
+#pragma unroll
+                for (int c4 = 0; c4 < 32; ++c4)
+                    *reinterpret_cast<float4*>(htile + (c4 * TILE_ROWS + r) * 4) = make_float4(h[c4 * 4], h[c4 * 4 + 1], h[c4 * 4 + 2], h[c4 * 4 + 3]);
+            }
+            const float* modn = vec + V_MODN + branch * 256;
+            ln_mod_store(h, modn, modn + D, 1e-6f, smem + TC_SM_A, r);
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(BAR(B_A3));
+            // q | k | v = a' W^T + b, stored fp16 in the attention kernel's smem image layout
+#pragma unroll 1
+            for (int which = 0; which < 3; ++which) {
+                mbar_wait(BAR(B_ACC + 4 + which), 0);
+                tc_fence_after();
+                const uint32_t tcol = which == 0 ? 128u : (which == 1 ? 256u : 0u);
+                const float* bq = vec + V_BQKV + which * D;
+                const int swz = (tok >> 1) & 3;
+#pragma unroll
+                for (int head = 0; head < 4; ++head) {
+                    float v[32];
+                    tmem_ld32(trow + tcol + head * 32, v);
+                    tmem_wait_ld();
+                    if (valid) {
+                        __half* dst = p.qkv + ((((size_t)seq * NHEAD + head) * 3 + which) * NTOK + tok) * HD;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(bq + head * 32 + c * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bq + head * 32 + c * 8 + 4);
+                            const float* x = v + c * 8;
+                            *reinterpret_cast<uint4*>(dst + ((c ^ swz) << 3)) =
+                                make_uint4(pack_h2(x[0] + b0.x, x[1] + b0.y), pack_h2(x[2] + b0.z, x[3] + b0.w),
+                                           pack_h2(x[4] + b1.x, x[5] + b1.y), pack_h2(x[6] + b1.z, x[7] + b1.w));
+                        }
+                    }
+                }
+            }
+        } else {
+            // final LN (eps 1e-5, affine folded) + Linear(128->4) + unpatchify (transformer.py:182-190)
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < D; ++c) s += h[c];
+            const float mean = s * (1.f / D);
+            float q = 0.f;
+#pragma unroll
+            for (int c = 0; c < D; ++c) { const float d = h[c] - mean; q = fmaf(d, d, q); }
+            const float rstd = rsqrtf(q * (1.f / D) + 1e-5f);
+            float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < D; c += 4) {
+                const float y0 = (h[c] - mean) * rstd, y1 = (h[c + 1] - mean) * rstd, y2 = (h[c + 2] - mean) * rstd, y3 = (h[c + 3] - mean) * rstd;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 w = *reinterpret_cast<const float4*>(vec + V_WFIN + c4 * D + c);
+                    d4[c4] = fmaf(y0, w.x, fmaf(y1, w.y, fmaf(y2, w.z, fmaf(y3, w.w, d4[c4]))));
+                }
+            }
+            float* vb = reinterpret_cast<float*>(smem + TC_SM_VB);
+            *reinterpret_cast<float4*>(vb + r * 4) =
+                make_float4(d4[0] + vec[V_BFIN], d4[1] + vec[V_BFIN + 1], d4[2] + vec[V_BFIN + 2], d4[3] + vec[V_BFIN + 3]);
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            if (p.out_mode == OUT_FWD) {
+                for (int idx = tid; idx < 2 * TILE_TOK * 4; idx += 128) {
+                    const int br = idx / (TILE_TOK * 4), rem = idx - br * (TILE_TOK * 4), t2 = rem >> 2, c4 = rem & 3;
+                    const int sq = 2 * pair + br;
+                    if (sq < p.nseq) {
+                        const int n = tt * TILE_TOK + t2, i = n >> 5, jx = n & 31;
+                        p.out[(size_t)sq * LAT + (2 * jx + (c4 & 1)) * LATP + 2 * i + (c4 >> 1)] = vb[(br * 64 + t2) * 4 + c4];
+                    }
+                }
+            } else {
+                // classifier-free guidance mix (infer.py:81/:87) + Euler (rectified_flow.py:5-7) or
+                // DDPM ancestral update (DDPM.py:28-36); the latent is updated in place
+                for (int idx = tid; idx < TILE_TOK * 4; idx += 128) {
+                    const int t2 = idx >> 2, c4 = idx & 3;
+                    const int n = tt * TILE_TOK + t2, i = n >> 5, jx = n & 31;
+                    const size_t xi = (size_t)pair * LAT + (2 * jx + (c4 & 1)) * LATP + 2 * i + (c4 >> 1);
+                    const float u = vb[t2 * 4 + c4], c = vb[(64 + t2) * 4 + c4];
+                    const float pred = u + p.cfg * (c - u);
+                    if (p.out != nullptr) p.out[xi] = pred;
+                    const float xo = p.x_upd[xi];
+                    float xn;
+                    if (p.out_mode == OUT_RF) {
+                        xn = xo + pred * p.c1;
+                    } else {
+                        const float mean2 = p.c1 * (xo - p.c2 * pred);
+                        xn = mean2 + p.c3 * p.noise[xi];
+                    }
+                    p.x_upd[xi] = xn;
+                }
+            }
         }
     }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem, 512);
 }
 
 // =================================================================================== attention
@@ -609,12 +592,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __half* __re
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
         const float i0 = 1.f / quad_sum(ls[mt][0]), i1 = 1.f / quad_sum(ls[mt][1]);
-        const int r0 = qrow0 + mt * 16 + g;
-        __half* dst = o + ((size_t)seq * NTOK + r0) * D + head * HD + 2 * t;
+        // output goes straight into the token kernel's A-operand image: [pair][tile][16 K chunks][16 row groups][8 rows][8 halves]
+        const int ra = qrow0 + mt * 16 + g, rb = ra + 8;
+        const int ta = ra / TILE_TOK, tb = rb / TILE_TOK;
+        const int rowa = (seq & 1) * 64 + (ra - ta * TILE_TOK), rowb = (seq & 1) * 64 + (rb - tb * TILE_TOK);
+        __half* da = o + ((size_t)(seq >> 1) * TILES_PER_PAIR + ta) * (TILE_ROWS * D) + (rowa >> 3) * 64 + (rowa & 7) * 8 + 2 * t;
+        __half* db = o + ((size_t)(seq >> 1) * TILES_PER_PAIR + tb) * (TILE_ROWS * D) + (rowb >> 3) * 64 + (rowb & 7) * 8 + 2 * t;
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-            *reinterpret_cast<uint32_t*>(dst + d * 8) = pack_h2(oacc[mt][d][0] * i0, oacc[mt][d][1] * i0);
-            *reinterpret_cast<uint32_t*>(dst + 8 * D + d * 8) = pack_h2(oacc[mt][d][2] * i1, oacc[mt][d][3] * i1);
+            *reinterpret_cast<uint32_t*>(da + (head * 4 + d) * 1024) = pack_h2(oacc[mt][d][0] * i0, oacc[mt][d][1] * i0);
+            *reinterpret_cast<uint32_t*>(db + (head * 4 + d) * 1024) = pack_h2(oacc[mt][d][2] * i1, oacc[mt][d][3] * i1);
         }
     }
 }

@@ -144,7 +144,7 @@ class Transformer(nn.Module):
         ws = self._workspaces.get(key)
         if ws is None:
             nbytes = _lib.load().t2s_dit_workspace_bytes(nseq)
-            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+            ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=device)
             if len(self._workspaces) > 4:
                 self._workspaces.clear()
             self._workspaces[key] = ws

@@ -15,19 +15,22 @@ from . import _lib
 D = 128
 
 
-def swizzle_stage(w: torch.Tensor) -> torch.Tensor:
-    """[N][K] weight (nn.Linear layout: row n = output feature, K contiguous) -> fp16 smem image.
+def umma_stage(w: torch.Tensor) -> torch.Tensor:
+    """[128 n][128 k] weight block (nn.Linear layout: row n = output feature, K contiguous) -> fp16
+    operand image in the tcgen05 no-swizzle K-major canonical layout: 8x8 core matrices (8 rows x 16 B,
+    contiguous 128 B), element (n,k) at byte (k//8)*2048 + (n//8)*128 + (n%8)*16 + (k%8)*2
+    (t2ms_b200/csrc/dit_kernels.cuh: tc_gemm, umma_desc with LBO=2048, SBO=128)."""
+    assert tuple(w.shape) == (128, 128)
+    w16 = w.detach().to(torch.float16).reshape(16, 8, 16, 8)            # [n//8][n%8][k//8][k%8]
+    return w16.permute(2, 0, 1, 3).contiguous().reshape(-1)              # [k//8][n//8][n%8][k%8]
 
-    Row n holds K/8 16-byte chunks; logical chunk c is stored at physical chunk c ^ (n & 7), which
-    makes every ldmatrix 8x8 read bank-conflict-free (t2ms_b200/csrc/dit_kernels.cuh: warp_gemm_*).
-    """
-    n, k = w.shape
-    assert k % 64 == 0
-    w16 = w.detach().to(torch.float16).reshape(n, k // 8, 8)
-    pc = torch.arange(k // 8, device=w.device).unsqueeze(0)                 # physical chunk
-    src = pc ^ (torch.arange(n, device=w.device).unsqueeze(1) & 7)          # logical chunk stored there
-    out = torch.gather(w16, 1, src.unsqueeze(-1).expand(n, k // 8, 8))
-    return out.reshape(-1).contiguous()
+
+def tile_rows(t: torch.Tensor) -> torch.Tensor:
+    """[480 tokens][128] fp32 -> [8 tiles][32 col chunks][64 rows][4] (60 valid rows per tile): the
+    residual-stream tile layout, in which a warp's 32 rows x 16 B of one column chunk are contiguous."""
+    out = torch.zeros(8, 32, 64, 4, dtype=t.dtype, device=t.device)
+    out[:, :, :60, :] = t.reshape(8, 60, 32, 4).permute(0, 2, 1, 3)
+    return out.contiguous()
 
 
 def _ptr(t: torch.Tensor) -> int:
@@ -45,12 +48,10 @@ class PackedDit:
         for l in range(4):
             p = f"layers.{l}."
             wq = g(p + "attn.qkv.weight")                                           # [384][128]
-            qkv = torch.cat([swizzle_stage(wq[i * D:(i + 1) * D]) for i in range(3)])
+            qkv = torch.cat([umma_stage(wq[i * D:(i + 1) * D]) for i in range(3)])
             w1, w2 = g(p + "mlp.fc1.weight"), g(p + "mlp.fc2.weight")               # [256][128], [128][256]
-            post = [swizzle_stage(g(p + "attn.proj.weight"))]
-            for c in range(4):
-                post.append(swizzle_stage(w1[c * 64:(c + 1) * 64]))                 # [64][128]  16 KB
-                post.append(swizzle_stage(w2[:, c * 64:(c + 1) * 64].contiguous()))  # [128][64]  16 KB
+            post = [umma_stage(g(p + "attn.proj.weight")), umma_stage(w1[:D]), umma_stage(w1[D:]),
+                    umma_stage(w2[:, :D].contiguous()), umma_stage(w2[:, D:].contiguous())]
             post = torch.cat(post)
             assert qkv.numel() * 2 == 3 * 32768 and post.numel() * 2 == 5 * 32768
             bq, bp = g(p + "attn.qkv.bias").contiguous(), g(p + "attn.proj.bias").contiguous()
@@ -63,7 +64,7 @@ class PackedDit:
         wpe, wc = g("patch_emb.weight"), g("conv.weight").reshape(4, 4)              # conv [oc][p*2+q]
         w_embed = (wpe @ wc).contiguous()                                            # [128][4]
         b_embed = (wpe @ g("conv.bias") + g("patch_emb.bias")).contiguous()
-        pos = g("pos_embed").reshape(480, D).contiguous()
+        pos = tile_rows(g("pos_embed").reshape(480, D))
         wl = g("linear_emb_to_patch.weight")
         w_final = (wl * g("ln.weight").unsqueeze(0)).contiguous()                    # [4][128]
         b_final = (wl @ g("ln.bias") + g("linear_emb_to_patch.bias")).contiguous()

@@ -53,8 +53,17 @@ class Workspace:
         s = self.base + self.off[i]
         return self.buf[s:s + nbytes].view(dtype).view(shape)
 
+    def _tiles(self, raw):
+        """(npair, 8 tiles, 128 rows, 128) tile rows -> (nseq, 480, 128): row = branch*64 + token%60."""
+        npair = (self.nseq + 1) // 2
+        t = raw.reshape(npair, 8, 2, 64, 128)[:, :, :, :60]                  # pair, tile, branch, tl, feat
+        t = t.permute(0, 2, 1, 3, 4).reshape(npair * 2, 480, 128)
+        return t[: self.nseq]
+
     def h(self):
-        return self._view(0, self.nseq * 480 * 128 * 4, torch.float32, (self.nseq, 480, 128))
+        npair = (self.nseq + 1) // 2
+        raw = self._view(0, npair * 8 * 128 * 128 * 4, torch.float32, (npair, 8, 32, 128, 4))   # [c4][row][4]
+        return self._tiles(raw.permute(0, 1, 3, 2, 4).reshape(npair, 8, 128, 128))
 
     def qkv(self):
         """-> (nseq, 3, 4 heads, 480, 32) fp32, de-swizzled."""
@@ -67,7 +76,9 @@ class Workspace:
         return logical.reshape(self.nseq, 4, 3, 480, 32).permute(0, 2, 1, 3, 4).float()
 
     def o(self):
-        return self._view(2, self.nseq * 480 * 128 * 2, torch.float16, (self.nseq, 480, 128)).float()
+        npair = (self.nseq + 1) // 2
+        raw = self._view(2, npair * 8 * 128 * 128 * 2, torch.float16, (npair, 8, 16, 16, 8, 8))  # [k//8][r//8][r%8][k%8]
+        return self._tiles(raw.permute(0, 1, 3, 4, 2, 5).reshape(npair, 8, 128, 128)).float()
 
     def mod(self):
         return self._view(3, self.nseq * 4 * 768 * 4, torch.float32, (self.nseq, 4, 768))

@@ -15,7 +15,7 @@ from conftest import ROOT, T, load_golden
 from oracle import t2s_oracle as O
 from t2ms_b200 import DDPM, RectifiedFlow, Transformer, _lib, synth, vqvae
 from t2ms_b200.compat import VAE_ARGS
-from t2ms_b200.packing import swizzle_stage
+from t2ms_b200.packing import tile_rows, umma_stage
 from t2ms_b200.sampler import gather_series, shard_range
 
 
@@ -40,7 +40,7 @@ def test_workspace_sizes(lib):
     off = (ctypes.c_size_t * 4)()
     lib.t2s_dit_workspace_offsets(2048, ctypes.byref(off))
     off = list(off)
-    assert off[0] == 0 and off[1] == 2048 * 480 * 128 * 4 and all(o % 256 == 0 for o in off)
+    assert off[0] == 0 and off[1] == 1024 * 8 * 128 * 128 * 4 and all(o % 256 == 0 for o in off)
     assert lib.t2s_dit_workspace_bytes(2048) >= off[3] + 2048 * 4 * 768 * 4
     assert lib.t2s_dit_workspace_bytes(1) < lib.t2s_dit_workspace_bytes(2)
 
@@ -73,15 +73,18 @@ def test_product_does_not_import_oracle():
                 assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
 
 
-def test_swizzle_stage_layout():
-    w = torch.arange(128 * 128, dtype=torch.float32).reshape(128, 128) % 2048      # exact in fp16
-    img = swizzle_stage(w).reshape(128, 16, 8)
-    for n in (0, 1, 7, 8, 77, 127):
-        for c in (0, 3, 9, 15):
-            assert torch.equal(img[n, c ^ (n & 7)].float(), w[n, c * 8:(c + 1) * 8])
-    w2 = torch.arange(128 * 64, dtype=torch.float32).reshape(128, 64) % 2048
-    img2 = swizzle_stage(w2).reshape(128, 8, 8)
-    assert torch.equal(img2[5, 2 ^ 5].float(), w2[5, 16:24])
+def test_umma_stage_layout():
+    """Weight stages are tcgen05 no-swizzle K-major operand images: (n,k) at (k//8)*2048 + (n//8)*128 + (n%8)*16 + (k%8)*2 bytes."""
+    w = (torch.arange(128 * 128, dtype=torch.float32).reshape(128, 128) % 2048)          # exact in fp16
+    img = umma_stage(w)
+    assert img.dtype == torch.float16 and img.numel() == 128 * 128
+    for n, k in ((0, 0), (1, 0), (7, 9), (8, 8), (77, 127), (127, 64), (127, 127)):
+        off = ((k // 8) * 2048 + (n // 8) * 128 + (n % 8) * 16 + (k % 8) * 2) // 2
+        assert float(img[off]) == float(w[n, k])
+    pos = torch.arange(480 * 128, dtype=torch.float32).reshape(480, 128)
+    tiled = tile_rows(pos)
+    assert tiled.shape == (8, 32, 64, 4)
+    assert torch.equal(tiled[3, 5, 17], pos[3 * 60 + 17, 20:24]) and float(tiled[:, :, 60:].abs().sum()) == 0.0
 
 
 def test_module_interfaces_match_reference_state_dict():
