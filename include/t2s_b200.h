@@ -78,6 +78,10 @@ const char* t2s_last_error(void);
 /* Sets kernel attributes for the current device; call once per device before stream capture. */
 int t2s_init(void);
 
+/* Profiling aid: when non-NULL, every token-block CTA writes clock64() stamps of its phase boundaries to
+ * device_buf[blockIdx.x*32 + i] (see tools/phase_trace.py).  NULL (default) switches it off. */
+void t2s_debug_set_phase_trace(long long* device_buf);
+
 /* Bytes of scratch for `nseq` sequences (residual stream, q|k|v, attention output, modulation).
  * Contents need no initialisation; rows of partially filled tiles are never read back. */
 size_t t2s_dit_workspace_bytes(int nseq);

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libt2s_b200.so")
 
 EXPORTS = [
-    "t2s_version", "t2s_last_error", "t2s_init", "t2s_dit_workspace_bytes", "t2s_dit_workspace_offsets",
+    "t2s_version", "t2s_last_error", "t2s_init", "t2s_debug_set_phase_trace", "t2s_dit_workspace_bytes", "t2s_dit_workspace_offsets",
     "t2s_dit_forward", "t2s_sample", "t2s_vae_decode", "t2s_vae_encode",
     "t2s_dit_cond", "t2s_dit_embed_qkv", "t2s_dit_attention", "t2s_dit_block_post", "t2s_dit_final",
 ]
@@ -56,6 +56,8 @@ def load() -> C.CDLL:
         lib.t2s_version.restype = i
         lib.t2s_last_error.restype = C.c_char_p
         lib.t2s_init.restype = i
+        lib.t2s_debug_set_phase_trace.restype = None
+        lib.t2s_debug_set_phase_trace.argtypes = [P]
         lib.t2s_dit_workspace_bytes.restype = sz
         lib.t2s_dit_workspace_bytes.argtypes = [i]
         lib.t2s_dit_workspace_offsets.restype = None

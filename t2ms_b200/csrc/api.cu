@@ -15,6 +15,7 @@ static_assert(sizeof(VaeEncWeights) == sizeof(t2s_vae_enc_weights), "VaeEncWeigh
 namespace {
 
 thread_local char g_err[512] = "";
+long long* g_trace = nullptr;   // t2s_debug_set_phase_trace
 
 int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
     snprintf(g_err, sizeof(g_err), fmt, a, b);
@@ -86,6 +87,7 @@ TokArgs base_args(const t2s_dit_weights* w, const Workspace& ws, int nseq) {
     memset(&a, 0, sizeof(a));
     memcpy(&a.w, w, sizeof(DitWeights));
     a.h = ws.h; a.qkv = ws.qkv; a.o = ws.o; a.mod = ws.mod; a.nseq = nseq;
+    a.trace = g_trace;
     return a;
 }
 
@@ -99,7 +101,7 @@ int launch_cond(const t2s_dit_weights* w, const float* t100, int t_stride, const
 int launch_embed(const t2s_dit_weights* w, const float* x, int x_shift, int nseq, const Workspace& ws, cudaStream_t st) {
     TokArgs a = base_args(w, ws, nseq);
     a.x = x; a.x_shift = x_shift;
-    token_kernel<TOK_EMBED><<<((nseq + 1) / 2) * TILES_PER_PAIR, TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
+    token_kernel<TOK_EMBED><<<((nseq + 1) / 2) * (TILES_PER_PAIR / 2), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
@@ -111,7 +113,7 @@ int launch_attn(int nseq, const Workspace& ws, cudaStream_t st) {
 int launch_mid(const t2s_dit_weights* w, int layer, int nseq, const Workspace& ws, cudaStream_t st) {
     TokArgs a = base_args(w, ws, nseq);
     a.layer = layer;
-    token_kernel<TOK_MID><<<((nseq + 1) / 2) * TILES_PER_PAIR, TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
+    token_kernel<TOK_MID><<<((nseq + 1) / 2) * (TILES_PER_PAIR / 2), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
@@ -121,7 +123,7 @@ int launch_final(const t2s_dit_weights* w, int nseq, const Workspace& ws, int ou
     a.layer = NLAYER - 1;
     a.out_mode = out_mode; a.out = out; a.x_upd = x_upd; a.noise = noise;
     a.cfg = cfg; a.c1 = c1; a.c2 = c2; a.c3 = c3;
-    token_kernel<TOK_FINAL><<<((nseq + 1) / 2) * TILES_PER_PAIR, TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
+    token_kernel<TOK_FINAL><<<((nseq + 1) / 2) * (TILES_PER_PAIR / 2), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
@@ -139,6 +141,7 @@ extern "C" {
 int t2s_version(void) { return 100; }
 const char* t2s_last_error(void) { return g_err; }
 int t2s_init(void) { return ensure_init(); }
+void t2s_debug_set_phase_trace(long long* device_buf) { g_trace = device_buf; }
 
 size_t t2s_dit_workspace_bytes(int nseq) {
     size_t off[4], total = 0;

@@ -51,6 +51,7 @@ struct TokArgs {
     float* x_upd;          // OUT_RF / OUT_DDPM: latent updated in place [npair][64][30]
     const float* noise;    // OUT_DDPM: [npair][64][30] for this step
     float cfg, c1, c2, c3; // RF: x += pred*c1 ; DDPM: x = c1*(x - c2*pred) + c3*noise
+    long long* trace;      // optional phase trace [grid][32] of clock64 stamps (tile 0, row 0), NULL = off
 };
 
 // =================================================================================== cond
@@ -103,24 +104,26 @@ __global__ void __launch_bounds__(256) cond_kernel(float* __restrict__ mod, cons
 }
 
 // =================================================================================== token block (tcgen05)
-// One CTA = one pair tile (128 rows = 60 tokens x {sequence 2p, sequence 2p+1}, 4+4 padding rows).
-// Everything that is local to a token runs here for one DiT block boundary:
+// One CTA = TWO consecutive pair tiles (each 128 rows = 60 tokens x {sequence 2p, sequence 2p+1} + 8 padding
+// rows) that march through the same weight stages in lock-step, so every 32 KB weight stage fetched from L2
+// feeds two 128x128x128 GEMM chunks.  Everything that is local to a token runs here for one DiT block boundary:
 //   MID  (block l):  x += gate_msa*proj(o) ; a2 = mod(LN2(x)) ; x += gate_mlp*fc2(GELU(fc1(a2))) ; store x ;
 //                    a' = mod(LN1(x)) of block l+1 ; q|k|v = a' Wqkv^T + b   (transformer.py:114-117, timm Attention/Mlp)
 //   EMBED:           x = patch-embed + pos ; a' of block 0 ; q|k|v
 //   FINAL (block 3): ... ; final LN + Linear(128->4) + unpatchify + CFG mix + Euler/DDPM update
-// Warp roles (192 threads): warps 0-3 = epilogue, one thread per tile row (= TMEM lane), the residual row
-// lives in 128 registers; warp 4 = producer (bulk async copies of 32 KB weight stages and of the
-// attention-output tile, completion on mbarriers); warp 5 = MMA issuer (one lane issues
+// Warp roles (320 threads): warps 0-3 / 4-7 = epilogue of tile 0 / 1, one thread per tile row (= TMEM lane),
+// the residual row lives in registers; warp 8 = producer (bulk async copies: weight stages, attention-output
+// tiles, per-tile vectors; completion on mbarriers); warp 9 = MMA issuer (one lane issues
 // tcgen05.mma.kind::f16 128x128x16, accumulators in TMEM, completion via tcgen05.commit).
-// The seven GEMM chunks of a tile (proj | fc1 a,b | fc2 K-halves | q,k,v), each 128x128x128, rotate over
-// three 128-column TMEM regions so that the MMA of chunk i+1 overlaps the epilogue of chunk i.
-constexpr int TC_THREADS = 192;
-constexpr int TC_NSTAGE = 3;
-constexpr int TC_SM_A = 0;                                       // 32 KB A operand: o tile / a2 / hidden-b / a'
-constexpr int TC_SM_HA = STAGE_BYTES;                            // 32 KB A operand: hidden-a
-constexpr int TC_SM_W = 2 * STAGE_BYTES;                         // weight ring
-constexpr int TC_SM_VEC = TC_SM_W + TC_NSTAGE * STAGE_BYTES;     // per-tile vectors (fp32)
+// Each tile owns two 128-column TMEM regions X, Y; its seven GEMM chunks alternate between them:
+//   proj->X | fc1[0:128]->Y | fc1[128:256]->X | fc2 (two K halves)->Y | q->X | k->Y | v->X
+// While tile 0's epilogue warps work on a chunk, the tensor pipe runs tile 1's chunk and vice versa.
+constexpr int TC_THREADS = 320;
+constexpr int TC_NSTAGE = 2;
+constexpr int TC_SM_A = 0;                                       // [2 tiles] 32 KB A operand: o tile / a2 / hidden-b / a'
+constexpr int TC_SM_HA = 2 * STAGE_BYTES;                        // [2 tiles] 32 KB A operand: hidden-a
+constexpr int TC_SM_W = 4 * STAGE_BYTES;                         // weight ring
+constexpr int TC_SM_VEC = TC_SM_W + TC_NSTAGE * STAGE_BYTES;     // per-pair vectors (fp32), shared by both tiles
 constexpr int V_MOD = 0;        // [2 branches][768]  adaLN chunk of block l
 constexpr int V_MODN = 1536;    // [2][256]           shift_msa | scale_msa of the next block
 constexpr int V_BPROJ = 2048, V_B1 = 2176, V_B2 = 2432, V_BQKV = 2560;
@@ -129,11 +132,14 @@ constexpr int V_BEMB = 3456;    // [128]
 constexpr int V_WFIN = 3584;    // [4][128]
 constexpr int V_BFIN = 4096;    // [4]
 constexpr int V_END = 4104;
-constexpr int TC_SM_VB = TC_SM_VEC + V_END * 4;                  // [128][4] fp32 final-projection exchange
-constexpr int TC_SM_BAR = TC_SM_VB + TILE_ROWS * 4 * 4;
-constexpr int TC_SM_TMEM = TC_SM_BAR + 32 * 8;
+constexpr int TC_SM_VB = TC_SM_VEC + V_END * 4;                  // [2 tiles][128][4] fp32 final-projection exchange
+constexpr int TC_SM_BAR = TC_SM_VB + 2 * TILE_ROWS * 4 * 4;
+constexpr int TC_SM_TMEM = TC_SM_BAR + 40 * 8;
 constexpr int TOK_SMEM_BYTES = TC_SM_TMEM + 16;
-enum { B_WFULL = 0, B_WEMPTY = 3, B_OFULL = 6, B_A2 = 7, B_HA = 8, B_HB = 9, B_A3 = 10, B_ACC = 11 /* ..17 */, B_COUNT = 18 };
+static_assert(TOK_SMEM_BYTES <= 232448, "token kernel shared memory exceeds 227 KB");
+// barrier ids
+enum { B_WFULL = 0, B_WEMPTY = 2, B_VFULL = 4, B_TILE = 5 };
+enum { T_OFULL = 0, T_A2 = 1, T_HA = 2, T_HB = 3, T_A3 = 4, T_XFREE = 5, T_ACC = 6 /* ..12 */, T_COUNT = 13 };
 constexpr uint32_t TC_IDESC = umma_idesc_f16(128, 128);
 constexpr uint32_t KCH = 2048;   // byte stride between K chunks (16 row groups x 128 B) in a [128][128] operand image
 
@@ -145,129 +151,191 @@ __device__ __forceinline__ void tc_gemm(uint32_t a_smem, uint32_t w_smem, uint32
                  (accumulate || k > 0) ? 1u : 0u);
 }
 
-// thread-per-row LayerNorm (no affine) + modulate, packed to fp16 and stored as the A operand image.
-__device__ __forceinline__ void ln_mod_store(const float (&h)[D], const float* __restrict__ shift, const float* __restrict__ scale,
-                                             float eps, uint8_t* abuf, int r) {
-    float s = 0.f;
-#pragma unroll
-    for (int c = 0; c < D; ++c) s += h[c];
-    const float mean = s * (1.f / D);
-    float q = 0.f;
-#pragma unroll
-    for (int c = 0; c < D; ++c) { const float d = h[c] - mean; q = fmaf(d, d, q); }
-    const float rstd = rsqrtf(q * (1.f / D) + eps);
-#pragma unroll
-    for (int c8 = 0; c8 < 16; ++c8) {
-        float y[8];
-#pragma unroll
-        for (int j = 0; j < 8; j += 4) {
-            const float4 sc = *reinterpret_cast<const float4*>(scale + c8 * 8 + j);
-            const float4 sh = *reinterpret_cast<const float4*>(shift + c8 * 8 + j);
-            y[j + 0] = fmaf((h[c8 * 8 + j + 0] - mean) * rstd, 1.f + sc.x, sh.x);
-            y[j + 1] = fmaf((h[c8 * 8 + j + 1] - mean) * rstd, 1.f + sc.y, sh.y);
-            y[j + 2] = fmaf((h[c8 * 8 + j + 2] - mean) * rstd, 1.f + sc.z, sh.z);
-            y[j + 3] = fmaf((h[c8 * 8 + j + 3] - mean) * rstd, 1.f + sc.w, sh.w);
-        }
-        *reinterpret_cast<uint4*>(abuf + c8 * KCH + r * 16) =
-            make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7]));
+// ---- thread-per-row epilogue building blocks.  A thread owns one tile row (= one TMEM lane); rows are
+// processed in 16-column blocks inside rolled loops (compact code, no large register arrays).  The updated
+// residual row is written back over the consumed accumulator in TMEM, which serves as the row buffer for the
+// LayerNorm's second pass.
+struct RowStats { float mean, rstd; };
+
+// Software-pipelined walk over the eight 16-column blocks of a TMEM region: the tcgen05.ld of block i+1 is in
+// flight while block i is processed (tcgen05.wait::ld waits for all of the thread's outstanding loads).
+template <class F>
+__device__ __forceinline__ void for_each_block16(uint32_t taddr, F&& body) {
+    float a[16], b[16];
+    tmem_ld16(taddr, a);
+#pragma unroll 1
+    for (int cb = 0; cb < 8; cb += 2) {
+        tmem_wait_ld();
+        tmem_ld16(taddr + (cb + 1) * 16, b);
+        body(cb, a);
+        tmem_wait_ld();
+        if (cb + 2 < 8) tmem_ld16(taddr + (cb + 2) * 16, a);
+        body(cb + 1, b);
     }
 }
 
-// x += gate * (acc + bias) over the 128 columns of a TMEM region
-__device__ __forceinline__ void residual_update(float (&h)[D], uint32_t taddr, const float* __restrict__ gate,
-                                                const float* __restrict__ bias) {
+// pass 1: hn = hin + gate * (acc + bias); writes hn over the accumulator (TMEM) and optionally to the residual
+// tile in global memory; returns LayerNorm statistics (shifted single-pass variance).
+// hsrc / hdst: residual tile base + row offset; element (col chunk c4, this row) at +c4*TILE_ROWS*4 floats.
+template <bool STORE>
+__device__ __forceinline__ RowStats resid_pass(uint32_t tacc, const float* __restrict__ gate, const float* __restrict__ bias,
+                                               const float* __restrict__ hsrc, float* __restrict__ hdst, bool valid, float eps) {
+    float sum = 0.f, sq = 0.f, shift = 0.f;
+    float4 hc4[4];
 #pragma unroll
-    for (int cb = 0; cb < 4; ++cb) {
-        float v[32];
-        tmem_ld32(taddr + cb * 32, v);
-        tmem_wait_ld();
+    for (int q = 0; q < 4; ++q) hc4[q] = valid ? *reinterpret_cast<const float4*>(hsrc + q * TILE_ROWS * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for_each_block16(tacc, [&](int cb, float (&a)[16]) {
+        float4 hn4[4];
+        if (cb < 7) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            const float4 g4 = *reinterpret_cast<const float4*>(gate + cb * 32 + j);
-            const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 32 + j);
-            h[cb * 32 + j + 0] = fmaf(g4.x, v[j + 0] + b4.x, h[cb * 32 + j + 0]);
-            h[cb * 32 + j + 1] = fmaf(g4.y, v[j + 1] + b4.y, h[cb * 32 + j + 1]);
-            h[cb * 32 + j + 2] = fmaf(g4.z, v[j + 2] + b4.z, h[cb * 32 + j + 2]);
-            h[cb * 32 + j + 3] = fmaf(g4.w, v[j + 3] + b4.w, h[cb * 32 + j + 3]);
+            for (int q = 0; q < 4; ++q)
+                hn4[q] = valid ? *reinterpret_cast<const float4*>(hsrc + ((cb + 1) * 4 + q) * TILE_ROWS * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 g4 = *reinterpret_cast<const float4*>(gate + cb * 16 + q * 4);
+            const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 16 + q * 4);
+            a[q * 4 + 0] = fmaf(g4.x, a[q * 4 + 0] + b4.x, hc4[q].x);
+            a[q * 4 + 1] = fmaf(g4.y, a[q * 4 + 1] + b4.y, hc4[q].y);
+            a[q * 4 + 2] = fmaf(g4.z, a[q * 4 + 2] + b4.z, hc4[q].z);
+            a[q * 4 + 3] = fmaf(g4.w, a[q * 4 + 3] + b4.w, hc4[q].w);
+        }
+        if (cb == 0) shift = a[0];
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            const float d0 = a[j] - shift, d1 = a[j + 1] - shift;
+            s0 += d0; s1 += d1; q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
+        }
+        sum += s0 + s1; sq += q0 + q1;
+        tmem_st16(tacc + cb * 16, a);
+        if (STORE && valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(hdst + (cb * 4 + q) * TILE_ROWS * 4) = make_float4(a[q * 4], a[q * 4 + 1], a[q * 4 + 2], a[q * 4 + 3]);
+        }
+        if (cb < 7) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hc4[q] = hn4[q];
+        }
+    });
+    tmem_wait_st();
+    const float ms = sum * (1.f / D);
+    RowStats st;
+    st.mean = shift + ms;
+    st.rstd = rsqrtf(fmaxf(sq * (1.f / D) - ms * ms, 0.f) + eps);
+    return st;
+}
+
+// pass 2: LayerNorm (no affine) + modulate x*(1+scale)+shift (transformer.py:7-8,102-103), packed to fp16 and
+// stored as the next GEMM's A operand image.
+__device__ __forceinline__ void ln_mod_store(uint32_t trow, RowStats st, const float* __restrict__ shift, const float* __restrict__ scale,
+                                             uint8_t* abuf, int r) {
+    for_each_block16(trow, [&](int cb, float (&a)[16]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 sc = *reinterpret_cast<const float4*>(scale + cb * 16 + q * 4);
+            const float4 sh = *reinterpret_cast<const float4*>(shift + cb * 16 + q * 4);
+            a[q * 4 + 0] = fmaf((a[q * 4 + 0] - st.mean) * st.rstd, 1.f + sc.x, sh.x);
+            a[q * 4 + 1] = fmaf((a[q * 4 + 1] - st.mean) * st.rstd, 1.f + sc.y, sh.y);
+            a[q * 4 + 2] = fmaf((a[q * 4 + 2] - st.mean) * st.rstd, 1.f + sc.z, sh.z);
+            a[q * 4 + 3] = fmaf((a[q * 4 + 3] - st.mean) * st.rstd, 1.f + sc.w, sh.w);
+        }
+#pragma unroll
+        for (int c8 = 0; c8 < 2; ++c8)
+            *reinterpret_cast<uint4*>(abuf + (cb * 2 + c8) * KCH + r * 16) =
+                make_uint4(pack_h2(a[c8 * 8 + 0], a[c8 * 8 + 1]), pack_h2(a[c8 * 8 + 2], a[c8 * 8 + 3]),
+                           pack_h2(a[c8 * 8 + 4], a[c8 * 8 + 5]), pack_h2(a[c8 * 8 + 6], a[c8 * 8 + 7]));
+    });
 }
 
 // hidden = GELU_tanh(acc + b1) packed to fp16 into an A operand image (timm Mlp, transformer.py:99,105)
 __device__ __forceinline__ void gelu_store(uint32_t taddr, const float* __restrict__ bias, uint8_t* abuf, int r) {
+    for_each_block16(taddr, [&](int cb, float (&v)[16]) {
 #pragma unroll
-    for (int cb = 0; cb < 4; ++cb) {
-        float v[32];
-        tmem_ld32(taddr + cb * 32, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bias + cb * 32 + c8 * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias + cb * 32 + c8 * 8 + 4);
-            const float* x = v + c8 * 8;
-            *reinterpret_cast<uint4*>(abuf + (cb * 4 + c8) * KCH + r * 16) =
-                make_uint4(pack_h2(gelu_tanh(x[0] + b0.x), gelu_tanh(x[1] + b0.y)), pack_h2(gelu_tanh(x[2] + b0.z), gelu_tanh(x[3] + b0.w)),
-                           pack_h2(gelu_tanh(x[4] + b1.x), gelu_tanh(x[5] + b1.y)), pack_h2(gelu_tanh(x[6] + b1.z), gelu_tanh(x[7] + b1.w)));
+        for (int q = 0; q < 4; ++q) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 16 + q * 4);
+            v[q * 4 + 0] = gelu_tanh(v[q * 4 + 0] + b4.x);
+            v[q * 4 + 1] = gelu_tanh(v[q * 4 + 1] + b4.y);
+            v[q * 4 + 2] = gelu_tanh(v[q * 4 + 2] + b4.z);
+            v[q * 4 + 3] = gelu_tanh(v[q * 4 + 3] + b4.w);
         }
-    }
+#pragma unroll
+        for (int c8 = 0; c8 < 2; ++c8)
+            *reinterpret_cast<uint4*>(abuf + (cb * 2 + c8) * KCH + r * 16) =
+                make_uint4(pack_h2(v[c8 * 8 + 0], v[c8 * 8 + 1]), pack_h2(v[c8 * 8 + 2], v[c8 * 8 + 3]),
+                           pack_h2(v[c8 * 8 + 4], v[c8 * 8 + 5]), pack_h2(v[c8 * 8 + 6], v[c8 * 8 + 7]));
+    });
 }
 
-// grid = npair * 8 tiles, block = 192
+// grid = npair * 4 (two tiles per CTA), block = 320
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pair = blockIdx.x / TILES_PER_PAIR, tt = blockIdx.x % TILES_PER_PAIR;
+    const int pair = blockIdx.x / (TILES_PER_PAIR / 2), tt0 = (blockIdx.x % (TILES_PER_PAIR / 2)) * 2;
     const uint32_t sb = smem_u32(smem);
     const uint32_t bar0 = sb + TC_SM_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * i; };
+    auto TBAR = [&](int e, int i) { return bar0 + 8u * (B_TILE + e * T_COUNT + i); };
     float* vec = reinterpret_cast<float*>(smem + TC_SM_VEC);
     const int l = p.layer;                                         // block whose second half runs here (MID / FINAL)
     const int ln = (MODE == TOK_EMBED) ? 0 : l + 1;                // block whose QKV is produced here (EMBED / MID)
     constexpr int N_STAGES = (MODE == TOK_EMBED) ? 3 : (MODE == TOK_MID ? 8 : 5);
+    if (p.trace != nullptr && tid == 0) p.trace[(size_t)blockIdx.x * 32 + 19] = clock64();
 
     if (tid == 0) {
-        for (int i = 0; i < 7; ++i) mbar_init(BAR(i), 1);
-        for (int i = B_A2; i <= B_A3; ++i) mbar_init(BAR(i), 128);
-        for (int i = B_ACC; i < B_COUNT; ++i) mbar_init(BAR(i), 1);
+        for (int i = 0; i < B_TILE; ++i) mbar_init(BAR(i), 1);
+        for (int e = 0; e < 2; ++e) {
+            mbar_init(TBAR(e, T_OFULL), 1);
+            for (int i = T_A2; i <= T_XFREE; ++i) mbar_init(TBAR(e, i), 128);
+            for (int i = T_ACC; i < T_COUNT; ++i) mbar_init(TBAR(e, i), 1);
+        }
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc(sb + TC_SM_TMEM, 512);
-    // stage the per-tile vectors
-    {
-        const int sq0 = min(2 * pair, p.nseq - 1), sq1 = min(2 * pair + 1, p.nseq - 1);
-        if (MODE != TOK_EMBED) {
-            for (int i = tid; i < 2 * MOD; i += TC_THREADS)
-                vec[V_MOD + i] = p.mod[((size_t)(i < MOD ? sq0 : sq1) * NLAYER + l) * MOD + (i < MOD ? i : i - MOD)];
-            for (int i = tid; i < D; i += TC_THREADS) { vec[V_BPROJ + i] = p.w.b_proj[l][i]; vec[V_B2 + i] = p.w.b_fc2[l][i]; }
-            for (int i = tid; i < DMLP; i += TC_THREADS) vec[V_B1 + i] = p.w.b_fc1[l][i];
-        }
-        if (MODE != TOK_FINAL) {
-            for (int i = tid; i < 512; i += TC_THREADS)
-                vec[V_MODN + i] = p.mod[((size_t)(i < 256 ? sq0 : sq1) * NLAYER + ln) * MOD + (i & 255)];
-            for (int i = tid; i < 3 * D; i += TC_THREADS) vec[V_BQKV + i] = p.w.b_qkv[ln][i];
-        }
-        if (MODE == TOK_EMBED) {
-            for (int i = tid; i < 4 * D; i += TC_THREADS) vec[V_WEMB + i] = p.w.w_embed[i];
-            for (int i = tid; i < D; i += TC_THREADS) vec[V_BEMB + i] = p.w.b_embed[i];
-        }
-        if (MODE == TOK_FINAL) {
-            for (int i = tid; i < 4 * D; i += TC_THREADS) vec[V_WFIN + i] = p.w.w_final[i];
-            if (tid < 4) vec[V_BFIN + tid] = p.w.b_final[tid];
-        }
-    }
+    if (warp == 8) tmem_alloc(sb + TC_SM_TMEM, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + TC_SM_TMEM);
-    const size_t tile = (size_t)pair * TILES_PER_PAIR + tt;
+    const size_t tile0 = (size_t)pair * TILES_PER_PAIR + tt0;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ================================================================= producer
         if (lane == 0) {
+            // per-pair vectors (adaLN chunks of the two sequences, biases, small weights)
+            {
+                const int sq0 = min(2 * pair, p.nseq - 1), sq1 = min(2 * pair + 1, p.nseq - 1);
+                uint32_t bytes = 0;
+                auto cp = [&](int voff, const float* src, uint32_t n) {
+                    bulk_g2s(sb + TC_SM_VEC + voff * 4, src, n * 4, BAR(B_VFULL));
+                    bytes += n * 4;
+                };
+                constexpr uint32_t VBYTES = (MODE == TOK_EMBED ? 0u : (2 * MOD + 2 * D + DMLP) * 4u) + (MODE == TOK_FINAL ? 0u : (512 + 3 * D) * 4u) +
+                                            (MODE == TOK_EMBED ? (5 * D) * 4u : 0u) + (MODE == TOK_FINAL ? (4 * D + 4) * 4u : 0u);
+                mbar_expect_tx(BAR(B_VFULL), VBYTES);
+                if (MODE != TOK_EMBED) {
+                    cp(V_MOD, p.mod + ((size_t)sq0 * NLAYER + l) * MOD, MOD);
+                    cp(V_MOD + MOD, p.mod + ((size_t)sq1 * NLAYER + l) * MOD, MOD);
+                    cp(V_BPROJ, p.w.b_proj[l], D);
+                    cp(V_B1, p.w.b_fc1[l], DMLP);
+                    cp(V_B2, p.w.b_fc2[l], D);
+                }
+                if (MODE != TOK_FINAL) {
+                    cp(V_MODN, p.mod + ((size_t)sq0 * NLAYER + ln) * MOD, 256);
+                    cp(V_MODN + 256, p.mod + ((size_t)sq1 * NLAYER + ln) * MOD, 256);
+                    cp(V_BQKV, p.w.b_qkv[ln], 3 * D);
+                }
+                if (MODE == TOK_EMBED) { cp(V_WEMB, p.w.w_embed, 4 * D); cp(V_BEMB, p.w.b_embed, D); }
+                if (MODE == TOK_FINAL) { cp(V_WFIN, p.w.w_final, 4 * D); cp(V_BFIN, p.w.b_final, 4); }
+                if (bytes != VBYTES) __trap();
+            }
             if (MODE != TOK_EMBED) {
-                mbar_expect_tx(BAR(B_OFULL), STAGE_BYTES);
-                bulk_g2s(sb + TC_SM_A, reinterpret_cast<const char*>(p.o) + tile * STAGE_BYTES, STAGE_BYTES, BAR(B_OFULL));
+                for (int e = 0; e < 2; ++e) {
+                    mbar_expect_tx(TBAR(e, T_OFULL), STAGE_BYTES);
+                    bulk_g2s(sb + TC_SM_A + e * STAGE_BYTES, reinterpret_cast<const char*>(p.o) + (tile0 + e) * STAGE_BYTES, STAGE_BYTES,
+                             TBAR(e, T_OFULL));
+                }
             }
             const char* src_a = reinterpret_cast<const char*>(MODE == TOK_EMBED ? p.w.w_qkv[0] : p.w.w_post[l]);
             const char* src_b = reinterpret_cast<const char*>(MODE == TOK_MID ? p.w.w_qkv[l + 1] : nullptr);
@@ -282,51 +350,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ================================================================= MMA issuer
         if (lane == 0) {
             int s = 0;
-            auto chunk = [&](uint32_t a_smem, uint32_t d_col, bool accumulate, int acc_bar) {
+            // one weight stage feeds the same GEMM chunk of both tiles
+            auto stage = [&](int wait_bar, uint32_t a_off, uint32_t d_col, bool accumulate, int acc_bar) {
                 const int slot = s % TC_NSTAGE;
                 mbar_wait(BAR(B_WFULL + slot), (s / TC_NSTAGE) & 1);
-                tc_fence_after();
-                tc_gemm(a_smem, sb + TC_SM_W + slot * STAGE_BYTES, tmem + d_col, accumulate);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (wait_bar >= 0) mbar_wait(TBAR(e, wait_bar), 0);
+                    tc_fence_after();
+                    tc_gemm(sb + a_off + e * STAGE_BYTES, sb + TC_SM_W + slot * STAGE_BYTES, tmem + e * 256 + d_col, accumulate);
+                    if (acc_bar >= 0) umma_commit(TBAR(e, T_ACC + acc_bar));
+                }
                 umma_commit(BAR(B_WEMPTY + slot));
-                if (acc_bar >= 0) umma_commit(BAR(B_ACC + acc_bar));
                 ++s;
             };
             if (MODE != TOK_EMBED) {
-                mbar_wait(BAR(B_OFULL), 0);
-                chunk(sb + TC_SM_A, 0, false, 0);                       // proj            -> R0
-                mbar_wait(BAR(B_A2), 0);
-                chunk(sb + TC_SM_A, 128, false, 1);                     // fc1 cols 0..127   -> R1
-                chunk(sb + TC_SM_A, 256, false, 2);                     // fc1 cols 128..255 -> R2
-                mbar_wait(BAR(B_HA), 0);
-                chunk(sb + TC_SM_HA, 0, false, -1);                     // fc2, K half 0   -> R0
-                mbar_wait(BAR(B_HB), 0);
-                chunk(sb + TC_SM_A, 0, true, 3);                        // fc2, K half 1   -> R0
+                stage(T_OFULL, TC_SM_A, 0, false, 0);        // proj               -> X
+                stage(T_A2, TC_SM_A, 128, false, 1);         // fc1 cols 0..127    -> Y
+                stage(-1, TC_SM_A, 0, false, 2);             // fc1 cols 128..255  -> X
+                stage(T_HA, TC_SM_HA, 128, false, -1);       // fc2, K half 0      -> Y
+                stage(T_HB, TC_SM_A, 128, true, 3);          // fc2, K half 1      -> Y
             }
             if (MODE != TOK_FINAL) {
-                mbar_wait(BAR(B_A3), 0);
-                chunk(sb + TC_SM_A, 128, false, 4);                     // q -> R1
-                chunk(sb + TC_SM_A, 256, false, 5);                     // k -> R2
-                chunk(sb + TC_SM_A, 0, false, 6);                       // v -> R0
+                stage(T_A3, TC_SM_A, 0, false, 4);           // q -> X
+                stage(-1, TC_SM_A, 128, false, 5);           // k -> Y
+                stage(T_XFREE, TC_SM_A, 0, false, 6);        // v -> X (after the q epilogue has drained X)
             }
         }
         __syncwarp();
     } else {
         // ================================================================= epilogue: thread r <-> tile row r <-> TMEM lane r
-        const int r = tid;
+        const int e = warp >> 2;                                        // tile handled by this warpgroup
+        const int r = tid & 127;
+        const int tt = tt0 + e;
         const int branch = r >> 6, tl = r & 63;
         const int seq = 2 * pair + branch;
         const bool valid = tl < TILE_TOK && seq < p.nseq;
         const int tok = tt * TILE_TOK + tl;
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + e * 256;
+        constexpr uint32_t X = 0, Y = 128;
         const float* modb = vec + V_MOD + branch * MOD;
-        float* htile = p.h + tile * (TILE_ROWS * D);                    // [32 col chunks][128 rows][4]
-        float h[D];
+        uint8_t* abuf = smem + TC_SM_A + e * STAGE_BYTES;
+        uint8_t* habuf = smem + TC_SM_HA + e * STAGE_BYTES;
+        float* htile = p.h + (tile0 + e) * (TILE_ROWS * D);             // [32 col chunks][128 rows][4]
+        const float* hrow_c = htile + r * 4;                            // + c4 * TILE_ROWS * 4
+        float* hrow = htile + r * 4;
+        const bool tr = p.trace != nullptr && e == 0 && r == 0;
+#define STAMP(i) do { if (tr) p.trace[(size_t)blockIdx.x * 32 + (i)] = clock64(); } while (0)
+        STAMP(0);
+        if (MODE != TOK_EMBED && r == 0) prefetch_l2(htile, TILE_ROWS * D * 4);
+        mbar_wait(BAR(B_VFULL), 0);
+        STAMP(2);
+        RowStats st;
         if (MODE == TOK_EMBED) {
-            // patchify + patch_emb + pos_embed (transformer.py:166-172), conv folded into the Linear
+            // patchify + patch_emb + pos_embed (transformer.py:166-172), conv folded into the Linear; the row is
+            // parked in TMEM region X (not yet an accumulator) for the LayerNorm pass
             float xv[4] = {0.f, 0.f, 0.f, 0.f};
             if (valid) {
                 const float* xs = p.x + (size_t)(seq >> p.x_shift) * LAT;
@@ -335,115 +417,131 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 for (int pq = 0; pq < 4; ++pq) xv[pq] = xs[(2 * j + (pq & 1)) * LATP + 2 * i + (pq >> 1)];
             }
             const float* pos = p.w.pos + ((size_t)tt * 32 * 64 + tl) * 4;   // [8 tiles][32 chunks][64 rows][4]
+            float sum = 0.f, sq = 0.f, shift = 0.f;
+#pragma unroll 1
+            for (int cb = 0; cb < 8; ++cb) {
+                float a[16];
 #pragma unroll
-            for (int c4 = 0; c4 < 32; ++c4) {
-                float4 pe = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) pe = *reinterpret_cast<const float4*>(pos + c4 * 64 * 4);
-                const float pev[4] = {pe.x, pe.y, pe.z, pe.w};
+                for (int q = 0; q < 4; ++q) {
+                    const float4 pe = valid ? *reinterpret_cast<const float4*>(pos + (cb * 4 + q) * 64 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float pev[4] = {pe.x, pe.y, pe.z, pe.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(vec + V_WEMB + (c4 * 4 + e) * 4);
-                    h[c4 * 4 + e] = valid ? (w4.x * xv[0] + w4.y * xv[1] + w4.z * xv[2] + w4.w * xv[3] + vec[V_BEMB + c4 * 4 + e] + pev[e]) : 0.f;
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = cb * 16 + q * 4 + u;
+                        const float4 w4 = *reinterpret_cast<const float4*>(vec + V_WEMB + c * 4);
+                        a[q * 4 + u] = valid ? (w4.x * xv[0] + w4.y * xv[1] + w4.z * xv[2] + w4.w * xv[3] + vec[V_BEMB + c] + pev[u]) : 0.f;
+                    }
+                }
+                if (cb == 0) shift = a[0];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const float d = a[j] - shift; sum += d; sq = fmaf(d, d, sq); }
+                tmem_st16(trow + X + cb * 16, a);
+                if (valid) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<float4*>(hrow + (cb * 4 + q) * TILE_ROWS * 4) = make_float4(a[q * 4], a[q * 4 + 1], a[q * 4 + 2], a[q * 4 + 3]);
                 }
             }
+            tmem_wait_st();
+            const float ms = sum * (1.f / D);
+            st.mean = shift + ms;
+            st.rstd = rsqrtf(fmaxf(sq * (1.f / D) - ms * ms, 0.f) + 1e-6f);
         } else {
-#pragma unroll
-            for (int c4 = 0; c4 < 32; ++c4) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) v = *reinterpret_cast<const float4*>(htile + (c4 * TILE_ROWS + r) * 4);
-                h[c4 * 4 + 0] = v.x; h[c4 * 4 + 1] = v.y; h[c4 * 4 + 2] = v.z; h[c4 * 4 + 3] = v.w;
-            }
-            // x = x + gate_msa * (o Wproj^T + b)        (transformer.py:116)
-            mbar_wait(BAR(B_ACC + 0), 0);
+            // x = x + gate_msa * (o Wproj^T + b)        (transformer.py:116); x parked in X, stored for the second half
+            mbar_wait(TBAR(e, T_ACC + 0), 0);
             tc_fence_after();
-            residual_update(h, trow + 0, modb + 2 * D, vec + V_BPROJ);
-            ln_mod_store(h, modb + 3 * D, modb + 4 * D, 1e-6f, smem + TC_SM_A, r);
+            STAMP(3);
+            st = resid_pass<true>(trow + X, modb + 2 * D, vec + V_BPROJ, hrow_c, hrow, valid, 1e-6f);
+            ln_mod_store(trow + X, st, modb + 3 * D, modb + 4 * D, abuf, r);
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(BAR(B_A2));
+            mbar_arrive(TBAR(e, T_A2));
+            STAMP(4);
             // hidden = GELU(fc1)                         (transformer.py:117)
-            mbar_wait(BAR(B_ACC + 1), 0);
+            mbar_wait(TBAR(e, T_ACC + 1), 0);
             tc_fence_after();
-            gelu_store(trow + 128, vec + V_B1, smem + TC_SM_HA, r);
+            STAMP(5);
+            gelu_store(trow + Y, vec + V_B1, habuf, r);
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(BAR(B_HA));
-            mbar_wait(BAR(B_ACC + 2), 0);
+            mbar_arrive(TBAR(e, T_HA));
+            STAMP(6);
+            mbar_wait(TBAR(e, T_ACC + 2), 0);
             tc_fence_after();
-            gelu_store(trow + 256, vec + V_B1 + D, smem + TC_SM_A, r);
+            STAMP(7);
+            gelu_store(trow + X, vec + V_B1 + D, abuf, r);
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(BAR(B_HB));
-            // x = x + gate_mlp * (hidden W2^T + b)
-            mbar_wait(BAR(B_ACC + 3), 0);
+            mbar_arrive(TBAR(e, T_HB));
+            STAMP(8);
+            // x = x + gate_mlp * (hidden W2^T + b); x parked in Y
+            mbar_wait(TBAR(e, T_ACC + 3), 0);
             tc_fence_after();
-            residual_update(h, trow + 0, modb + 5 * D, vec + V_B2);
+            STAMP(9);
+            st = resid_pass<MODE == TOK_MID>(trow + Y, modb + 5 * D, vec + V_B2, hrow_c, hrow, valid, MODE == TOK_FINAL ? 1e-5f : 1e-6f);
+            STAMP(10);
         }
+        constexpr uint32_t HREG = (MODE == TOK_EMBED) ? X : Y;          // TMEM region holding the residual row now
 
         if (MODE != TOK_FINAL) {
-            if (valid) {
-#pragma unroll
-                for (int c4 = 0; c4 < 32; ++c4)
-                    *reinterpret_cast<float4*>(htile + (c4 * TILE_ROWS + r) * 4) = make_float4(h[c4 * 4], h[c4 * 4 + 1], h[c4 * 4 + 2], h[c4 * 4 + 3]);
-            }
             const float* modn = vec + V_MODN + branch * 256;
-            ln_mod_store(h, modn, modn + D, 1e-6f, smem + TC_SM_A, r);
+            ln_mod_store(trow + HREG, st, modn, modn + D, abuf, r);
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(BAR(B_A3));
+            mbar_arrive(TBAR(e, T_A3));
+            STAMP(11);
             // q | k | v = a' W^T + b, stored fp16 in the attention kernel's smem image layout
 #pragma unroll 1
             for (int which = 0; which < 3; ++which) {
-                mbar_wait(BAR(B_ACC + 4 + which), 0);
+                mbar_wait(TBAR(e, T_ACC + 4 + which), 0);
                 tc_fence_after();
-                const uint32_t tcol = which == 0 ? 128u : (which == 1 ? 256u : 0u);
+                STAMP(12 + 2 * which);
+                const uint32_t tcol = which == 1 ? Y : X;
                 const float* bq = vec + V_BQKV + which * D;
                 const int swz = (tok >> 1) & 3;
-#pragma unroll
-                for (int head = 0; head < 4; ++head) {
-                    float v[32];
-                    tmem_ld32(trow + tcol + head * 32, v);
-                    tmem_wait_ld();
+                for_each_block16(trow + tcol, [&](int cb, float (&v)[16]) {
                     if (valid) {
+                        const int head = cb >> 1, half = cb & 1;
                         __half* dst = p.qkv + ((((size_t)seq * NHEAD + head) * 3 + which) * NTOK + tok) * HD;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const float4 b0 = *reinterpret_cast<const float4*>(bq + head * 32 + c * 8);
-                            const float4 b1 = *reinterpret_cast<const float4*>(bq + head * 32 + c * 8 + 4);
+                        for (int c = 0; c < 2; ++c) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(bq + cb * 16 + c * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bq + cb * 16 + c * 8 + 4);
                             const float* x = v + c * 8;
-                            *reinterpret_cast<uint4*>(dst + ((c ^ swz) << 3)) =
+                            *reinterpret_cast<uint4*>(dst + (((half * 2 + c) ^ swz) << 3)) =
                                 make_uint4(pack_h2(x[0] + b0.x, x[1] + b0.y), pack_h2(x[2] + b0.z, x[3] + b0.w),
                                            pack_h2(x[4] + b1.x, x[5] + b1.y), pack_h2(x[6] + b1.z, x[7] + b1.w));
                         }
                     }
+                });
+                STAMP(13 + 2 * which);
+                if (which == 0) {                                        // X drained: the v chunk may overwrite it
+                    tc_fence_before();
+                    mbar_arrive(TBAR(e, T_XFREE));
                 }
             }
         } else {
             // final LN (eps 1e-5, affine folded) + Linear(128->4) + unpatchify (transformer.py:182-190)
-            float s = 0.f;
-#pragma unroll
-            for (int c = 0; c < D; ++c) s += h[c];
-            const float mean = s * (1.f / D);
-            float q = 0.f;
-#pragma unroll
-            for (int c = 0; c < D; ++c) { const float d = h[c] - mean; q = fmaf(d, d, q); }
-            const float rstd = rsqrtf(q * (1.f / D) + 1e-5f);
             float d4[4] = {0.f, 0.f, 0.f, 0.f};
+            for_each_block16(trow + HREG, [&](int cb, float (&a)[16]) {
 #pragma unroll
-            for (int c = 0; c < D; c += 4) {
-                const float y0 = (h[c] - mean) * rstd, y1 = (h[c + 1] - mean) * rstd, y2 = (h[c + 2] - mean) * rstd, y3 = (h[c + 3] - mean) * rstd;
+                for (int j = 0; j < 16; j += 4) {
+                    const float y0 = (a[j] - st.mean) * st.rstd, y1 = (a[j + 1] - st.mean) * st.rstd;
+                    const float y2 = (a[j + 2] - st.mean) * st.rstd, y3 = (a[j + 3] - st.mean) * st.rstd;
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const float4 w = *reinterpret_cast<const float4*>(vec + V_WFIN + c4 * D + c);
-                    d4[c4] = fmaf(y0, w.x, fmaf(y1, w.y, fmaf(y2, w.z, fmaf(y3, w.w, d4[c4]))));
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 w = *reinterpret_cast<const float4*>(vec + V_WFIN + c4 * D + cb * 16 + j);
+                        d4[c4] = fmaf(y0, w.x, fmaf(y1, w.y, fmaf(y2, w.z, fmaf(y3, w.w, d4[c4]))));
+                    }
                 }
-            }
-            float* vb = reinterpret_cast<float*>(smem + TC_SM_VB);
+            });
+            float* vb = reinterpret_cast<float*>(smem + TC_SM_VB) + e * TILE_ROWS * 4;
             *reinterpret_cast<float4*>(vb + r * 4) =
                 make_float4(d4[0] + vec[V_BFIN], d4[1] + vec[V_BFIN + 1], d4[2] + vec[V_BFIN + 2], d4[3] + vec[V_BFIN + 3]);
-            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            if (e == 0) asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            else asm volatile("bar.sync 2, 128;\n" ::: "memory");
             if (p.out_mode == OUT_FWD) {
-                for (int idx = tid; idx < 2 * TILE_TOK * 4; idx += 128) {
+                for (int idx = r; idx < 2 * TILE_TOK * 4; idx += 128) {
                     const int br = idx / (TILE_TOK * 4), rem = idx - br * (TILE_TOK * 4), t2 = rem >> 2, c4 = rem & 3;
                     const int sq = 2 * pair + br;
                     if (sq < p.nseq) {
@@ -454,7 +552,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             } else {
                 // classifier-free guidance mix (infer.py:81/:87) + Euler (rectified_flow.py:5-7) or
                 // DDPM ancestral update (DDPM.py:28-36); the latent is updated in place
-                for (int idx = tid; idx < TILE_TOK * 4; idx += 128) {
+                for (int idx = r; idx < TILE_TOK * 4; idx += 128) {
                     const int t2 = idx >> 2, c4 = idx & 3;
                     const int n = tt * TILE_TOK + t2, i = n >> 5, jx = n & 31;
                     const size_t xi = (size_t)pair * LAT + (2 * jx + (c4 & 1)) * LATP + 2 * i + (c4 >> 1);
@@ -474,9 +572,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             }
         }
     }
+    if (p.trace != nullptr && tid == 0) p.trace[(size_t)blockIdx.x * 32 + 20] = clock64();
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, 512);
+    if (p.trace != nullptr && tid == 0) p.trace[(size_t)blockIdx.x * 32 + 21] = clock64();
+    if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
 // =================================================================================== attention
