@@ -62,7 +62,7 @@ void ws_offsets(int nseq, size_t off[4], size_t* total) {
     size_t p = 0;
     const size_t ntile = (size_t)((nseq + 1) / 2) * TILES_PER_PAIR;           // pair tiles of 128 rows
     off[0] = p; p = align256(p + ntile * TILE_ROWS * D * 4);                   // residual stream tiles, fp32
-    off[1] = p; p = align256(p + (size_t)nseq * NTOK * 3 * D * 2);             // q|k|v, fp16
+    off[1] = p; p = align256(p + (size_t)nseq * NHEAD * QKV_HEAD_HALVES * 2);  // q|k|v operand images, fp16
     off[2] = p; p = align256(p + ntile * TILE_ROWS * D * 2);                   // attention-output tiles, fp16
     off[3] = p; p = align256(p + (size_t)nseq * NLAYER * MOD * 4);
     if (total) *total = p;
@@ -106,7 +106,7 @@ int launch_embed(const t2s_dit_weights* w, const float* x, int x_shift, int nseq
     return T2S_OK;
 }
 int launch_attn(int nseq, const Workspace& ws, cudaStream_t st) {
-    attn_kernel<<<nseq * NHEAD, ATT_THREADS, ATT_SMEM_BYTES, st>>>(ws.qkv, ws.o);
+    attn_kernel<<<nseq * NHEAD, ATT_THREADS, ATT_SMEM_BYTES, st>>>(ws.qkv, ws.o, g_trace);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }

@@ -27,6 +27,14 @@ constexpr int TILE_ROWS = 128;
 
 constexpr int STAGE_BYTES = 32768;                // one weight stage: [128][128] fp16
 
+// q|k|v scratch: per (sequence, head) three tcgen05 operand images (layouts at attn_kernel)
+constexpr int QKV_Q_HALVES = 4 * 4 * 128 * 8;          // 16384
+constexpr int QKV_K_HALVES = 4 * NTOK * 8;             // 15360
+constexpr int QKV_V_HALVES = NTOK * HD;                // 15360
+constexpr int QKV_HEAD_HALVES = QKV_Q_HALVES + QKV_K_HALVES + QKV_V_HALVES;   // 47104 per (sequence, head)
+constexpr int QT_ROWS = 120;                           // valid query rows per q-tile
+constexpr int KCHUNK = 160;                            // keys per chunk
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -6,7 +6,7 @@
 // Kernels (one sampling step = cond + embed_qkv + 4 x (attention + token)):
 //   cond_kernel       time embedding + text conditioning + SiLU + adaLN Linear for all 4 blocks
 //   token_kernel<EMBED>  patch-embed + pos  -> h ; LN1+modulate -> QKV(l=0)
-//   attn_kernel       softmax(q k^T / sqrt(32)) v per (sequence, head), flash-style, P kept in registers
+//   attn_kernel       softmax(q k^T / sqrt(32)) v per (sequence, head): tcgen05 QK^T / PV, thread-per-row softmax
 //   token_kernel<MID>    proj+gate+residual, LN2+modulate, fc1+GELU, fc2+gate+residual -> h ;
 //                        LN1+modulate -> QKV(l+1)
 //   token_kernel<FINAL>  ... + final LN + Linear(128->4) + unpatchify + CFG mix + Euler / DDPM update
@@ -40,7 +40,7 @@ struct TokArgs {
     const float* x;        // latents [(nseq >> x_shift)][64][30]
     int x_shift;           // 1 when the two sequences of a pair share one latent (CFG), else 0
     float* h;              // residual stream, tiled: [npair][8 tiles][32 col chunks][128 rows][4] fp32
-    __half* qkv;           // [nseq][4 heads][3][480][32] fp16, 16B chunks XOR-swizzled by (tok>>1)&3
+    __half* qkv;           // [nseq][4 heads] x {Q, K, V tcgen05 operand images} fp16 (see attn_kernel)
     const __half* o;       // attention output, tiled A-operand images: [npair][8 tiles][16 K chunks][16 row groups][8][8] fp16
     const float* mod;      // adaLN modulation [nseq][4][768] fp32
     int nseq;
@@ -144,11 +144,13 @@ constexpr uint32_t TC_IDESC = umma_idesc_f16(128, 128);
 constexpr uint32_t KCH = 2048;   // byte stride between K chunks (16 row groups x 128 B) in a [128][128] operand image
 
 // one 128x128x128 GEMM chunk: 8 x tcgen05.mma (K = 16 each); operands in the canonical no-swizzle K-major image
-__device__ __forceinline__ void tc_gemm(uint32_t a_smem, uint32_t w_smem, uint32_t d_tmem, bool accumulate) {
+// Called by the whole (converged) MMA warp so that descriptors live in uniform registers; only `lead` issues.
+__device__ __forceinline__ void tc_gemm(uint32_t a_smem, uint32_t w_smem, uint32_t d_tmem, bool accumulate, bool lead) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-        umma_f16(d_tmem, umma_desc(a_smem + k * 2 * KCH, KCH, 128), umma_desc(w_smem + k * 2 * KCH, KCH, 128), TC_IDESC,
-                 (accumulate || k > 0) ? 1u : 0u);
+    for (int k = 0; k < 8; ++k) {
+        const uint64_t ad = umma_desc(a_smem + k * 2 * KCH, KCH, 128), bd = umma_desc(w_smem + k * 2 * KCH, KCH, 128);
+        if (lead) umma_f16(d_tmem, ad, bd, TC_IDESC, (accumulate || k > 0) ? 1u : 0u);
+    }
 }
 
 // ---- thread-per-row epilogue building blocks.  A thread owns one tile row (= one TMEM lane); rows are
@@ -272,7 +274,7 @@ __device__ __forceinline__ void gelu_store(uint32_t taddr, const float* __restri
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform
     const int pair = blockIdx.x / (TILES_PER_PAIR / 2), tt0 = (blockIdx.x % (TILES_PER_PAIR / 2)) * 2;
     const uint32_t sb = smem_u32(smem);
     const uint32_t bar0 = sb + TC_SM_BAR;
@@ -297,23 +299,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + TC_SM_TMEM);
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + TC_SM_TMEM), 0);
     const size_t tile0 = (size_t)pair * TILES_PER_PAIR + tt0;
 
     if (warp == 8) {
-        // ================================================================= producer
-        if (lane == 0) {
+        // ================================================================= producer (whole warp converged; lane 0 issues)
+        const bool lead = lane == 0;
+        {
             // per-pair vectors (adaLN chunks of the two sequences, biases, small weights)
             {
                 const int sq0 = min(2 * pair, p.nseq - 1), sq1 = min(2 * pair + 1, p.nseq - 1);
                 uint32_t bytes = 0;
                 auto cp = [&](int voff, const float* src, uint32_t n) {
-                    bulk_g2s(sb + TC_SM_VEC + voff * 4, src, n * 4, BAR(B_VFULL));
+                    if (lead) bulk_g2s(sb + TC_SM_VEC + voff * 4, src, n * 4, BAR(B_VFULL));
                     bytes += n * 4;
                 };
                 constexpr uint32_t VBYTES = (MODE == TOK_EMBED ? 0u : (2 * MOD + 2 * D + DMLP) * 4u) + (MODE == TOK_FINAL ? 0u : (512 + 3 * D) * 4u) +
                                             (MODE == TOK_EMBED ? (5 * D) * 4u : 0u) + (MODE == TOK_FINAL ? (4 * D + 4) * 4u : 0u);
-                mbar_expect_tx(BAR(B_VFULL), VBYTES);
+                if (lead) mbar_expect_tx(BAR(B_VFULL), VBYTES);
                 if (MODE != TOK_EMBED) {
                     cp(V_MOD, p.mod + ((size_t)sq0 * NLAYER + l) * MOD, MOD);
                     cp(V_MOD + MOD, p.mod + ((size_t)sq1 * NLAYER + l) * MOD, MOD);
@@ -332,9 +335,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             }
             if (MODE != TOK_EMBED) {
                 for (int e = 0; e < 2; ++e) {
-                    mbar_expect_tx(TBAR(e, T_OFULL), STAGE_BYTES);
-                    bulk_g2s(sb + TC_SM_A + e * STAGE_BYTES, reinterpret_cast<const char*>(p.o) + (tile0 + e) * STAGE_BYTES, STAGE_BYTES,
-                             TBAR(e, T_OFULL));
+                    if (lead) {
+                        mbar_expect_tx(TBAR(e, T_OFULL), STAGE_BYTES);
+                        bulk_g2s(sb + TC_SM_A + e * STAGE_BYTES, reinterpret_cast<const char*>(p.o) + (tile0 + e) * STAGE_BYTES, STAGE_BYTES,
+                                 TBAR(e, T_OFULL));
+                    }
                 }
             }
             const char* src_a = reinterpret_cast<const char*>(MODE == TOK_EMBED ? p.w.w_qkv[0] : p.w.w_post[l]);
@@ -344,15 +349,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             for (int s = 0; s < N_STAGES; ++s) {
                 const int slot = s % TC_NSTAGE, use = s / TC_NSTAGE;
                 if (use > 0) mbar_wait(BAR(B_WEMPTY + slot), (use - 1) & 1);
-                mbar_expect_tx(BAR(B_WFULL + slot), STAGE_BYTES);
-                bulk_g2s(sb + TC_SM_W + slot * STAGE_BYTES, s < N_A ? src_a + (size_t)s * STAGE_BYTES : src_b + (size_t)(s - N_A) * STAGE_BYTES,
-                         STAGE_BYTES, BAR(B_WFULL + slot));
+                if (lead) {
+                    mbar_expect_tx(BAR(B_WFULL + slot), STAGE_BYTES);
+                    bulk_g2s(sb + TC_SM_W + slot * STAGE_BYTES, s < N_A ? src_a + (size_t)s * STAGE_BYTES : src_b + (size_t)(s - N_A) * STAGE_BYTES,
+                             STAGE_BYTES, BAR(B_WFULL + slot));
+                }
+                __syncwarp();
             }
         }
         __syncwarp();
     } else if (warp == 9) {
-        // ================================================================= MMA issuer
-        if (lane == 0) {
+        // ================================================================= MMA issuer (whole warp converged; lane 0 issues)
+        const bool lead = lane == 0;
+        {
             int s = 0;
             // one weight stage feeds the same GEMM chunk of both tiles
             auto stage = [&](int wait_bar, uint32_t a_off, uint32_t d_col, bool accumulate, int acc_bar) {
@@ -362,10 +371,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 for (int e = 0; e < 2; ++e) {
                     if (wait_bar >= 0) mbar_wait(TBAR(e, wait_bar), 0);
                     tc_fence_after();
-                    tc_gemm(sb + a_off + e * STAGE_BYTES, sb + TC_SM_W + slot * STAGE_BYTES, tmem + e * 256 + d_col, accumulate);
-                    if (acc_bar >= 0) umma_commit(TBAR(e, T_ACC + acc_bar));
+                    tc_gemm(sb + a_off + e * STAGE_BYTES, sb + TC_SM_W + slot * STAGE_BYTES, tmem + e * 256 + d_col, accumulate, lead);
+                    if (lead && acc_bar >= 0) umma_commit(TBAR(e, T_ACC + acc_bar));
                 }
-                umma_commit(BAR(B_WEMPTY + slot));
+                if (lead) umma_commit(BAR(B_WEMPTY + slot));
+                __syncwarp();
                 ++s;
             };
             if (MODE != TOK_EMBED) {
@@ -498,17 +508,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 STAMP(12 + 2 * which);
                 const uint32_t tcol = which == 1 ? Y : X;
                 const float* bq = vec + V_BQKV + which * D;
-                const int swz = (tok >> 1) & 3;
                 for_each_block16(trow + tcol, [&](int cb, float (&v)[16]) {
                     if (valid) {
                         const int head = cb >> 1, half = cb & 1;
-                        __half* dst = p.qkv + ((((size_t)seq * NHEAD + head) * 3 + which) * NTOK + tok) * HD;
+                        __half* hb = p.qkv + ((size_t)seq * NHEAD + head) * QKV_HEAD_HALVES;
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
+                            const int dc = half * 2 + c;
+                            __half* dst;      // tcgen05 operand images read by attn_kernel (a warp's 32 rows are contiguous)
+                            if (which == 0) dst = hb + (tok / QT_ROWS) * 4096 + dc * 1024 + (tok % QT_ROWS) * 8;
+                            else if (which == 1) dst = hb + QKV_Q_HALVES + dc * (NTOK * 8) + tok * 8;
+                            else dst = hb + QKV_Q_HALVES + QKV_K_HALVES + (tok >> 3) * 256 + dc * 64 + (tok & 7) * 8;
                             const float4 b0 = *reinterpret_cast<const float4*>(bq + cb * 16 + c * 8);
                             const float4 b1 = *reinterpret_cast<const float4*>(bq + cb * 16 + c * 8 + 4);
                             const float* x = v + c * 8;
-                            *reinterpret_cast<uint4*>(dst + (((half * 2 + c) ^ swz) << 3)) =
+                            *reinterpret_cast<uint4*>(dst) =
                                 make_uint4(pack_h2(x[0] + b0.x, x[1] + b0.y), pack_h2(x[2] + b0.z, x[3] + b0.w),
                                            pack_h2(x[4] + b1.x, x[5] + b1.y), pack_h2(x[6] + b1.z, x[7] + b1.w));
                         }
@@ -579,131 +593,247 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
     if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
-// =================================================================================== attention
-// softmax(q k^T / sqrt(32)) v for one (sequence, head) per CTA; 15 warps x 32 query rows.
-// K/V/Q arrive with three bulk async copies (the global layout is already the swizzled smem image).
-// S and P never leave registers: the S accumulator fragments are re-packed as the A operand of P.V.
-constexpr int ATT_THREADS = 480;
-constexpr int ATT_SMEM_Q = 0, ATT_SMEM_K = NTOK * HD * 2, ATT_SMEM_V = 2 * NTOK * HD * 2;
-constexpr int ATT_SMEM_BAR = 3 * NTOK * HD * 2;
-constexpr int ATT_SMEM_BYTES = ATT_SMEM_BAR + 32;
-constexpr int ATT_KC = 32;          // keys per online-softmax chunk
+// =================================================================================== attention (tcgen05)
+// softmax(q k^T / sqrt(32)) v for one (sequence, head) per CTA (timm Attention -> F.scaled_dot_product_attention).
+// The 480 queries form four 120-row q-tiles (M = 128 with 8 padding rows), the 480 keys five 96-key chunks.
+// Exact two-pass softmax with the score GEMM recomputed (the tensor pipe is nearly idle, the MUFU is the bound):
+//   pass A: S_j = Q_tile K_j^T for the five chunks (tcgen05.mma M128 N96 K16 x2, double-buffered in TMEM);
+//           a thread per query row (= TMEM lane) takes the running row maximum;
+//   pass B: the same five S_j again; P_j = exp2((S_j - rowmax) * log2e/sqrt(32)) in fp16 to a (double-buffered)
+//           shared-memory A-operand image, row sum in registers; O += P_j V_j (tcgen05.mma M128 N32 K16 x6, V as
+//           MN-major B operand) accumulates over the chunks in one 32-column TMEM accumulator; O / rowsum is
+//           written straight into the out-projection's A-operand tile.
+// Two softmax warpgroups (q-tiles 0,2 / 1,3), each with its own MMA-issuing lane, share the SM: while one is in
+// its MUFU-free pass A the other's exps run at full MUFU rate.
+// Q, K, V arrive by bulk async copies: the token kernel stores them directly as tcgen05 operand images
+//   Q: [q-tile][d/8][row 0..127][8]     (A, K-major)         32768 B
+//   K: [d/8][key 0..479][8]             (B, K-major)         30720 B
+//   V: [key/8][d/8][key%8][8]           (B, MN-major)        30720 B
+constexpr int ATT_THREADS = 320;
+constexpr int ATT_KC = 96;                                            // keys per chunk
+constexpr int ATT_NCH = NTOK / ATT_KC;                                // 5
+constexpr int ATT_SM_Q = 0, ATT_SM_K = QKV_Q_HALVES * 2, ATT_SM_V = ATT_SM_K + QKV_K_HALVES * 2;
+constexpr int ATT_SM_P = ATT_SM_V + QKV_V_HALVES * 2;                // [2 warpgroups][2 buffers] P image [96/8][128 rows][8] fp16
+constexpr int ATT_P_BYTES = (ATT_KC / 8) * 2048;                     // 24576
+constexpr int ATT_SM_BAR = ATT_SM_P + 4 * ATT_P_BYTES;
+constexpr int ATT_SM_TMEM = ATT_SM_BAR + 32 * 8;
+constexpr int ATT_SMEM_BYTES = ATT_SM_TMEM + 16;
+static_assert(ATT_SMEM_BYTES <= 232448, "attention kernel shared memory exceeds 227 KB");
+enum { AB_QFULL = 0, AB_KFULL = 1, AB_VFULL = 2, AB_WG = 3 };
+// per warpgroup barriers: S_FULL[2], S_FREE[2], P_FULL[2], P_FREE[2], O_FULL, O_FREE
+enum { AW_SFULL = 0, AW_SFREE = 2, AW_PFULL = 4, AW_PFREE = 6, AW_OFULL = 8, AW_OFREE = 9, AW_COUNT = 10 };
+#ifndef ATT_STAGGER_CLKS
+#define ATT_STAGGER_CLKS 1500
+#endif
+constexpr uint32_t ATT_IDESC_S = umma_idesc_f16(128, ATT_KC);
+constexpr uint32_t ATT_IDESC_PV = umma_idesc_f16(128, HD) | (1u << 16);   // B (V) is MN-major
+// TMEM columns of a warpgroup (256 each): two S buffers and the O accumulator
+constexpr uint32_t ATT_T_S = 0, ATT_T_O = 2 * ATT_KC;
 
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ o) {
+// pipelined walk over NB 16-column blocks of a TMEM region (NB even)
+template <int NB, class F>
+__device__ __forceinline__ void for_blocks16(uint32_t taddr, F&& body) {
+    float a[16], b[16];
+    tmem_ld16(taddr, a);
+#pragma unroll 1
+    for (int cb = 0; cb < NB; cb += 2) {
+        tmem_wait_ld();
+        tmem_ld16(taddr + (cb + 1) * 16, b);
+        body(cb, a);
+        tmem_wait_ld();
+        if (cb + 2 < NB) tmem_ld16(taddr + (cb + 2) * 16, a);
+        body(cb + 1, b);
+    }
+}
+
+// grid = nseq * 4, block = 320: warps 0-3 / 4-7 = softmax warpgroups (thread = query row = TMEM lane),
+// warp 8 / 9 = MMA issuer of warpgroup 0 / 1 (warp 8 also issues the loads)
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ o, long long* trace) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform
     const int seq = blockIdx.x >> 2, head = blockIdx.x & 3;
     const uint32_t sb = smem_u32(smem);
-    const uint32_t bar = sb + ATT_SMEM_BAR;
-    constexpr uint32_t PIECE = NTOK * HD * 2;   // 30720 B
+    const uint32_t bar0 = sb + ATT_SM_BAR;
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    auto WBAR = [&](int w, int i) { return bar0 + 8u * (AB_WG + w * AW_COUNT + i); };
     if (tid == 0) {
-        mbar_init(bar, 1); mbar_init(bar + 8, 1); mbar_init(bar + 16, 1);
+        for (int i = 0; i < 3; ++i) mbar_init(BAR(i), 1);
+        for (int w = 0; w < 2; ++w) {
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(WBAR(w, AW_SFULL + b), 1);
+                mbar_init(WBAR(w, AW_SFREE + b), 128);
+                mbar_init(WBAR(w, AW_PFULL + b), 128);
+                mbar_init(WBAR(w, AW_PFREE + b), 1);
+            }
+            mbar_init(WBAR(w, AW_OFULL), 1);
+            mbar_init(WBAR(w, AW_OFREE), 128);
+        }
         mbar_fence_init();
-        const char* src = reinterpret_cast<const char*>(qkv) + (size_t)blockIdx.x * 3 * PIECE;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            mbar_expect_tx(bar + 8 * i, PIECE);
-            bulk_g2s(sb + i * PIECE, src + (size_t)i * PIECE, PIECE, bar + 8 * i);
-        }
     }
+    if (warp == 8) tmem_alloc(sb + ATT_SM_TMEM, 512);
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + ATT_SM_TMEM), 0);
 
-    // Q fragments: 2 m-tiles x 2 k-steps
-    const int qrow0 = warp * 32;
-    uint32_t qf[2][2][4];
-    mbar_wait(bar, 0);
+    if (warp >= 8) {
+        // ================================================================= MMA issuer of warpgroup w (+ loads); whole warp converged
+        const bool lead = lane == 0;
+        {
+            const int w = warp - 8;
+            if (w == 0 && lead) {
+                const char* src = reinterpret_cast<const char*>(qkv + (size_t)blockIdx.x * QKV_HEAD_HALVES);
+                mbar_expect_tx(BAR(AB_QFULL), QKV_Q_HALVES * 2);
+                bulk_g2s(sb + ATT_SM_Q, src, QKV_Q_HALVES * 2, BAR(AB_QFULL));
+                mbar_expect_tx(BAR(AB_KFULL), QKV_K_HALVES * 2);
+                bulk_g2s(sb + ATT_SM_K, src + QKV_Q_HALVES * 2, QKV_K_HALVES * 2, BAR(AB_KFULL));
+                mbar_expect_tx(BAR(AB_VFULL), QKV_V_HALVES * 2);
+                bulk_g2s(sb + ATT_SM_V, src + (QKV_Q_HALVES + QKV_K_HALVES) * 2, QKV_V_HALVES * 2, BAR(AB_VFULL));
+            }
+            const uint32_t tw = tmem + w * 256;
+            // score chunk g (0..19): q-tile (g/10), pass (g/5)%2, key chunk g%5 -> S buffer g&1
+            auto issue_s = [&](int g) {
+                const int qt = w + 2 * (g / (2 * ATT_NCH)), j = g % ATT_NCH;
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-        const int row = qrow0 + mt * 16 + (lane & 15);
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk)
-            ldmatrix_x4(qf[mt][kk][0], qf[mt][kk][1], qf[mt][kk][2], qf[mt][kk][3],
-                        sb + ATT_SMEM_Q + row * 64 + (((2 * kk + (lane >> 4)) ^ ((row >> 1) & 3)) << 4));
-    }
-    float oacc[2][4][4];
-    float mx[2][2], ls[2][2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-        mx[mt][0] = mx[mt][1] = -INFINITY;
-        ls[mt][0] = ls[mt][1] = 0.f;
-#pragma unroll
-        for (int d = 0; d < 4; ++d) oacc[mt][d][0] = oacc[mt][d][1] = oacc[mt][d][2] = oacc[mt][d][3] = 0.f;
-    }
-    const float sc = 0.25503486f;   // log2(e) / sqrt(32)
-    mbar_wait(bar + 8, 0);
-    mbar_wait(bar + 16, 0);
-
+                for (int kk = 0; kk < 2; ++kk) {
+                    const uint64_t ad = umma_desc(sb + ATT_SM_Q + qt * 8192 + kk * 2 * 2048, 2048, 128);
+                    const uint64_t bd = umma_desc(sb + ATT_SM_K + j * (ATT_KC * 16) + kk * 2 * (NTOK * 16), NTOK * 16, 128);
+                    if (lead) umma_f16(tw + ATT_T_S + (g & 1) * ATT_KC, ad, bd, ATT_IDESC_S, kk > 0);
+                }
+                if (lead) umma_commit(WBAR(w, AW_SFULL + (g & 1)));
+                __syncwarp();
+            };
+            mbar_wait(BAR(AB_QFULL), 0);
+            mbar_wait(BAR(AB_KFULL), 0);
+            tc_fence_after();
+            if (w == 1) {                                    // stagger the warpgroups: one group's MUFU-free pass A
+                const long long t0 = clock64();              // overlaps the other group's exp pass
+                while (clock64() - t0 < ATT_STAGGER_CLKS) {}
+            }
+            issue_s(0);
+            issue_s(1);
+            mbar_wait(BAR(AB_VFULL), 0);
 #pragma unroll 1
-    for (int c0 = 0; c0 < NTOK; c0 += ATT_KC) {
-        float s[2][4][4];
+            for (int g = 0; g < 4 * ATT_NCH; ++g) {
+                const int b = g & 1;
+                mbar_wait(WBAR(w, AW_SFREE + b), (g >> 1) & 1);      // softmax threads have drained S chunk g
+                tc_fence_after();
+                if (g + 2 < 4 * ATT_NCH) issue_s(g + 2);
+                if ((g / ATT_NCH) & 1) {                             // pass B chunk: O += P V_j
+                    const int it = g / (2 * ATT_NCH), j = g % ATT_NCH, pj = it * ATT_NCH + j, pb = pj & 1;
+                    mbar_wait(WBAR(w, AW_PFULL + pb), (pj >> 1) & 1);
+                    if (it == 1 && j == 0) mbar_wait(WBAR(w, AW_OFREE), 0);   // previous q-tile's O has been read
+                    tc_fence_after();
+                    const uint32_t p_smem = sb + ATT_SM_P + (w * 2 + pb) * ATT_P_BYTES;
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) {
-            const int key = c0 + nb * 8 + (lane & 7);
-            uint32_t k0, k1, k2, k3;
-            ldmatrix_x4(k0, k1, k2, k3, sb + ATT_SMEM_K + key * 64 + (((lane >> 3) ^ ((key >> 1) & 3)) << 4));
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                s[mt][nb][0] = s[mt][nb][1] = s[mt][nb][2] = s[mt][nb][3] = 0.f;
-                mma_f16(s[mt][nb], qf[mt][0][0], qf[mt][0][1], qf[mt][0][2], qf[mt][0][3], k0, k1);
-                mma_f16(s[mt][nb], qf[mt][1][0], qf[mt][1][1], qf[mt][1][2], qf[mt][1][3], k2, k3);
-            }
-        }
-        uint32_t pf[2][2][4];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            float a0 = fmaxf(fmaxf(s[mt][0][0], s[mt][0][1]), fmaxf(s[mt][1][0], s[mt][1][1]));
-            float a1 = fmaxf(fmaxf(s[mt][0][2], s[mt][0][3]), fmaxf(s[mt][1][2], s[mt][1][3]));
-            a0 = fmaxf(a0, fmaxf(fmaxf(s[mt][2][0], s[mt][2][1]), fmaxf(s[mt][3][0], s[mt][3][1])));
-            a1 = fmaxf(a1, fmaxf(fmaxf(s[mt][2][2], s[mt][2][3]), fmaxf(s[mt][3][2], s[mt][3][3])));
-            const float n0 = fmaxf(mx[mt][0], quad_max(a0)), n1 = fmaxf(mx[mt][1], quad_max(a1));
-            const float cr0 = ex2_approx((mx[mt][0] - n0) * sc), cr1 = ex2_approx((mx[mt][1] - n1) * sc);
-            mx[mt][0] = n0; mx[mt][1] = n1;
-            const float b0 = -n0 * sc, b1 = -n1 * sc;
-            float l0 = ls[mt][0] * cr0, l1 = ls[mt][1] * cr1;
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-                oacc[mt][d][0] *= cr0; oacc[mt][d][1] *= cr0; oacc[mt][d][2] *= cr1; oacc[mt][d][3] *= cr1;
-            }
-#pragma unroll
-            for (int nb = 0; nb < 4; ++nb) {
-                const float p0 = ex2_approx(fmaf(s[mt][nb][0], sc, b0)), p1 = ex2_approx(fmaf(s[mt][nb][1], sc, b0));
-                const float p2 = ex2_approx(fmaf(s[mt][nb][2], sc, b1)), p3 = ex2_approx(fmaf(s[mt][nb][3], sc, b1));
-                l0 += p0 + p1; l1 += p2 + p3;
-                pf[mt][nb >> 1][(nb & 1) * 2 + 0] = pack_h2(p0, p1);
-                pf[mt][nb >> 1][(nb & 1) * 2 + 1] = pack_h2(p2, p3);
-            }
-            ls[mt][0] = l0; ls[mt][1] = l1;
-        }
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            const int key = c0 + ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
-#pragma unroll
-            for (int dc = 0; dc < 4; dc += 2) {
-                uint32_t v0, v1, v2, v3;
-                ldmatrix_x4_trans(v0, v1, v2, v3, sb + ATT_SMEM_V + key * 64 + (((dc + (lane >> 4)) ^ ((key >> 1) & 3)) << 4));
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    mma_f16(oacc[mt][dc], pf[mt][ks][0], pf[mt][ks][1], pf[mt][ks][2], pf[mt][ks][3], v0, v1);
-                    mma_f16(oacc[mt][dc + 1], pf[mt][ks][0], pf[mt][ks][1], pf[mt][ks][2], pf[mt][ks][3], v2, v3);
+                    for (int ks = 0; ks < ATT_KC / 16; ++ks) {
+                        const uint64_t ad = umma_desc(p_smem + ks * 2 * 2048, 2048, 128);
+                        const uint64_t bd = umma_desc(sb + ATT_SM_V + (j * (ATT_KC / 8) + 2 * ks) * 512, 512, 128);
+                        if (lead) umma_f16(tw + ATT_T_O, ad, bd, ATT_IDESC_PV, (j > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    if (lead) {
+                        umma_commit(WBAR(w, AW_PFREE + pb));
+                        if (j == ATT_NCH - 1) umma_commit(WBAR(w, AW_OFULL));
+                    }
+                    __syncwarp();
                 }
             }
         }
-    }
+        __syncwarp();
+    } else {
+        // ================================================================= softmax warpgroup w: thread = query row
+        const int w = warp >> 2, r = tid & 127;
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + w * 256;
+        const float sc = 0.25503486f;                        // log2(e) / sqrt(32)
+        const bool tr = trace != nullptr && tid == 0;
+#define ASTAMP(i) do { if (tr) trace[(size_t)blockIdx.x * 32 + (i)] = clock64(); } while (0)
+        ASTAMP(0);
+        // O / rowsum of q-tile `it` -> the out-projection A-operand tile of the token kernel
+        auto finish = [&](int it, float lsum) {
+            const int qt = w + 2 * it;
+            const float inv = 1.f / lsum;
+            mbar_wait(WBAR(w, AW_OFULL), it & 1);
+            tc_fence_after();
+            const int tok = qt * QT_ROWS + r;
+            const int tt = tok / TILE_TOK, tilerow = (seq & 1) * 64 + (tok - tt * TILE_TOK);
+            __half* dst = o + ((size_t)(seq >> 1) * TILES_PER_PAIR + tt) * (TILE_ROWS * D) + head * 4 * 1024 + tilerow * 8;
+            float a0[32];
+            tmem_ld32(trow + ATT_T_O, a0);
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(WBAR(w, AW_OFREE));
+            if (r < QT_ROWS) {
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-        const float i0 = 1.f / quad_sum(ls[mt][0]), i1 = 1.f / quad_sum(ls[mt][1]);
-        // output goes straight into the token kernel's A-operand image: [pair][tile][16 K chunks][16 row groups][8 rows][8 halves]
-        const int ra = qrow0 + mt * 16 + g, rb = ra + 8;
-        const int ta = ra / TILE_TOK, tb = rb / TILE_TOK;
-        const int rowa = (seq & 1) * 64 + (ra - ta * TILE_TOK), rowb = (seq & 1) * 64 + (rb - tb * TILE_TOK);
-        __half* da = o + ((size_t)(seq >> 1) * TILES_PER_PAIR + ta) * (TILE_ROWS * D) + (rowa >> 3) * 64 + (rowa & 7) * 8 + 2 * t;
-        __half* db = o + ((size_t)(seq >> 1) * TILES_PER_PAIR + tb) * (TILE_ROWS * D) + (rowb >> 3) * 64 + (rowb & 7) * 8 + 2 * t;
+                for (int c8 = 0; c8 < 4; ++c8)
+                    *reinterpret_cast<uint4*>(dst + c8 * 1024) =
+                        make_uint4(pack_h2(a0[c8 * 8 + 0] * inv, a0[c8 * 8 + 1] * inv), pack_h2(a0[c8 * 8 + 2] * inv, a0[c8 * 8 + 3] * inv),
+                                   pack_h2(a0[c8 * 8 + 4] * inv, a0[c8 * 8 + 5] * inv), pack_h2(a0[c8 * 8 + 6] * inv, a0[c8 * 8 + 7] * inv));
+            }
+        };
+        float lprev = 1.f;
+#pragma unroll 1
+        for (int it = 0; it < 2; ++it) {
+            // ---- pass A: running row maximum over the five score chunks
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll 1
+            for (int j = 0; j < ATT_NCH; ++j) {
+                const int g = it * 2 * ATT_NCH + j, b = g & 1;
+                mbar_wait(WBAR(w, AW_SFULL + b), (g >> 1) & 1);
+                tc_fence_after();
+                const uint32_t ts = trow + ATT_T_S + b * ATT_KC;
+                float x[32], y[32];
+                auto red = [&](const float (&v)[32]) {
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            *reinterpret_cast<uint32_t*>(da + (head * 4 + d) * 1024) = pack_h2(oacc[mt][d][0] * i0, oacc[mt][d][1] * i0);
-            *reinterpret_cast<uint32_t*>(db + (head * 4 + d) * 1024) = pack_h2(oacc[mt][d][2] * i1, oacc[mt][d][3] * i1);
+                    for (int q = 0; q < 32; q += 2) { m0 = fmaxf(m0, v[q]); m1 = fmaxf(m1, v[q + 1]); }
+                };
+                tmem_ld32(ts, x); tmem_ld32(ts + 32, y); tmem_wait_ld();
+                red(x); tmem_ld32(ts + 64, x);
+                red(y); tmem_wait_ld();
+                tc_fence_before();
+                mbar_arrive(WBAR(w, AW_SFREE + b));
+                red(x);
+            }
+            ASTAMP(1 + it * 8);
+            if (it == 1) finish(0, lprev);               // q-tile 0's last P.V finished during pass A
+            ASTAMP(2 + it * 8);
+            // ---- pass B: P = exp2((S - max) * log2e/sqrt(32)) -> fp16 A-operand image, row sum; O += P V
+            const float nb = -fmaxf(m0, m1) * sc;
+            float l0 = 0.f, l1 = 0.f;
+#pragma unroll 1
+            for (int j = 0; j < ATT_NCH; ++j) {
+                const int g = it * 2 * ATT_NCH + ATT_NCH + j, b = g & 1;
+                const int pj = it * ATT_NCH + j, pb = pj & 1;
+                mbar_wait(WBAR(w, AW_SFULL + b), (g >> 1) & 1);
+                if (pj >= 2) mbar_wait(WBAR(w, AW_PFREE + pb), ((pj >> 1) - 1) & 1);   // P.V two chunks back has read this P buffer
+                tc_fence_after();
+                uint8_t* pbuf = smem + ATT_SM_P + (w * 2 + pb) * ATT_P_BYTES;
+                for_blocks16<ATT_KC / 16>(trow + ATT_T_S + b * ATT_KC, [&](int cb, float (&a)[16]) {
+#pragma unroll
+                    for (int q = 0; q < 16; q += 2) {
+                        a[q] = ex2_approx(fmaf(a[q], sc, nb));
+                        a[q + 1] = ex2_approx(fmaf(a[q + 1], sc, nb));
+                        l0 += a[q]; l1 += a[q + 1];
+                    }
+#pragma unroll
+                    for (int c8 = 0; c8 < 2; ++c8)
+                        *reinterpret_cast<uint4*>(pbuf + (cb * 2 + c8) * 2048 + r * 16) =
+                            make_uint4(pack_h2(a[c8 * 8 + 0], a[c8 * 8 + 1]), pack_h2(a[c8 * 8 + 2], a[c8 * 8 + 3]),
+                                       pack_h2(a[c8 * 8 + 4], a[c8 * 8 + 5]), pack_h2(a[c8 * 8 + 6], a[c8 * 8 + 7]));
+                });
+                tc_fence_before();
+                mbar_arrive(WBAR(w, AW_SFREE + b));
+                fence_async_smem();
+                mbar_arrive(WBAR(w, AW_PFULL + pb));
+            }
+            ASTAMP(3 + it * 8);
+            lprev = l0 + l1;
         }
+        finish(1, lprev);
+        ASTAMP(20);
     }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace t2s

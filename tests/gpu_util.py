@@ -66,14 +66,14 @@ class Workspace:
         return self._tiles(raw.permute(0, 1, 3, 2, 4).reshape(npair, 8, 128, 128))
 
     def qkv(self):
-        """-> (nseq, 3, 4 heads, 480, 32) fp32, de-swizzled."""
-        raw = self._view(1, self.nseq * 480 * 384 * 2, torch.float16, (self.nseq, 4, 3, 480, 4, 8))
-        tok = torch.arange(480, device=raw.device)
-        pc = torch.arange(4, device=raw.device)
-        src = pc.unsqueeze(0) ^ ((tok.unsqueeze(1) >> 1) & 3)            # logical chunk c lives at physical c ^ s
-        idx = src.view(1, 1, 1, 480, 4, 1).expand(self.nseq, 4, 3, 480, 4, 8)
-        logical = torch.gather(raw, 4, idx)                               # logical[c] = raw[c ^ s]
-        return logical.reshape(self.nseq, 4, 3, 480, 32).permute(0, 2, 1, 3, 4).float()
+        """-> (nseq, 3, 4 heads, 480, 32) fp32 from the per-(sequence, head) tcgen05 operand images."""
+        n = self.nseq
+        raw = self._view(1, n * 4 * 47104 * 2, torch.float16, (n, 4, 47104))
+        q = raw[:, :, :16384].reshape(n, 4, 4, 4, 128, 8)[:, :, :, :, :120]          # [qt][d/8][row][8]
+        q = q.permute(0, 1, 2, 4, 3, 5).reshape(n, 4, 480, 32)
+        k = raw[:, :, 16384:31744].reshape(n, 4, 4, 480, 8).permute(0, 1, 3, 2, 4).reshape(n, 4, 480, 32)   # [d/8][key][8]
+        v = raw[:, :, 31744:].reshape(n, 4, 60, 4, 8, 8).permute(0, 1, 2, 4, 3, 5).reshape(n, 4, 480, 32)   # [key/8][d/8][key%8][8]
+        return torch.stack([q, k, v], dim=1).float()
 
     def o(self):
         npair = (self.nseq + 1) // 2

@@ -42,3 +42,21 @@ for label, fn in (("MID", lambda: lib.t2s_dit_block_post(pk.ref, 1, B, ws.ptr, s
         v = m.mean().item()
         print(f"  {names[i]:16s} {v:9.0f}  (+{v - prev:7.0f})")
         prev = v
+
+# ---- attention kernel: softmax warpgroup 0, row 0
+lib.t2s_dit_embed_qkv(pk.ref, x.data_ptr(), 1, B, ws.ptr, stream())
+lib.t2s_dit_attention(B, ws.ptr, stream()); torch.cuda.synchronize()
+buf = torch.zeros(B * 4, 32, dtype=torch.int64, device=DEV)
+lib.t2s_debug_set_phase_trace(buf.data_ptr())
+lib.t2s_dit_attention(B, ws.ptr, stream()); torch.cuda.synchronize()
+lib.t2s_debug_set_phase_trace(None)
+b = buf.cpu().double()
+rel = b - b[:, 0:1]
+print(f"== ATTENTION (warpgroup 0, row 0): mean cycles since softmax start over {B*4} CTAs")
+prev = 0.0
+labels = {0: "start", 1: "it0 passA done", 2: "it0 (finish prev)", 3: "it0 passB done", 9: "it1 passA done", 10: "it1 finish(0) done",
+          11: "it1 passB done", 20: "finish(1) done"}
+for i in [0, 1, 2, 3, 9, 10, 11, 20]:
+    v = rel[:, i].mean().item()
+    print(f"  {labels[i]:20s} {v:9.0f}  (+{v - prev:7.0f})")
+    prev = v
