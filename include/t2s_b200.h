@@ -128,6 +128,76 @@ int t2s_dit_attention(int nseq, void* workspace, t2s_stream_t stream);
 int t2s_dit_block_post(const t2s_dit_weights* w, int layer, int nseq, void* workspace, t2s_stream_t stream);
 int t2s_dit_final(const t2s_dit_weights* w, float* out, int nseq, void* workspace, t2s_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step (train.py:66-87): forward + MSE loss + backward of the DiT, and the AdamW update.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* The DiT parameters as the reference state dict holds them (fp32, nn.Linear / nn.Conv2d layouts; key names in
+ * SURVEY.md 8b).  The same struct type carries the gradient pointers (pos and freqs are ignored there). */
+typedef struct {
+    float* conv_w;     /* conv.weight (4,1,2,2) */
+    float* conv_b;     /* conv.bias (4) */
+    float* pe_w;       /* patch_emb.weight (128,4) */
+    float* pe_b;       /* patch_emb.bias (128) */
+    float* pos;        /* pos_embed (1,480,128), not trained (transformer.py:139-140) */
+    float* ln_w;       /* ln.weight (128) */
+    float* ln_b;       /* ln.bias (128) */
+    float* lf_w;       /* linear_emb_to_patch.weight (4,128) */
+    float* lf_b;       /* linear_emb_to_patch.bias (4) */
+    float* freqs;      /* [64] 10000 ** linspace(0,1,64) (TimeEmbedding, transformer.py:34); no gradient */
+    float* qkv_w[4];   /* layers.{l}.attn.qkv.weight (384,128) */
+    float* qkv_b[4];   /* (384) */
+    float* proj_w[4];  /* layers.{l}.attn.proj.weight (128,128) */
+    float* proj_b[4];  /* (128) */
+    float* fc1_w[4];   /* layers.{l}.mlp.fc1.weight (256,128) */
+    float* fc1_b[4];   /* (256) */
+    float* fc2_w[4];   /* layers.{l}.mlp.fc2.weight (128,256) */
+    float* fc2_b[4];   /* (128) */
+    float* ada_w[4];   /* layers.{l}.adaLN_modulation.1.weight (768,128) */
+    float* ada_b[4];   /* (768) */
+} t2s_dit_params;
+
+/* Scratch for a training step over `nseq` sequences (saved activations of every block + backward temporaries). */
+size_t t2s_train_workspace_bytes(int nseq);
+
+/* pred = Transformer.forward(x_t, t, emb | None) (transformer.py:158-193), loss = F.mse_loss(pred, target)
+ * (rectified_flow.py:13-16 / DDPM.py:37-38), backward to every trainable parameter (train.py:83-85).
+ *   x_t, target [nseq][64][30]; t100 [nseq] = 100 * t; emb [nseq][128] or NULL (the CFG-dropped batch, train.py:80-82)
+ *   loss_sum  device float, += sum (pred - target)^2   (caller zeroes; loss = loss_sum / (nseq * 1920))
+ *   pred      [nseq][64][30] or NULL
+ *   grads     += dL/dparam for loss = mean over loss_numel elements (pass nseq*1920 for a single batch; the global
+ *             element count when the batch is split into micro-batches / data-parallel ranks).  Caller zeroes.
+ * With grads == NULL only the forward and the loss are evaluated. */
+int t2s_dit_train_step(const t2s_dit_params* params, const t2s_dit_params* grads, const float* x_t, const float* t100,
+                       const float* emb, const float* target, float* loss_sum, float* pred, int nseq, double loss_numel,
+                       void* workspace, size_t workspace_bytes, t2s_stream_t stream);
+
+/* The same step split in two for autograd-style callers (Transformer.forward in training mode followed by
+ * loss.backward(), train.py:83-85): the forward keeps every activation in `workspace`; the backward consumes
+ * dL/dpred [nseq][64][30] and the SAME workspace contents, and accumulates into grads. */
+int t2s_dit_train_forward(const t2s_dit_params* params, const float* x_t, const float* t100, const float* emb, float* pred,
+                          int nseq, void* workspace, size_t workspace_bytes, t2s_stream_t stream);
+int t2s_dit_train_backward(const t2s_dit_params* params, const t2s_dit_params* grads, const float* dpred, int nseq,
+                           void* workspace, size_t workspace_bytes, t2s_stream_t stream);
+
+/* Training inputs.  kind 0: RectifiedFlow.create_flow (rectified_flow.py:8-12) + target of train.py:71:
+ *   x_t = t x1 + (1 - t) x0, target = x1 - x0, ca = t [batch].
+ * kind 1: DDPM.q_sample (DDPM.py:19-27), target = eps (train.py:74-76): x_t = ca x1 + cb eps with
+ *   ca = sqrt(alpha_bar_t), cb = sqrt(1 - alpha_bar_t) per sample.   x1, noise, x_t, target: [batch][64][30]. */
+int t2s_train_make_inputs(int kind, const float* x1, const float* noise, const float* ca, const float* cb, float* x_t,
+                          float* target, int batch, t2s_stream_t stream);
+
+/* torch.optim.AdamW single step over a flat fp32 buffer (train.py:37: lr 1e-4, betas (0.9, 0.999), eps 1e-8, wd 0):
+ * g is multiplied by grad_scale first (1/world_size after a SUM all-reduce).  step counts from 1. */
+int t2s_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int step, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, float grad_scale, t2s_stream_t stream);
+
+/* The tcgen05 tf32 GEMM every training Linear runs on, exported for unit tests:
+ * C[m][n] (mode 0: =, 1: +=, 2: atomic +=) alpha * sum_k A(m,k) B(n,k) (+ bias[n]);  a_mn / b_mn = 1: the operand is
+ * stored transposed (element (m,k) at k*ld + m). */
+int t2s_gemm_tf32(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
+                  int ldc, int a_mn, int b_mn, int mode, float alpha, int ksplit, t2s_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

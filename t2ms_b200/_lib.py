@@ -16,6 +16,8 @@ EXPORTS = [
     "t2s_version", "t2s_last_error", "t2s_init", "t2s_debug_set_phase_trace", "t2s_dit_workspace_bytes", "t2s_dit_workspace_offsets",
     "t2s_dit_forward", "t2s_sample", "t2s_vae_decode", "t2s_vae_encode",
     "t2s_dit_cond", "t2s_dit_embed_qkv", "t2s_dit_attention", "t2s_dit_block_post", "t2s_dit_final",
+    "t2s_train_workspace_bytes", "t2s_dit_train_step", "t2s_dit_train_forward", "t2s_dit_train_backward",
+    "t2s_train_make_inputs", "t2s_adamw_step", "t2s_gemm_tf32",
 ]
 
 P = C.c_void_p
@@ -25,6 +27,14 @@ class DitWeights(C.Structure):
     _fields_ = [("w_qkv", P * 4), ("w_post", P * 4), ("b_qkv", P * 4), ("b_proj", P * 4), ("b_fc1", P * 4),
                 ("b_fc2", P * 4), ("w_ada_t", P), ("b_ada", P), ("w_embed", P), ("b_embed", P), ("pos", P),
                 ("w_final", P), ("b_final", P), ("freqs", P)]
+
+
+class DitParams(C.Structure):
+    """t2s_dit_params: raw fp32 parameter (or gradient) pointers in the reference state-dict layouts."""
+    _fields_ = [("conv_w", P), ("conv_b", P), ("pe_w", P), ("pe_b", P), ("pos", P), ("ln_w", P), ("ln_b", P),
+                ("lf_w", P), ("lf_b", P), ("freqs", P), ("qkv_w", P * 4), ("qkv_b", P * 4), ("proj_w", P * 4),
+                ("proj_b", P * 4), ("fc1_w", P * 4), ("fc1_b", P * 4), ("fc2_w", P * 4), ("fc2_b", P * 4),
+                ("ada_w", P * 4), ("ada_b", P * 4)]
 
 
 class VaeDecWeights(C.Structure):
@@ -80,6 +90,21 @@ def load() -> C.CDLL:
         lib.t2s_dit_block_post.argtypes = [C.POINTER(DitWeights), i, i, P, P]
         lib.t2s_dit_final.restype = i
         lib.t2s_dit_final.argtypes = [C.POINTER(DitWeights), P, i, P, P]
+        d = C.c_double
+        lib.t2s_train_workspace_bytes.restype = sz
+        lib.t2s_train_workspace_bytes.argtypes = [i]
+        lib.t2s_dit_train_step.restype = i
+        lib.t2s_dit_train_step.argtypes = [C.POINTER(DitParams), C.POINTER(DitParams), P, P, P, P, P, P, i, d, P, sz, P]
+        lib.t2s_dit_train_forward.restype = i
+        lib.t2s_dit_train_forward.argtypes = [C.POINTER(DitParams), P, P, P, P, i, P, sz, P]
+        lib.t2s_dit_train_backward.restype = i
+        lib.t2s_dit_train_backward.argtypes = [C.POINTER(DitParams), C.POINTER(DitParams), P, i, P, sz, P]
+        lib.t2s_train_make_inputs.restype = i
+        lib.t2s_train_make_inputs.argtypes = [i, P, P, P, P, P, P, i, P]
+        lib.t2s_adamw_step.restype = i
+        lib.t2s_adamw_step.argtypes = [P, P, P, P, sz, i, f, f, f, f, f, f, P]
+        lib.t2s_gemm_tf32.restype = i
+        lib.t2s_gemm_tf32.argtypes = [P, P, P, P, i, i, i, i, i, i, i, i, i, f, i, P]
         _lib = lib
         return lib
 

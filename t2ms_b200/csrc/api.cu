@@ -12,25 +12,24 @@ static_assert(sizeof(DitWeights) == sizeof(t2s_dit_weights), "DitWeights must mi
 static_assert(sizeof(VaeDecWeights) == sizeof(t2s_vae_dec_weights), "VaeDecWeights must mirror t2s_vae_dec_weights");
 static_assert(sizeof(VaeEncWeights) == sizeof(t2s_vae_enc_weights), "VaeEncWeights must mirror t2s_vae_enc_weights");
 
-namespace {
+#include "api_common.h"
 
+namespace t2s_api {
 thread_local char g_err[512] = "";
-long long* g_trace = nullptr;   // t2s_debug_set_phase_trace
-
-int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+int fail(int code, const char* fmt, const char* a, const char* b) {
     snprintf(g_err, sizeof(g_err), fmt, a, b);
     return code;
 }
-#define CUDA_OK(expr)                                                                   \
-    do {                                                                                \
-        cudaError_t e_ = (expr);                                                        \
-        if (e_ != cudaSuccess) return fail(T2S_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
-    } while (0)
+}  // namespace t2s_api
+using namespace t2s_api;
 
+namespace {
+long long* g_trace = nullptr;   // t2s_debug_set_phase_trace
 constexpr int MAX_DEV = 64;
 bool g_inited[MAX_DEV] = {};
+}  // namespace
 
-int ensure_init() {
+int t2s_api::ensure_init() {
     int dev = 0;
     CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= MAX_DEV) return fail(T2S_EINVAL, "device index out of range%s%s");
@@ -52,6 +51,8 @@ int ensure_init() {
     g_inited[dev] = true;
     return T2S_OK;
 }
+
+namespace {
 
 size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
@@ -127,12 +128,6 @@ int launch_final(const t2s_dit_weights* w, int nseq, const Workspace& ws, int ou
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
-
-#define TRY(expr)                 \
-    do {                          \
-        int rc_ = (expr);         \
-        if (rc_ != T2S_OK) return rc_; \
-    } while (0)
 
 }  // namespace
 

@@ -1,0 +1,327 @@
+// C ABI of the training step (include/t2s_b200.h: t2s_dit_train_step and friends): host-side orchestration of the
+// modular forward / backward in train_kernels.cuh.  Enqueue-only on the caller's stream; caller-owned workspace.
+#include <cmath>
+#include <cstring>
+
+#include "api_common.h"
+#include "train_kernels.cuh"
+
+using namespace t2s;
+using namespace t2s_api;
+
+namespace {
+
+constexpr int MAX_DEV = 64;
+bool g_train_inited[MAX_DEV] = {};
+int g_sms[MAX_DEV] = {};
+
+int train_init() {
+    TRY(ensure_init());
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    if (g_train_inited[dev]) return T2S_OK;
+    CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));
+    CUDA_OK(cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev));
+    g_train_inited[dev] = true;
+    return T2S_OK;
+}
+int sm_count() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return g_sms[dev] > 0 ? g_sms[dev] : 148;
+}
+
+struct Gemm {
+    GemmArgs a;
+    int batch = 1;
+    Gemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc) {
+        memset(&a, 0, sizeof(a));
+        a.A = A; a.B = B; a.C = C; a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldb = ldb; a.ldc = ldc;
+        a.bdiv = 1; a.ksplit = 1; a.mode = GEMM_STORE; a.alpha = 1.f;
+        a.bn = N <= 32 ? 32 : (N <= 64 ? 64 : (N % 128 != 0 && N % 96 == 0 ? 96 : 128));
+    }
+    Gemm& bias(const float* b) { a.bias = b; return *this; }
+    Gemm& amn() { a.a_mn = 1; return *this; }
+    Gemm& bmn() { a.b_mn = 1; return *this; }
+    Gemm& mode(int m) { a.mode = m; return *this; }
+    Gemm& alpha(float v) { a.alpha = v; return *this; }
+    Gemm& ksplit(int k) { a.ksplit = k < 1 ? 1 : k; return *this; }
+    Gemm& batched(int n, int bdiv, long long sah, long long sal, long long sbh, long long sbl, long long sch, long long scl) {
+        batch = n; a.bdiv = bdiv; a.sa_hi = sah; a.sa_lo = sal; a.sb_hi = sbh; a.sb_lo = sbl; a.sc_hi = sch; a.sc_lo = scl;
+        return *this;
+    }
+    // weight-gradient form: few output tiles, long K -> split K so that about two waves of CTAs run
+    Gemm& wgrad() {
+        const int tiles = ((a.M + G_BM - 1) / G_BM) * ((a.N + a.bn - 1) / a.bn), ksteps = (a.K + G_BK - 1) / G_BK;
+        int ks = (2 * sm_count() + tiles - 1) / tiles;
+        if (ks > ksteps) ks = ksteps;
+        a.ksplit = ks < 1 ? 1 : ks;
+        a.mode = GEMM_ATOMIC;
+        return *this;
+    }
+    int launch(cudaStream_t st) const {
+        if ((a.lda & 3) || (a.ldb & 3) || (!a.a_mn && (a.K & 3)) || (!a.b_mn && (a.K & 3)) || (a.a_mn && (a.M & 3)) || (a.b_mn && (a.N & 3)))
+            return fail(T2S_EINVAL, "gemm_tf32: leading dimensions / extents must be multiples of 4%s%s");
+        if (((uintptr_t)a.A | (uintptr_t)a.B) & 15) return fail(T2S_EINVAL, "gemm_tf32: operands must be 16-byte aligned%s%s");
+        if (a.mode == GEMM_ATOMIC && a.bias != nullptr) return fail(T2S_EINVAL, "gemm_tf32: bias with atomic accumulation%s%s");
+        if (a.ksplit > 1 && a.mode != GEMM_ATOMIC) return fail(T2S_EINVAL, "gemm_tf32: split-K needs atomic accumulation%s%s");
+        dim3 grid((a.M + G_BM - 1) / G_BM, (a.N + a.bn - 1) / a.bn, batch * a.ksplit);
+        gemm_tf32_kernel<<<grid, G_THREADS, G_SMEM_BYTES, st>>>(a);
+        CUDA_OK(cudaGetLastError());
+        return T2S_OK;
+    }
+};
+
+size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+constexpr int ATT_CHUNK = 256;                       // sequences per attention score buffer (1.9 GB for S and dP)
+
+struct TrainWs {
+    float *sc, *mod, *dmod, *xp, *wemb, *bemb, *red;
+    float* h[NLAYER + 1];
+    float *a1[NLAYER], *qkv[NLAYER], *o[NLAYER], *y1[NLAYER], *hm[NLAYER], *a2[NLAYER], *z1[NLAYER], *hid[NLAYER], *y2[NLAYER];
+    float *g, *g2, *d1, *d2, *dqkv, *dob, *s, *dp;
+    size_t total;
+};
+TrainWs train_ws(void* base, int nseq) {
+    TrainWs w;
+    char* b = static_cast<char*>(base);
+    size_t p = 0;
+    const size_t T = (size_t)nseq * NTOK;
+    auto take = [&](size_t floats) { float* r = reinterpret_cast<float*>(b + p); p = align256(p + floats * 4); return r; };
+    w.sc = take((size_t)nseq * D); w.mod = take((size_t)nseq * NLAYER * MOD); w.dmod = take((size_t)nseq * NLAYER * MOD);
+    w.xp = take(T * 4); w.wemb = take(D * 4); w.bemb = take(D); w.red = take(D * 5);
+    for (int l = 0; l <= NLAYER; ++l) w.h[l] = take(T * D);
+    for (int l = 0; l < NLAYER; ++l) {
+        w.a1[l] = take(T * D); w.qkv[l] = take(T * 3 * D); w.o[l] = take(T * D); w.y1[l] = take(T * D); w.hm[l] = take(T * D);
+        w.a2[l] = take(T * D); w.z1[l] = take(T * DMLP); w.hid[l] = take(T * DMLP); w.y2[l] = take(T * D);
+    }
+    w.g = take(T * D); w.g2 = take(T * D); w.d1 = take(T * D); w.d2 = take(T * DMLP); w.dqkv = take(T * 3 * D); w.dob = take(T * D);
+    const size_t ch = (size_t)(nseq < ATT_CHUNK ? nseq : ATT_CHUNK) * NHEAD * NTOK * NTOK;
+    w.s = take(ch); w.dp = take(ch);
+    w.total = p;
+    return w;
+}
+
+const float kScale = 0.17677669529663687f;           // 1 / sqrt(32)
+const float kScaleLog2e = 0.25503486f;               // log2(e) / sqrt(32)
+
+// S = Q K^T and P = softmax(S / sqrt(32)) for sequences [c0, c0 + nb) of one block (timm Attention -> SDPA)
+int attn_probs(const float* qkv, float* s, int c0, int nb, cudaStream_t st) {
+    const float* q = qkv + (size_t)c0 * NTOK * 3 * D;
+    TRY(Gemm(q, q + D, s, NTOK, NTOK, HD, 3 * D, 3 * D, NTOK)
+            .batched(nb * NHEAD, NHEAD, (long long)NTOK * 3 * D, HD, (long long)NTOK * 3 * D, HD, (long long)NHEAD * NTOK * NTOK, (long long)NTOK * NTOK)
+            .launch(st));
+    const size_t rows = (size_t)nb * NHEAD * NTOK;
+    softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(s, rows, kScaleLog2e);
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+
+int colsum(const float* x, size_t rows, int ld, int cols, float* out, cudaStream_t st) {
+    const int gy = (int)(rows / 64 < 1 ? 1 : (rows / 64 > 592 ? 592 : rows / 64));
+    colsum_kernel<<<dim3((cols + D - 1) / D, gy), 256, 0, st>>>(x, rows, ld, cols, out);
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t t2s_train_workspace_bytes(int nseq) { return train_ws(nullptr, nseq > 0 ? nseq : 0).total; }
+
+int t2s_gemm_tf32(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb, int ldc,
+                  int a_mn, int b_mn, int mode, float alpha, int ksplit, t2s_stream_t stream) {
+    if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return fail(T2S_EINVAL, "t2s_gemm_tf32: bad argument%s%s");
+    TRY(train_init());
+    Gemm g(A, B, C, M, N, K, lda, ldb, ldc);
+    g.bias(bias).mode(mode).alpha(alpha).ksplit(ksplit);
+    if (a_mn) g.amn();
+    if (b_mn) g.bmn();
+    return g.launch((cudaStream_t)stream);
+}
+
+int t2s_train_make_inputs(int kind, const float* x1, const float* noise, const float* ca, const float* cb, float* x_t, float* target,
+                          int batch, t2s_stream_t stream) {
+    if (!x1 || !noise || !ca || !x_t || !target || batch <= 0 || (kind != 0 && kind != 1) || (kind == 1 && !cb))
+        return fail(T2S_EINVAL, "t2s_train_make_inputs: bad argument%s%s");
+    TRY(train_init());
+    const size_t n = (size_t)batch * LAT;
+    make_train_inputs_kernel<<<(unsigned)((n + 255) / 256 > 4736 ? 4736 : (n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, x1, noise, ca, cb, x_t, target, n);
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+
+int t2s_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int step, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float grad_scale, t2s_stream_t stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq || n == 0 || step < 1) return fail(T2S_EINVAL, "t2s_adamw_step: bad argument%s%s");
+    TRY(train_init());
+    const float bc1 = (float)(1.0 - std::pow((double)beta1, step)), bc2s = (float)std::sqrt(1.0 - std::pow((double)beta2, step));
+    adamw_kernel<<<(unsigned)((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale);
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+
+}  // extern "C"
+
+namespace {
+struct Dims {
+    int nseq, T, MS; dim3 rgrid; size_t n256; unsigned egrid;
+    explicit Dims(int n) : nseq(n), T(n * NTOK), MS(NLAYER * MOD), rgrid(n, NTOK / ROW_CHUNK), n256((size_t)n * NTOK * DMLP / 4) {
+        egrid = (unsigned)((n256 + 255) / 256 > 4736 ? 4736 : (n256 + 255) / 256);
+    }
+};
+
+int train_forward(const t2s_dit_params* P, const float* x_t, const float* t100, const float* emb, const TrainWs& w, const Dims& d, cudaStream_t st) {
+    const int nseq = d.nseq, T = d.T, MS = d.MS;
+    const dim3 rgrid = d.rgrid;
+    const size_t n256 = d.n256;
+    const unsigned egrid = d.egrid;
+    // ------------------------------------------------------------------ forward (transformer.py:158-193)
+    embed_fold_kernel<<<1, D, 0, st>>>(P->pe_w, P->pe_b, P->conv_w, P->conv_b, w.wemb, w.bemb);
+    cond_act_kernel<<<(nseq * D + 255) / 256, 256, 0, st>>>(w.sc, t100, emb, P->freqs, nseq);
+    CUDA_OK(cudaGetLastError());
+    for (int l = 0; l < NLAYER; ++l)                                      // adaLN_modulation (:106-109,115)
+        TRY(Gemm(w.sc, P->ada_w[l], w.mod + l * MOD, nseq, MOD, D, D, D, MS).bias(P->ada_b[l]).launch(st));
+    embed_fwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(x_t, w.wemb, w.bemb, P->pos, w.h[0], w.xp, nseq);
+    CUDA_OK(cudaGetLastError());
+    for (int l = 0; l < NLAYER; ++l) {
+        const int mo = l * MOD;
+        ln_mod_fwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(w.h[l], w.mod, MS, mo, w.a1[l], 1e-6f);
+        TRY(Gemm(w.a1[l], P->qkv_w[l], w.qkv[l], T, 3 * D, D, D, D, 3 * D).bias(P->qkv_b[l]).launch(st));
+        for (int c0 = 0; c0 < nseq; c0 += ATT_CHUNK) {
+            const int nb = nseq - c0 < ATT_CHUNK ? nseq - c0 : ATT_CHUNK;
+            TRY(attn_probs(w.qkv[l], w.s, c0, nb, st));
+            const float* v = w.qkv[l] + (size_t)c0 * NTOK * 3 * D + 2 * D;
+            TRY(Gemm(w.s, v, w.o[l] + (size_t)c0 * NTOK * D, NTOK, HD, NTOK, NTOK, 3 * D, D).bmn()
+                    .batched(nb * NHEAD, NHEAD, (long long)NHEAD * NTOK * NTOK, (long long)NTOK * NTOK, (long long)NTOK * 3 * D, HD, (long long)NTOK * D, HD)
+                    .launch(st));
+        }
+        TRY(Gemm(w.o[l], P->proj_w[l], w.y1[l], T, D, D, D, D, D).bias(P->proj_b[l]).launch(st));
+        gate_res_fwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(w.h[l], w.y1[l], w.mod, MS, mo + 2 * D, w.hm[l]);
+        ln_mod_fwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(w.hm[l], w.mod, MS, mo + 3 * D, w.a2[l], 1e-6f);
+        TRY(Gemm(w.a2[l], P->fc1_w[l], w.z1[l], T, DMLP, D, D, D, DMLP).bias(P->fc1_b[l]).launch(st));
+        gelu_fwd_kernel<<<egrid, 256, 0, st>>>(w.z1[l], w.hid[l], n256);
+        TRY(Gemm(w.hid[l], P->fc2_w[l], w.y2[l], T, D, DMLP, DMLP, DMLP, D).bias(P->fc2_b[l]).launch(st));
+        gate_res_fwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(w.hm[l], w.y2[l], w.mod, MS, mo + 5 * D, w.h[l + 1]);
+        CUDA_OK(cudaGetLastError());
+    }
+    return T2S_OK;
+}
+
+int train_backward(const t2s_dit_params* P, const t2s_dit_params* Gp, const TrainWs& w, const Dims& d, cudaStream_t st) {
+    const int nseq = d.nseq, T = d.T, MS = d.MS;
+    const dim3 rgrid = d.rgrid;
+    const size_t n256 = d.n256;
+    const unsigned egrid = d.egrid;
+    // ------------------------------------------------------------------ backward
+    CUDA_OK(cudaMemsetAsync(w.dmod, 0, (size_t)nseq * MS * 4, st));
+    for (int l = NLAYER - 1; l >= 0; --l) {
+        const int mo = l * MOD;
+        // MLP branch: h' = hm + gate_mlp * fc2(GELU(fc1(a2)))
+        gate_res_bwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(w.g, w.y2[l], w.mod, w.dmod, MS, mo + 5 * D, w.d1, Gp->fc2_b[l]);
+        TRY(Gemm(w.d1, w.hid[l], Gp->fc2_w[l], D, DMLP, T, D, DMLP, DMLP).amn().bmn().wgrad().launch(st));
+        TRY(Gemm(w.d1, P->fc2_w[l], w.d2, T, DMLP, D, D, DMLP, DMLP).bmn().launch(st));
+        gelu_bwd_kernel<<<egrid, 256, 0, st>>>(w.z1[l], w.d2, n256);
+        TRY(colsum(w.d2, T, DMLP, DMLP, Gp->fc1_b[l], st));
+        TRY(Gemm(w.d2, w.a2[l], Gp->fc1_w[l], DMLP, D, T, DMLP, D, D).amn().bmn().wgrad().launch(st));
+        TRY(Gemm(w.d2, P->fc1_w[l], w.d1, T, D, DMLP, DMLP, D, D).bmn().launch(st));
+        ln_mod_bwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(w.d1, w.hm[l], w.mod, w.dmod, MS, mo + 3 * D, w.g, w.g2, 1e-6f);
+        // attention branch: hm = h + gate_msa * proj(attn(a1))
+        gate_res_bwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(w.g2, w.y1[l], w.mod, w.dmod, MS, mo + 2 * D, w.d1, Gp->proj_b[l]);
+        TRY(Gemm(w.d1, w.o[l], Gp->proj_w[l], D, D, T, D, D, D).amn().bmn().wgrad().launch(st));
+        TRY(Gemm(w.d1, P->proj_w[l], w.dob, T, D, D, D, D, D).bmn().launch(st));
+        CUDA_OK(cudaGetLastError());
+        for (int c0 = 0; c0 < nseq; c0 += ATT_CHUNK) {
+            const int nb = nseq - c0 < ATT_CHUNK ? nseq - c0 : ATT_CHUNK, nbh = nb * NHEAD;
+            const long long SQ = (long long)NTOK * NTOK, SH = (long long)NHEAD * SQ, RQ = (long long)NTOK * 3 * D, RO = (long long)NTOK * D;
+            TRY(attn_probs(w.qkv[l], w.s, c0, nb, st));
+            const float* q = w.qkv[l] + (size_t)c0 * RQ;
+            const float* dO = w.dob + (size_t)c0 * RO;
+            float* dq = w.dqkv + (size_t)c0 * RQ;
+            // dP = dO V^T ; dS = P * (dP - rowsum(P dP)) / sqrt(32)
+            TRY(Gemm(dO, q + 2 * D, w.dp, NTOK, NTOK, HD, D, 3 * D, NTOK).batched(nbh, NHEAD, RO, HD, RQ, HD, SH, SQ).launch(st));
+            const size_t rows = (size_t)nbh * NTOK;
+            softmax_bwd_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w.s, w.dp, rows, kScale);
+            CUDA_OK(cudaGetLastError());
+            // dV = P^T dO ; dQ = dS K ; dK = dS^T Q
+            TRY(Gemm(w.s, dO, dq + 2 * D, NTOK, HD, NTOK, NTOK, D, 3 * D).amn().bmn().batched(nbh, NHEAD, SH, SQ, RO, HD, RQ, HD).launch(st));
+            TRY(Gemm(w.dp, q + D, dq, NTOK, HD, NTOK, NTOK, 3 * D, 3 * D).bmn().batched(nbh, NHEAD, SH, SQ, RQ, HD, RQ, HD).launch(st));
+            TRY(Gemm(w.dp, q, dq + D, NTOK, HD, NTOK, NTOK, 3 * D, 3 * D).amn().bmn().batched(nbh, NHEAD, SH, SQ, RQ, HD, RQ, HD).launch(st));
+        }
+        TRY(colsum(w.dqkv, T, 3 * D, 3 * D, Gp->qkv_b[l], st));
+        TRY(Gemm(w.dqkv, w.a1[l], Gp->qkv_w[l], 3 * D, D, T, 3 * D, D, D).amn().bmn().wgrad().launch(st));
+        TRY(Gemm(w.dqkv, P->qkv_w[l], w.d1, T, D, 3 * D, 3 * D, D, D).bmn().launch(st));
+        ln_mod_bwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(w.d1, w.h[l], w.mod, w.dmod, MS, mo, w.g2, w.g, 1e-6f);
+        CUDA_OK(cudaGetLastError());
+    }
+    // patch embedding (transformer.py:166-172)
+    CUDA_OK(cudaMemsetAsync(w.red, 0, D * 5 * 4, st));
+    embed_bwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(w.g, w.xp, w.red);
+    embed_bwd_finish_kernel<<<1, D, 0, st>>>(w.red, P->pe_w, P->conv_w, P->conv_b, Gp->pe_w, Gp->pe_b, Gp->conv_w, Gp->conv_b);
+    CUDA_OK(cudaGetLastError());
+    // adaLN Linear: mod_l = SiLU(c) W_l^T + b_l  (c = time embedding + text has no trainable ancestors)
+    for (int l = 0; l < NLAYER; ++l) {
+        TRY(Gemm(w.dmod + l * MOD, w.sc, Gp->ada_w[l], MOD, D, nseq, MS, D, D).amn().bmn().wgrad().launch(st));
+        TRY(colsum(w.dmod + l * MOD, nseq, MS, MOD, Gp->ada_b[l], st));
+    }
+    return T2S_OK;
+}
+
+int check_train_args(const void* workspace, size_t workspace_bytes, int nseq) {
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(T2S_EINVAL, "workspace must be 256-byte aligned%s%s");
+    if (workspace_bytes < t2s_train_workspace_bytes(nseq)) return fail(T2S_EWORKSPACE, "training workspace too small%s%s");
+    return train_init();
+}
+}  // namespace
+
+extern "C" {
+
+int t2s_dit_train_step(const t2s_dit_params* P, const t2s_dit_params* Gp, const float* x_t, const float* t100, const float* emb,
+                       const float* target, float* loss_sum, float* pred, int nseq, double loss_numel, void* workspace,
+                       size_t workspace_bytes, t2s_stream_t stream) {
+    if (!P || !x_t || !t100 || nseq <= 0 || !workspace) return fail(T2S_EINVAL, "t2s_dit_train_step: bad argument%s%s");
+    if (Gp != nullptr && (!target || !loss_sum || !(loss_numel > 0))) return fail(T2S_EINVAL, "t2s_dit_train_step: backward needs target / loss_sum / loss_numel%s%s");
+    if (target != nullptr && loss_sum == nullptr) return fail(T2S_EINVAL, "t2s_dit_train_step: target without loss_sum%s%s");
+    TRY(check_train_args(workspace, workspace_bytes, nseq));
+    cudaStream_t st = (cudaStream_t)stream;
+    const TrainWs w = train_ws(workspace, nseq);
+    const Dims d(nseq);
+    TRY(train_forward(P, x_t, t100, emb, w, d, st));
+    const bool bwd = Gp != nullptr;
+    final_kernel<<<d.rgrid, ROW_THREADS, 0, st>>>(w.h[NLAYER], P->ln_w, P->ln_b, P->lf_w, P->lf_b, pred, target, nullptr,
+                                                  bwd ? (float)(2.0 / loss_numel) : 0.f, loss_sum, bwd ? w.g : nullptr,
+                                                  bwd ? Gp->ln_w : nullptr, bwd ? Gp->ln_b : nullptr, bwd ? Gp->lf_w : nullptr, bwd ? Gp->lf_b : nullptr);
+    CUDA_OK(cudaGetLastError());
+    return bwd ? train_backward(P, Gp, w, d, st) : T2S_OK;
+}
+
+int t2s_dit_train_forward(const t2s_dit_params* P, const float* x_t, const float* t100, const float* emb, float* pred, int nseq,
+                          void* workspace, size_t workspace_bytes, t2s_stream_t stream) {
+    if (!P || !x_t || !t100 || !pred || nseq <= 0 || !workspace) return fail(T2S_EINVAL, "t2s_dit_train_forward: bad argument%s%s");
+    TRY(check_train_args(workspace, workspace_bytes, nseq));
+    cudaStream_t st = (cudaStream_t)stream;
+    const TrainWs w = train_ws(workspace, nseq);
+    const Dims d(nseq);
+    TRY(train_forward(P, x_t, t100, emb, w, d, st));
+    final_kernel<<<d.rgrid, ROW_THREADS, 0, st>>>(w.h[NLAYER], P->ln_w, P->ln_b, P->lf_w, P->lf_b, pred, nullptr, nullptr, 0.f, nullptr,
+                                                  nullptr, nullptr, nullptr, nullptr, nullptr);
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+
+int t2s_dit_train_backward(const t2s_dit_params* P, const t2s_dit_params* Gp, const float* dpred, int nseq, void* workspace,
+                           size_t workspace_bytes, t2s_stream_t stream) {
+    if (!P || !Gp || !dpred || nseq <= 0 || !workspace) return fail(T2S_EINVAL, "t2s_dit_train_backward: bad argument%s%s");
+    TRY(check_train_args(workspace, workspace_bytes, nseq));
+    cudaStream_t st = (cudaStream_t)stream;
+    const TrainWs w = train_ws(workspace, nseq);
+    const Dims d(nseq);
+    final_kernel<<<d.rgrid, ROW_THREADS, 0, st>>>(w.h[NLAYER], P->ln_w, P->ln_b, P->lf_w, P->lf_b, nullptr, nullptr, dpred, 0.f, nullptr,
+                                                  w.g, Gp->ln_w, Gp->ln_b, Gp->lf_w, Gp->lf_b);
+    CUDA_OK(cudaGetLastError());
+    return train_backward(P, Gp, w, d, st);
+}
+
+}  // extern "C"

@@ -1,8 +1,268 @@
-"""Training step of the DiT (train.py:66-87).  Placeholder until the backward kernels land."""
+"""Training step of the T2S-DiT (train.py:66-87) on the sm_100a kernels.
+
+Two ways in, both ending in the same C-ABI calls (include/t2s_b200.h, "Training step"):
+
+* drop-in: ``Transformer.forward`` in training mode returns a tensor with a ``grad_fn``
+  (``dit_forward_autograd``), so the reference loop ``pred = model(x_t, t, emb); loss = mse(pred, target);
+  loss.backward(); optimizer.step()`` (train.py:83-87) runs unchanged; the forward is
+  ``t2s_dit_train_forward`` and ``loss.backward()`` lands in ``t2s_dit_train_backward``;
+* fused: ``DitTrainer.step`` enqueues create_flow / q_sample, forward, MSE, backward, the data-parallel
+  gradient all-reduce (NCCL, one flat 3.7 MB bucket) and AdamW without any host synchronisation.
+
+There is no PyTorch fallback: the backward is the hand-written kernel chain, CPU tensors raise.
+"""
 from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+N_LAYER = 4
+_TOP = {"conv.weight": "conv_w", "conv.bias": "conv_b", "patch_emb.weight": "pe_w", "patch_emb.bias": "pe_b",
+        "ln.weight": "ln_w", "ln.bias": "ln_b", "linear_emb_to_patch.weight": "lf_w", "linear_emb_to_patch.bias": "lf_b"}
+_LAYER = {"attn.qkv.weight": "qkv_w", "attn.qkv.bias": "qkv_b", "attn.proj.weight": "proj_w", "attn.proj.bias": "proj_b",
+          "mlp.fc1.weight": "fc1_w", "mlp.fc1.bias": "fc1_b", "mlp.fc2.weight": "fc2_w", "mlp.fc2.bias": "fc2_b",
+          "adaLN_modulation.1.weight": "ada_w", "adaLN_modulation.1.bias": "ada_b"}
+
+
+def trainable_names() -> List[str]:
+    """The 48 parameters that receive a gradient: everything except the fixed ``pos_embed``, the
+    unused ``unpatch.*`` head (transformer.py:150) and the attached frozen ``encoder.*`` (train.py:31-33)."""
+    names = list(_TOP)
+    for l in range(N_LAYER):
+        names += [f"layers.{l}.{k}" for k in _LAYER]
+    return names
+
+
+def _struct(tensors: Dict[str, torch.Tensor], pos: Optional[torch.Tensor], freqs: Optional[torch.Tensor]) -> _lib.DitParams:
+    st = _lib.DitParams()
+    for name, field in _TOP.items():
+        setattr(st, field, tensors[name].data_ptr())
+    for l in range(N_LAYER):
+        for k, field in _LAYER.items():
+            getattr(st, field)[l] = tensors[f"layers.{l}.{k}"].data_ptr()
+    st.pos = pos.data_ptr() if pos is not None else None
+    st.freqs = freqs.data_ptr() if freqs is not None else None
+    return st
+
+
+def _freqs(device) -> torch.Tensor:
+    return torch.pow(10000, torch.linspace(0, 1, 64)).to(device=device, dtype=torch.float32).contiguous()   # transformer.py:34
+
+
+def _aligned_ptr(buf: torch.Tensor) -> int:
+    return (buf.data_ptr() + 255) & ~255
+
+
+class _Workspace:
+    def __init__(self):
+        self.buf = None
+        self.nseq = 0
+
+    def get(self, nseq: int, device) -> Tuple[int, int]:
+        lib = _lib.load()
+        nbytes = lib.t2s_train_workspace_bytes(nseq)
+        if self.buf is None or self.nseq < nseq or self.buf.device != device:
+            self.buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+            self.nseq = nseq
+        return _aligned_ptr(self.buf), nbytes
+
+
+class FlatBuffer:
+    """One contiguous fp32 buffer holding every trainable tensor at a 256-byte aligned offset."""
+
+    def __init__(self, shapes: Dict[str, torch.Size], device):
+        self.offsets, off = {}, 0
+        for n, s in shapes.items():
+            self.offsets[n] = (off, s)
+            off += (s.numel() + 63) // 64 * 64
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+
+    def view(self, name: str) -> torch.Tensor:
+        off, s = self.offsets[name]
+        return self.flat[off:off + s.numel()].view(s)
+
+    def views(self) -> Dict[str, torch.Tensor]:
+        return {n: self.view(n) for n in self.offsets}
+
+
+def _own_trainable(model) -> Dict[str, torch.nn.Parameter]:
+    named = dict(model.named_parameters())
+    return {n: named[n] for n in trainable_names()}
+
+
+def _prep_inputs(x, t, text):
+    if not x.is_cuda:
+        raise RuntimeError("t2ms_b200 training needs CUDA tensors (no CPU / PyTorch fallback)")
+    B = x.shape[0]
+    assert tuple(x.shape[1:]) == (64, 30), f"latent must be (B,64,30), got {tuple(x.shape)}"
+    x = x.detach().to(torch.float32).contiguous()
+    t100 = (t.detach() * 100.0).to(device=x.device, dtype=torch.float32).contiguous()       # transformer.py:31
+    assert t100.shape == (B,)
+    if text is not None:
+        text = text.detach().to(device=x.device, dtype=torch.float32).contiguous()
+        assert tuple(text.shape) == (B, 128)
+    return x, t100, text
+
+
+class _DitFunction(torch.autograd.Function):
+    """pred = Transformer.forward(x_t, t, text) with the hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, model, x, t100, text, *params):
+        lib = _lib.load()
+        names = trainable_names()
+        tensors = {n: p.detach() for n, p in zip(names, params)}
+        for n, p in tensors.items():
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                raise RuntimeError(f"parameter {n} must be a contiguous fp32 CUDA tensor")
+        dev = x.device
+        st = _struct(tensors, model.pos_embed.detach(), model._train_freqs(dev))
+        ws = model._train_ws
+        ptr, nbytes = ws.get(x.shape[0], dev)
+        pred = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            rc = lib.t2s_dit_train_forward(C.byref(st), x.data_ptr(), t100.data_ptr(), text.data_ptr() if text is not None else None,
+                                           pred.data_ptr(), x.shape[0], ptr, nbytes, torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "t2s_dit_train_forward")
+        ctx.model, ctx.st, ctx.nseq, ctx.keep = model, st, x.shape[0], (tensors, ws.buf)
+        ctx.shapes = {n: p.shape for n, p in tensors.items()}
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        lib = _lib.load()
+        model = ctx.model
+        if ctx.keep[1] is not model._train_ws.buf:
+            raise RuntimeError("the training workspace was reused by another forward before backward() ran")
+        dev = dpred.device
+        gbuf = FlatBuffer(ctx.shapes, dev)
+        gst = _struct(gbuf.views(), None, None)
+        dpred = dpred.to(torch.float32).contiguous()
+        ptr, nbytes = model._train_ws.get(ctx.nseq, dev)
+        with torch.cuda.device(dev):
+            rc = lib.t2s_dit_train_backward(C.byref(ctx.st), C.byref(gst), dpred.data_ptr(), ctx.nseq, ptr, nbytes,
+                                            torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "t2s_dit_train_backward")
+        return (None, None, None, None, *[gbuf.view(n) for n in trainable_names()])
 
 
 def dit_forward_autograd(model, x, t, text):
-    raise NotImplementedError(
-        "t2ms_b200: the DiT backward kernels are not built yet; call the model under torch.no_grad() / .eval() "
-        "for generation (there is deliberately no PyTorch fallback)")
+    """Transformer.forward in training mode (called from t2ms_b200.denoiser.Transformer.forward)."""
+    x, t100, text = _prep_inputs(x, t, text)
+    if not hasattr(model, "_train_ws"):
+        model._train_ws = _Workspace()
+        fcache = {}
+        model._train_freqs = lambda dev: fcache.setdefault(str(dev), _freqs(dev))
+    params = [p for p in _own_trainable(model).values()]
+    return _DitFunction.apply(model, x, t100, text, *params)
+
+
+class DitTrainer:
+    """Fused training step: forward + MSE + backward + (data-parallel all-reduce) + AdamW, all enqueued on the
+    current stream.  Mirrors train.py:37 (AdamW lr 1e-4, weight_decay 0) and train.py:66-87.
+
+    The trainable parameters are re-homed into one flat fp32 buffer (the module's ``nn.Parameter`` objects become
+    views of it, state-dict names and shapes unchanged) so that the optimizer and the gradient all-reduce are one
+    kernel / one collective over 3.7 MB.
+    """
+
+    def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, group=None):
+        params = _own_trainable(model)
+        dev = next(iter(params.values())).device
+        if dev.type != "cuda":
+            raise RuntimeError("DitTrainer needs the model on a CUDA device (no CPU fallback)")
+        self.model, self.device, self.group = model, dev, group
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        shapes = {n: p.shape for n, p in params.items()}
+        self.params, self.grads = FlatBuffer(shapes, dev), FlatBuffer(shapes, dev)
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.params.flat), torch.zeros_like(self.params.flat)
+        with torch.no_grad():
+            for n, p in params.items():
+                v = self.params.view(n)
+                v.copy_(p.data)
+                p.data = v
+                p.grad = self.grads.view(n)
+        self._pst = _struct(self.params.views(), model.pos_embed.detach(), _freqs(dev))
+        self._gst = _struct(self.grads.views(), None, None)
+        self._keep = _freqs(dev)
+        self._pst.freqs = self._keep.data_ptr()
+        self.ws = _Workspace()
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.step_count = 0
+
+    # ------------------------------------------------------------------ pieces
+    def zero_grad(self):
+        self.grads.flat.zero_()
+        self.loss_sum.zero_()
+
+    def forward_backward(self, x_t, t, emb, target, loss_numel: Optional[float] = None, backward: bool = True, pred=None):
+        """Accumulates dL/dparam into ``self.grads`` and sum((pred-target)^2) into ``self.loss_sum``."""
+        lib = _lib.load()
+        x_t, t100, emb = _prep_inputs(x_t, t, emb)
+        target = target.detach().to(torch.float32).contiguous()
+        B = x_t.shape[0]
+        numel = float(loss_numel if loss_numel is not None else B * 1920)
+        ptr, nbytes = self.ws.get(B, self.device)
+        with torch.cuda.device(self.device):
+            rc = lib.t2s_dit_train_step(C.byref(self._pst), C.byref(self._gst) if backward else None, x_t.data_ptr(), t100.data_ptr(),
+                                        emb.data_ptr() if emb is not None else None, target.data_ptr(), self.loss_sum.data_ptr(),
+                                        pred.data_ptr() if pred is not None else None, B, numel, ptr, nbytes,
+                                        torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "t2s_dit_train_step")
+
+    def allreduce_grads(self):
+        """Data-parallel exchange: one SUM all-reduce of the flat gradient bucket (+ the loss sum)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.loss_sum, op=dist.ReduceOp.SUM, group=self.group)
+
+    def optimizer_step(self, lr: Optional[float] = None, grad_scale: float = 1.0):
+        lib = _lib.load()
+        self.step_count += 1
+        with torch.cuda.device(self.device):
+            rc = lib.t2s_adamw_step(self.params.flat.data_ptr(), self.grads.flat.data_ptr(), self.exp_avg.data_ptr(),
+                                    self.exp_avg_sq.data_ptr(), self.params.flat.numel(), self.step_count,
+                                    float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                    float(grad_scale), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "t2s_adamw_step")
+        self.model._packed = None                     # inference weight images are stale now
+
+    # ------------------------------------------------------------------ inputs (train.py:68-76)
+    def make_inputs(self, backbone: str, x1, noise, t, ddpm=None):
+        """RF: x_t = t x1 + (1-t) x0, target = x1 - x0 (rectified_flow.py:8-12, train.py:71);
+        DDPM: x_t = sqrt(ab_t) x1 + sqrt(1-ab_t) eps, target = eps (DDPM.py:19-27)."""
+        lib = _lib.load()
+        x1 = x1.detach().to(torch.float32).contiguous()
+        noise = noise.detach().to(torch.float32).contiguous()
+        xt, target = torch.empty_like(x1), torch.empty_like(x1)
+        if backbone in ("flowmatching", "rf", "rectified_flow"):
+            kind, ca, cb = 0, t.detach().to(device=x1.device, dtype=torch.float32).contiguous(), None
+        else:
+            ab = ddpm.alpha_bar.to(x1.device).gather(-1, t.to(x1.device))
+            kind, ca, cb = 1, (ab ** 0.5).contiguous(), ((1 - ab) ** 0.5).contiguous()
+        with torch.cuda.device(x1.device):
+            rc = lib.t2s_train_make_inputs(kind, x1.data_ptr(), noise.data_ptr(), ca.data_ptr(), cb.data_ptr() if cb is not None else None,
+                                           xt.data_ptr(), target.data_ptr(), x1.shape[0], torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "t2s_train_make_inputs")
+        return xt, target
+
+    # ------------------------------------------------------------------ one optimizer step
+    def step(self, x_t, t, emb, target, lr: Optional[float] = None, micro_batch: Optional[int] = None) -> torch.Tensor:
+        """One optimizer step on (x_t, t, emb | None, target); returns the (global) loss as a device scalar."""
+        import torch.distributed as dist
+        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        B = x_t.shape[0]
+        numel = float(B * 1920 * world)                                  # global mean (equal shards)
+        self.zero_grad()
+        mb = B if not micro_batch else min(int(micro_batch), B)
+        for b0 in range(0, B, mb):
+            sl = slice(b0, min(B, b0 + mb))
+            self.forward_backward(x_t[sl], t[sl], emb[sl] if emb is not None else None, target[sl], loss_numel=numel)
+        self.allreduce_grads()
+        self.optimizer_step(lr)
+        return self.loss_sum[0] / numel
