@@ -67,6 +67,9 @@ __device__ __forceinline__ float round_tf32(float x) {
     return __uint_as_float(u);
 }
 
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
 __global__ void __launch_bounds__(G_THREADS, 2) gemm_tf32_kernel(const GemmArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_slot;
@@ -102,10 +105,10 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_tf32_kernel(const GemmArgs 
         auto load_stage = [&](int it) {
             const int s = it % G_STAGES, k0 = (k_begin + it) * G_BK;
             const uint32_t sa = sb + s * G_STAGE_BYTES, sbb = sa + G_BM * G_BK * 4;
-            if (!p.a_mn) {                                   // [k/4][row][4]: lanes = consecutive rows
+            if (!p.a_mn) {                                   // [k/4][row][4]: 8 lanes read one row's 128 contiguous bytes
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int c = j * 128 + tid, row = c & 127, kc = c >> 7;
+                    const int c = j * 128 + tid, kc = c & 7, row = c >> 3;
                     const int gm = m0 + row, gk = k0 + kc * 4;
                     const bool ok = gm < p.M && gk < p.K;
                     cp_async16_zfill(sa + kc * 2048 + row * 16, ok ? A + (long long)gm * p.lda + gk : A, ok ? 16u : 0u);
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_tf32_kernel(const GemmArgs 
             const int nchunk = bn * 8;
             if (!p.b_mn) {
                 for (int c = tid; c < nchunk; c += 128) {
-                    const int row = c % bn, kc = c / bn;
+                    const int kc = c & 7, row = c >> 3;
                     const int gn = n0 + row, gk = k0 + kc * 4;
                     const bool ok = gn < p.N && gk < p.K;
                     cp_async16_zfill(sbb + kc * (bn * 16) + row * 16, ok ? B + (long long)gn * p.ldb + gk : B, ok ? 16u : 0u);
@@ -154,42 +157,50 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_tf32_kernel(const GemmArgs 
         cp_async_wait<0>();
         publish(nk - 1);
 
-        // ------------------------------------------------------------------ epilogue: thread = accumulator row
+        // ------------------------------------------------------------------ epilogue
+        // thread = accumulator row (TMEM lane): rows are staged in this warp's slice of the (now idle) operand
+        // stages and written out row by row, a lane owning 4 consecutive columns (coalesced 16-byte accesses)
         mbar_wait(ACC, 0);
         tc_fence_after();
-        const int gm = m0 + tid;
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-        float* crow = C + (long long)gm * p.ldc;
-        const bool vec_ok = (p.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        const int pitch = bn + 4;                                          // floats; +4 keeps the float4 stores conflict-free
+        float* stg = reinterpret_cast<float*>(smem) + warp * 32 * (G_BM + 4);
 #pragma unroll 1
         for (int cb = 0; cb < bn / 16; ++cb) {
             float v[16];
             tmem_ld16(trow + cb * 16, v);
             tmem_wait_ld();
-            if (gm < p.M) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int gn = n0 + cb * 16 + q * 4;
-                    float r[4];
+            for (int q = 0; q < 4; ++q) st4(stg + lane * pitch + cb * 16 + q * 4, make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]));
+        }
+        __syncwarp();
+        const int lpr = bn >> 2;                                           // lanes per row
+        const int rpi = 32 / lpr > 0 ? 32 / lpr : 1;                       // rows per warp instruction
+        const int cl = (lane % lpr) * 4, rsub = lane / lpr;
+        const int gn = n0 + cl;
+        const bool lane_ok = lane < lpr * rpi && gn < p.N;
+        const bool vec_ok = (p.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && gn + 3 < p.N;
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.bias != nullptr && lane_ok) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        r[u] = v[q * 4 + u] * p.alpha;
-                        if (p.bias != nullptr && gn + u < p.N) r[u] += p.bias[gn + u];
-                    }
-                    if (p.mode == GEMM_ATOMIC) {
+            for (int u = 0; u < 4; ++u) if (gn + u < p.N) bv[u] = p.bias[gn + u];
+        }
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += rpi) {
+            const int r = r0 + rsub, gm = m0 + warp * 32 + r;
+            if (!lane_ok || gm >= p.M) continue;
+            const float4 a = ld4(stg + r * pitch + cl);
+            float rr[4] = {fmaf(a.x, p.alpha, bv[0]), fmaf(a.y, p.alpha, bv[1]), fmaf(a.z, p.alpha, bv[2]), fmaf(a.w, p.alpha, bv[3])};
+            float* dst = C + (long long)gm * p.ldc + gn;
+            if (p.mode == GEMM_ATOMIC) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (gn + u < p.N) atomicAdd(crow + gn + u, r[u]);
-                    } else if (gn + 3 < p.N && vec_ok) {
-                        float4* dst = reinterpret_cast<float4*>(crow + gn);
-                        if (p.mode == GEMM_ADD) { const float4 o = *dst; r[0] += o.x; r[1] += o.y; r[2] += o.z; r[3] += o.w; }
-                        *dst = make_float4(r[0], r[1], r[2], r[3]);
-                    } else {
+                for (int u = 0; u < 4; ++u) if (gn + u < p.N) atomicAdd(dst + u, rr[u]);
+            } else if (vec_ok) {
+                if (p.mode == GEMM_ADD) { const float4 o = ld4(dst); rr[0] += o.x; rr[1] += o.y; rr[2] += o.z; rr[3] += o.w; }
+                st4(dst, make_float4(rr[0], rr[1], rr[2], rr[3]));
+            } else {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (gn + u < p.N) crow[gn + u] = (p.mode == GEMM_ADD ? crow[gn + u] : 0.f) + r[u];
-                    }
-                }
+                for (int u = 0; u < 4; ++u) if (gn + u < p.N) dst[u] = (p.mode == GEMM_ADD ? dst[u] : 0.f) + rr[u];
             }
         }
     } else {
@@ -230,8 +241,6 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 round4(float4 v) { return make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w)); }
 
 // Row kernels over [T][128] buffers use: grid (nseq, 8), block 256 = 8 warps; a CTA owns 60 tokens of one sequence,

@@ -14,6 +14,7 @@ There is no PyTorch fallback: the backward is the hand-written kernel chain, CPU
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -49,8 +50,14 @@ def _struct(tensors: Dict[str, torch.Tensor], pos: Optional[torch.Tensor], freqs
     return st
 
 
+_FREQS: Dict[str, torch.Tensor] = {}
+
+
 def _freqs(device) -> torch.Tensor:
-    return torch.pow(10000, torch.linspace(0, 1, 64)).to(device=device, dtype=torch.float32).contiguous()   # transformer.py:34
+    key = str(device)
+    if key not in _FREQS:
+        _FREQS[key] = torch.pow(10000, torch.linspace(0, 1, 64)).to(device=device, dtype=torch.float32).contiguous()   # transformer.py:34
+    return _FREQS[key]
 
 
 def _aligned_ptr(buf: torch.Tensor) -> int:
@@ -69,6 +76,15 @@ class _Workspace:
             self.buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
             self.nseq = nseq
         return _aligned_ptr(self.buf), nbytes
+
+
+_MODULE_WS = weakref.WeakKeyDictionary()
+
+
+def _module_ws(model) -> _Workspace:
+    if model not in _MODULE_WS:
+        _MODULE_WS[model] = _Workspace()
+    return _MODULE_WS[model]
 
 
 class FlatBuffer:
@@ -120,8 +136,8 @@ class _DitFunction(torch.autograd.Function):
             if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
                 raise RuntimeError(f"parameter {n} must be a contiguous fp32 CUDA tensor")
         dev = x.device
-        st = _struct(tensors, model.pos_embed.detach(), model._train_freqs(dev))
-        ws = model._train_ws
+        st = _struct(tensors, model.pos_embed.detach(), _freqs(dev))
+        ws = _module_ws(model)
         ptr, nbytes = ws.get(x.shape[0], dev)
         pred = torch.empty_like(x)
         with torch.cuda.device(dev):
@@ -136,13 +152,13 @@ class _DitFunction(torch.autograd.Function):
     def backward(ctx, dpred):
         lib = _lib.load()
         model = ctx.model
-        if ctx.keep[1] is not model._train_ws.buf:
+        if ctx.keep[1] is not _module_ws(model).buf:
             raise RuntimeError("the training workspace was reused by another forward before backward() ran")
         dev = dpred.device
         gbuf = FlatBuffer(ctx.shapes, dev)
         gst = _struct(gbuf.views(), None, None)
         dpred = dpred.to(torch.float32).contiguous()
-        ptr, nbytes = model._train_ws.get(ctx.nseq, dev)
+        ptr, nbytes = _module_ws(model).get(ctx.nseq, dev)
         with torch.cuda.device(dev):
             rc = lib.t2s_dit_train_backward(C.byref(ctx.st), C.byref(gst), dpred.data_ptr(), ctx.nseq, ptr, nbytes,
                                             torch.cuda.current_stream().cuda_stream)
@@ -153,10 +169,6 @@ class _DitFunction(torch.autograd.Function):
 def dit_forward_autograd(model, x, t, text):
     """Transformer.forward in training mode (called from t2ms_b200.denoiser.Transformer.forward)."""
     x, t100, text = _prep_inputs(x, t, text)
-    if not hasattr(model, "_train_ws"):
-        model._train_ws = _Workspace()
-        fcache = {}
-        model._train_freqs = lambda dev: fcache.setdefault(str(dev), _freqs(dev))
     params = [p for p in _own_trainable(model).values()]
     return _DitFunction.apply(model, x, t100, text, *params)
 
@@ -188,8 +200,6 @@ class DitTrainer:
                 p.grad = self.grads.view(n)
         self._pst = _struct(self.params.views(), model.pos_embed.detach(), _freqs(dev))
         self._gst = _struct(self.grads.views(), None, None)
-        self._keep = _freqs(dev)
-        self._pst.freqs = self._keep.data_ptr()
         self.ws = _Workspace()
         self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_count = 0
@@ -266,3 +276,31 @@ class DitTrainer:
         self.allreduce_grads()
         self.optimizer_step(lr)
         return self.loss_sum[0] / numel
+
+    # ------------------------------------------------------------------ train.py:60-87 for one (sub-)batch
+    def train_batch(self, series, emb, backbone: str = "flowmatching", total_step: int = 100, p_uncond: float = 0.3,
+                    encoder=None, ddpm=None, lr: Optional[float] = None, generator: Optional[torch.Generator] = None,
+                    micro_batch: Optional[int] = None) -> torch.Tensor:
+        """One optimizer step exactly as the reference loop does it for a length-grouped sub-batch:
+        frozen LA-VAE encoder (train.py:66), t / noise draws and create_flow | q_sample (:68-76), the per-BATCH
+        classifier-free-guidance dropout coin (:80-82, shared by all data-parallel ranks), forward, MSE, backward,
+        gradient all-reduce, AdamW (:83-87).  ``series`` (B,L) or an already encoded latent (B,64,30)."""
+        import torch.distributed as dist
+        dev = self.device
+        enc = encoder if encoder is not None else getattr(self.model, "encoder", None)
+        with torch.no_grad():
+            x1 = series if series.dim() == 3 else enc(series.to(dev))[0]
+        B = x1.shape[0]
+        if backbone in ("flowmatching", "rf", "rectified_flow"):
+            t = torch.round(torch.rand(B, device=dev, generator=generator) * total_step) / total_step          # train.py:69
+        else:
+            t = torch.floor(torch.rand(B, device=dev, generator=generator) * total_step).long()               # train.py:73
+        noise = torch.randn(x1.shape, device=dev, generator=generator)
+        x_t, target = self.make_inputs(backbone, x1, noise, t, ddpm)
+        coin = torch.rand(1)                                                                                   # CPU RNG, train.py:80
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            c = coin.to(dev)
+            dist.broadcast(c, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+            coin = c.cpu()
+        text = None if coin.item() < p_uncond else emb
+        return self.step(x_t, t.to(torch.float32) if t.dtype != torch.float32 else t, text, target, lr=lr, micro_batch=micro_batch)
