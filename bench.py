@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--chunk", type=int, default=0, help="samples per launch wave (0 = whole batch)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="series in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=256, help="latents per GPU per optimizer step of the training leg (0 = skip)")
     return ap.parse_args()
 
 
@@ -186,6 +187,54 @@ def kernel_breakdown(smp, dit, vae, a, dev):
     return res, nseq
 
 
+def train_leg(a, dev, rank, world, dist):
+    """BASELINE config 4: DiT + frozen LA-VAE training step on mixed lengths 24/48/96 (train.py:52-90), data-parallel:
+    one optimizer step per length-grouped sub-batch = encoder, create_flow, CFG-drop coin, forward, MSE, backward,
+    NCCL all-reduce of the flat gradient bucket, AdamW.  Returns optimizer steps/s (max over ranks timing)."""
+    from t2ms_b200 import Transformer, synth, vqvae
+    from t2ms_b200.compat import VAE_ARGS
+    from t2ms_b200.training import DitTrainer
+    dit = Transformer()
+    dit.load_state_dict(synth.make_dit_state(0))
+    dit = dit.to(dev).train()
+    vae = vqvae(VAE_ARGS)
+    vae.load_state_dict(synth.make_vae_state(1))
+    vae = vae.to(dev).eval()
+    tr = DitTrainer(dit)
+    B = a.train_batch
+    g = torch.Generator().manual_seed(77 + rank)
+    batches = [(torch.rand(B, L, generator=g).to(dev), torch.nn.functional.normalize(torch.randn(B, 128, generator=g), dim=-1).to(dev))
+               for L in (24, 48, 96)]
+
+    def one_pass():
+        for series, emb in batches:
+            tr.train_batch(series, emb, backbone="flowmatching", total_step=100, encoder=vae.encoder)
+
+    for _ in range(2):
+        one_pass()
+    reps = 3
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        one_pass()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    nsteps = reps * len(batches)
+    sps = nsteps / (ms.item() / 1e3)
+    return {"metric": "t2s_dit_train_steps_per_sec", "value": sps, "unit": "optimizer steps/s", "samples_per_sec": sps * B * world,
+            "ms_per_step": ms.item() / nsteps, "batch_per_gpu": B, "global_batch": B * world, "lengths": [24, 48, 96],
+            "dtype": "tf32 operands / f32 accumulate, fp32 master weights and AdamW state",
+            "workload": "BASELINE config 4: frozen LA-VAE encode + rectified-flow training step, mixed lengths 24/48/96, "
+                        f"data-parallel x{world} (one flat-bucket NCCL all-reduce per step)",
+            "tflops_algorithmic": sps * B * world * 3 * FLOP_FWD / 1e12, "final_loss": float(tr.loss_sum.item() / (B * 1920 * world))}
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -258,6 +307,8 @@ def main():
 
     value = world * B * a.steps / (ms / 1e3)
     e2e = world * B * a.steps / (ms_e2e / 1e3)
+    del flush
+    train = train_leg(a, dev, rank, world, dist) if a.train_batch > 0 else None
     line = None
     if rank == 0:
         pk = peaks()
@@ -288,7 +339,8 @@ def main():
             "kernel_ms": {k: round(v, 4) for k, v in kb.items()},
             "kernel_share_of_step": shares,
         }
-        if not a.no_cpu_baseline:
+        line["train"] = train
+        if not a.no_cpu_baseline and world == 1:       # reported at N=1 only (host cores are shared by the ranks otherwise)
             v, dt, threads = cpu_reference_run(a, a.cpu_sample)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{a.cpu_sample} series x {a.rf_steps} guided steps + decode in {dt:.1f} s, oracle port (torch fp32 CPU)"}

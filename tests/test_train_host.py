@@ -1,0 +1,108 @@
+"""CPU-side checks of the training path: parameter bookkeeping, C-ABI argument validation (no compute without a
+GPU), the no-fallback rule, and the data-parallel gradient convention (world-size-2 gloo, oracle arithmetic)."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from t2ms_b200 import Transformer, _lib, synth
+from t2ms_b200.training import FlatBuffer, trainable_names, _struct
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from t2ms_b200.build import build
+    build()
+    return _lib.load()
+
+
+def test_trainable_names_match_reference_gradients():
+    g = load_golden("train.npz")
+    ref = sorted(str(n).replace("grad_norm/", "") for n in g["names"])      # parameters with a .grad after loss.backward()
+    assert sorted(trainable_names()) == ref and len(ref) == 48
+    m = Transformer()
+    named = dict(m.named_parameters())
+    assert sum(named[n].numel() for n in trainable_names()) == 925_592       # the all-reduce payload
+
+
+def test_flat_buffer_layout_and_param_struct():
+    m = Transformer()
+    shapes = {n: p.shape for n, p in m.named_parameters() if n in set(trainable_names())}
+    fb = FlatBuffer(shapes, "cpu")
+    for n, (off, s) in fb.offsets.items():
+        assert off % 64 == 0 and fb.view(n).shape == s
+    assert fb.flat.numel() >= 925_592
+    st = _struct(fb.views(), None, None)
+    assert ctypes.sizeof(_lib.DitParams) == (10 + 10 * 4) * 8
+    assert st.qkv_w[3] == fb.view("layers.3.attn.qkv.weight").data_ptr() and st.lf_b == fb.view("linear_emb_to_patch.bias").data_ptr()
+
+
+def test_training_entry_points_validate_arguments(lib):
+    assert lib.t2s_dit_train_step(None, None, None, None, None, None, None, None, 0, 1.0, None, 0, None) == -1
+    assert b"bad argument" in lib.t2s_last_error()
+    assert lib.t2s_dit_train_forward(None, None, None, None, None, 1, None, 0, None) == -1
+    assert lib.t2s_dit_train_backward(None, None, None, 1, None, 0, None) == -1
+    assert lib.t2s_gemm_tf32(None, None, None, None, 1, 1, 1, 4, 4, 4, 0, 0, 0, 1.0, 1, None) == -1
+    assert lib.t2s_adamw_step(None, None, None, None, 0, 1, 1e-4, 0.9, 0.999, 1e-8, 0.0, 1.0, None) == -1
+    assert lib.t2s_train_make_inputs(2, None, None, None, None, None, None, 1, None) == -1
+    assert lib.t2s_train_workspace_bytes(2) > lib.t2s_train_workspace_bytes(1) > 480 * 8000 * 4
+
+
+def test_training_has_no_cpu_fallback():
+    m = Transformer().train()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(input=torch.zeros(2, 64, 30), t=torch.zeros(2), text_input=torch.zeros(2, 128))
+    from t2ms_b200.training import DitTrainer
+    with pytest.raises(RuntimeError, match="CUDA"):
+        DitTrainer(m)
+
+
+_DP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from oracle import t2s_oracle as O
+from t2ms_b200 import synth
+from t2ms_b200.sampler import shard_range
+torch.set_num_threads(2)
+dist.init_process_group("gloo", init_method="env://")
+rank, world = dist.get_rank(), dist.get_world_size()
+B = 4
+dsd = synth.make_dit_state(15, bias_std=0.02)
+x1, x0, emb = synth.make_noise(B, seed=5), synth.make_noise(B, seed=6), synth.make_text_embeddings(B, seed=7)
+t = torch.tensor([0.1, 0.5, 0.73, 1.0])
+x_t, target = O.rf_create_flow(x1, t, x0), x1 - x0
+_, full = O.train_step_grads(dsd, x_t, t, emb, target)
+lo, hi = shard_range(B, rank, world)
+# DitTrainer.step convention: every rank normalises by the GLOBAL element count, then one SUM all-reduce
+loss_local, g = O.train_step_grads(dsd, x_t[lo:hi], t[lo:hi], emb[lo:hi], target[lo:hi])
+scale = (hi - lo) / B
+for n in g:
+    buf = g[n] * scale
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    err = ((buf - full[n]).norm() / full[n].norm()).item()
+    assert err < 1e-5, (n, err)
+# the shared classifier-free-guidance coin (train.py:80-82): rank 0's draw wins on every rank
+torch.manual_seed(100 + rank)
+coin = torch.rand(1)
+dist.broadcast(coin, src=0)
+ref = torch.tensor([0.0]); 
+if rank == 0: ref = coin.clone()
+dist.broadcast(ref, src=0)
+assert torch.equal(coin, ref)
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_data_parallel_gradient_convention_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_DP_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29537", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
