@@ -598,37 +598,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
 // The 480 queries form four 120-row q-tiles (M = 128 with 8 padding rows), the 480 keys five 96-key chunks.
 // Exact two-pass softmax with the score GEMM recomputed (the tensor pipe is nearly idle, the MUFU is the bound):
 //   pass A: S_j = Q_tile K_j^T for the five chunks (tcgen05.mma M128 N96 K16 x2, double-buffered in TMEM);
-//           a thread per query row (= TMEM lane) takes the running row maximum;
-//   pass B: the same five S_j again; P_j = exp2((S_j - rowmax) * log2e/sqrt(32)) in fp16 to a (double-buffered)
-//           shared-memory A-operand image, row sum in registers; O += P_j V_j (tcgen05.mma M128 N32 K16 x6, V as
-//           MN-major B operand) accumulates over the chunks in one 32-column TMEM accumulator; O / rowsum is
-//           written straight into the out-projection's A-operand tile.
-// Two softmax warpgroups (q-tiles 0,2 / 1,3), each with its own MMA-issuing lane, share the SM: while one is in
-// its MUFU-free pass A the other's exps run at full MUFU rate.
+//           a thread per query row (= TMEM lane) takes the running row maximum (FMNMX3);
+//   pass B: the same five S_j again; P_j = exp2((S_j - rowmax) * log2e/sqrt(32)) is packed to fp16 and written back
+//           over the first 48 columns of its own S buffer in TMEM (tcgen05.st); row sum in registers;
+//           O += P_j V_j is a tcgen05.mma with the A operand read from TMEM (M128 N32 K16 x6, V as MN-major B operand)
+//           accumulating over the chunks in one 32-column accumulator; O / rowsum is written straight into the
+//           out-projection's A-operand tile.
+// CTA = one softmax warpgroup (thread = query row) + one MMA/load warp, 92 KB of shared memory and 256 TMEM
+// columns, so TWO CTAs share an SM: one CTA's loads, pass A and epilogue hide under the other's exp pass.
 // Q, K, V arrive by bulk async copies: the token kernel stores them directly as tcgen05 operand images
 //   Q: [q-tile][d/8][row 0..127][8]     (A, K-major)         32768 B
 //   K: [d/8][key 0..479][8]             (B, K-major)         30720 B
 //   V: [key/8][d/8][key%8][8]           (B, MN-major)        30720 B
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 160;
 constexpr int ATT_KC = 96;                                            // keys per chunk
 constexpr int ATT_NCH = NTOK / ATT_KC;                                // 5
+constexpr int ATT_NQT = 4;                                            // q-tiles
 constexpr int ATT_SM_Q = 0, ATT_SM_K = QKV_Q_HALVES * 2, ATT_SM_V = ATT_SM_K + QKV_K_HALVES * 2;
-constexpr int ATT_SM_P = ATT_SM_V + QKV_V_HALVES * 2;                // [2 warpgroups][2 buffers] P image [96/8][128 rows][8] fp16
-constexpr int ATT_P_BYTES = (ATT_KC / 8) * 2048;                     // 24576
-constexpr int ATT_SM_BAR = ATT_SM_P + 4 * ATT_P_BYTES;
-constexpr int ATT_SM_TMEM = ATT_SM_BAR + 32 * 8;
+constexpr int ATT_SM_BAR = ATT_SM_V + QKV_V_HALVES * 2;
+constexpr int ATT_SM_TMEM = ATT_SM_BAR + 16 * 8;
 constexpr int ATT_SMEM_BYTES = ATT_SM_TMEM + 16;
-static_assert(ATT_SMEM_BYTES <= 232448, "attention kernel shared memory exceeds 227 KB");
-enum { AB_QFULL = 0, AB_KFULL = 1, AB_VFULL = 2, AB_WG = 3 };
-// per warpgroup barriers: S_FULL[2], S_FREE[2], P_FULL[2], P_FREE[2], O_FULL, O_FREE
-enum { AW_SFULL = 0, AW_SFREE = 2, AW_PFULL = 4, AW_PFREE = 6, AW_OFULL = 8, AW_OFREE = 9, AW_COUNT = 10 };
-#ifndef ATT_STAGGER_CLKS
-#define ATT_STAGGER_CLKS 1500
-#endif
+static_assert(2 * (ATT_SMEM_BYTES + 1024) <= 233472, "two attention CTAs must fit one SM");
+enum { AB_QFULL = 0, AB_KFULL = 1, AB_VFULL = 2, AB_SFULL = 3, AB_SFREE = 5, AB_PFULL = 7, AB_PVDONE = 9, AB_OFULL = 11, AB_OFREE = 12 };
 constexpr uint32_t ATT_IDESC_S = umma_idesc_f16(128, ATT_KC);
 constexpr uint32_t ATT_IDESC_PV = umma_idesc_f16(128, HD) | (1u << 16);   // B (V) is MN-major
-// TMEM columns of a warpgroup (256 each): two S buffers and the O accumulator
+constexpr uint32_t ATT_TCOLS = 256;                                   // two S buffers (2 x 96) + O (32)
 constexpr uint32_t ATT_T_S = 0, ATT_T_O = 2 * ATT_KC;
+
+// D[tmem] (+)= A[tmem] . B[smem]: the A operand (M128 x K16 fp16, lane = row, column c = elements 2c, 2c+1) is read
+// from tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
+                 :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&u)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n"
+                 :: "r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]) : "memory");
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
 
 // pipelined walk over NB 16-column blocks of a TMEM region (NB even)
 template <int NB, class F>
@@ -646,113 +658,106 @@ __device__ __forceinline__ void for_blocks16(uint32_t taddr, F&& body) {
     }
 }
 
-// grid = nseq * 4, block = 320: warps 0-3 / 4-7 = softmax warpgroups (thread = query row = TMEM lane),
-// warp 8 / 9 = MMA issuer of warpgroup 0 / 1 (warp 8 also issues the loads)
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ o, long long* trace) {
+// grid = nseq * 4, block = 160: warps 0-3 = softmax (thread = query row = TMEM lane), warp 4 = loads + MMA issue
+__global__ void __launch_bounds__(ATT_THREADS, 2) attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ o, long long* trace) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform
     const int seq = blockIdx.x >> 2, head = blockIdx.x & 3;
     const uint32_t sb = smem_u32(smem);
     const uint32_t bar0 = sb + ATT_SM_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    auto WBAR = [&](int w, int i) { return bar0 + 8u * (AB_WG + w * AW_COUNT + i); };
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) mbar_init(BAR(i), 1);
-        for (int w = 0; w < 2; ++w) {
-            for (int b = 0; b < 2; ++b) {
-                mbar_init(WBAR(w, AW_SFULL + b), 1);
-                mbar_init(WBAR(w, AW_SFREE + b), 128);
-                mbar_init(WBAR(w, AW_PFULL + b), 128);
-                mbar_init(WBAR(w, AW_PFREE + b), 1);
-            }
-            mbar_init(WBAR(w, AW_OFULL), 1);
-            mbar_init(WBAR(w, AW_OFREE), 128);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(BAR(AB_SFULL + b), 1);
+            mbar_init(BAR(AB_SFREE + b), 128);
+            mbar_init(BAR(AB_PFULL + b), 128);
+            mbar_init(BAR(AB_PVDONE + b), 1);
         }
+        mbar_init(BAR(AB_OFULL), 1);
+        mbar_init(BAR(AB_OFREE), 128);
         mbar_fence_init();
     }
-    if (warp == 8) tmem_alloc(sb + ATT_SM_TMEM, 512);
+    if (warp == 4) tmem_alloc(sb + ATT_SM_TMEM, ATT_TCOLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + ATT_SM_TMEM), 0);
+    constexpr int NG = ATT_NQT * 2 * ATT_NCH;                           // 40 score chunks: q-tile, pass, key chunk
 
-    if (warp >= 8) {
-        // ================================================================= MMA issuer of warpgroup w (+ loads); whole warp converged
+    if (warp == 4) {
+        // ================================================================= loads + MMA issue; whole warp converged
         const bool lead = lane == 0;
-        {
-            const int w = warp - 8;
-            if (w == 0 && lead) {
-                const char* src = reinterpret_cast<const char*>(qkv + (size_t)blockIdx.x * QKV_HEAD_HALVES);
-                mbar_expect_tx(BAR(AB_QFULL), QKV_Q_HALVES * 2);
-                bulk_g2s(sb + ATT_SM_Q, src, QKV_Q_HALVES * 2, BAR(AB_QFULL));
-                mbar_expect_tx(BAR(AB_KFULL), QKV_K_HALVES * 2);
-                bulk_g2s(sb + ATT_SM_K, src + QKV_Q_HALVES * 2, QKV_K_HALVES * 2, BAR(AB_KFULL));
-                mbar_expect_tx(BAR(AB_VFULL), QKV_V_HALVES * 2);
-                bulk_g2s(sb + ATT_SM_V, src + (QKV_Q_HALVES + QKV_K_HALVES) * 2, QKV_V_HALVES * 2, BAR(AB_VFULL));
-            }
-            const uint32_t tw = tmem + w * 256;
-            // score chunk g (0..19): q-tile (g/10), pass (g/5)%2, key chunk g%5 -> S buffer g&1
-            auto issue_s = [&](int g) {
-                const int qt = w + 2 * (g / (2 * ATT_NCH)), j = g % ATT_NCH;
+        if (lead) {
+            const char* src = reinterpret_cast<const char*>(qkv + (size_t)blockIdx.x * QKV_HEAD_HALVES);
+            mbar_expect_tx(BAR(AB_QFULL), QKV_Q_HALVES * 2);
+            bulk_g2s(sb + ATT_SM_Q, src, QKV_Q_HALVES * 2, BAR(AB_QFULL));
+            mbar_expect_tx(BAR(AB_KFULL), QKV_K_HALVES * 2);
+            bulk_g2s(sb + ATT_SM_K, src + QKV_Q_HALVES * 2, QKV_K_HALVES * 2, BAR(AB_KFULL));
+            mbar_expect_tx(BAR(AB_VFULL), QKV_V_HALVES * 2);
+            bulk_g2s(sb + ATT_SM_V, src + (QKV_Q_HALVES + QKV_K_HALVES) * 2, QKV_V_HALVES * 2, BAR(AB_VFULL));
+        }
+        // score chunk G: q-tile G/10, key chunk G%5 -> S buffer G&1
+        auto issue_s = [&](int G) {
+            const int qt = G / (2 * ATT_NCH), j = G % ATT_NCH;
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const uint64_t ad = umma_desc(sb + ATT_SM_Q + qt * 8192 + kk * 2 * 2048, 2048, 128);
-                    const uint64_t bd = umma_desc(sb + ATT_SM_K + j * (ATT_KC * 16) + kk * 2 * (NTOK * 16), NTOK * 16, 128);
-                    if (lead) umma_f16(tw + ATT_T_S + (g & 1) * ATT_KC, ad, bd, ATT_IDESC_S, kk > 0);
-                }
-                if (lead) umma_commit(WBAR(w, AW_SFULL + (g & 1)));
-                __syncwarp();
-            };
-            mbar_wait(BAR(AB_QFULL), 0);
-            mbar_wait(BAR(AB_KFULL), 0);
-            tc_fence_after();
-            if (w == 1) {                                    // stagger the warpgroups: one group's MUFU-free pass A
-                const long long t0 = clock64();              // overlaps the other group's exp pass
-                while (clock64() - t0 < ATT_STAGGER_CLKS) {}
+            for (int kk = 0; kk < 2; ++kk) {
+                const uint64_t ad = umma_desc(sb + ATT_SM_Q + qt * 8192 + kk * 2 * 2048, 2048, 128);
+                const uint64_t bd = umma_desc(sb + ATT_SM_K + j * (ATT_KC * 16) + kk * 2 * (NTOK * 16), NTOK * 16, 128);
+                if (lead) umma_f16(tmem + ATT_T_S + (G & 1) * ATT_KC, ad, bd, ATT_IDESC_S, kk > 0);
             }
-            issue_s(0);
-            issue_s(1);
-            mbar_wait(BAR(AB_VFULL), 0);
+            if (lead) umma_commit(BAR(AB_SFULL + (G & 1)));
+            __syncwarp();
+        };
+        mbar_wait(BAR(AB_QFULL), 0);
+        mbar_wait(BAR(AB_KFULL), 0);
+        tc_fence_after();
+        issue_s(0);
+        issue_s(1);
+        mbar_wait(BAR(AB_VFULL), 0);
+        uint32_t ph_sfree = 0, ph_pfull = 0;                 // per-buffer phase parity bits
 #pragma unroll 1
-            for (int g = 0; g < 4 * ATT_NCH; ++g) {
-                const int b = g & 1;
-                mbar_wait(WBAR(w, AW_SFREE + b), (g >> 1) & 1);      // softmax threads have drained S chunk g
+        for (int G = 0; G < NG; ++G) {
+            const int b = G & 1, qt = G / (2 * ATT_NCH), g = G % (2 * ATT_NCH), j = g % ATT_NCH;
+            if (g < ATT_NCH) {                                   // pass A chunk: wait until its S has been read
+                mbar_wait(BAR(AB_SFREE + b), (ph_sfree >> b) & 1);
+                ph_sfree ^= 1u << b;
                 tc_fence_after();
-                if (g + 2 < 4 * ATT_NCH) issue_s(g + 2);
-                if ((g / ATT_NCH) & 1) {                             // pass B chunk: O += P V_j
-                    const int it = g / (2 * ATT_NCH), j = g % ATT_NCH, pj = it * ATT_NCH + j, pb = pj & 1;
-                    mbar_wait(WBAR(w, AW_PFULL + pb), (pj >> 1) & 1);
-                    if (it == 1 && j == 0) mbar_wait(WBAR(w, AW_OFREE), 0);   // previous q-tile's O has been read
-                    tc_fence_after();
-                    const uint32_t p_smem = sb + ATT_SM_P + (w * 2 + pb) * ATT_P_BYTES;
+            } else {                                             // pass B chunk: O += P_j V_j, P_j in TMEM over S_j
+                mbar_wait(BAR(AB_PFULL + b), (ph_pfull >> b) & 1);
+                if (j == 0 && qt > 0) mbar_wait(BAR(AB_OFREE), (qt - 1) & 1);   // previous q-tile's O has been read
+                tc_fence_after();
 #pragma unroll
-                    for (int ks = 0; ks < ATT_KC / 16; ++ks) {
-                        const uint64_t ad = umma_desc(p_smem + ks * 2 * 2048, 2048, 128);
-                        const uint64_t bd = umma_desc(sb + ATT_SM_V + (j * (ATT_KC / 8) + 2 * ks) * 512, 512, 128);
-                        if (lead) umma_f16(tw + ATT_T_O, ad, bd, ATT_IDESC_PV, (j > 0 || ks > 0) ? 1u : 0u);
-                    }
-                    if (lead) {
-                        umma_commit(WBAR(w, AW_PFREE + pb));
-                        if (j == ATT_NCH - 1) umma_commit(WBAR(w, AW_OFULL));
-                    }
-                    __syncwarp();
+                for (int ks = 0; ks < ATT_KC / 16; ++ks) {
+                    const uint64_t bd = umma_desc(sb + ATT_SM_V + (j * (ATT_KC / 8) + 2 * ks) * 512, 512, 128);
+                    if (lead) umma_f16_ts(tmem + ATT_T_O, tmem + ATT_T_S + b * ATT_KC + ks * 8, bd, ATT_IDESC_PV, (j > 0 || ks > 0) ? 1u : 0u);
                 }
+                if (lead) {
+                    umma_commit(BAR(AB_PVDONE + b));
+                    if (j == ATT_NCH - 1) umma_commit(BAR(AB_OFULL));
+                }
+                __syncwarp();
+                if (G + 2 < NG) {                                // the next S into this buffer overwrites P_j
+                    mbar_wait(BAR(AB_PVDONE + b), (ph_pfull >> b) & 1);
+                    tc_fence_after();
+                }
+                ph_pfull ^= 1u << b;
             }
+            if (G + 2 < NG) issue_s(G + 2);
         }
         __syncwarp();
     } else {
-        // ================================================================= softmax warpgroup w: thread = query row
-        const int w = warp >> 2, r = tid & 127;
-        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + w * 256;
+        // ================================================================= softmax: thread = query row
+        const int r = tid;
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
         const float sc = 0.25503486f;                        // log2(e) / sqrt(32)
         const bool tr = trace != nullptr && tid == 0;
 #define ASTAMP(i) do { if (tr) trace[(size_t)blockIdx.x * 32 + (i)] = clock64(); } while (0)
         ASTAMP(0);
-        // O / rowsum of q-tile `it` -> the out-projection A-operand tile of the token kernel
-        auto finish = [&](int it, float lsum) {
-            const int qt = w + 2 * it;
+        // O / rowsum of q-tile qt -> the out-projection A-operand tile of the token kernel
+        auto finish = [&](int qt, float lsum) {
             const float inv = 1.f / lsum;
-            mbar_wait(WBAR(w, AW_OFULL), it & 1);
+            mbar_wait(BAR(AB_OFULL), qt & 1);
             tc_fence_after();
             const int tok = qt * QT_ROWS + r;
             const int tt = tok / TILE_TOK, tilerow = (seq & 1) * 64 + (tok - tt * TILE_TOK);
@@ -761,7 +766,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __half* __re
             tmem_ld32(trow + ATT_T_O, a0);
             tmem_wait_ld();
             tc_fence_before();
-            mbar_arrive(WBAR(w, AW_OFREE));
+            mbar_arrive(BAR(AB_OFREE));
             if (r < QT_ROWS) {
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8)
@@ -772,68 +777,63 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __half* __re
         };
         float lprev = 1.f;
 #pragma unroll 1
-        for (int it = 0; it < 2; ++it) {
+        for (int qt = 0; qt < ATT_NQT; ++qt) {
             // ---- pass A: running row maximum over the five score chunks
             float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll 1
             for (int j = 0; j < ATT_NCH; ++j) {
-                const int g = it * 2 * ATT_NCH + j, b = g & 1;
-                mbar_wait(WBAR(w, AW_SFULL + b), (g >> 1) & 1);
+                const int G = qt * 2 * ATT_NCH + j, b = G & 1;
+                mbar_wait(BAR(AB_SFULL + b), (G >> 1) & 1);
                 tc_fence_after();
                 const uint32_t ts = trow + ATT_T_S + b * ATT_KC;
                 float x[32], y[32];
                 auto red = [&](const float (&v)[32]) {
 #pragma unroll
-                    for (int q = 0; q < 32; q += 2) { m0 = fmaxf(m0, v[q]); m1 = fmaxf(m1, v[q + 1]); }
+                    for (int q = 0; q < 32; q += 4) { m0 = max3(m0, v[q], v[q + 1]); m1 = max3(m1, v[q + 2], v[q + 3]); }
                 };
                 tmem_ld32(ts, x); tmem_ld32(ts + 32, y); tmem_wait_ld();
                 red(x); tmem_ld32(ts + 64, x);
                 red(y); tmem_wait_ld();
                 tc_fence_before();
-                mbar_arrive(WBAR(w, AW_SFREE + b));
+                mbar_arrive(BAR(AB_SFREE + b));
                 red(x);
             }
-            ASTAMP(1 + it * 8);
-            if (it == 1) finish(0, lprev);               // q-tile 0's last P.V finished during pass A
-            ASTAMP(2 + it * 8);
-            // ---- pass B: P = exp2((S - max) * log2e/sqrt(32)) -> fp16 A-operand image, row sum; O += P V
+            ASTAMP(1 + qt * 4);
+            if (qt > 0) finish(qt - 1, lprev);               // the previous q-tile's last P.V finished during pass A
+            // ---- pass B: P = exp2((S - max) * log2e/sqrt(32)) -> fp16 pairs over S in TMEM, row sum; O += P V
             const float nb = -fmaxf(m0, m1) * sc;
             float l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
             for (int j = 0; j < ATT_NCH; ++j) {
-                const int g = it * 2 * ATT_NCH + ATT_NCH + j, b = g & 1;
-                const int pj = it * ATT_NCH + j, pb = pj & 1;
-                mbar_wait(WBAR(w, AW_SFULL + b), (g >> 1) & 1);
-                if (pj >= 2) mbar_wait(WBAR(w, AW_PFREE + pb), ((pj >> 1) - 1) & 1);   // P.V two chunks back has read this P buffer
+                const int G = qt * 2 * ATT_NCH + ATT_NCH + j, b = G & 1;
+                mbar_wait(BAR(AB_SFULL + b), (G >> 1) & 1);
                 tc_fence_after();
-                uint8_t* pbuf = smem + ATT_SM_P + (w * 2 + pb) * ATT_P_BYTES;
-                for_blocks16<ATT_KC / 16>(trow + ATT_T_S + b * ATT_KC, [&](int cb, float (&a)[16]) {
+                const uint32_t ts = trow + ATT_T_S + b * ATT_KC;
+                for_blocks16<ATT_KC / 16>(ts, [&](int cb, float (&a)[16]) {
 #pragma unroll
                     for (int q = 0; q < 16; q += 2) {
                         a[q] = ex2_approx(fmaf(a[q], sc, nb));
                         a[q + 1] = ex2_approx(fmaf(a[q + 1], sc, nb));
                         l0 += a[q]; l1 += a[q + 1];
                     }
+                    uint32_t pk[8];
 #pragma unroll
-                    for (int c8 = 0; c8 < 2; ++c8)
-                        *reinterpret_cast<uint4*>(pbuf + (cb * 2 + c8) * 2048 + r * 16) =
-                            make_uint4(pack_h2(a[c8 * 8 + 0], a[c8 * 8 + 1]), pack_h2(a[c8 * 8 + 2], a[c8 * 8 + 3]),
-                                       pack_h2(a[c8 * 8 + 4], a[c8 * 8 + 5]), pack_h2(a[c8 * 8 + 6], a[c8 * 8 + 7]));
+                    for (int q = 0; q < 8; ++q) pk[q] = pack_h2(a[2 * q], a[2 * q + 1]);
+                    tmem_st8(ts + cb * 8, pk);                // P columns [8cb, 8cb+8) <= S columns already consumed
                 });
+                tmem_wait_st();
                 tc_fence_before();
-                mbar_arrive(WBAR(w, AW_SFREE + b));
-                fence_async_smem();
-                mbar_arrive(WBAR(w, AW_PFULL + pb));
+                mbar_arrive(BAR(AB_PFULL + b));
             }
-            ASTAMP(3 + it * 8);
+            ASTAMP(2 + qt * 4);
             lprev = l0 + l1;
         }
-        finish(1, lprev);
+        finish(ATT_NQT - 1, lprev);
         ASTAMP(20);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem, 512);
+    if (warp == 4) tmem_dealloc(tmem, ATT_TCOLS);
 }
 
 }  // namespace t2s

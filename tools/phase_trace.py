@@ -52,11 +52,11 @@ lib.t2s_dit_attention(B, ws.ptr, stream()); torch.cuda.synchronize()
 lib.t2s_debug_set_phase_trace(None)
 b = buf.cpu().double()
 rel = b - b[:, 0:1]
-print(f"== ATTENTION (warpgroup 0, row 0): mean cycles since softmax start over {B*4} CTAs")
+print(f"== ATTENTION (row 0): mean cycles since softmax start over {B*4} CTAs")
 prev = 0.0
-labels = {0: "start", 1: "it0 passA done", 2: "it0 (finish prev)", 3: "it0 passB done", 9: "it1 passA done", 10: "it1 finish(0) done",
-          11: "it1 passB done", 20: "finish(1) done"}
-for i in [0, 1, 2, 3, 9, 10, 11, 20]:
+labels = {0: "start", 1: "qt0 passA", 2: "qt0 passB", 5: "qt1 passA", 6: "qt1 passB", 9: "qt2 passA", 10: "qt2 passB",
+          13: "qt3 passA", 14: "qt3 passB", 20: "finish(3) done"}
+for i in [0, 1, 2, 5, 6, 9, 10, 13, 14, 20]:
     v = rel[:, i].mean().item()
     print(f"  {labels[i]:20s} {v:9.0f}  (+{v - prev:7.0f})")
     prev = v
