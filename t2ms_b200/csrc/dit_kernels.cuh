@@ -596,14 +596,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
 // =================================================================================== attention (tcgen05)
 // softmax(q k^T / sqrt(32)) v for one (sequence, head) per CTA (timm Attention -> F.scaled_dot_product_attention).
 // The 480 queries form four 120-row q-tiles (M = 128 with 8 padding rows), the 480 keys five 96-key chunks.
-// Exact two-pass softmax with the score GEMM recomputed (the tensor pipe is nearly idle, the MUFU is the bound):
-//   pass A: S_j = Q_tile K_j^T for the five chunks (tcgen05.mma M128 N96 K16 x2, double-buffered in TMEM);
-//           a thread per query row (= TMEM lane) takes the running row maximum (FMNMX3);
-//   pass B: the same five S_j again; P_j = exp2((S_j - rowmax) * log2e/sqrt(32)) is packed to fp16 and written back
-//           over the first 48 columns of its own S buffer in TMEM (tcgen05.st); row sum in registers;
-//           O += P_j V_j is a tcgen05.mma with the A operand read from TMEM (M128 N32 K16 x6, V as MN-major B operand)
-//           accumulating over the chunks in one 32-column accumulator; O / rowsum is written straight into the
-//           out-projection's A-operand tile.
+// Single pass, thread per query row (= TMEM lane), a 96-key score chunk held in registers:
+//   S_j = Q_tile K_j^T (tcgen05.mma M128 N96 K16 x2, double-buffered in TMEM) is read ONCE (the TMEM read port, not
+//   the tensor pipe, is the scarce resource next to the MUFU); the row maximum of the chunk is taken with FMNMX3;
+//   P_j = exp2((S_j - m) * log2e/sqrt(32)) is packed to fp16 and written back over the first 48 columns of its own
+//   S buffer (tcgen05.st); O += P_j V_j is a tcgen05.mma with the A operand read from TMEM (M128 N32 K16 x6, V as
+//   MN-major B operand) accumulating over the chunks in one 32-column accumulator; O / rowsum is written straight
+//   into the out-projection's A-operand tile.
+//   The reference point m is the maximum of the first chunk and is only moved when a later chunk exceeds it by more
+//   than 2^8 in the exp2 domain (P <= 256 stays exact in fp16, sums are fp32): then the row sum and the O row are
+//   rescaled (rare; taken warp-uniformly after the previous P.V has completed).  The result is the exact softmax.
 // CTA = one softmax warpgroup (thread = query row) + one MMA/load warp, 92 KB of shared memory and 256 TMEM
 // columns, so TWO CTAs share an SM: one CTA's loads, pass A and epilogue hide under the other's exp pass.
 // Q, K, V arrive by bulk async copies: the token kernel stores them directly as tcgen05 operand images
@@ -683,7 +685,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_kernel(const __half* __re
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + ATT_SM_TMEM), 0);
-    constexpr int NG = ATT_NQT * 2 * ATT_NCH;                           // 40 score chunks: q-tile, pass, key chunk
+    constexpr int NG = ATT_NQT * ATT_NCH;                               // 20 score chunks: q-tile, key chunk
 
     if (warp == 4) {
         // ================================================================= loads + MMA issue; whole warp converged
@@ -697,9 +699,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_kernel(const __half* __re
             mbar_expect_tx(BAR(AB_VFULL), QKV_V_HALVES * 2);
             bulk_g2s(sb + ATT_SM_V, src + (QKV_Q_HALVES + QKV_K_HALVES) * 2, QKV_V_HALVES * 2, BAR(AB_VFULL));
         }
-        // score chunk G: q-tile G/10, key chunk G%5 -> S buffer G&1
+        // score chunk G: q-tile G/5, key chunk G%5 -> S buffer G&1
         auto issue_s = [&](int G) {
-            const int qt = G / (2 * ATT_NCH), j = G % ATT_NCH;
+            const int qt = G / ATT_NCH, j = G % ATT_NCH;
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
                 const uint64_t ad = umma_desc(sb + ATT_SM_Q + qt * 8192 + kk * 2 * 2048, 2048, 128);
@@ -715,35 +717,28 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_kernel(const __half* __re
         issue_s(0);
         issue_s(1);
         mbar_wait(BAR(AB_VFULL), 0);
-        uint32_t ph_sfree = 0, ph_pfull = 0;                 // per-buffer phase parity bits
 #pragma unroll 1
         for (int G = 0; G < NG; ++G) {
-            const int b = G & 1, qt = G / (2 * ATT_NCH), g = G % (2 * ATT_NCH), j = g % ATT_NCH;
-            if (g < ATT_NCH) {                                   // pass A chunk: wait until its S has been read
-                mbar_wait(BAR(AB_SFREE + b), (ph_sfree >> b) & 1);
-                ph_sfree ^= 1u << b;
-                tc_fence_after();
-            } else {                                             // pass B chunk: O += P_j V_j, P_j in TMEM over S_j
-                mbar_wait(BAR(AB_PFULL + b), (ph_pfull >> b) & 1);
-                if (j == 0 && qt > 0) mbar_wait(BAR(AB_OFREE), (qt - 1) & 1);   // previous q-tile's O has been read
-                tc_fence_after();
+            const int b = G & 1, qt = G / ATT_NCH, j = G % ATT_NCH;
+            const uint32_t par = (G >> 1) & 1;
+            mbar_wait(BAR(AB_PFULL + b), par);                   // P_j is in TMEM over S_j
+            if (j == 0 && qt > 0) mbar_wait(BAR(AB_OFREE), (qt - 1) & 1);   // previous q-tile's O has been read
+            tc_fence_after();
 #pragma unroll
-                for (int ks = 0; ks < ATT_KC / 16; ++ks) {
-                    const uint64_t bd = umma_desc(sb + ATT_SM_V + (j * (ATT_KC / 8) + 2 * ks) * 512, 512, 128);
-                    if (lead) umma_f16_ts(tmem + ATT_T_O, tmem + ATT_T_S + b * ATT_KC + ks * 8, bd, ATT_IDESC_PV, (j > 0 || ks > 0) ? 1u : 0u);
-                }
-                if (lead) {
-                    umma_commit(BAR(AB_PVDONE + b));
-                    if (j == ATT_NCH - 1) umma_commit(BAR(AB_OFULL));
-                }
-                __syncwarp();
-                if (G + 2 < NG) {                                // the next S into this buffer overwrites P_j
-                    mbar_wait(BAR(AB_PVDONE + b), (ph_pfull >> b) & 1);
-                    tc_fence_after();
-                }
-                ph_pfull ^= 1u << b;
+            for (int ks = 0; ks < ATT_KC / 16; ++ks) {
+                const uint64_t bd = umma_desc(sb + ATT_SM_V + (j * (ATT_KC / 8) + 2 * ks) * 512, 512, 128);
+                if (lead) umma_f16_ts(tmem + ATT_T_O, tmem + ATT_T_S + b * ATT_KC + ks * 8, bd, ATT_IDESC_PV, (j > 0 || ks > 0) ? 1u : 0u);
             }
-            if (G + 2 < NG) issue_s(G + 2);
+            if (lead) {
+                umma_commit(BAR(AB_PVDONE + b));
+                if (j == ATT_NCH - 1) umma_commit(BAR(AB_OFULL));
+            }
+            __syncwarp();
+            if (G + 2 < NG) {                                    // the next S into this buffer overwrites P_j
+                mbar_wait(BAR(AB_PVDONE + b), par);
+                tc_fence_after();
+                issue_s(G + 2);
+            }
         }
         __syncwarp();
     } else {
@@ -778,54 +773,64 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_kernel(const __half* __re
         float lprev = 1.f;
 #pragma unroll 1
         for (int qt = 0; qt < ATT_NQT; ++qt) {
-            // ---- pass A: running row maximum over the five score chunks
-            float m0 = -INFINITY, m1 = -INFINITY;
+            float mref = 0.f, l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
             for (int j = 0; j < ATT_NCH; ++j) {
-                const int G = qt * 2 * ATT_NCH + j, b = G & 1;
+                const int G = qt * ATT_NCH + j, b = G & 1;
                 mbar_wait(BAR(AB_SFULL + b), (G >> 1) & 1);
                 tc_fence_after();
                 const uint32_t ts = trow + ATT_T_S + b * ATT_KC;
-                float x[32], y[32];
-                auto red = [&](const float (&v)[32]) {
+                float x[32], y[32], z[32];
+                tmem_ld32(ts, x); tmem_ld32(ts + 32, y); tmem_ld32(ts + 64, z);
+                tmem_wait_ld();
+                float c0 = -INFINITY, c1 = -INFINITY;
 #pragma unroll
-                    for (int q = 0; q < 32; q += 4) { m0 = max3(m0, v[q], v[q + 1]); m1 = max3(m1, v[q + 2], v[q + 3]); }
-                };
-                tmem_ld32(ts, x); tmem_ld32(ts + 32, y); tmem_wait_ld();
-                red(x); tmem_ld32(ts + 64, x);
-                red(y); tmem_wait_ld();
-                tc_fence_before();
-                mbar_arrive(BAR(AB_SFREE + b));
-                red(x);
-            }
-            ASTAMP(1 + qt * 4);
-            if (qt > 0) finish(qt - 1, lprev);               // the previous q-tile's last P.V finished during pass A
-            // ---- pass B: P = exp2((S - max) * log2e/sqrt(32)) -> fp16 pairs over S in TMEM, row sum; O += P V
-            const float nb = -fmaxf(m0, m1) * sc;
-            float l0 = 0.f, l1 = 0.f;
-#pragma unroll 1
-            for (int j = 0; j < ATT_NCH; ++j) {
-                const int G = qt * 2 * ATT_NCH + ATT_NCH + j, b = G & 1;
-                mbar_wait(BAR(AB_SFULL + b), (G >> 1) & 1);
-                tc_fence_after();
-                const uint32_t ts = trow + ATT_T_S + b * ATT_KC;
-                for_blocks16<ATT_KC / 16>(ts, [&](int cb, float (&a)[16]) {
+                for (int q = 0; q < 32; q += 4) {
+                    c0 = max3(c0, x[q], x[q + 1]); c1 = max3(c1, x[q + 2], x[q + 3]);
+                    c0 = max3(c0, y[q], y[q + 1]); c1 = max3(c1, y[q + 2], y[q + 3]);
+                    c0 = max3(c0, z[q], z[q + 1]); c1 = max3(c1, z[q + 2], z[q + 3]);
+                }
+                const float cm = fmaxf(c0, c1);
+                if (j == 0) {
+                    mref = cm;
+                } else {
+                    const bool need = (cm - mref) * sc > 8.f;    // P would exceed 2^8: move the reference point
+                    if (__any_sync(0xffffffffu, need)) {
+                        const float alpha = need ? ex2_approx((mref - cm) * sc) : 1.f;
+                        if (need) mref = cm;
+                        l0 *= alpha; l1 *= alpha;
+                        mbar_wait(BAR(AB_PVDONE + (b ^ 1)), ((G - 1) >> 1) & 1);      // every earlier P.V has landed in O
+                        tc_fence_after();
+                        float a0[32];
+                        tmem_ld32(trow + ATT_T_O, a0);
+                        tmem_wait_ld();
 #pragma unroll
-                    for (int q = 0; q < 16; q += 2) {
-                        a[q] = ex2_approx(fmaf(a[q], sc, nb));
-                        a[q + 1] = ex2_approx(fmaf(a[q + 1], sc, nb));
-                        l0 += a[q]; l1 += a[q + 1];
+                        for (int q = 0; q < 32; ++q) a0[q] *= alpha;
+                        tmem_st16(trow + ATT_T_O, *reinterpret_cast<float (*)[16]>(&a0[0]));
+                        tmem_st16(trow + ATT_T_O + 16, *reinterpret_cast<float (*)[16]>(&a0[16]));
                     }
-                    uint32_t pk[8];
+                }
+                const float nb = -mref * sc;
+                auto block = [&](const float (&v)[32], int c32) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) pk[q] = pack_h2(a[2 * q], a[2 * q + 1]);
-                    tmem_st8(ts + cb * 8, pk);                // P columns [8cb, 8cb+8) <= S columns already consumed
-                });
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float e0 = ex2_approx(fmaf(v[h * 16 + 2 * q], sc, nb)), e1 = ex2_approx(fmaf(v[h * 16 + 2 * q + 1], sc, nb));
+                            l0 += e0; l1 += e1;
+                            pk[q] = pack_h2(e0, e1);
+                        }
+                        tmem_st8(ts + c32 * 16 + h * 8, pk);  // P columns: 16 per 32 scores
+                    }
+                };
+                block(x, 0); block(y, 1); block(z, 2);
+                if (j == 0 && qt > 0) finish(qt - 1, lprev);  // previous q-tile's O -> global before its accumulator is reused
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(BAR(AB_PFULL + b));
             }
-            ASTAMP(2 + qt * 4);
+            ASTAMP(1 + qt);
             lprev = l0 + l1;
         }
         finish(ATT_NQT - 1, lprev);

@@ -86,3 +86,14 @@ class Workspace:
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def pack_qkv_images(q, k, v):
+    """(nseq, 4 heads, 480, 32) fp32 x3 -> the per-(sequence, head) fp16 operand images attn_kernel reads
+    (inverse of Workspace.qkv): Q [q-tile][d/8][128 rows][8], K [d/8][key][8], V [key/8][d/8][key%8][8]."""
+    n = q.shape[0]
+    qi = torch.zeros(n, 4, 4, 4, 128, 8, dtype=torch.float16)
+    qi[:, :, :, :, :120] = q.to(torch.float16).reshape(n, 4, 4, 120, 4, 8).permute(0, 1, 2, 4, 3, 5)
+    ki = k.to(torch.float16).reshape(n, 4, 480, 4, 8).permute(0, 1, 3, 2, 4)
+    vi = v.to(torch.float16).reshape(n, 4, 60, 8, 4, 8).permute(0, 1, 2, 4, 3, 5)
+    return torch.cat([qi.reshape(n, 4, -1), ki.reshape(n, 4, -1), vi.reshape(n, 4, -1)], dim=2).contiguous()

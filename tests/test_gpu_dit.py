@@ -166,3 +166,30 @@ def test_errors_are_loud():
         model(input=torch.zeros(1, 64, 30), t=torch.zeros(1), text_input=None)       # CPU tensor: no fallback
     with pytest.raises(AssertionError):
         model(input=torch.zeros(1, 30, 64, device=DEV), t=torch.zeros(1, device=DEV), text_input=None)
+
+
+@pytest.mark.parametrize("boost", [1.0, 6.0])
+def test_attention_kernel_against_exact_softmax(boost):
+    """attn_kernel alone on crafted q|k|v: with boost > 1 the keys of the later chunks score far above the first
+    chunk's maximum, which drives many (not all) rows through the reference-point move + O rescale path."""
+    from gpu_util import DEV, Workspace, make_dit, pack_qkv_images, stream
+    from t2ms_b200 import _lib
+    lib = _lib.load()
+    model, _ = make_dit(3)
+    nseq = 3
+    g = torch.Generator().manual_seed(17)
+    q, k, v = (torch.randn(nseq, 4, 480, 32, generator=g) for _ in range(3))
+    k[:, :, 200:] *= boost
+    k[:, :, 430:] *= boost ** 0.5
+    q16, k16, v16 = (t.to(torch.float16).double() for t in (q, k, v))
+    ref = torch.softmax(q16 @ k16.transpose(-1, -2) / 32 ** 0.5, dim=-1) @ v16         # (nseq, 4, 480, 32)
+    ref = ref.permute(0, 2, 1, 3).reshape(nseq, 480, 128)
+    ws = Workspace(model, nseq)
+    img = pack_qkv_images(q, k, v).to(DEV)
+    s = ws.base + ws.off[1]
+    ws.buf[s:s + img.numel() * 2].view(torch.float16).copy_(img.reshape(-1))
+    _lib.check(lib.t2s_dit_attention(nseq, ws.ptr, stream()), "t2s_dit_attention")
+    torch.cuda.synchronize()
+    got = ws.o()[:nseq].double().cpu()
+    err = ((got - ref).norm() / ref.norm()).item()
+    assert err < 1e-3, err

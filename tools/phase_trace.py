@@ -54,9 +54,8 @@ b = buf.cpu().double()
 rel = b - b[:, 0:1]
 print(f"== ATTENTION (row 0): mean cycles since softmax start over {B*4} CTAs")
 prev = 0.0
-labels = {0: "start", 1: "qt0 passA", 2: "qt0 passB", 5: "qt1 passA", 6: "qt1 passB", 9: "qt2 passA", 10: "qt2 passB",
-          13: "qt3 passA", 14: "qt3 passB", 20: "finish(3) done"}
-for i in [0, 1, 2, 5, 6, 9, 10, 13, 14, 20]:
+labels = {0: "start", 1: "q-tile 0", 2: "q-tile 1", 3: "q-tile 2", 4: "q-tile 3", 20: "finish(3) done"}
+for i in [0, 1, 2, 3, 4, 20]:
     v = rel[:, i].mean().item()
     print(f"  {labels[i]:20s} {v:9.0f}  (+{v - prev:7.0f})")
     prev = v
