@@ -111,14 +111,17 @@ __global__ void __launch_bounds__(256) cond_kernel(float* __restrict__ mod, cons
 //                    a' = mod(LN1(x)) of block l+1 ; q|k|v = a' Wqkv^T + b   (transformer.py:114-117, timm Attention/Mlp)
 //   EMBED:           x = patch-embed + pos ; a' of block 0 ; q|k|v
 //   FINAL (block 3): ... ; final LN + Linear(128->4) + unpatchify + CFG mix + Euler/DDPM update
-// Warp roles (320 threads): warps 0-3 / 4-7 = epilogue of tile 0 / 1, one thread per tile row (= TMEM lane),
-// the residual row lives in registers; warp 8 = producer (bulk async copies: weight stages, attention-output
-// tiles, per-tile vectors; completion on mbarriers); warp 9 = MMA issuer (one lane issues
+// Warp roles (576 threads): warps 0-7 / 8-15 = epilogue of tile 0 / 1, TWO threads per tile row (= TMEM lane), each
+// owning 64 of the 128 columns of the current region (warp w: lanes 32 (w % 4).., column half (w / 4) % 2);
+// warp 16 = producer (bulk async copies: weight stages, attention-output
+// tiles, per-tile vectors; completion on mbarriers); warp 17 = MMA issuer (one lane issues
 // tcgen05.mma.kind::f16 128x128x16, accumulators in TMEM, completion via tcgen05.commit).
-// Each tile owns two 128-column TMEM regions X, Y; its seven GEMM chunks alternate between them:
-//   proj->X | fc1[0:128]->Y | fc1[128:256]->X | fc2 (two K halves)->Y | q->X | k->Y | v->X
+// Each tile owns two 128-column TMEM regions X, Y:
+//   proj->X (the updated residual is parked in X until the MLP branch adds to it: it never leaves the SM)
+//   fc1[0:128]->Y | fc1[128:256]->Y | fc2 (two K halves)->Y (each after the previous occupant has been drained)
+//   q->X | k->Y | v->X
 // While tile 0's epilogue warps work on a chunk, the tensor pipe runs tile 1's chunk and vice versa.
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 576;                                   // 16 epilogue warps + producer + MMA issuer
 constexpr int TC_NSTAGE = 2;
 constexpr int TC_SM_A = 0;                                       // [2 tiles] 32 KB A operand: o tile / a2 / hidden-b / a'
 constexpr int TC_SM_HA = 2 * STAGE_BYTES;                        // [2 tiles] 32 KB A operand: hidden-a
@@ -133,7 +136,8 @@ constexpr int V_WFIN = 3584;    // [4][128]
 constexpr int V_BFIN = 4096;    // [4]
 constexpr int V_END = 4104;
 constexpr int TC_SM_VB = TC_SM_VEC + V_END * 4;                  // [2 tiles][128][4] fp32 final-projection exchange
-constexpr int TC_SM_BAR = TC_SM_VB + 2 * TILE_ROWS * 4 * 4;
+constexpr int TC_SM_ST = TC_SM_VB + 2 * TILE_ROWS * 4 * 4;        // [2 tiles][2 uses][2 halves][128] float2 LayerNorm statistics exchange
+constexpr int TC_SM_BAR = TC_SM_ST + 2 * 2 * 2 * TILE_ROWS * 8;
 constexpr int TC_SM_TMEM = TC_SM_BAR + 40 * 8;
 constexpr int TOK_SMEM_BYTES = TC_SM_TMEM + 16;
 static_assert(TOK_SMEM_BYTES <= 232448, "token kernel shared memory exceeds 227 KB");
@@ -153,87 +157,128 @@ __device__ __forceinline__ void tc_gemm(uint32_t a_smem, uint32_t w_smem, uint32
     }
 }
 
-// ---- thread-per-row epilogue building blocks.  A thread owns one tile row (= one TMEM lane); rows are
-// processed in 16-column blocks inside rolled loops (compact code, no large register arrays).  The updated
-// residual row is written back over the consumed accumulator in TMEM, which serves as the row buffer for the
-// LayerNorm's second pass.
+// ---- epilogue building blocks.  TWO threads own one tile row (= one TMEM lane): thread (r, hh) works on the 64
+// columns [64 hh, 64 hh + 64) of whatever 128-column region is current, in 16-column blocks inside rolled loops
+// (compact code, no large register arrays).  The updated residual row is written back over the consumed accumulator
+// in TMEM, which serves as the row buffer for the LayerNorm's second pass.  LayerNorm statistics of the two halves
+// are merged through shared memory (Chan's parallel-variance formula) behind a 256-thread named barrier.
 struct RowStats { float mean, rstd; };
+struct HalfStats { float mean, m2; };
 
-// Software-pipelined walk over the eight 16-column blocks of a TMEM region: the tcgen05.ld of block i+1 is in
-// flight while block i is processed (tcgen05.wait::ld waits for all of the thread's outstanding loads).
-template <class F>
-__device__ __forceinline__ void for_each_block16(uint32_t taddr, F&& body) {
+// pipelined walk over NB 16-column blocks of a TMEM region (NB even)
+template <int NB, class F>
+__device__ __forceinline__ void for_blocks16(uint32_t taddr, F&& body) {
     float a[16], b[16];
     tmem_ld16(taddr, a);
 #pragma unroll 1
-    for (int cb = 0; cb < 8; cb += 2) {
+    for (int cb = 0; cb < NB; cb += 2) {
         tmem_wait_ld();
         tmem_ld16(taddr + (cb + 1) * 16, b);
         body(cb, a);
         tmem_wait_ld();
-        if (cb + 2 < 8) tmem_ld16(taddr + (cb + 2) * 16, a);
+        if (cb + 2 < NB) tmem_ld16(taddr + (cb + 2) * 16, a);
         body(cb + 1, b);
     }
 }
 
-// pass 1: hn = hin + gate * (acc + bias); writes hn over the accumulator (TMEM) and optionally to the residual
-// tile in global memory; returns LayerNorm statistics (shifted single-pass variance).
-// hsrc / hdst: residual tile base + row offset; element (col chunk c4, this row) at +c4*TILE_ROWS*4 floats.
-template <bool STORE>
-__device__ __forceinline__ RowStats resid_pass(uint32_t tacc, const float* __restrict__ gate, const float* __restrict__ bias,
-                                               const float* __restrict__ hsrc, float* __restrict__ hdst, bool valid, float eps) {
+
+// pass 1 over this thread's 64 columns: hn = hin + gate * (acc + bias), written back over the accumulator (TMEM),
+// returning the half-row mean and centred sum of squares.  All pointers / addresses are already offset to the
+// thread's column half.
+//   resid_pass_regs: hin was prefetched from the residual tile into registers (before the accumulator wait);
+//   resid_pass_tmem: hin is the row parked in another TMEM region (the residual after the attention branch never
+//                    leaves the SM); optionally stores hn to the residual tile in global memory
+//                    (element (col chunk c4, this row) at +c4*TILE_ROWS*4 floats).
+__device__ __forceinline__ void block_stats(const float (&a)[16], float shift, float& sum, float& sq) {
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        const float d0 = a[j] - shift, d1 = a[j + 1] - shift;
+        s0 += d0; s1 += d1; q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
+    }
+    sum += s0 + s1; sq += q0 + q1;
+}
+__device__ __forceinline__ HalfStats half_stats(float shift, float sum, float sq) {
+    HalfStats st;
+    st.mean = shift + sum * (1.f / 64);
+    st.m2 = fmaxf(sq - sum * sum * (1.f / 64), 0.f);
+    return st;
+}
+__device__ __forceinline__ HalfStats resid_pass_regs(uint32_t tacc, const float* __restrict__ gate, const float* __restrict__ bias,
+                                                     const float4 (&hq)[16]) {
     float sum = 0.f, sq = 0.f, shift = 0.f;
-    float4 hc4[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) hc4[q] = valid ? *reinterpret_cast<const float4*>(hsrc + q * TILE_ROWS * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    for_each_block16(tacc, [&](int cb, float (&a)[16]) {
-        float4 hn4[4];
-        if (cb < 7) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                hn4[q] = valid ? *reinterpret_cast<const float4*>(hsrc + ((cb + 1) * 4 + q) * TILE_ROWS * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    for (int cb = 0; cb < 4; ++cb) {
+        float a[16];
+        tmem_ld16(tacc + cb * 16, a);
+        tmem_wait_ld();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 g4 = *reinterpret_cast<const float4*>(gate + cb * 16 + q * 4);
             const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 16 + q * 4);
-            a[q * 4 + 0] = fmaf(g4.x, a[q * 4 + 0] + b4.x, hc4[q].x);
-            a[q * 4 + 1] = fmaf(g4.y, a[q * 4 + 1] + b4.y, hc4[q].y);
-            a[q * 4 + 2] = fmaf(g4.z, a[q * 4 + 2] + b4.z, hc4[q].z);
-            a[q * 4 + 3] = fmaf(g4.w, a[q * 4 + 3] + b4.w, hc4[q].w);
+            a[q * 4 + 0] = fmaf(g4.x, a[q * 4 + 0] + b4.x, hq[cb * 4 + q].x);
+            a[q * 4 + 1] = fmaf(g4.y, a[q * 4 + 1] + b4.y, hq[cb * 4 + q].y);
+            a[q * 4 + 2] = fmaf(g4.z, a[q * 4 + 2] + b4.z, hq[cb * 4 + q].z);
+            a[q * 4 + 3] = fmaf(g4.w, a[q * 4 + 3] + b4.w, hq[cb * 4 + q].w);
         }
         if (cb == 0) shift = a[0];
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        block_stats(a, shift, sum, sq);
+        tmem_st16(tacc + cb * 16, a);
+    }
+    tmem_wait_st();
+    return half_stats(shift, sum, sq);
+}
+template <bool STORE>
+__device__ __forceinline__ HalfStats resid_pass_tmem(uint32_t tacc, uint32_t thin, const float* __restrict__ gate, const float* __restrict__ bias,
+                                                     float* __restrict__ hdst, bool valid) {
+    float sum = 0.f, sq = 0.f, shift = 0.f;
+    float a[16], h[16];
+    tmem_ld16(tacc, a);
+    tmem_ld16(thin, h);
+#pragma unroll 1
+    for (int cb = 0; cb < 4; ++cb) {
+        tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-            const float d0 = a[j] - shift, d1 = a[j + 1] - shift;
-            s0 += d0; s1 += d1; q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
+        for (int q = 0; q < 4; ++q) {
+            const float4 g4 = *reinterpret_cast<const float4*>(gate + cb * 16 + q * 4);
+            const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 16 + q * 4);
+            a[q * 4 + 0] = fmaf(g4.x, a[q * 4 + 0] + b4.x, h[q * 4 + 0]);
+            a[q * 4 + 1] = fmaf(g4.y, a[q * 4 + 1] + b4.y, h[q * 4 + 1]);
+            a[q * 4 + 2] = fmaf(g4.z, a[q * 4 + 2] + b4.z, h[q * 4 + 2]);
+            a[q * 4 + 3] = fmaf(g4.w, a[q * 4 + 3] + b4.w, h[q * 4 + 3]);
         }
-        sum += s0 + s1; sq += q0 + q1;
+        if (cb < 3) tmem_ld16(thin + (cb + 1) * 16, h);
+        if (cb == 0) shift = a[0];
+        block_stats(a, shift, sum, sq);
         tmem_st16(tacc + cb * 16, a);
         if (STORE && valid) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<float4*>(hdst + (cb * 4 + q) * TILE_ROWS * 4) = make_float4(a[q * 4], a[q * 4 + 1], a[q * 4 + 2], a[q * 4 + 3]);
         }
-        if (cb < 7) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) hc4[q] = hn4[q];
-        }
-    });
+        if (cb < 3) { tmem_wait_st(); tmem_ld16(tacc + (cb + 1) * 16, a); }
+    }
     tmem_wait_st();
-    const float ms = sum * (1.f / D);
+    return half_stats(shift, sum, sq);
+}
+
+// merge the two half-row statistics of a row: slot = exchange buffer [2 halves][128 rows] float2 of this tile
+__device__ __forceinline__ RowStats merge_stats(HalfStats hs, float2* slot, int r, int hh, int bar_id, float eps) {
+    slot[hh * TILE_ROWS + r] = make_float2(hs.mean, hs.m2);
+    asm volatile("bar.sync %0, 256;\n" :: "r"(bar_id) : "memory");
+    const float2 o = slot[(hh ^ 1) * TILE_ROWS + r];
+    const float dm = hs.mean - o.x;
     RowStats st;
-    st.mean = shift + ms;
-    st.rstd = rsqrtf(fmaxf(sq * (1.f / D) - ms * ms, 0.f) + eps);
+    st.mean = 0.5f * (hs.mean + o.x);
+    st.rstd = rsqrtf((hs.m2 + o.y + 32.f * dm * dm) * (1.f / D) + eps);
     return st;
 }
 
-// pass 2: LayerNorm (no affine) + modulate x*(1+scale)+shift (transformer.py:7-8,102-103), packed to fp16 and
-// stored as the next GEMM's A operand image.
+// pass 2 over this thread's 64 columns: LayerNorm (no affine) + modulate x*(1+scale)+shift (transformer.py:7-8,102-103),
+// packed to fp16 and stored as the next GEMM's A operand image.  kc0 = first 8-column K chunk of the half (8 hh).
 __device__ __forceinline__ void ln_mod_store(uint32_t trow, RowStats st, const float* __restrict__ shift, const float* __restrict__ scale,
-                                             uint8_t* abuf, int r) {
-    for_each_block16(trow, [&](int cb, float (&a)[16]) {
+                                             uint8_t* abuf, int r, int kc0) {
+    for_blocks16<4>(trow, [&](int cb, float (&a)[16]) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 sc = *reinterpret_cast<const float4*>(scale + cb * 16 + q * 4);
@@ -245,15 +290,16 @@ __device__ __forceinline__ void ln_mod_store(uint32_t trow, RowStats st, const f
         }
 #pragma unroll
         for (int c8 = 0; c8 < 2; ++c8)
-            *reinterpret_cast<uint4*>(abuf + (cb * 2 + c8) * KCH + r * 16) =
+            *reinterpret_cast<uint4*>(abuf + (kc0 + cb * 2 + c8) * KCH + r * 16) =
                 make_uint4(pack_h2(a[c8 * 8 + 0], a[c8 * 8 + 1]), pack_h2(a[c8 * 8 + 2], a[c8 * 8 + 3]),
                            pack_h2(a[c8 * 8 + 4], a[c8 * 8 + 5]), pack_h2(a[c8 * 8 + 6], a[c8 * 8 + 7]));
     });
 }
 
-// hidden = GELU_tanh(acc + b1) packed to fp16 into an A operand image (timm Mlp, transformer.py:99,105)
-__device__ __forceinline__ void gelu_store(uint32_t taddr, const float* __restrict__ bias, uint8_t* abuf, int r) {
-    for_each_block16(taddr, [&](int cb, float (&v)[16]) {
+// hidden = GELU_tanh(acc + b1) over this thread's 64 columns, packed to fp16 into an A operand image (timm Mlp,
+// transformer.py:99,105)
+__device__ __forceinline__ void gelu_store(uint32_t taddr, const float* __restrict__ bias, uint8_t* abuf, int r, int kc0) {
+    for_blocks16<4>(taddr, [&](int cb, float (&v)[16]) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 16 + q * 4);
@@ -264,13 +310,13 @@ __device__ __forceinline__ void gelu_store(uint32_t taddr, const float* __restri
         }
 #pragma unroll
         for (int c8 = 0; c8 < 2; ++c8)
-            *reinterpret_cast<uint4*>(abuf + (cb * 2 + c8) * KCH + r * 16) =
+            *reinterpret_cast<uint4*>(abuf + (kc0 + cb * 2 + c8) * KCH + r * 16) =
                 make_uint4(pack_h2(v[c8 * 8 + 0], v[c8 * 8 + 1]), pack_h2(v[c8 * 8 + 2], v[c8 * 8 + 3]),
                            pack_h2(v[c8 * 8 + 4], v[c8 * 8 + 5]), pack_h2(v[c8 * 8 + 6], v[c8 * 8 + 7]));
     });
 }
 
-// grid = npair * 4 (two tiles per CTA), block = 320
+// grid = npair * 4 (two tiles per CTA), block = 576
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -290,19 +336,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
         for (int i = 0; i < B_TILE; ++i) mbar_init(BAR(i), 1);
         for (int e = 0; e < 2; ++e) {
             mbar_init(TBAR(e, T_OFULL), 1);
-            for (int i = T_A2; i <= T_XFREE; ++i) mbar_init(TBAR(e, i), 128);
+            for (int i = T_A2; i <= T_XFREE; ++i) mbar_init(TBAR(e, i), 256);
             for (int i = T_ACC; i < T_COUNT; ++i) mbar_init(TBAR(e, i), 1);
         }
         mbar_fence_init();
     }
-    if (warp == 8) tmem_alloc(sb + TC_SM_TMEM, 512);
+    if (warp == 16) tmem_alloc(sb + TC_SM_TMEM, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + TC_SM_TMEM), 0);
     const size_t tile0 = (size_t)pair * TILES_PER_PAIR + tt0;
 
-    if (warp == 8) {
+    if (warp == 16) {
         // ================================================================= producer (whole warp converged; lane 0 issues)
         const bool lead = lane == 0;
         {
@@ -358,7 +404,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             }
         }
         __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == 17) {
         // ================================================================= MMA issuer (whole warp converged; lane 0 issues)
         const bool lead = lane == 0;
         {
@@ -381,9 +427,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             if (MODE != TOK_EMBED) {
                 stage(T_OFULL, TC_SM_A, 0, false, 0);        // proj               -> X
                 stage(T_A2, TC_SM_A, 128, false, 1);         // fc1 cols 0..127    -> Y
-                stage(-1, TC_SM_A, 0, false, 2);             // fc1 cols 128..255  -> X
-                stage(T_HA, TC_SM_HA, 128, false, -1);       // fc2, K half 0      -> Y
-                stage(T_HB, TC_SM_A, 128, true, 3);          // fc2, K half 1      -> Y
+                stage(T_HA, TC_SM_A, 128, false, 2);         // fc1 cols 128..255  -> Y (hidden-a done: Y drained)
+                stage(T_HB, TC_SM_HA, 128, false, -1);       // fc2, K half 0      -> Y (hidden-b done: Y drained)
+                stage(-1, TC_SM_A, 128, true, 3);            // fc2, K half 1      -> Y
             }
             if (MODE != TOK_FINAL) {
                 stage(T_A3, TC_SM_A, 0, false, 4);           // q -> X
@@ -393,26 +439,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
         }
         __syncwarp();
     } else {
-        // ================================================================= epilogue: thread r <-> tile row r <-> TMEM lane r
-        const int e = warp >> 2;                                        // tile handled by this warpgroup
-        const int r = tid & 127;
+        // ================================================================= epilogue: threads (r, hh) <-> tile row r, columns 64 hh ..
+        const int e = warp >> 3;                                        // tile handled by these eight warps
+        const int hh = (warp >> 2) & 1;                                 // column half
+        const int r = (warp & 3) * 32 + lane;
         const int tt = tt0 + e;
         const int branch = r >> 6, tl = r & 63;
         const int seq = 2 * pair + branch;
         const bool valid = tl < TILE_TOK && seq < p.nseq;
         const int tok = tt * TILE_TOK + tl;
-        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + e * 256;
+        const int c0 = hh * 64, kc0 = hh * 8;                           // first column / first 8-column K chunk of the half
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + e * 256 + c0;
         constexpr uint32_t X = 0, Y = 128;
         const float* modb = vec + V_MOD + branch * MOD;
         uint8_t* abuf = smem + TC_SM_A + e * STAGE_BYTES;
         uint8_t* habuf = smem + TC_SM_HA + e * STAGE_BYTES;
+        float2* stx = reinterpret_cast<float2*>(smem + TC_SM_ST) + e * (2 * 2 * TILE_ROWS);
         float* htile = p.h + (tile0 + e) * (TILE_ROWS * D);             // [32 col chunks][128 rows][4]
-        const float* hrow_c = htile + r * 4;                            // + c4 * TILE_ROWS * 4
-        float* hrow = htile + r * 4;
-        const bool tr = p.trace != nullptr && e == 0 && r == 0;
+        const float* hrow_c = htile + (c0 / 4) * TILE_ROWS * 4 + r * 4; // + c4 * TILE_ROWS * 4
+        float* hrow = htile + (c0 / 4) * TILE_ROWS * 4 + r * 4;
+        const bool tr = p.trace != nullptr && e == 0 && r == 0 && hh == 0;
 #define STAMP(i) do { if (tr) p.trace[(size_t)blockIdx.x * 32 + (i)] = clock64(); } while (0)
         STAMP(0);
-        if (MODE != TOK_EMBED && r == 0) prefetch_l2(htile, TILE_ROWS * D * 4);
+        if (MODE != TOK_EMBED && r == 0 && hh == 0) prefetch_l2(htile, TILE_ROWS * D * 4);
         mbar_wait(BAR(B_VFULL), 0);
         STAMP(2);
         RowStats st;
@@ -426,10 +475,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
 #pragma unroll
                 for (int pq = 0; pq < 4; ++pq) xv[pq] = xs[(2 * j + (pq & 1)) * LATP + 2 * i + (pq >> 1)];
             }
-            const float* pos = p.w.pos + ((size_t)tt * 32 * 64 + tl) * 4;   // [8 tiles][32 chunks][64 rows][4]
+            const float* pos = p.w.pos + ((size_t)tt * 32 * 64 + tl) * 4 + (c0 / 4) * 64 * 4;   // [8 tiles][32 chunks][64 rows][4]
             float sum = 0.f, sq = 0.f, shift = 0.f;
 #pragma unroll 1
-            for (int cb = 0; cb < 8; ++cb) {
+            for (int cb = 0; cb < 4; ++cb) {
                 float a[16];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -437,7 +486,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                     const float pev[4] = {pe.x, pe.y, pe.z, pe.w};
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int c = cb * 16 + q * 4 + u;
+                        const int c = c0 + cb * 16 + q * 4 + u;
                         const float4 w4 = *reinterpret_cast<const float4*>(vec + V_WEMB + c * 4);
                         a[q * 4 + u] = valid ? (w4.x * xv[0] + w4.y * xv[1] + w4.z * xv[2] + w4.w * xv[3] + vec[V_BEMB + c] + pev[u]) : 0.f;
                     }
@@ -453,16 +502,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 }
             }
             tmem_wait_st();
-            const float ms = sum * (1.f / D);
-            st.mean = shift + ms;
-            st.rstd = rsqrtf(fmaxf(sq * (1.f / D) - ms * ms, 0.f) + 1e-6f);
+            HalfStats hs;
+            hs.mean = shift + sum * (1.f / 64);
+            hs.m2 = fmaxf(sq - sum * sum * (1.f / 64), 0.f);
+            st = merge_stats(hs, stx, r, hh, 1 + e, 1e-6f);
         } else {
-            // x = x + gate_msa * (o Wproj^T + b)        (transformer.py:116); x parked in X, stored for the second half
+            // x = x + gate_msa * (o Wproj^T + b)        (transformer.py:116); x stays parked in X until the MLP branch adds to it
+            float4 hq[16];                                               // this thread's 64 residual values, in flight during the wait
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4) hq[c4] = valid ? *reinterpret_cast<const float4*>(hrow_c + c4 * TILE_ROWS * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             mbar_wait(TBAR(e, T_ACC + 0), 0);
             tc_fence_after();
             STAMP(3);
-            st = resid_pass<true>(trow + X, modb + 2 * D, vec + V_BPROJ, hrow_c, hrow, valid, 1e-6f);
-            ln_mod_store(trow + X, st, modb + 3 * D, modb + 4 * D, abuf, r);
+            HalfStats hs = resid_pass_regs(trow + X, modb + 2 * D + c0, vec + V_BPROJ + c0, hq);
+            st = merge_stats(hs, stx, r, hh, 1 + e, 1e-6f);
+            ln_mod_store(trow + X, st, modb + 3 * D + c0, modb + 4 * D + c0, abuf, r, kc0);
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(TBAR(e, T_A2));
@@ -471,7 +525,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             mbar_wait(TBAR(e, T_ACC + 1), 0);
             tc_fence_after();
             STAMP(5);
-            gelu_store(trow + Y, vec + V_B1, habuf, r);
+            gelu_store(trow + Y, vec + V_B1 + c0, habuf, r, kc0);
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(TBAR(e, T_HA));
@@ -479,23 +533,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             mbar_wait(TBAR(e, T_ACC + 2), 0);
             tc_fence_after();
             STAMP(7);
-            gelu_store(trow + X, vec + V_B1 + D, abuf, r);
+            gelu_store(trow + Y, vec + V_B1 + D + c0, abuf, r, kc0);
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(TBAR(e, T_HB));
             STAMP(8);
-            // x = x + gate_mlp * (hidden W2^T + b); x parked in Y
+            // x = x + gate_mlp * (hidden W2^T + b): X (parked x) + gate * Y -> Y
             mbar_wait(TBAR(e, T_ACC + 3), 0);
             tc_fence_after();
             STAMP(9);
-            st = resid_pass<MODE == TOK_MID>(trow + Y, modb + 5 * D, vec + V_B2, hrow_c, hrow, valid, MODE == TOK_FINAL ? 1e-5f : 1e-6f);
+            hs = resid_pass_tmem<MODE == TOK_MID>(trow + Y, trow + X, modb + 5 * D + c0, vec + V_B2 + c0, hrow, valid);
+            st = merge_stats(hs, stx + 2 * TILE_ROWS, r, hh, 1 + e, MODE == TOK_FINAL ? 1e-5f : 1e-6f);
             STAMP(10);
         }
         constexpr uint32_t HREG = (MODE == TOK_EMBED) ? X : Y;          // TMEM region holding the residual row now
 
         if (MODE != TOK_FINAL) {
             const float* modn = vec + V_MODN + branch * 256;
-            ln_mod_store(trow + HREG, st, modn, modn + D, abuf, r);
+            ln_mod_store(trow + HREG, st, modn + c0, modn + D + c0, abuf, r, kc0);
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(TBAR(e, T_A3));
@@ -507,10 +562,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 tc_fence_after();
                 STAMP(12 + 2 * which);
                 const uint32_t tcol = which == 1 ? Y : X;
-                const float* bq = vec + V_BQKV + which * D;
-                for_each_block16(trow + tcol, [&](int cb, float (&v)[16]) {
+                const float* bq = vec + V_BQKV + which * D + c0;
+                for_blocks16<4>(trow + tcol, [&](int cb, float (&v)[16]) {
                     if (valid) {
-                        const int head = cb >> 1, half = cb & 1;
+                        const int head = hh * 2 + (cb >> 1), half = cb & 1;
                         __half* hb = p.qkv + ((size_t)seq * NHEAD + head) * QKV_HEAD_HALVES;
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
@@ -537,25 +592,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
         } else {
             // final LN (eps 1e-5, affine folded) + Linear(128->4) + unpatchify (transformer.py:182-190)
             float d4[4] = {0.f, 0.f, 0.f, 0.f};
-            for_each_block16(trow + HREG, [&](int cb, float (&a)[16]) {
+            for_blocks16<4>(trow + HREG, [&](int cb, float (&a)[16]) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
                     const float y0 = (a[j] - st.mean) * st.rstd, y1 = (a[j + 1] - st.mean) * st.rstd;
                     const float y2 = (a[j + 2] - st.mean) * st.rstd, y3 = (a[j + 3] - st.mean) * st.rstd;
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
-                        const float4 w = *reinterpret_cast<const float4*>(vec + V_WFIN + c4 * D + cb * 16 + j);
+                        const float4 w = *reinterpret_cast<const float4*>(vec + V_WFIN + c4 * D + c0 + cb * 16 + j);
                         d4[c4] = fmaf(y0, w.x, fmaf(y1, w.y, fmaf(y2, w.z, fmaf(y3, w.w, d4[c4]))));
                     }
                 }
             });
             float* vb = reinterpret_cast<float*>(smem + TC_SM_VB) + e * TILE_ROWS * 4;
-            *reinterpret_cast<float4*>(vb + r * 4) =
-                make_float4(d4[0] + vec[V_BFIN], d4[1] + vec[V_BFIN + 1], d4[2] + vec[V_BFIN + 2], d4[3] + vec[V_BFIN + 3]);
-            if (e == 0) asm volatile("bar.sync 1, 128;\n" ::: "memory");
-            else asm volatile("bar.sync 2, 128;\n" ::: "memory");
+            float4* px = reinterpret_cast<float4*>(stx);                 // the statistics exchange is idle now: partial sums of half 1
+            if (hh == 1) px[r] = make_float4(d4[0], d4[1], d4[2], d4[3]);
+            asm volatile("bar.sync %0, 256;\n" :: "r"(1 + e) : "memory");
+            if (hh == 0) {
+                const float4 o4 = px[r];
+                *reinterpret_cast<float4*>(vb + r * 4) = make_float4(d4[0] + o4.x + vec[V_BFIN], d4[1] + o4.y + vec[V_BFIN + 1],
+                                                                     d4[2] + o4.z + vec[V_BFIN + 2], d4[3] + o4.w + vec[V_BFIN + 3]);
+            }
+            asm volatile("bar.sync %0, 256;\n" :: "r"(1 + e) : "memory");
+            const int t256 = hh * TILE_ROWS + r;
             if (p.out_mode == OUT_FWD) {
-                for (int idx = r; idx < 2 * TILE_TOK * 4; idx += 128) {
+                for (int idx = t256; idx < 2 * TILE_TOK * 4; idx += 256) {
                     const int br = idx / (TILE_TOK * 4), rem = idx - br * (TILE_TOK * 4), t2 = rem >> 2, c4 = rem & 3;
                     const int sq = 2 * pair + br;
                     if (sq < p.nseq) {
@@ -566,7 +627,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             } else {
                 // classifier-free guidance mix (infer.py:81/:87) + Euler (rectified_flow.py:5-7) or
                 // DDPM ancestral update (DDPM.py:28-36); the latent is updated in place
-                for (int idx = r; idx < TILE_TOK * 4; idx += 128) {
+                for (int idx = t256; idx < TILE_TOK * 4; idx += 256) {
                     const int t2 = idx >> 2, c4 = idx & 3;
                     const int n = tt * TILE_TOK + t2, i = n >> 5, jx = n & 31;
                     const size_t xi = (size_t)pair * LAT + (2 * jx + (c4 & 1)) * LATP + 2 * i + (c4 >> 1);
@@ -590,7 +651,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
     tc_fence_before();
     __syncthreads();
     if (p.trace != nullptr && tid == 0) p.trace[(size_t)blockIdx.x * 32 + 21] = clock64();
-    if (warp == 8) tmem_dealloc(tmem, 512);
+    if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
 // =================================================================================== attention (tcgen05)
@@ -642,22 +703,6 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
-}
-
-// pipelined walk over NB 16-column blocks of a TMEM region (NB even)
-template <int NB, class F>
-__device__ __forceinline__ void for_blocks16(uint32_t taddr, F&& body) {
-    float a[16], b[16];
-    tmem_ld16(taddr, a);
-#pragma unroll 1
-    for (int cb = 0; cb < NB; cb += 2) {
-        tmem_wait_ld();
-        tmem_ld16(taddr + (cb + 1) * 16, b);
-        body(cb, a);
-        tmem_wait_ld();
-        if (cb + 2 < NB) tmem_ld16(taddr + (cb + 2) * 16, a);
-        body(cb + 1, b);
-    }
 }
 
 // grid = nseq * 4, block = 160: warps 0-3 = softmax (thread = query row = TMEM lane), warp 4 = loads + MMA issue
