@@ -27,6 +27,7 @@ namespace {
 long long* g_trace = nullptr;   // t2s_debug_set_phase_trace
 constexpr int MAX_DEV = 64;
 bool g_inited[MAX_DEV] = {};
+int g_sms[MAX_DEV] = {};
 }  // namespace
 
 int t2s_api::ensure_init() {
@@ -48,6 +49,7 @@ int t2s_api::ensure_init() {
     CUDA_OK(cudaFuncSetAttribute(vae_encode_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc));
     CUDA_OK(cudaFuncSetAttribute(vae_encode_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc));
     CUDA_OK(cudaFuncSetAttribute(vae_encode_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc));
+    CUDA_OK(cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev));
     g_inited[dev] = true;
     return T2S_OK;
 }
@@ -83,6 +85,13 @@ int check_ws(const void* ws, size_t bytes, int nseq) {
     return T2S_OK;
 }
 
+int token_grid(int nseq) {           // persistent: one CTA per SM, each looping over work items (two pair tiles)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int items = ((nseq + 1) / 2) * (TILES_PER_PAIR / 2), sms = g_sms[dev] > 0 ? g_sms[dev] : 148;
+    return items < sms ? items : sms;
+}
+
 TokArgs base_args(const t2s_dit_weights* w, const Workspace& ws, int nseq) {
     TokArgs a;
     memset(&a, 0, sizeof(a));
@@ -102,7 +111,7 @@ int launch_cond(const t2s_dit_weights* w, const float* t100, int t_stride, const
 int launch_embed(const t2s_dit_weights* w, const float* x, int x_shift, int nseq, const Workspace& ws, cudaStream_t st) {
     TokArgs a = base_args(w, ws, nseq);
     a.x = x; a.x_shift = x_shift;
-    token_kernel<TOK_EMBED><<<((nseq + 1) / 2) * (TILES_PER_PAIR / 2), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
+    token_kernel<TOK_EMBED><<<token_grid(nseq), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
@@ -114,7 +123,7 @@ int launch_attn(int nseq, const Workspace& ws, cudaStream_t st) {
 int launch_mid(const t2s_dit_weights* w, int layer, int nseq, const Workspace& ws, cudaStream_t st) {
     TokArgs a = base_args(w, ws, nseq);
     a.layer = layer;
-    token_kernel<TOK_MID><<<((nseq + 1) / 2) * (TILES_PER_PAIR / 2), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
+    token_kernel<TOK_MID><<<token_grid(nseq), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
@@ -124,7 +133,7 @@ int launch_final(const t2s_dit_weights* w, int nseq, const Workspace& ws, int ou
     a.layer = NLAYER - 1;
     a.out_mode = out_mode; a.out = out; a.x_upd = x_upd; a.noise = noise;
     a.cfg = cfg; a.c1 = c1; a.c2 = c2; a.c3 = c3;
-    token_kernel<TOK_FINAL><<<((nseq + 1) / 2) * (TILES_PER_PAIR / 2), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
+    token_kernel<TOK_FINAL><<<token_grid(nseq), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }

@@ -121,29 +121,34 @@ __global__ void __launch_bounds__(256) cond_kernel(float* __restrict__ mod, cons
 //   fc1[0:128]->Y | fc1[128:256]->Y | fc2 (two K halves)->Y (each after the previous occupant has been drained)
 //   q->X | k->Y | v->X
 // While tile 0's epilogue warps work on a chunk, the tensor pipe runs tile 1's chunk and vice versa.
+// Persistent: grid = min(#work items, #SMs), a work item = two consecutive pair tiles; every per-tile barrier
+// completes once per item (wait parity = item iteration & 1), the weight ring and the two vector buffers run on
+// their own counters.  While an item is in its second half the producer already fetches the next item's vectors,
+// attention-output tiles (into the HA buffers, free once fc2's first K half has been consumed) and L2-prefetches its
+// residual tiles, so the next item starts with everything on the SM.
 constexpr int TC_THREADS = 576;                                   // 16 epilogue warps + producer + MMA issuer
 constexpr int TC_NSTAGE = 2;
 constexpr int TC_SM_A = 0;                                       // [2 tiles] 32 KB A operand: o tile / a2 / hidden-b / a'
 constexpr int TC_SM_HA = 2 * STAGE_BYTES;                        // [2 tiles] 32 KB A operand: hidden-a
 constexpr int TC_SM_W = 4 * STAGE_BYTES;                         // weight ring
-constexpr int TC_SM_VEC = TC_SM_W + TC_NSTAGE * STAGE_BYTES;     // per-pair vectors (fp32), shared by both tiles
+constexpr int TC_SM_VEC = TC_SM_W + TC_NSTAGE * STAGE_BYTES;     // [2 buffers] per-pair vectors (fp32), shared by both tiles
 constexpr int V_MOD = 0;        // [2 branches][768]  adaLN chunk of block l
 constexpr int V_MODN = 1536;    // [2][256]           shift_msa | scale_msa of the next block
 constexpr int V_BPROJ = 2048, V_B1 = 2176, V_B2 = 2432, V_BQKV = 2560;
-constexpr int V_WEMB = 2944;    // [128][4]
-constexpr int V_BEMB = 3456;    // [128]
-constexpr int V_WFIN = 3584;    // [4][128]
-constexpr int V_BFIN = 4096;    // [4]
-constexpr int V_END = 4104;
-constexpr int TC_SM_VB = TC_SM_VEC + V_END * 4;                  // [2 tiles][128][4] fp32 final-projection exchange
-constexpr int TC_SM_ST = TC_SM_VB + 2 * TILE_ROWS * 4 * 4;        // [2 tiles][2 uses][2 halves][128] float2 LayerNorm statistics exchange
-constexpr int TC_SM_BAR = TC_SM_ST + 2 * 2 * 2 * TILE_ROWS * 8;
-constexpr int TC_SM_TMEM = TC_SM_BAR + 40 * 8;
+constexpr int V_WEMB = 0;       // [128][4]   EMBED only: aliases the V_MOD area it does not use
+constexpr int V_BEMB = 512;     // [128]
+constexpr int V_WFIN = 1536;    // [4][128]   FINAL only: aliases the V_MODN area it does not use
+constexpr int V_BFIN = 2560;    // [4]        FINAL only: aliases V_BQKV
+constexpr int V_FLOATS = 2944;                                   // one vector buffer
+constexpr int TC_SM_VB = TC_SM_VEC + 2 * V_FLOATS * 4;           // [2 tiles][128][4] fp32 final-projection exchange
+constexpr int TC_SM_ST = TC_SM_VB + 2 * TILE_ROWS * 4 * 4;        // [2 tiles][2 halves][128] float2 LayerNorm statistics exchange
+constexpr int TC_SM_BAR = TC_SM_ST + 2 * 2 * TILE_ROWS * 8;
+constexpr int TC_SM_TMEM = TC_SM_BAR + 48 * 8;
 constexpr int TOK_SMEM_BYTES = TC_SM_TMEM + 16;
 static_assert(TOK_SMEM_BYTES <= 232448, "token kernel shared memory exceeds 227 KB");
 // barrier ids
-enum { B_WFULL = 0, B_WEMPTY = 2, B_VFULL = 4, B_TILE = 5 };
-enum { T_OFULL = 0, T_A2 = 1, T_HA = 2, T_HB = 3, T_A3 = 4, T_XFREE = 5, T_ACC = 6 /* ..12 */, T_COUNT = 13 };
+enum { B_WFULL = 0, B_WEMPTY = 2, B_VFULL = 4, B_VFREE = 6, B_TILE = 8 };
+enum { T_OFULL = 0, T_A2 = 1, T_HA = 2, T_HB = 3, T_A3 = 4, T_XFREE = 5, T_DONE = 6, T_HAFREE = 7, T_ACC = 8 /* ..14 */, T_COUNT = 15 };
 constexpr uint32_t TC_IDESC = umma_idesc_f16(128, 128);
 constexpr uint32_t KCH = 2048;   // byte stride between K chunks (16 row groups x 128 B) in a [128][128] operand image
 
@@ -321,22 +326,22 @@ template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform
-    const int pair = blockIdx.x / (TILES_PER_PAIR / 2), tt0 = (blockIdx.x % (TILES_PER_PAIR / 2)) * 2;
     const uint32_t sb = smem_u32(smem);
     const uint32_t bar0 = sb + TC_SM_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * i; };
     auto TBAR = [&](int e, int i) { return bar0 + 8u * (B_TILE + e * T_COUNT + i); };
-    float* vec = reinterpret_cast<float*>(smem + TC_SM_VEC);
     const int l = p.layer;                                         // block whose second half runs here (MID / FINAL)
     const int ln = (MODE == TOK_EMBED) ? 0 : l + 1;                // block whose QKV is produced here (EMBED / MID)
     constexpr int N_STAGES = (MODE == TOK_EMBED) ? 3 : (MODE == TOK_MID ? 8 : 5);
-    if (p.trace != nullptr && tid == 0) p.trace[(size_t)blockIdx.x * 32 + 19] = clock64();
+    const int n_items = ((p.nseq + 1) / 2) * (TILES_PER_PAIR / 2);  // work item = two consecutive pair tiles
 
     if (tid == 0) {
-        for (int i = 0; i < B_TILE; ++i) mbar_init(BAR(i), 1);
+        for (int i = 0; i < B_VFREE; ++i) mbar_init(BAR(i), 1);                  // WFULL, WEMPTY, VFULL
+        for (int i = 0; i < 2; ++i) mbar_init(BAR(B_VFREE + i), 512);
         for (int e = 0; e < 2; ++e) {
             mbar_init(TBAR(e, T_OFULL), 1);
-            for (int i = T_A2; i <= T_XFREE; ++i) mbar_init(TBAR(e, i), 256);
+            for (int i = T_A2; i <= T_DONE; ++i) mbar_init(TBAR(e, i), 256);
+            mbar_init(TBAR(e, T_HAFREE), 1);
             for (int i = T_ACC; i < T_COUNT; ++i) mbar_init(TBAR(e, i), 1);
         }
         mbar_fence_init();
@@ -346,54 +351,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + TC_SM_TMEM), 0);
-    const size_t tile0 = (size_t)pair * TILES_PER_PAIR + tt0;
 
     if (warp == 16) {
         // ================================================================= producer (whole warp converged; lane 0 issues)
         const bool lead = lane == 0;
-        {
-            // per-pair vectors (adaLN chunks of the two sequences, biases, small weights)
-            {
-                const int sq0 = min(2 * pair, p.nseq - 1), sq1 = min(2 * pair + 1, p.nseq - 1);
-                uint32_t bytes = 0;
-                auto cp = [&](int voff, const float* src, uint32_t n) {
-                    if (lead) bulk_g2s(sb + TC_SM_VEC + voff * 4, src, n * 4, BAR(B_VFULL));
-                    bytes += n * 4;
-                };
-                constexpr uint32_t VBYTES = (MODE == TOK_EMBED ? 0u : (2 * MOD + 2 * D + DMLP) * 4u) + (MODE == TOK_FINAL ? 0u : (512 + 3 * D) * 4u) +
-                                            (MODE == TOK_EMBED ? (5 * D) * 4u : 0u) + (MODE == TOK_FINAL ? (4 * D + 4) * 4u : 0u);
-                if (lead) mbar_expect_tx(BAR(B_VFULL), VBYTES);
-                if (MODE != TOK_EMBED) {
-                    cp(V_MOD, p.mod + ((size_t)sq0 * NLAYER + l) * MOD, MOD);
-                    cp(V_MOD + MOD, p.mod + ((size_t)sq1 * NLAYER + l) * MOD, MOD);
-                    cp(V_BPROJ, p.w.b_proj[l], D);
-                    cp(V_B1, p.w.b_fc1[l], DMLP);
-                    cp(V_B2, p.w.b_fc2[l], D);
-                }
-                if (MODE != TOK_FINAL) {
-                    cp(V_MODN, p.mod + ((size_t)sq0 * NLAYER + ln) * MOD, 256);
-                    cp(V_MODN + 256, p.mod + ((size_t)sq1 * NLAYER + ln) * MOD, 256);
-                    cp(V_BQKV, p.w.b_qkv[ln], 3 * D);
-                }
-                if (MODE == TOK_EMBED) { cp(V_WEMB, p.w.w_embed, 4 * D); cp(V_BEMB, p.w.b_embed, D); }
-                if (MODE == TOK_FINAL) { cp(V_WFIN, p.w.w_final, 4 * D); cp(V_BFIN, p.w.b_final, 4); }
-                if (bytes != VBYTES) __trap();
-            }
+        const char* src_a = reinterpret_cast<const char*>(MODE == TOK_EMBED ? p.w.w_qkv[0] : p.w.w_post[l]);
+        const char* src_b = reinterpret_cast<const char*>(MODE == TOK_MID ? p.w.w_qkv[l + 1] : nullptr);
+        constexpr int N_A = (MODE == TOK_EMBED) ? 3 : 5;
+        // inputs of work item `item` (iteration it): per-pair vectors into vector buffer it & 1, the two
+        // attention-output tiles into the HA buffers, the residual tiles towards L2
+        auto fetch_inputs = [&](int it, int item) {
+            const int pair = item / (TILES_PER_PAIR / 2), vb = it & 1;
+            if (it >= 2) mbar_wait(BAR(B_VFREE + vb), ((it >> 1) - 1) & 1);     // the item two back has released this buffer
+            const int sq0 = min(2 * pair, p.nseq - 1), sq1 = min(2 * pair + 1, p.nseq - 1);
+            const uint32_t vdst = sb + TC_SM_VEC + vb * (V_FLOATS * 4), vbar = BAR(B_VFULL + vb);
+            uint32_t bytes = 0;
+            auto cp = [&](int voff, const float* src, uint32_t n) {
+                if (lead) bulk_g2s(vdst + voff * 4, src, n * 4, vbar);
+                bytes += n * 4;
+            };
+            constexpr uint32_t VBYTES = (MODE == TOK_EMBED ? 0u : (2 * MOD + 2 * D + DMLP) * 4u) + (MODE == TOK_FINAL ? 0u : (512 + 3 * D) * 4u) +
+                                        (MODE == TOK_EMBED ? (5 * D) * 4u : 0u) + (MODE == TOK_FINAL ? (4 * D + 4) * 4u : 0u);
+            if (lead) mbar_expect_tx(vbar, VBYTES);
             if (MODE != TOK_EMBED) {
+                cp(V_MOD, p.mod + ((size_t)sq0 * NLAYER + l) * MOD, MOD);
+                cp(V_MOD + MOD, p.mod + ((size_t)sq1 * NLAYER + l) * MOD, MOD);
+                cp(V_BPROJ, p.w.b_proj[l], D);
+                cp(V_B1, p.w.b_fc1[l], DMLP);
+                cp(V_B2, p.w.b_fc2[l], D);
+            }
+            if (MODE != TOK_FINAL) {
+                cp(V_MODN, p.mod + ((size_t)sq0 * NLAYER + ln) * MOD, 256);
+                cp(V_MODN + 256, p.mod + ((size_t)sq1 * NLAYER + ln) * MOD, 256);
+                cp(V_BQKV, p.w.b_qkv[ln], 3 * D);
+            }
+            if (MODE == TOK_EMBED) { cp(V_WEMB, p.w.w_embed, 4 * D); cp(V_BEMB, p.w.b_embed, D); }
+            if (MODE == TOK_FINAL) { cp(V_WFIN, p.w.w_final, 4 * D); cp(V_BFIN, p.w.b_final, 4); }
+            if (bytes != VBYTES) __trap();
+            if (MODE != TOK_EMBED) {
+                if (lead) prefetch_l2(p.h + (size_t)item * 2 * (TILE_ROWS * D), 2 * TILE_ROWS * D * 4);
+#pragma unroll
                 for (int e = 0; e < 2; ++e) {
+                    if (it >= 1) mbar_wait(TBAR(e, T_HAFREE), (it - 1) & 1);     // fc2's first K half of the previous item has read HA
                     if (lead) {
                         mbar_expect_tx(TBAR(e, T_OFULL), STAGE_BYTES);
-                        bulk_g2s(sb + TC_SM_A + e * STAGE_BYTES, reinterpret_cast<const char*>(p.o) + (tile0 + e) * STAGE_BYTES, STAGE_BYTES,
-                                 TBAR(e, T_OFULL));
+                        bulk_g2s(sb + TC_SM_HA + e * STAGE_BYTES, reinterpret_cast<const char*>(p.o) + ((size_t)item * 2 + e) * STAGE_BYTES,
+                                 STAGE_BYTES, TBAR(e, T_OFULL));
                     }
                 }
             }
-            const char* src_a = reinterpret_cast<const char*>(MODE == TOK_EMBED ? p.w.w_qkv[0] : p.w.w_post[l]);
-            const char* src_b = reinterpret_cast<const char*>(MODE == TOK_MID ? p.w.w_qkv[l + 1] : nullptr);
-            constexpr int N_A = (MODE == TOK_EMBED) ? 3 : 5;
+            __syncwarp();
+        };
+        int gs = 0;                                                     // global weight-stage counter (ring of TC_NSTAGE slots)
+        if ((int)blockIdx.x < n_items) fetch_inputs(0, blockIdx.x);
 #pragma unroll 1
-            for (int s = 0; s < N_STAGES; ++s) {
-                const int slot = s % TC_NSTAGE, use = s / TC_NSTAGE;
+        for (int it = 0, item = blockIdx.x; item < n_items; ++it, item += gridDim.x) {
+#pragma unroll 1
+            for (int s = 0; s < N_STAGES; ++s, ++gs) {
+                const int slot = gs % TC_NSTAGE, use = gs / TC_NSTAGE;
                 if (use > 0) mbar_wait(BAR(B_WEMPTY + slot), (use - 1) & 1);
                 if (lead) {
                     mbar_expect_tx(BAR(B_WFULL + slot), STAGE_BYTES);
@@ -401,40 +416,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                              STAGE_BYTES, BAR(B_WFULL + slot));
                 }
                 __syncwarp();
+                // the next item's inputs: as early as its buffers can be free (MID / FINAL: after the fc2 stages have been queued)
+                if (s == (MODE == TOK_EMBED ? 0 : 4) && item + (int)gridDim.x < n_items) fetch_inputs(it + 1, item + gridDim.x);
             }
         }
         __syncwarp();
     } else if (warp == 17) {
         // ================================================================= MMA issuer (whole warp converged; lane 0 issues)
         const bool lead = lane == 0;
-        {
-            int s = 0;
+        int gs = 0;
+#pragma unroll 1
+        for (int it = 0, item = blockIdx.x; item < n_items; ++it, item += gridDim.x) {
+            const uint32_t par = it & 1;
             // one weight stage feeds the same GEMM chunk of both tiles
-            auto stage = [&](int wait_bar, uint32_t a_off, uint32_t d_col, bool accumulate, int acc_bar) {
-                const int slot = s % TC_NSTAGE;
-                mbar_wait(BAR(B_WFULL + slot), (s / TC_NSTAGE) & 1);
+            auto stage = [&](int wait_bar, uint32_t a_off, uint32_t d_col, bool accumulate, int acc_bar, bool first, bool ha_free) {
+                const int slot = gs % TC_NSTAGE;
+                mbar_wait(BAR(B_WFULL + slot), (gs / TC_NSTAGE) & 1);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    if (wait_bar >= 0) mbar_wait(TBAR(e, wait_bar), 0);
+                    if (first && it > 0) mbar_wait(TBAR(e, T_DONE), (it - 1) & 1);   // the previous item's epilogue has drained X / Y
+                    if (wait_bar >= 0) mbar_wait(TBAR(e, wait_bar), par);
                     tc_fence_after();
                     tc_gemm(sb + a_off + e * STAGE_BYTES, sb + TC_SM_W + slot * STAGE_BYTES, tmem + e * 256 + d_col, accumulate, lead);
                     if (lead && acc_bar >= 0) umma_commit(TBAR(e, T_ACC + acc_bar));
+                    if (lead && ha_free) umma_commit(TBAR(e, T_HAFREE));
                 }
                 if (lead) umma_commit(BAR(B_WEMPTY + slot));
                 __syncwarp();
-                ++s;
+                ++gs;
             };
             if (MODE != TOK_EMBED) {
-                stage(T_OFULL, TC_SM_A, 0, false, 0);        // proj               -> X
-                stage(T_A2, TC_SM_A, 128, false, 1);         // fc1 cols 0..127    -> Y
-                stage(T_HA, TC_SM_A, 128, false, 2);         // fc1 cols 128..255  -> Y (hidden-a done: Y drained)
-                stage(T_HB, TC_SM_HA, 128, false, -1);       // fc2, K half 0      -> Y (hidden-b done: Y drained)
-                stage(-1, TC_SM_A, 128, true, 3);            // fc2, K half 1      -> Y
+                stage(T_OFULL, TC_SM_HA, 0, false, 0, true, false);      // proj (o tile sits in HA)  -> X
+                stage(T_A2, TC_SM_A, 128, false, 1, false, false);       // fc1 cols 0..127    -> Y
+                stage(T_HA, TC_SM_A, 128, false, 2, false, false);       // fc1 cols 128..255  -> Y (hidden-a done: Y drained)
+                stage(T_HB, TC_SM_HA, 128, false, -1, false, true);      // fc2, K half 0      -> Y (hidden-b done: Y drained)
+                stage(-1, TC_SM_A, 128, true, 3, false, false);          // fc2, K half 1      -> Y
             }
             if (MODE != TOK_FINAL) {
-                stage(T_A3, TC_SM_A, 0, false, 4);           // q -> X
-                stage(-1, TC_SM_A, 128, false, 5);           // k -> Y
-                stage(T_XFREE, TC_SM_A, 0, false, 6);        // v -> X (after the q epilogue has drained X)
+                stage(T_A3, TC_SM_A, 0, false, 4, MODE == TOK_EMBED, false);   // q -> X
+                stage(-1, TC_SM_A, 128, false, 5, false, false);         // k -> Y
+                stage(T_XFREE, TC_SM_A, 0, false, 6, false, false);      // v -> X (after the q epilogue has drained X)
             }
         }
         __syncwarp();
@@ -443,26 +464,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
         const int e = warp >> 3;                                        // tile handled by these eight warps
         const int hh = (warp >> 2) & 1;                                 // column half
         const int r = (warp & 3) * 32 + lane;
-        const int tt = tt0 + e;
         const int branch = r >> 6, tl = r & 63;
-        const int seq = 2 * pair + branch;
-        const bool valid = tl < TILE_TOK && seq < p.nseq;
-        const int tok = tt * TILE_TOK + tl;
         const int c0 = hh * 64, kc0 = hh * 8;                           // first column / first 8-column K chunk of the half
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + e * 256 + c0;
         constexpr uint32_t X = 0, Y = 128;
-        const float* modb = vec + V_MOD + branch * MOD;
         uint8_t* abuf = smem + TC_SM_A + e * STAGE_BYTES;
         uint8_t* habuf = smem + TC_SM_HA + e * STAGE_BYTES;
-        float2* stx = reinterpret_cast<float2*>(smem + TC_SM_ST) + e * (2 * 2 * TILE_ROWS);
-        float* htile = p.h + (tile0 + e) * (TILE_ROWS * D);             // [32 col chunks][128 rows][4]
-        const float* hrow_c = htile + (c0 / 4) * TILE_ROWS * 4 + r * 4; // + c4 * TILE_ROWS * 4
-        float* hrow = htile + (c0 / 4) * TILE_ROWS * 4 + r * 4;
+        float2* stx = reinterpret_cast<float2*>(smem + TC_SM_ST) + e * (2 * TILE_ROWS);
         const bool tr = p.trace != nullptr && e == 0 && r == 0 && hh == 0;
 #define STAMP(i) do { if (tr) p.trace[(size_t)blockIdx.x * 32 + (i)] = clock64(); } while (0)
+#pragma unroll 1
+        for (int it = 0, item = blockIdx.x; item < n_items; ++it, item += gridDim.x) {
+        const uint32_t par = it & 1;
+        const int pair = item / (TILES_PER_PAIR / 2), tt = (item % (TILES_PER_PAIR / 2)) * 2 + e;
+        const int seq = 2 * pair + branch;
+        const bool valid = tl < TILE_TOK && seq < p.nseq;
+        const int tok = tt * TILE_TOK + tl;
+        const float* vec = reinterpret_cast<const float*>(smem + TC_SM_VEC) + (it & 1) * V_FLOATS;
+        const float* modb = vec + V_MOD + branch * MOD;
+        float* htile = p.h + ((size_t)item * 2 + e) * (TILE_ROWS * D);  // [32 col chunks][128 rows][4]
+        const float* hrow_c = htile + (c0 / 4) * TILE_ROWS * 4 + r * 4; // + c4 * TILE_ROWS * 4
+        float* hrow = htile + (c0 / 4) * TILE_ROWS * 4 + r * 4;
         STAMP(0);
-        if (MODE != TOK_EMBED && r == 0 && hh == 0) prefetch_l2(htile, TILE_ROWS * D * 4);
-        mbar_wait(BAR(B_VFULL), 0);
+        mbar_wait(BAR(B_VFULL + (it & 1)), (it >> 1) & 1);
         STAMP(2);
         RowStats st;
         if (MODE == TOK_EMBED) {
@@ -511,7 +535,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             float4 hq[16];                                               // this thread's 64 residual values, in flight during the wait
 #pragma unroll
             for (int c4 = 0; c4 < 16; ++c4) hq[c4] = valid ? *reinterpret_cast<const float4*>(hrow_c + c4 * TILE_ROWS * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            mbar_wait(TBAR(e, T_ACC + 0), 0);
+            mbar_wait(TBAR(e, T_ACC + 0), par);
             tc_fence_after();
             STAMP(3);
             HalfStats hs = resid_pass_regs(trow + X, modb + 2 * D + c0, vec + V_BPROJ + c0, hq);
@@ -522,7 +546,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             mbar_arrive(TBAR(e, T_A2));
             STAMP(4);
             // hidden = GELU(fc1)                         (transformer.py:117)
-            mbar_wait(TBAR(e, T_ACC + 1), 0);
+            mbar_wait(TBAR(e, T_ACC + 1), par);
             tc_fence_after();
             STAMP(5);
             gelu_store(trow + Y, vec + V_B1 + c0, habuf, r, kc0);
@@ -530,7 +554,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             tc_fence_before();
             mbar_arrive(TBAR(e, T_HA));
             STAMP(6);
-            mbar_wait(TBAR(e, T_ACC + 2), 0);
+            mbar_wait(TBAR(e, T_ACC + 2), par);
             tc_fence_after();
             STAMP(7);
             gelu_store(trow + Y, vec + V_B1 + D + c0, abuf, r, kc0);
@@ -539,11 +563,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             mbar_arrive(TBAR(e, T_HB));
             STAMP(8);
             // x = x + gate_mlp * (hidden W2^T + b): X (parked x) + gate * Y -> Y
-            mbar_wait(TBAR(e, T_ACC + 3), 0);
+            mbar_wait(TBAR(e, T_ACC + 3), par);
             tc_fence_after();
             STAMP(9);
             hs = resid_pass_tmem<MODE == TOK_MID>(trow + Y, trow + X, modb + 5 * D + c0, vec + V_B2 + c0, hrow, valid);
-            st = merge_stats(hs, stx + 2 * TILE_ROWS, r, hh, 1 + e, MODE == TOK_FINAL ? 1e-5f : 1e-6f);
+            st = merge_stats(hs, stx, r, hh, 1 + e, MODE == TOK_FINAL ? 1e-5f : 1e-6f);
             STAMP(10);
         }
         constexpr uint32_t HREG = (MODE == TOK_EMBED) ? X : Y;          // TMEM region holding the residual row now
@@ -558,7 +582,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             // q | k | v = a' W^T + b, stored fp16 in the attention kernel's smem image layout
 #pragma unroll 1
             for (int which = 0; which < 3; ++which) {
-                mbar_wait(TBAR(e, T_ACC + 4 + which), 0);
+                mbar_wait(TBAR(e, T_ACC + 4 + which), par);
                 tc_fence_after();
                 STAMP(12 + 2 * which);
                 const uint32_t tcol = which == 1 ? Y : X;
@@ -606,6 +630,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             });
             float* vb = reinterpret_cast<float*>(smem + TC_SM_VB) + e * TILE_ROWS * 4;
             float4* px = reinterpret_cast<float4*>(stx);                 // the statistics exchange is idle now: partial sums of half 1
+            asm volatile("bar.sync %0, 256;\n" :: "r"(1 + e) : "memory");  // ... once every thread has read its merge partner
             if (hh == 1) px[r] = make_float4(d4[0], d4[1], d4[2], d4[3]);
             asm volatile("bar.sync %0, 256;\n" :: "r"(1 + e) : "memory");
             if (hh == 0) {
@@ -646,11 +671,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 }
             }
         }
+        // item done: X / Y and this vector buffer may be reused (the next item's MMAs / vector copies wait on these)
+        tc_fence_before();
+        mbar_arrive(TBAR(e, T_DONE));
+        mbar_arrive(BAR(B_VFREE + (it & 1)));
+        STAMP(18);
+        }
     }
-    if (p.trace != nullptr && tid == 0) p.trace[(size_t)blockIdx.x * 32 + 20] = clock64();
     tc_fence_before();
     __syncthreads();
-    if (p.trace != nullptr && tid == 0) p.trace[(size_t)blockIdx.x * 32 + 21] = clock64();
     if (warp == 16) tmem_dealloc(tmem, 512);
 }
 

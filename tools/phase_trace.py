@@ -15,13 +15,13 @@ emb = torch.randn(B // 2, 128, device=DEV)
 t100 = torch.full((1,), 37.0, device=DEV)
 pk = model.packed()
 ws = Workspace(model, B)
-grid = (B // 2) * 4
+grid = min((B // 2) * 4, 148)
 lib.t2s_dit_cond(pk.ref, t100.data_ptr(), 0, emb.data_ptr(), 1, B, ws.ptr, stream())
 lib.t2s_dit_embed_qkv(pk.ref, x.data_ptr(), 1, B, ws.ptr, stream())
 lib.t2s_dit_attention(B, ws.ptr, stream())
 names = {0: "start(epi)", 1: "h loaded", 2: "vec ready", 3: "acc proj", 4: "E0 done", 5: "acc fc1a", 6: "E1a done", 7: "acc fc1b", 8: "E1b done",
          9: "acc fc2", 10: "E2 resid", 11: "h store+LN", 12: "acc q", 13: "q stored", 14: "acc k", 15: "k stored", 16: "acc v", 17: "v stored",
-         19: "kernel start", 20: "pre-final-sync", 21: "post-final-sync"}
+         18: "item done"}
 for label, fn in (("MID", lambda: lib.t2s_dit_block_post(pk.ref, 1, B, ws.ptr, stream())),
                   ("EMBED", lambda: lib.t2s_dit_embed_qkv(pk.ref, x.data_ptr(), 1, B, ws.ptr, stream()))):
     fn(); torch.cuda.synchronize()
@@ -30,11 +30,11 @@ for label, fn in (("MID", lambda: lib.t2s_dit_block_post(pk.ref, 1, B, ws.ptr, s
     fn(); torch.cuda.synchronize()
     lib.t2s_debug_set_phase_trace(None)
     b = buf.cpu().double()
-    base = b[:, 19:20]
+    base = b[:, 0:1]
     rel = (b - base)
-    print(f"== {label}: mean cycles since kernel start (over {grid} CTAs), delta from previous stamp")
+    print(f"== {label}: last work item of each CTA, mean cycles since item start (over {grid} CTAs), delta from previous stamp")
     prev = 0.0
-    for i in [19, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 20, 21]:
+    for i in [0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18]:
         col = rel[:, i]
         m = col[b[:, i] > 0]
         if len(m) == 0:
