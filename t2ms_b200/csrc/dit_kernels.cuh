@@ -261,7 +261,7 @@ __device__ __forceinline__ HalfStats resid_pass_tmem(uint32_t tacc, uint32_t thi
             for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<float4*>(hdst + (cb * 4 + q) * TILE_ROWS * 4) = make_float4(a[q * 4], a[q * 4 + 1], a[q * 4 + 2], a[q * 4 + 3]);
         }
-        if (cb < 3) { tmem_wait_st(); tmem_ld16(tacc + (cb + 1) * 16, a); }
+        if (cb < 3) tmem_ld16(tacc + (cb + 1) * 16, a);
     }
     tmem_wait_st();
     return half_stats(shift, sum, sq);
@@ -424,38 +424,82 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
     } else if (warp == 17) {
         // ================================================================= MMA issuer (whole warp converged; lane 0 issues)
         const bool lead = lane == 0;
-        int gs = 0;
+        int gs = 0;                                                     // global weight-stage counter
+        auto wfull = [&](int g) { mbar_wait(BAR(B_WFULL + g % TC_NSTAGE), (g / TC_NSTAGE) & 1); };
+        auto wslot = [&](int g) { return sb + TC_SM_W + (g % TC_NSTAGE) * STAGE_BYTES; };
+        auto wdone = [&](int g) { if (lead) umma_commit(BAR(B_WEMPTY + g % TC_NSTAGE)); __syncwarp(); };
 #pragma unroll 1
         for (int it = 0, item = blockIdx.x; item < n_items; ++it, item += gridDim.x) {
             const uint32_t par = it & 1;
-            // one weight stage feeds the same GEMM chunk of both tiles
-            auto stage = [&](int wait_bar, uint32_t a_off, uint32_t d_col, bool accumulate, int acc_bar, bool first, bool ha_free) {
-                const int slot = gs % TC_NSTAGE;
-                mbar_wait(BAR(B_WFULL + slot), (gs / TC_NSTAGE) & 1);
+            const uint32_t X = (it & 1) * 128, Y = 128 - X;             // the two TMEM regions swap roles every item
+            // one weight stage feeds the same GEMM chunk of both tiles; chunks that wait on the same epilogue event
+            // (fc2's two K halves; q and k) are issued tile by tile so that a tile never waits for its neighbour
+            auto A_ = [&](int e) { return sb + TC_SM_A + e * STAGE_BYTES; };
+            auto HA_ = [&](int e) { return sb + TC_SM_HA + e * STAGE_BYTES; };
+            auto D_ = [&](int e, uint32_t col) { return tmem + e * 256 + col; };
+            auto acc = [&](int e, int i) { if (lead) umma_commit(TBAR(e, T_ACC + i)); };
+            if (MODE != TOK_EMBED) {
+                wfull(gs);                                               // proj (o tile sits in HA) -> X
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    if (first && it > 0) mbar_wait(TBAR(e, T_DONE), (it - 1) & 1);   // the previous item's epilogue has drained X / Y
-                    if (wait_bar >= 0) mbar_wait(TBAR(e, wait_bar), par);
+                    if (it > 0) mbar_wait(TBAR(e, T_DONE), (it - 1) & 1);   // the previous item has drained this region
+                    mbar_wait(TBAR(e, T_OFULL), par);
                     tc_fence_after();
-                    tc_gemm(sb + a_off + e * STAGE_BYTES, sb + TC_SM_W + slot * STAGE_BYTES, tmem + e * 256 + d_col, accumulate, lead);
-                    if (lead && acc_bar >= 0) umma_commit(TBAR(e, T_ACC + acc_bar));
-                    if (lead && ha_free) umma_commit(TBAR(e, T_HAFREE));
+                    tc_gemm(HA_(e), wslot(gs), D_(e, X), false, lead);
+                    acc(e, 0);
                 }
-                if (lead) umma_commit(BAR(B_WEMPTY + slot));
-                __syncwarp();
-                ++gs;
-            };
-            if (MODE != TOK_EMBED) {
-                stage(T_OFULL, TC_SM_HA, 0, false, 0, true, false);      // proj (o tile sits in HA)  -> X
-                stage(T_A2, TC_SM_A, 128, false, 1, false, false);       // fc1 cols 0..127    -> Y
-                stage(T_HA, TC_SM_A, 128, false, 2, false, false);       // fc1 cols 128..255  -> Y (hidden-a done: Y drained)
-                stage(T_HB, TC_SM_HA, 128, false, -1, false, true);      // fc2, K half 0      -> Y (hidden-b done: Y drained)
-                stage(-1, TC_SM_A, 128, true, 3, false, false);          // fc2, K half 1      -> Y
+                wdone(gs); ++gs;
+                wfull(gs);                                               // fc1 cols 0..127 -> Y
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    mbar_wait(TBAR(e, T_A2), par);
+                    tc_fence_after();
+                    tc_gemm(A_(e), wslot(gs), D_(e, Y), false, lead);
+                    acc(e, 1);
+                }
+                wdone(gs); ++gs;
+                wfull(gs);                                               // fc1 cols 128..255 -> Y (hidden-a done: Y drained)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    mbar_wait(TBAR(e, T_HA), par);
+                    tc_fence_after();
+                    tc_gemm(A_(e), wslot(gs), D_(e, Y), false, lead);
+                    acc(e, 2);
+                }
+                wdone(gs); ++gs;
+                wfull(gs); wfull(gs + 1);                                // fc2, both K halves -> Y (hidden-b done: Y drained)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    mbar_wait(TBAR(e, T_HB), par);
+                    tc_fence_after();
+                    tc_gemm(HA_(e), wslot(gs), D_(e, Y), false, lead);
+                    if (lead) umma_commit(TBAR(e, T_HAFREE));
+                    tc_gemm(A_(e), wslot(gs + 1), D_(e, Y), true, lead);
+                    acc(e, 3);
+                }
+                wdone(gs); wdone(gs + 1); gs += 2;
             }
             if (MODE != TOK_FINAL) {
-                stage(T_A3, TC_SM_A, 0, false, 4, MODE == TOK_EMBED, false);   // q -> X
-                stage(-1, TC_SM_A, 128, false, 5, false, false);         // k -> Y
-                stage(T_XFREE, TC_SM_A, 0, false, 6, false, false);      // v -> X (after the q epilogue has drained X)
+                wfull(gs); wfull(gs + 1);                                // q -> X, k -> Y
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    mbar_wait(TBAR(e, T_A3), par);
+                    tc_fence_after();
+                    tc_gemm(A_(e), wslot(gs), D_(e, X), false, lead);
+                    acc(e, 4);
+                    tc_gemm(A_(e), wslot(gs + 1), D_(e, Y), false, lead);
+                    acc(e, 5);
+                }
+                wdone(gs); wdone(gs + 1); gs += 2;
+                wfull(gs);                                               // v -> X (after the q epilogue has drained X)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    mbar_wait(TBAR(e, T_XFREE), par);
+                    tc_fence_after();
+                    tc_gemm(A_(e), wslot(gs), D_(e, X), false, lead);
+                    acc(e, 6);
+                }
+                wdone(gs); ++gs;
             }
         }
         __syncwarp();
@@ -467,7 +511,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
         const int branch = r >> 6, tl = r & 63;
         const int c0 = hh * 64, kc0 = hh * 8;                           // first column / first 8-column K chunk of the half
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + e * 256 + c0;
-        constexpr uint32_t X = 0, Y = 128;
         uint8_t* abuf = smem + TC_SM_A + e * STAGE_BYTES;
         uint8_t* habuf = smem + TC_SM_HA + e * STAGE_BYTES;
         float2* stx = reinterpret_cast<float2*>(smem + TC_SM_ST) + e * (2 * TILE_ROWS);
@@ -476,6 +519,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
 #pragma unroll 1
         for (int it = 0, item = blockIdx.x; item < n_items; ++it, item += gridDim.x) {
         const uint32_t par = it & 1;
+        const uint32_t X = (it & 1) * 128, Y = 128 - X;                 // the two TMEM regions swap roles every item
         const int pair = item / (TILES_PER_PAIR / 2), tt = (item % (TILES_PER_PAIR / 2)) * 2 + e;
         const int seq = 2 * pair + branch;
         const bool valid = tl < TILE_TOK && seq < p.nseq;
@@ -570,7 +614,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             st = merge_stats(hs, stx, r, hh, 1 + e, MODE == TOK_FINAL ? 1e-5f : 1e-6f);
             STAMP(10);
         }
-        constexpr uint32_t HREG = (MODE == TOK_EMBED) ? X : Y;          // TMEM region holding the residual row now
+        const uint32_t HREG = (MODE == TOK_EMBED) ? X : Y;              // TMEM region holding the residual row now
 
         if (MODE != TOK_FINAL) {
             const float* modn = vec + V_MODN + branch * 256;
@@ -587,21 +631,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 STAMP(12 + 2 * which);
                 const uint32_t tcol = which == 1 ? Y : X;
                 const float* bq = vec + V_BQKV + which * D + c0;
+                // tcgen05 operand images read by attn_kernel (a warp's 32 rows are contiguous): element offset of this
+                // token inside a (sequence, head) image and the stride between 8-wide d chunks
+                const int off = which == 0 ? (tok / QT_ROWS) * 4096 + (tok % QT_ROWS) * 8
+                              : which == 1 ? QKV_Q_HALVES + tok * 8
+                                           : QKV_Q_HALVES + QKV_K_HALVES + (tok >> 3) * 256 + (tok & 7) * 8;
+                const int dstride = which == 0 ? 1024 : (which == 1 ? NTOK * 8 : 64);
+                __half* hb0 = p.qkv + ((size_t)seq * NHEAD + hh * 2) * QKV_HEAD_HALVES + off;
                 for_blocks16<4>(trow + tcol, [&](int cb, float (&v)[16]) {
                     if (valid) {
-                        const int head = hh * 2 + (cb >> 1), half = cb & 1;
-                        __half* hb = p.qkv + ((size_t)seq * NHEAD + head) * QKV_HEAD_HALVES;
+                        __half* hb = hb0 + (cb >> 1) * QKV_HEAD_HALVES + (cb & 1) * 2 * dstride;
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
-                            const int dc = half * 2 + c;
-                            __half* dst;      // tcgen05 operand images read by attn_kernel (a warp's 32 rows are contiguous)
-                            if (which == 0) dst = hb + (tok / QT_ROWS) * 4096 + dc * 1024 + (tok % QT_ROWS) * 8;
-                            else if (which == 1) dst = hb + QKV_Q_HALVES + dc * (NTOK * 8) + tok * 8;
-                            else dst = hb + QKV_Q_HALVES + QKV_K_HALVES + (tok >> 3) * 256 + dc * 64 + (tok & 7) * 8;
                             const float4 b0 = *reinterpret_cast<const float4*>(bq + cb * 16 + c * 8);
                             const float4 b1 = *reinterpret_cast<const float4*>(bq + cb * 16 + c * 8 + 4);
                             const float* x = v + c * 8;
-                            *reinterpret_cast<uint4*>(dst) =
+                            *reinterpret_cast<uint4*>(hb + c * dstride) =
                                 make_uint4(pack_h2(x[0] + b0.x, x[1] + b0.y), pack_h2(x[2] + b0.z, x[3] + b0.w),
                                            pack_h2(x[4] + b1.x, x[5] + b1.y), pack_h2(x[6] + b1.z, x[7] + b1.w));
                         }
@@ -611,6 +656,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 if (which == 0) {                                        // X drained: the v chunk may overwrite it
                     tc_fence_before();
                     mbar_arrive(TBAR(e, T_XFREE));
+                } else if (which == 1 && MODE == TOK_MID) {              // Y drained: the next item's proj may overwrite it
+                    tc_fence_before();
+                    mbar_arrive(TBAR(e, T_DONE));
                 }
             }
         } else {
@@ -628,6 +676,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                     }
                 }
             });
+            tc_fence_before();
+            mbar_arrive(TBAR(e, T_DONE));                                // Y drained: the next item's proj may overwrite it
             float* vb = reinterpret_cast<float*>(smem + TC_SM_VB) + e * TILE_ROWS * 4;
             float4* px = reinterpret_cast<float4*>(stx);                 // the statistics exchange is idle now: partial sums of half 1
             asm volatile("bar.sync %0, 256;\n" :: "r"(1 + e) : "memory");  // ... once every thread has read its merge partner
@@ -671,9 +721,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 }
             }
         }
-        // item done: X / Y and this vector buffer may be reused (the next item's MMAs / vector copies wait on these)
-        tc_fence_before();
-        mbar_arrive(TBAR(e, T_DONE));
+        // item done: this vector buffer may be reused (the producer's copies for the item after next wait on it)
         mbar_arrive(BAR(B_VFREE + (it & 1)));
         STAMP(18);
         }
