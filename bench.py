@@ -32,6 +32,12 @@ FLOP_FWD = 976_960_512                 # per DiT forward per sequence (SURVEY §
 FLOP_ATTN_LAYER = 2 * 58_982_400       # QK^T + PV per sequence per block
 FLOP_TOKEN_MID = 15_728_640 + 31_457_280 + 31_457_280 + 47_185_920   # proj + fc1 + fc2 + next-block QKV
 FLOP_DECODE_96 = 15_360_000
+# algorithmic HBM bytes per sequence and launch: attention reads q|k|v images (4 heads x 94,208 B) and writes the
+# fp16 attention output (480 x 128 x 2); the MID token kernel reads the residual (fp32) and the attention output,
+# writes the residual and the next block's q|k|v images
+ALGO_BYTES_PER_SEQ = {"attention": 4 * 94_208 + 480 * 128 * 2, "token_mid": 2 * 480 * 128 * 4 + 480 * 128 * 2 + 4 * 94_208}
+# DRAM bytes per launch measured by ncu at nseq = 2048 (profiles/r01_ncu_full_v9_summary.json)
+NCU_DRAM_BYTES_PER_LAUNCH = {"attention": 772_190_208 + 229_606_144, "token_mid": 904_835_840 + 1_250_365_000}
 
 
 def parse():
@@ -335,7 +341,13 @@ def main():
             "tflops_algorithmic": world * B * a.steps * (2 * a.rf_steps * FLOP_FWD + FLOP_DECODE_96) / (ms / 1e3) / 1e12,
             "roofline": {"bound": "tensor", "kernel": "attn_kernel" if dom == "attention" else "token_kernel<MID>",
                          "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                         "traffic": None, "peak_source": pk["src"], "flop_per_launch": flop, "launch_ms": kb[dom]},
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dom) if nseq == 2048 else None,
+                         "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum at this workload size "
+                                           "(profiles/r01_ncu_full_v9_summary.json)",
+                         "algorithmic_bytes": ALGO_BYTES_PER_SEQ[dom] * nseq,
+                         "co_bound": "MUFU ex2: 0.9216 M exp per sequence-block at 16/clk/SM = 0.41 ms per 2048-sequence launch "
+                                     "(ncu: XU pipe 72 % busy)" if dom == "attention" else "epilogue issue + HBM",
+                         "peak_source": pk["src"], "flop_per_launch": flop, "launch_ms": kb[dom]},
             "kernel_ms": {k: round(v, 4) for k, v in kb.items()},
             "kernel_share_of_step": shares,
         }
