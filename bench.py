@@ -258,6 +258,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     dit = Transformer()
     dit.load_state_dict(synth.make_dit_state(0))
