@@ -9,7 +9,8 @@ from .backbone import DDPM, RectifiedFlow
 from .denoiser import Transformer, Transformerlayer, TimeEmbedding
 from .lavae import Decoder, Encoder, vqvae
 from .sampler import T2SSampler, gather_series, shard_range
+from .training import DitTrainer
 
 __all__ = ["Transformer", "Transformerlayer", "TimeEmbedding", "RectifiedFlow", "DDPM", "vqvae", "Encoder", "Decoder",
-           "T2SSampler", "gather_series", "shard_range"]
+           "T2SSampler", "gather_series", "shard_range", "DitTrainer"]
 __version__ = "0.1.0"

@@ -106,3 +106,30 @@ def test_data_parallel_gradient_convention_gloo_world2(tmp_path):
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_one_cycle_lr_matches_torch_scheduler():
+    from t2ms_b200.train_loop import one_cycle_lr
+    for total in (10, 57, 1000):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.AdamW([p], lr=1e-4, weight_decay=0.0)
+        sch = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-4, total_steps=total)      # train.py:38
+        for k in range(total):
+            assert abs(one_cycle_lr(k, total) - sch.get_last_lr()[0]) < 1e-12, (total, k)
+            opt.step()
+            if k < total - 1:
+                sch.step()
+
+
+def test_collate_by_length_groups_like_the_reference():
+    import numpy as np
+    from t2ms_b200.train_loop import collate_by_length
+    rng = np.random.default_rng(0)
+    items = []
+    for i, (idx, L) in enumerate([(2, 96), (0, 24), (1, 48), (0, 24), (2, 96), (2, 96)]):
+        items.append(((np.array([i]), rng.random(L, dtype=np.float32), rng.random(128, dtype=np.float32)), idx))
+    out = collate_by_length(items)
+    assert [tuple(x.shape) for _, x, _ in out] == [(2, 24), (1, 48), (3, 96)]
+    assert [int(t[0]) for t in out[2][0]] == [0, 4, 5] and out[2][2].shape == (3, 128)
+    only = collate_by_length(items[:1])
+    assert len(only) == 1 and only[0][1].shape == (1, 96)
