@@ -192,6 +192,17 @@ int t2s_train_make_inputs(int kind, const float* x1, const float* noise, const f
 int t2s_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, int step, float lr,
                    float beta1, float beta2, float eps, float weight_decay, float grad_scale, t2s_stream_t stream);
 
+/* The fused attention of the training step (timm Attention -> F.scaled_dot_product_attention at transformer.py:116
+ * and its autograd backward at train.py:83-85), exported for unit tests.  qkv / dqkv: [nseq*480][384] fp32 rows
+ * (q | k | v, head h in columns 32 h .. of each part); o / dout: [nseq*480][128]; nlse: [nseq][4][480] written by the
+ * forward (4 - log2-sum-exp of the scaled scores) and consumed by the backward.  scratch: caller-owned, 256-byte
+ * aligned, t2s_train_attention_scratch_bytes(nseq). */
+size_t t2s_train_attention_scratch_bytes(int nseq);
+int t2s_train_attention_forward(const float* qkv, float* o, float* nlse, int nseq, void* scratch, size_t scratch_bytes,
+                                t2s_stream_t stream);
+int t2s_train_attention_backward(const float* qkv, const float* o, const float* nlse, const float* dout, float* dqkv,
+                                 int nseq, void* scratch, size_t scratch_bytes, t2s_stream_t stream);
+
 /* The tcgen05 tf32 GEMM every training Linear runs on, exported for unit tests:
  * C[m][n] (mode 0: =, 1: +=, 2: atomic +=) alpha * sum_k A(m,k) B(n,k) (+ bias[n]);  a_mn / b_mn = 1: the operand is
  * stored transposed (element (m,k) at k*ld + m). */

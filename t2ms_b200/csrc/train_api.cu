@@ -5,6 +5,7 @@
 
 #include "api_common.h"
 #include "train_kernels.cuh"
+#include "train_attn.cuh"
 
 using namespace t2s;
 using namespace t2s_api;
@@ -21,6 +22,9 @@ int train_init() {
     CUDA_OK(cudaGetDevice(&dev));
     if (g_train_inited[dev]) return T2S_OK;
     CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(ta_attn_kernel<TA_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(ta_attn_kernel<TA_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(ta_attn_kernel<TA_DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM_BYTES));
     CUDA_OK(cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev));
     g_train_inited[dev] = true;
     return T2S_OK;
@@ -46,10 +50,6 @@ struct Gemm {
     Gemm& mode(int m) { a.mode = m; return *this; }
     Gemm& alpha(float v) { a.alpha = v; return *this; }
     Gemm& ksplit(int k) { a.ksplit = k < 1 ? 1 : k; return *this; }
-    Gemm& batched(int n, int bdiv, long long sah, long long sal, long long sbh, long long sbl, long long sch, long long scl) {
-        batch = n; a.bdiv = bdiv; a.sa_hi = sah; a.sa_lo = sal; a.sb_hi = sbh; a.sb_lo = sbl; a.sc_hi = sch; a.sc_lo = scl;
-        return *this;
-    }
     // weight-gradient form: few output tiles, long K -> split K so that about two waves of CTAs run
     Gemm& wgrad() {
         const int tiles = ((a.M + G_BM - 1) / G_BM) * ((a.N + a.bn - 1) / a.bn), ksteps = (a.K + G_BK - 1) / G_BK;
@@ -73,13 +73,34 @@ struct Gemm {
 };
 
 size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
-constexpr int ATT_CHUNK = 256;                       // sequences per attention score buffer (1.9 GB for S and dP)
+
+// scratch of the fused attention (train_attn.cuh): fp16 operand images of q | k | v and of the scaled dO, the per-row
+// D = rowsum(dO . O) and the per-(sequence, head) inverse dO scale
+struct AttnScratch {
+    __half *img, *doimg;
+    float *dvec, *dinv;
+    size_t total;
+};
+AttnScratch attn_scratch(void* base, int nseq) {
+    AttnScratch a;
+    char* b = static_cast<char*>(base);
+    size_t p = 0;
+    auto take = [&](size_t bytes) { char* r = b + p; p = align256(p + bytes); return r; };
+    a.img = reinterpret_cast<__half*>(take((size_t)nseq * NHEAD * 3 * TA_IMG_BYTES + 1024));
+    a.doimg = reinterpret_cast<__half*>(take((size_t)nseq * NHEAD * TA_IMG_BYTES + 1024));
+    a.dvec = reinterpret_cast<float*>(take((size_t)nseq * NHEAD * NTOK * 4));
+    a.dinv = reinterpret_cast<float*>(take((size_t)nseq * NHEAD * 4));
+    a.total = p;
+    return a;
+}
 
 struct TrainWs {
     float *sc, *mod, *dmod, *xp, *wemb, *bemb, *red;
     float* h[NLAYER + 1];
     float *a1[NLAYER], *qkv[NLAYER], *o[NLAYER], *y1[NLAYER], *hm[NLAYER], *a2[NLAYER], *z1[NLAYER], *hid[NLAYER], *y2[NLAYER];
-    float *g, *g2, *d1, *d2, *dqkv, *dob, *s, *dp;
+    float* nlse[NLAYER];
+    float *g, *g2, *d1, *d2, *dqkv, *dob;
+    AttnScratch att;
     size_t total;
 };
 TrainWs train_ws(void* base, int nseq) {
@@ -96,23 +117,34 @@ TrainWs train_ws(void* base, int nseq) {
         w.a2[l] = take(T * D); w.z1[l] = take(T * DMLP); w.hid[l] = take(T * DMLP); w.y2[l] = take(T * D);
     }
     w.g = take(T * D); w.g2 = take(T * D); w.d1 = take(T * D); w.d2 = take(T * DMLP); w.dqkv = take(T * 3 * D); w.dob = take(T * D);
-    const size_t ch = (size_t)(nseq < ATT_CHUNK ? nseq : ATT_CHUNK) * NHEAD * NTOK * NTOK;
-    w.s = take(ch); w.dp = take(ch);
+    for (int l = 0; l < NLAYER; ++l) w.nlse[l] = take((size_t)nseq * NHEAD * NTOK);
+    w.att = attn_scratch(b + p, nseq);
+    p = align256(p + w.att.total);
     w.total = p;
     return w;
 }
 
-const float kScale = 0.17677669529663687f;           // 1 / sqrt(32)
-const float kScaleLog2e = 0.25503486f;               // log2(e) / sqrt(32)
-
-// S = Q K^T and P = softmax(S / sqrt(32)) for sequences [c0, c0 + nb) of one block (timm Attention -> SDPA)
-int attn_probs(const float* qkv, float* s, int c0, int nb, cudaStream_t st) {
-    const float* q = qkv + (size_t)c0 * NTOK * 3 * D;
-    TRY(Gemm(q, q + D, s, NTOK, NTOK, HD, 3 * D, 3 * D, NTOK)
-            .batched(nb * NHEAD, NHEAD, (long long)NTOK * 3 * D, HD, (long long)NTOK * 3 * D, HD, (long long)NHEAD * NTOK * NTOK, (long long)NTOK * NTOK)
-            .launch(st));
-    const size_t rows = (size_t)nb * NHEAD * NTOK;
-    softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(s, rows, kScaleLog2e);
+// softmax(q k^T / sqrt(32)) v of every (sequence, head), keeping 4 - log2-sum-exp per row for the backward
+// (timm Attention -> F.scaled_dot_product_attention, transformer.py:116)
+int attn_forward(const float* qkv, float* o, float* nlse, const AttnScratch& a, int nseq, cudaStream_t st) {
+    const long long warps = (long long)nseq * (NTOK / 8) * 12;
+    ta_pack_qkv_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(qkv, a.img, nseq);
+    TaArgs p{};
+    p.img = a.img; p.o = o; p.nlse = nlse;
+    ta_attn_kernel<TA_FWD><<<nseq * NHEAD * TA_NTILE, TA_THREADS, TA_SMEM_BYTES, st>>>(p);
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+// d(q | k | v) from dO, recomputing the probabilities from q, k and the saved log-sum-exp
+int attn_backward(const float* qkv, const float* o, const float* nlse, const float* dout, float* dqkv, const AttnScratch& a, int nseq,
+                  cudaStream_t st) {
+    const long long warps = (long long)nseq * (NTOK / 8) * 12;
+    ta_pack_qkv_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(qkv, a.img, nseq);
+    ta_pack_do_kernel<<<nseq * NHEAD, 512, 0, st>>>(dout, o, a.doimg, a.dvec, a.dinv);
+    TaArgs p{};
+    p.img = a.img; p.doimg = a.doimg; p.nlse = const_cast<float*>(nlse); p.dvec = a.dvec; p.dinv = a.dinv; p.dqkv = dqkv;
+    ta_attn_kernel<TA_DQ><<<nseq * NHEAD * TA_NTILE, TA_THREADS, TA_SMEM_BYTES, st>>>(p);
+    ta_attn_kernel<TA_DKV><<<nseq * NHEAD * TA_NTILE, TA_THREADS, TA_SMEM_BYTES, st>>>(p);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
@@ -139,6 +171,25 @@ int t2s_gemm_tf32(const float* A, const float* B, float* C, const float* bias, i
     if (a_mn) g.amn();
     if (b_mn) g.bmn();
     return g.launch((cudaStream_t)stream);
+}
+
+size_t t2s_train_attention_scratch_bytes(int nseq) { return attn_scratch(nullptr, nseq > 0 ? nseq : 0).total; }
+
+int t2s_train_attention_forward(const float* qkv, float* o, float* nlse, int nseq, void* scratch, size_t scratch_bytes, t2s_stream_t stream) {
+    if (!qkv || !o || !nlse || nseq <= 0 || !scratch) return fail(T2S_EINVAL, "t2s_train_attention_forward: bad argument%s%s");
+    if ((reinterpret_cast<uintptr_t>(scratch) & 255) != 0) return fail(T2S_EINVAL, "scratch must be 256-byte aligned%s%s");
+    if (scratch_bytes < t2s_train_attention_scratch_bytes(nseq)) return fail(T2S_EWORKSPACE, "attention scratch too small%s%s");
+    TRY(train_init());
+    return attn_forward(qkv, o, nlse, attn_scratch(scratch, nseq), nseq, (cudaStream_t)stream);
+}
+
+int t2s_train_attention_backward(const float* qkv, const float* o, const float* nlse, const float* dout, float* dqkv, int nseq,
+                                 void* scratch, size_t scratch_bytes, t2s_stream_t stream) {
+    if (!qkv || !o || !nlse || !dout || !dqkv || nseq <= 0 || !scratch) return fail(T2S_EINVAL, "t2s_train_attention_backward: bad argument%s%s");
+    if ((reinterpret_cast<uintptr_t>(scratch) & 255) != 0) return fail(T2S_EINVAL, "scratch must be 256-byte aligned%s%s");
+    if (scratch_bytes < t2s_train_attention_scratch_bytes(nseq)) return fail(T2S_EWORKSPACE, "attention scratch too small%s%s");
+    TRY(train_init());
+    return attn_backward(qkv, o, nlse, dout, dqkv, attn_scratch(scratch, nseq), nseq, (cudaStream_t)stream);
 }
 
 int t2s_train_make_inputs(int kind, const float* x1, const float* noise, const float* ca, const float* cb, float* x_t, float* target,
@@ -190,14 +241,7 @@ int train_forward(const t2s_dit_params* P, const float* x_t, const float* t100, 
         const int mo = l * MOD;
         ln_mod_fwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(w.h[l], w.mod, MS, mo, w.a1[l], 1e-6f);
         TRY(Gemm(w.a1[l], P->qkv_w[l], w.qkv[l], T, 3 * D, D, D, D, 3 * D).bias(P->qkv_b[l]).launch(st));
-        for (int c0 = 0; c0 < nseq; c0 += ATT_CHUNK) {
-            const int nb = nseq - c0 < ATT_CHUNK ? nseq - c0 : ATT_CHUNK;
-            TRY(attn_probs(w.qkv[l], w.s, c0, nb, st));
-            const float* v = w.qkv[l] + (size_t)c0 * NTOK * 3 * D + 2 * D;
-            TRY(Gemm(w.s, v, w.o[l] + (size_t)c0 * NTOK * D, NTOK, HD, NTOK, NTOK, 3 * D, D).bmn()
-                    .batched(nb * NHEAD, NHEAD, (long long)NHEAD * NTOK * NTOK, (long long)NTOK * NTOK, (long long)NTOK * 3 * D, HD, (long long)NTOK * D, HD)
-                    .launch(st));
-        }
+        TRY(attn_forward(w.qkv[l], w.o[l], w.nlse[l], w.att, nseq, st));
         TRY(Gemm(w.o[l], P->proj_w[l], w.y1[l], T, D, D, D, D, D).bias(P->proj_b[l]).launch(st));
         gate_res_fwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(w.h[l], w.y1[l], w.mod, MS, mo + 2 * D, w.hm[l]);
         ln_mod_fwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(w.hm[l], w.mod, MS, mo + 3 * D, w.a2[l], 1e-6f);
@@ -233,23 +277,7 @@ int train_backward(const t2s_dit_params* P, const t2s_dit_params* Gp, const Trai
         TRY(Gemm(w.d1, w.o[l], Gp->proj_w[l], D, D, T, D, D, D).amn().bmn().wgrad().launch(st));
         TRY(Gemm(w.d1, P->proj_w[l], w.dob, T, D, D, D, D, D).bmn().launch(st));
         CUDA_OK(cudaGetLastError());
-        for (int c0 = 0; c0 < nseq; c0 += ATT_CHUNK) {
-            const int nb = nseq - c0 < ATT_CHUNK ? nseq - c0 : ATT_CHUNK, nbh = nb * NHEAD;
-            const long long SQ = (long long)NTOK * NTOK, SH = (long long)NHEAD * SQ, RQ = (long long)NTOK * 3 * D, RO = (long long)NTOK * D;
-            TRY(attn_probs(w.qkv[l], w.s, c0, nb, st));
-            const float* q = w.qkv[l] + (size_t)c0 * RQ;
-            const float* dO = w.dob + (size_t)c0 * RO;
-            float* dq = w.dqkv + (size_t)c0 * RQ;
-            // dP = dO V^T ; dS = P * (dP - rowsum(P dP)) / sqrt(32)
-            TRY(Gemm(dO, q + 2 * D, w.dp, NTOK, NTOK, HD, D, 3 * D, NTOK).batched(nbh, NHEAD, RO, HD, RQ, HD, SH, SQ).launch(st));
-            const size_t rows = (size_t)nbh * NTOK;
-            softmax_bwd_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w.s, w.dp, rows, kScale);
-            CUDA_OK(cudaGetLastError());
-            // dV = P^T dO ; dQ = dS K ; dK = dS^T Q
-            TRY(Gemm(w.s, dO, dq + 2 * D, NTOK, HD, NTOK, NTOK, D, 3 * D).amn().bmn().batched(nbh, NHEAD, SH, SQ, RO, HD, RQ, HD).launch(st));
-            TRY(Gemm(w.dp, q + D, dq, NTOK, HD, NTOK, NTOK, 3 * D, 3 * D).bmn().batched(nbh, NHEAD, SH, SQ, RQ, HD, RQ, HD).launch(st));
-            TRY(Gemm(w.dp, q, dq + D, NTOK, HD, NTOK, NTOK, 3 * D, 3 * D).amn().bmn().batched(nbh, NHEAD, SH, SQ, RQ, HD, RQ, HD).launch(st));
-        }
+        TRY(attn_backward(w.qkv[l], w.o[l], w.nlse[l], w.dob, w.dqkv, w.att, nseq, st));
         TRY(colsum(w.dqkv, T, 3 * D, 3 * D, Gp->qkv_b[l], st));
         TRY(Gemm(w.dqkv, w.a1[l], Gp->qkv_w[l], 3 * D, D, T, 3 * D, D, D).amn().bmn().wgrad().launch(st));
         TRY(Gemm(w.dqkv, P->qkv_w[l], w.d1, T, D, 3 * D, 3 * D, D, D).bmn().launch(st));

@@ -3,8 +3,9 @@
 // The training path is modular: activations live in plain row-major fp32 [tokens][features] buffers
 // (token row = seq * 480 + n), every Linear (forward, input-gradient and weight-gradient form) goes through one
 // generic tcgen05 GEMM (kind::tf32, fp32 operands straight from the parameter / activation buffers, fp32
-// accumulation in TMEM), and the token-local maths (LayerNorm + modulate, gates, GELU, softmax and their
-// backward forms, the per-sequence adaLN reductions, bias column sums, loss) runs in warp-per-row kernels.
+// accumulation in TMEM), the token-local maths (LayerNorm + modulate, gates, GELU and their backward forms, the
+// per-sequence adaLN reductions, bias column sums, loss) runs in warp-per-row kernels, and attention (forward and
+// backward) is fused on tcgen05 without materialised scores (train_attn.cuh).
 #pragma once
 #include "common.cuh"
 
@@ -416,39 +417,6 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
         for (int w = 0; w < 8; ++w) s += sm[w][threadIdx.x];
         atomicAdd(out + blockIdx.x * D + threadIdx.x, s);
     }
-}
-
-// ---- softmax over the rows of the score matrices S [nmat][480][480] in place: P = softmax(S * scale)
-// one warp per row (15 elements per lane)
-__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ s, size_t nrows, float scale_log2e) {
-    const int lane = threadIdx.x & 31;
-    const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= nrows) return;
-    float* r = s + row * NTOK;
-    float v[15], m = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 15; ++i) { v[i] = r[lane + 32 * i]; m = fmaxf(m, v[i]); }
-    m = warp_max(m);
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < 15; ++i) { v[i] = exp2f((v[i] - m) * scale_log2e); sum += v[i]; }
-    const float inv = 1.f / warp_sum(sum);
-#pragma unroll
-    for (int i = 0; i < 15; ++i) r[lane + 32 * i] = round_tf32(v[i] * inv);
-}
-// dS = P * (dP - sum_j P dP) * scale, in place over dP
-__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const float* __restrict__ p, float* __restrict__ dp, size_t nrows, float scale) {
-    const int lane = threadIdx.x & 31;
-    const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= nrows) return;
-    const float* pr = p + row * NTOK;
-    float* dr = dp + row * NTOK;
-    float a[15], b[15], dot = 0.f;
-#pragma unroll
-    for (int i = 0; i < 15; ++i) { a[i] = pr[lane + 32 * i]; b[i] = dr[lane + 32 * i]; dot = fmaf(a[i], b[i], dot); }
-    dot = warp_sum(dot);
-#pragma unroll
-    for (int i = 0; i < 15; ++i) dr[lane + 32 * i] = round_tf32(a[i] * (b[i] - dot) * scale);
 }
 
 // ---- final LN (affine, eps 1e-5) + Linear(128 -> 4) + unpatchify (transformer.py:182-190), fused with the MSE loss

@@ -66,6 +66,60 @@ def test_gemm_epilogues():
     assert rel(gemm(A, B, M, N, K, K, K, 0, 0, mode=2, ksplit=5, C0=c0.to(DEV)), ref + c0.double()) < 1.5e-3
 
 
+def _attention(qkv, dout):
+    """Fused training attention through the C ABI: returns (o, dqkv)."""
+    lib = _lib.load()
+    nseq = qkv.shape[0]
+    nb = lib.t2s_train_attention_scratch_bytes(nseq)
+    scratch = torch.empty(nb + 256, dtype=torch.uint8, device=DEV)
+    sp = (scratch.data_ptr() + 255) // 256 * 256
+    o = torch.empty(nseq, 480, 128, device=DEV)
+    nlse = torch.empty(nseq, 4, 480, device=DEV)
+    dqkv = torch.full((nseq, 480, 384), float("nan"), device=DEV)
+    _lib.check(lib.t2s_train_attention_forward(qkv.data_ptr(), o.data_ptr(), nlse.data_ptr(), nseq, sp, nb, stream()), "attention forward")
+    _lib.check(lib.t2s_train_attention_backward(qkv.data_ptr(), o.data_ptr(), nlse.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), nseq, sp, nb,
+                                                stream()), "attention backward")
+    torch.cuda.synchronize()
+    return o, nlse, dqkv
+
+
+def _attention_reference(qkv, dout):
+    """fp64 torch reference of timm Attention's core (transformer.py:116 -> F.scaled_dot_product_attention) and its autograd."""
+    x = qkv.double().clone().requires_grad_(True)
+    nseq = x.shape[0]
+    q, k, v = x.view(nseq, 480, 3, 4, 32).permute(2, 0, 3, 1, 4).unbind(0)
+    s = (q @ k.transpose(-1, -2)) / 32 ** 0.5
+    o = (s.softmax(-1) @ v).transpose(1, 2).reshape(nseq, 480, 128)
+    o.backward(dout.double())
+    lse2 = torch.logsumexp(s, -1) / np.log(2.0)
+    return o.detach(), lse2.detach(), x.grad
+
+
+@pytest.mark.parametrize("nseq,qscale,dscale", [(1, 1.0, 1.0), (3, 1.0, 1e-6), (2, 4.0, 30.0)])
+def test_fused_attention_forward_backward(nseq, qscale, dscale):
+    """Fused tcgen05 attention forward (saved log-sum-exp) and backward (dq, dk, dv) against the fp64 torch autograd of the
+    same op.  fp16 operands / fp32 accumulation: rel-L2 <= 2e-3 forward, <= 5e-3 per gradient part.  dscale exercises
+    the per-(sequence, head) power-of-two dO scaling (tiny MSE-mean gradients, large gradients); qscale 4 gives peaked
+    softmax rows that move the forward's reference point."""
+    g = torch.Generator().manual_seed(11 + nseq)
+    qkv = torch.randn(nseq, 480, 384, generator=g)
+    qkv[..., :256] *= qscale
+    dout = torch.randn(nseq, 480, 128, generator=g) * dscale
+    dout[:, :, 32:64] *= 1e-3                                  # heads with very different gradient magnitudes
+    qkv, dout = qkv.to(DEV), dout.to(DEV)
+    o, nlse, dqkv = _attention(qkv, dout)
+    ro, rlse2, rd = _attention_reference(qkv, dout)
+    assert rel(o, ro) < 2e-3, rel(o, ro)
+    # log-sum-exp: absolute error scales with the score magnitude (fp16 operand rounding of q, k: ~5e-4 relative)
+    assert (4.0 - nlse.double().cpu() - rlse2.cpu()).abs().max().item() < 2e-3 * (1.0 + rlse2.abs().max().item())
+    assert torch.isfinite(dqkv).all()
+    for name, sl in (("dq", slice(0, 128)), ("dk", slice(128, 256)), ("dv", slice(256, 384))):
+        for h in range(4):
+            hs = slice(sl.start + 32 * h, sl.start + 32 * h + 32)
+            e = rel(dqkv[..., hs], rd[..., hs])
+            assert e < 5e-3, (name, h, e)
+
+
 def _golden_case():
     g = load_golden("train.npz")
     dsd = synth.make_dit_state(int(g["dit_seed"]), bias_std=float(g["bias_std"]))
