@@ -118,6 +118,15 @@ int t2s_vae_decode(const t2s_vae_dec_weights* w, const float* z, float* series, 
 int t2s_vae_encode(const t2s_vae_enc_weights* w, const float* x, float* z, float* before, int batch, int length,
                    t2s_stream_t stream);
 
+/* Evaluation of generated series on the device (the step after the path): evaluation.py:166-181 calculate_mse and
+ * evaluation.py:184-206 calculate_wape on univariate series (the (N, L, 1) arrays written at infer.py:117-121).
+ *   ori, gen    [n][length] fp32
+ *   per_sample  [n][3] fp32 out: sum (ori-gen)^2, sum |ori-gen|, sum |ori| of every sample
+ *   out         [3] fp64 DEVICE: MSE = mean_i mean_t (ori-gen)^2 ; WAPE = nanmean_i (sum|ori-gen| / sum|ori|) ; number of
+ *               samples with a nonzero denominator (WAPE is NaN when there is none, like np.nanmean)                  */
+int t2s_series_metrics(const float* ori, const float* gen, int n, int length, float* per_sample, double* out,
+                       t2s_stream_t stream);
+
 /* Single stages of the denoiser, exported for stage-wise parity tests.  Workspace layout:
  * t2s_dit_workspace_offsets() fills {h, qkv, o, mod} byte offsets. */
 void t2s_dit_workspace_offsets(int nseq, size_t offsets[4]);

@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Golden fixtures for the rows SURVEY.md §8(f) marks "next", generated from the UNMODIFIED reference on CPU.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (where /root/reference is mounted):
+
+    python oracle/make_golden_next.py [--only eval,dit_tokens,vae_train]
+
+Writes tests/golden/eval.npz (evaluation.py calculate_mse / calculate_wape; the module cannot be imported here — it pulls
+dtaidistance and TS2Vec at import time — so the two function definitions are compiled from the reference file's own
+source text, unmodified, via ``ast``), and further fixtures as the corresponding rows are built.  Nothing from
+/root/reference is copied into the repo; only numeric outputs are committed, together with this script.
+"""
+from __future__ import annotations
+
+import argparse
+import ast
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def reference_functions(path: str, names):
+    """Compile the named top-level functions of a reference file from its own source (no module import)."""
+    src = open(path).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert len(keep) == len(names), [n.name for n in keep]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def make_eval(ref: str, out: str):
+    mse, wape = reference_functions(os.path.join(ref, "evaluation.py"), ["calculate_mse", "calculate_wape"])
+    rng = np.random.default_rng(5)
+    cases = {}
+    for name, (n, L) in {"a": (7, 24), "b": (33, 96), "c": (5, 48)}.items():
+        ori = rng.random((n, L, 1)).astype(np.float32)                 # the saved layout (infer.py:115-116)
+        gen = (ori + 0.1 * rng.standard_normal((n, L, 1))).astype(np.float32)
+        if name == "c":
+            ori[2] = 0.0                                               # a sample with a zero denominator -> NaN -> nanmean skips it
+        o, g = np.transpose(ori, (0, 2, 1)), np.transpose(gen, (0, 2, 1))   # evaluation.py:295-296
+        cases[f"{name}/ori"], cases[f"{name}/gen"] = ori, gen
+        cases[f"{name}/mse"], cases[f"{name}/wape"] = np.float64(mse(o, g)), np.float64(wape(o, g))
+    np.savez_compressed(os.path.join(out, "eval.npz"), **cases)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    only = set(filter(None, a.only.split(",")))
+    torch.set_num_threads(8)
+    makers = {"eval": make_eval}
+    for name, fn in makers.items():
+        if not only or name in only:
+            fn(a.ref, a.out)
+            print("wrote", name)
+    for f in sorted(os.listdir(a.out)):
+        print(f, os.path.getsize(os.path.join(a.out, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -300,3 +300,25 @@ def adamw_step(p, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-
     denom = (v.sqrt() / math.sqrt(bc2)) + eps
     p = p - (lr / bc1) * m / denom
     return p, m, v
+
+
+# ---------------------------------------------------------------------------------- evaluation of generated series
+def calculate_mse(ori_data, gen_data) -> float:
+    """evaluation.py:166-181: arrays (n_samples, a, b); per sample the mean over axis 1 of the squared error, averaged
+    over the b slices and then over the samples (= the plain mean for equal-sized slices, kept in the reference's order
+    of means)."""
+    import numpy as np
+    ori, gen = np.asarray(ori_data, dtype=np.float64), np.asarray(gen_data, dtype=np.float64)
+    per_slice = ((ori - gen) ** 2).mean(axis=1)          # (n, b): np.mean over [i, :, j]
+    return float(per_slice.mean(axis=1).mean())
+
+
+def calculate_wape(ori_data, gen_data) -> float:
+    """evaluation.py:184-206: per sample sum |ori - gen| / sum |ori| over all its elements (NaN when the denominator
+    is 0), then np.nanmean over the samples."""
+    import numpy as np
+    ori, gen = np.asarray(ori_data, dtype=np.float64), np.asarray(gen_data, dtype=np.float64)
+    num = np.abs(ori - gen).reshape(ori.shape[0], -1).sum(axis=1)
+    den = np.abs(ori).reshape(ori.shape[0], -1).sum(axis=1)
+    ratio = np.where(den != 0, num / np.where(den != 0, den, 1.0), np.nan)
+    return float(np.nanmean(ratio)) if np.any(den != 0) else float("nan")

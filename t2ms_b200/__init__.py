@@ -10,7 +10,9 @@ from .denoiser import Transformer, Transformerlayer, TimeEmbedding
 from .lavae import Decoder, Encoder, vqvae
 from .sampler import T2SSampler, gather_series, shard_range
 from .training import DitTrainer
+from .outputs import load_generation, run_inference, save_generation, series_metrics
 
 __all__ = ["Transformer", "Transformerlayer", "TimeEmbedding", "RectifiedFlow", "DDPM", "vqvae", "Encoder", "Decoder",
-           "T2SSampler", "gather_series", "shard_range", "DitTrainer"]
+           "T2SSampler", "gather_series", "shard_range", "DitTrainer",
+           "series_metrics", "run_inference", "save_generation", "load_generation"]
 __version__ = "0.1.0"

@@ -18,7 +18,7 @@ EXPORTS = [
     "t2s_dit_cond", "t2s_dit_embed_qkv", "t2s_dit_attention", "t2s_dit_block_post", "t2s_dit_final",
     "t2s_train_workspace_bytes", "t2s_dit_train_step", "t2s_dit_train_forward", "t2s_dit_train_backward",
     "t2s_train_make_inputs", "t2s_adamw_step", "t2s_gemm_tf32",
-    "t2s_train_attention_scratch_bytes", "t2s_train_attention_forward", "t2s_train_attention_backward",
+    "t2s_series_metrics", "t2s_train_attention_scratch_bytes", "t2s_train_attention_forward", "t2s_train_attention_backward",
 ]
 
 P = C.c_void_p
@@ -112,6 +112,8 @@ def load() -> C.CDLL:
         lib.t2s_train_attention_forward.argtypes = [P, P, P, i, P, sz, P]
         lib.t2s_train_attention_backward.restype = i
         lib.t2s_train_attention_backward.argtypes = [P, P, P, P, P, i, P, sz, P]
+        lib.t2s_series_metrics.restype = i
+        lib.t2s_series_metrics.argtypes = [P, P, i, i, P, P, P]
         _lib = lib
         return lib
 

@@ -5,6 +5,7 @@
 #include "../../include/t2s_b200.h"
 #include "dit_kernels.cuh"
 #include "vae_kernels.cuh"
+#include "eval_kernels.cuh"
 
 using namespace t2s;
 
@@ -255,6 +256,16 @@ int t2s_vae_encode(const t2s_vae_enc_weights* w, const float* x, float* z, float
         case 96: vae_encode_kernel<24><<<batch, 256, smem, st>>>(ew, x, z, before); break;
         default: return fail(T2S_EINVAL, "t2s_vae_encode: length must be 24, 48 or 96%s%s");
     }
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+
+int t2s_series_metrics(const float* ori, const float* gen, int n, int length, float* per_sample, double* out, t2s_stream_t stream) {
+    if (!ori || !gen || !per_sample || !out || n <= 0 || length <= 0) return fail(T2S_EINVAL, "t2s_series_metrics: bad argument%s%s");
+    TRY(ensure_init());
+    cudaStream_t st = (cudaStream_t)stream;
+    series_sums_kernel<<<(n + 7) / 8, 256, 0, st>>>(ori, gen, n, length, per_sample);
+    series_metrics_finish_kernel<<<1, 1024, 0, st>>>(per_sample, n, length, out);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }

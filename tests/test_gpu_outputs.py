@@ -1,0 +1,66 @@
+"""GPU parity of the step after the hot path: on-device MSE / WAPE (evaluation.py:166-206) and the generation file
+formats of infer.py:100-123, through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from gpu_util import make_dit, make_vae
+from oracle import t2s_oracle as O
+from t2ms_b200 import T2SSampler, load_generation, run_inference, series_metrics, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_series_metrics_match_reference_golden(case):
+    """fp32 per-sample sums, fp64 means: relative 2e-6 against the reference's (float32) numpy loops."""
+    g = load_golden("eval.npz")
+    ori, gen = torch.from_numpy(g[f"{case}/ori"]).to(DEV), torch.from_numpy(g[f"{case}/gen"]).to(DEV)
+    m = series_metrics(ori, gen)
+    assert abs(m["MSE"] - float(g[f"{case}/mse"])) <= 2e-6 * float(g[f"{case}/mse"])
+    assert abs(m["WAPE"] - float(g[f"{case}/wape"])) <= 2e-6 * float(g[f"{case}/wape"])
+    assert m["valid"] == ori.shape[0] - (1 if case == "c" else 0)
+    # the (N, 1, L) layout of evaluation.py:295-296 gives the same numbers
+    m2 = series_metrics(ori.transpose(1, 2), gen.transpose(1, 2))
+    assert m2 == m
+
+
+def test_series_metrics_edge_cases():
+    z = torch.zeros(4, 24, device=DEV)
+    m = series_metrics(z, z + 1.0)
+    assert m["MSE"] == 1.0 and np.isnan(m["WAPE"]) and m["valid"] == 0          # np.nanmean of all-NaN
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.rand(100_000, 96, generator=g), torch.rand(100_000, 96, generator=g)
+    m = series_metrics(a.to(DEV), b.to(DEV))
+    ref_mse, ref_wape = O.calculate_mse(a.numpy()[:, None, :], b.numpy()[:, None, :]), O.calculate_wape(a.numpy()[:, None, :], b.numpy()[:, None, :])
+    assert abs(m["MSE"] - ref_mse) <= 1e-6 * ref_mse and abs(m["WAPE"] - ref_wape) <= 1e-6 * ref_wape
+    with pytest.raises(RuntimeError):
+        series_metrics(a, b)                                                        # CPU tensors: no fallback
+
+
+def test_run_inference_writes_reference_formats(tmp_path):
+    """infer.py:66-123 on the fused sampler: two batches, saved arrays have the reference's shapes / dtypes, the
+    generated series equal a direct sampler call with the same generator state, metrics equal the oracle's."""
+    dit, vae = make_dit(31), make_vae(32)
+    smp = T2SSampler(dit, vae)
+    L, steps = 48, 4
+    gen = torch.Generator().manual_seed(9)
+    batches = [("text", torch.rand(3, L, generator=gen), synth.make_text_embeddings(3, seed=40)),
+               ("text", torch.rand(2, L, generator=gen), synth.make_text_embeddings(2, seed=41))]
+    g1 = torch.Generator(device=DEV).manual_seed(123)
+    x_1, x_t, dec, enc, metrics = run_inference(smp, vae, batches, "flowmatching", steps, 7.0, save_path=str(tmp_path / "run_0"), generator=g1)
+    assert x_1.shape == (5, L, 1) and x_t.shape == (5, L, 1) and dec.shape == (5, 64, 30) and enc.shape == (5, 64, 30)
+    assert x_1.dtype == np.float32 and x_t.dtype == np.float32
+    saved = load_generation(str(tmp_path / "run_0"))
+    assert sorted(os.listdir(tmp_path / "run_0")) == ["x_1.npy", "x_t.npy", "x_t_latent_dec_array.npy", "x_t_latent_enc_array.npy"]
+    assert np.array_equal(saved["x_t"], x_t) and np.array_equal(saved["x_1"], x_1)
+    g2 = torch.Generator(device=DEV).manual_seed(123)
+    direct = torch.cat([smp.sample(b[2].to(DEV), L, steps=steps, cfg_scale=7.0, generator=g2) for b in batches], 0)
+    assert np.array_equal(direct.cpu().numpy(), x_t[:, :, 0])
+    o, x = np.transpose(x_1, (0, 2, 1)), np.transpose(x_t, (0, 2, 1))               # evaluation.py:295-296
+    assert abs(metrics["MSE"] - O.calculate_mse(o, x)) <= 1e-6 * O.calculate_mse(o, x)
+    assert abs(metrics["WAPE"] - O.calculate_wape(o, x)) <= 1e-6 * O.calculate_wape(o, x)

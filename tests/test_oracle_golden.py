@@ -132,3 +132,14 @@ def test_train_step():
             close(grads[n].reshape(-1)[:256], g[k], 1e-7, rtol=2e-4)
             p, m, v = O.adamw_step(dit[n], grads[n], torch.zeros_like(dit[n]), torch.zeros_like(dit[n]), 1, 1e-4)
             close(p.reshape(-1)[:256], g["param_after/" + n], 2e-7)
+
+
+def test_series_metrics_oracle_matches_reference_functions():
+    """oracle calculate_mse / calculate_wape against the reference's own functions (evaluation.py:166-206) on the
+    transposed (N, 1, L) layout evaluation.py:295-296 feeds them, incl. a zero-denominator sample (nanmean).  The
+    reference accumulates in the arrays' float32, the oracle in float64: relative 1e-6."""
+    g = load_golden("eval.npz")
+    for c in "abc":
+        o, x = np.transpose(g[f"{c}/ori"], (0, 2, 1)), np.transpose(g[f"{c}/gen"], (0, 2, 1))
+        assert abs(O.calculate_mse(o, x) - float(g[f"{c}/mse"])) <= 1e-6 * float(g[f"{c}/mse"])
+        assert abs(O.calculate_wape(o, x) - float(g[f"{c}/wape"])) <= 1e-6 * float(g[f"{c}/wape"])
