@@ -41,10 +41,15 @@ typedef struct {
     const float* b_ada;     /* [4][768] */
     const float* w_embed;   /* [128][4]  patch_emb.weight @ conv.weight.view(4,4) */
     const float* b_embed;   /* [128]     patch_emb.weight @ conv.bias + patch_emb.bias */
-    const float* pos;       /* [8 tiles][32 col chunks][64 rows][4] pos_embed in the residual tile layout */
+    const float* pos;       /* [tiles][32 col chunks][64 rows][4] pos_embed in the residual tile layout (8 tiles of 60 tokens for H = 30) */
     const float* w_final;   /* [4][128]  linear_emb_to_patch.weight * ln.weight */
     const float* b_final;   /* [4]       linear_emb_to_patch.weight @ ln.bias + linear_emb_to_patch.bias */
     const float* freqs;     /* [64]      10000 ** linspace(0,1,64)   (TimeEmbedding, transformer.py:34) */
+    /* latent width H (axis 2 of the (B,64,H) latent): 0 or 30 = T2S (transformer.py:132); 50 / 64 = the fork's
+     * Transformer(dim) (model/denoiser/mytransformer.py:128-136 with config.yaml:46,91 flow_dim).  Tokens = 16 H;
+     * pos is [16 H / T tiles][32][64][4] with T = 60 | 50 | 64 tokens per tile; every latent buffer of the calls
+     * below is [..][64][H]. */
+    int latent_h;
 } t2s_dit_weights;
 
 /* LA-VAE decoder / encoder weights (model/pretrained/vqvae.py:36-105), fp32, [ic][k][oc] layouts. */
@@ -84,7 +89,8 @@ void t2s_debug_set_phase_trace(long long* device_buf);
 
 /* Bytes of scratch for `nseq` sequences (residual stream, q|k|v, attention output, modulation).
  * Contents need no initialisation; rows of partially filled tiles are never read back. */
-size_t t2s_dit_workspace_bytes(int nseq);
+size_t t2s_dit_workspace_bytes(int nseq);                       /* H = 30 */
+size_t t2s_dit_workspace_bytes_h(int nseq, int latent_h);       /* 0 when latent_h is unsupported */
 
 /* Transformer.forward (model/denoiser/transformer.py:158-193).
  *   x    [nseq][64][30] fp32      latent
@@ -130,10 +136,12 @@ int t2s_series_metrics(const float* ori, const float* gen, int n, int length, fl
 /* Single stages of the denoiser, exported for stage-wise parity tests.  Workspace layout:
  * t2s_dit_workspace_offsets() fills {h, qkv, o, mod} byte offsets. */
 void t2s_dit_workspace_offsets(int nseq, size_t offsets[4]);
+int t2s_dit_workspace_offsets_h(int nseq, int latent_h, size_t offsets[4]);
 int t2s_dit_cond(const t2s_dit_weights* w, const float* t100, int t_stride, const float* emb, int cfg_pairs,
                  int nseq, void* workspace, t2s_stream_t stream);
 int t2s_dit_embed_qkv(const t2s_dit_weights* w, const float* x, int x_shared, int nseq, void* workspace, t2s_stream_t stream);
 int t2s_dit_attention(int nseq, void* workspace, t2s_stream_t stream);
+int t2s_dit_attention_h(int nseq, int latent_h, void* workspace, t2s_stream_t stream);
 int t2s_dit_block_post(const t2s_dit_weights* w, int layer, int nseq, void* workspace, t2s_stream_t stream);
 int t2s_dit_final(const t2s_dit_weights* w, float* out, int nseq, void* workspace, t2s_stream_t stream);
 

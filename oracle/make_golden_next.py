@@ -51,6 +51,60 @@ def make_eval(ref: str, out: str):
     np.savez_compressed(os.path.join(out, "eval.npz"), **cases)
 
 
+def make_dit_tokens(ref: str, out: str):
+    """The fork's variable-width denoiser, model/denoiser/mytransformer.py ``Transformer(dim)`` with dim = 50 and 64
+    (config.yaml:46,91 flow_dim): forward (float and int64 t, with / without text) and a 3-step guided rectified-flow and
+    DDPM loop (infer.py:75-88 semantics, as myinfer.py drives it) on the same synthetic weights / inputs as the tests."""
+    from make_golden import install_shims
+    from t2ms_b200 import synth
+    install_shims(ref)
+    sys.path.insert(0, ref)
+    from model.denoiser.mytransformer import Transformer
+    from model.backbone.rectified_flow import RectifiedFlow
+    from model.backbone.DDPM import DDPM
+    res = {}
+    for dim in (50, 64):
+        sd = synth.make_dit_state(40 + dim, bias_std=0.05, dim=dim)
+        m = Transformer(dim)
+        m.load_state_dict(sd, strict=True)
+        m.eval()
+        B = 2
+        x = synth.make_noise(B, seed=50 + dim, dim=dim)
+        emb = synth.make_text_embeddings(B, seed=60 + dim)
+        t_f, t_i = torch.tensor([0.25, 0.9]), torch.tensor([3, 871], dtype=torch.long)
+        k = f"h{dim}/"
+        with torch.no_grad():
+            res[k + "cond_float"] = m(input=x, t=t_f, text_input=emb).numpy()
+            res[k + "uncond_float"] = m(input=x, t=t_f, text_input=None).numpy()
+            res[k + "cond_int"] = m(input=x, t=t_i, text_input=emb).numpy()
+            steps, cfg = 3, 7.0
+            rf, x_t, vel = RectifiedFlow(), x.clone(), []
+            for j in range(steps):
+                t = torch.round(torch.full((B,), j * 1.0 / steps) * steps) / steps
+                u, c = m(input=x_t, t=t, text_input=None), m(input=x_t, t=t, text_input=emb)
+                pred = u + cfg * (c - u)
+                vel.append(pred.numpy())
+                x_t = rf.euler(x_t, pred, 1.0 / steps)
+            res[k + "rf_vel"], res[k + "rf_final"] = np.stack(vel), x_t.numpy()
+            ddpm, x_t, eps = DDPM(steps, "cpu"), x.clone(), []
+            sn = synth.make_step_noise(steps, B, seed=70 + dim, dim=dim)
+            for j in range(steps):
+                t = torch.full((B,), steps - 1 - j, dtype=torch.long)
+                u, c = m(input=x_t, t=t, text_input=None), m(input=x_t, t=t, text_input=emb)
+                pred = u + cfg * (c - u)
+                eps.append(pred.numpy())
+                torch.manual_seed(0)
+                real_randn = torch.randn
+                torch.randn = lambda *a, **kw: sn[j].clone()            # DDPM.p_sample draws its noise inside (DDPM.py:35)
+                try:
+                    x_t = ddpm.p_sample(x_t, pred, t)
+                finally:
+                    torch.randn = real_randn
+            res[k + "ddpm_eps"], res[k + "ddpm_final"] = np.stack(eps), x_t.numpy()
+        res[k + "checksum"] = np.array(synth.state_checksum(sd))
+    np.savez_compressed(os.path.join(out, "dit_tokens.npz"), **res)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -59,7 +113,7 @@ def main():
     a = ap.parse_args()
     only = set(filter(None, a.only.split(",")))
     torch.set_num_threads(8)
-    makers = {"eval": make_eval}
+    makers = {"eval": make_eval, "dit_tokens": make_dit_tokens}
     for name, fn in makers.items():
         if not only or name in only:
             fn(a.ref, a.out)

@@ -97,23 +97,26 @@ def dit_layer(sd: SD, l: int, x: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
 
 
 def dit_embed(sd: SD, inp: torch.Tensor) -> torch.Tensor:
-    """Patchify + embed, transformer.py:166-172.  inp (B,64,30) -> (B,480,128)."""
-    x = inp.permute(0, 2, 1).unsqueeze(1)                      # (B,1,30,64)
-    x = F.conv2d(x, sd["conv.weight"], sd["conv.bias"], stride=2)   # (B,4,15,32)
+    """Patchify + embed, transformer.py:166-172.  inp (B,64,H) -> (B,16 H,128); H = 30 in T2S, H = dim in the fork's
+    Transformer(dim) (mytransformer.py:128-136,166-172: identical code with self.H = dim)."""
+    x = inp.permute(0, 2, 1).unsqueeze(1)                      # (B,1,H,64)
+    x = F.conv2d(x, sd["conv.weight"], sd["conv.bias"], stride=2)   # (B,4,H/2,32)
     x = x.permute(0, 2, 3, 1)
-    x = x.reshape(x.size(0), N_TOK, x.size(3))
+    x = x.reshape(x.size(0), x.size(1) * x.size(2), x.size(3))
     x = F.linear(x, sd["patch_emb.weight"], sd["patch_emb.bias"])
     return x + sd["pos_embed"]
 
 
 def dit_unembed(sd: SD, x: torch.Tensor) -> torch.Tensor:
-    """Final LN + projection + unpatchify, transformer.py:182-190.  (B,480,128) -> (B,64,30)."""
+    """Final LN + projection + unpatchify, transformer.py:182-190 (mytransformer.py:182-190 with H = dim).
+    (B,16 H,128) -> (B,64,H)."""
     x = F.layer_norm(x, (D_MODEL,), sd["ln.weight"], sd["ln.bias"], eps=1e-5)
     x = F.linear(x, sd["linear_emb_to_patch.weight"], sd["linear_emb_to_patch.bias"])
     B = x.size(0)
-    x = x.view(B, LAT_P // 2, LAT_C // 2, 1, 2, 2)
+    lat_p = x.size(1) // (LAT_C // 2) * 2                      # H
+    x = x.view(B, lat_p // 2, LAT_C // 2, 1, 2, 2)
     x = x.permute(0, 3, 1, 2, 4, 5).permute(0, 1, 2, 4, 3, 5)
-    x = x.reshape(B, 1, LAT_P, LAT_C).squeeze(1)
+    x = x.reshape(B, 1, lat_p, LAT_C).squeeze(1)
     return x.permute(0, 2, 1)
 
 

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libt2s_b200.so")
 
 EXPORTS = [
     "t2s_version", "t2s_last_error", "t2s_init", "t2s_debug_set_phase_trace", "t2s_dit_workspace_bytes", "t2s_dit_workspace_offsets",
+    "t2s_dit_workspace_bytes_h", "t2s_dit_workspace_offsets_h", "t2s_dit_attention_h",
     "t2s_dit_forward", "t2s_sample", "t2s_vae_decode", "t2s_vae_encode",
     "t2s_dit_cond", "t2s_dit_embed_qkv", "t2s_dit_attention", "t2s_dit_block_post", "t2s_dit_final",
     "t2s_train_workspace_bytes", "t2s_dit_train_step", "t2s_dit_train_forward", "t2s_dit_train_backward",
@@ -27,7 +28,7 @@ P = C.c_void_p
 class DitWeights(C.Structure):
     _fields_ = [("w_qkv", P * 4), ("w_post", P * 4), ("b_qkv", P * 4), ("b_proj", P * 4), ("b_fc1", P * 4),
                 ("b_fc2", P * 4), ("w_ada_t", P), ("b_ada", P), ("w_embed", P), ("b_embed", P), ("pos", P),
-                ("w_final", P), ("b_final", P), ("freqs", P)]
+                ("w_final", P), ("b_final", P), ("freqs", P), ("latent_h", C.c_int)]
 
 
 class DitParams(C.Structure):
@@ -73,6 +74,12 @@ def load() -> C.CDLL:
         lib.t2s_dit_workspace_bytes.argtypes = [i]
         lib.t2s_dit_workspace_offsets.restype = None
         lib.t2s_dit_workspace_offsets.argtypes = [i, C.POINTER(sz * 4)]
+        lib.t2s_dit_workspace_bytes_h.restype = sz
+        lib.t2s_dit_workspace_bytes_h.argtypes = [i, i]
+        lib.t2s_dit_workspace_offsets_h.restype = i
+        lib.t2s_dit_workspace_offsets_h.argtypes = [i, i, C.POINTER(sz * 4)]
+        lib.t2s_dit_attention_h.restype = i
+        lib.t2s_dit_attention_h.argtypes = [i, i, P, P]
         lib.t2s_dit_forward.restype = i
         lib.t2s_dit_forward.argtypes = [C.POINTER(DitWeights), P, P, P, P, i, P, sz, P]
         lib.t2s_sample.restype = i

@@ -39,10 +39,15 @@ int t2s_api::ensure_init() {
     int major = 0;
     CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     if (major != 10) return fail(T2S_EARCH, "t2s_b200 is built for sm_100a only%s%s");
-    CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_EMBED>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+#define T2S_SET_ATTRS(HH)                                                                                                          \
+    CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_EMBED, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));       \
+    CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_MID, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));         \
+    CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_FINAL, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));       \
+    CUDA_OK(cudaFuncSetAttribute(attn_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttShape<HH>::SMEM_BYTES));
+    T2S_SET_ATTRS(30)
+    T2S_SET_ATTRS(50)
+    T2S_SET_ATTRS(64)
+#undef T2S_SET_ATTRS
     const int dec = VAE_DEC_SMEM_FLOATS * 4, enc = VAE_ENC_SMEM_FLOATS * 4;
     CUDA_OK(cudaFuncSetAttribute(vae_decode_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec));
     CUDA_OK(cudaFuncSetAttribute(vae_decode_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec));
@@ -62,34 +67,53 @@ size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 struct Workspace {
     float* h; __half* qkv; __half* o; float* mod;
 };
-void ws_offsets(int nseq, size_t off[4], size_t* total) {
+// run-time view of DitShape<H>
+struct Shape { int H, ntok, tiles_per_pair, head_halves, lat; };
+int get_shape(int latent_h, Shape* s) {
+    const int H = latent_h == 0 ? 30 : latent_h;
+    switch (H) {
+        case 30: *s = Shape{30, DitShape<30>::NTOK, DitShape<30>::TILES_PER_PAIR, DitShape<30>::HEAD_HALVES, DitShape<30>::LAT}; return T2S_OK;
+        case 50: *s = Shape{50, DitShape<50>::NTOK, DitShape<50>::TILES_PER_PAIR, DitShape<50>::HEAD_HALVES, DitShape<50>::LAT}; return T2S_OK;
+        case 64: *s = Shape{64, DitShape<64>::NTOK, DitShape<64>::TILES_PER_PAIR, DitShape<64>::HEAD_HALVES, DitShape<64>::LAT}; return T2S_OK;
+    }
+    return fail(T2S_EINVAL, "latent width must be 30 (T2S), 50 or 64 (fork configs)%s%s");
+}
+#define T2S_DISPATCH_H(H, STMT)                                     \
+    switch (H) {                                                    \
+        case 30: { constexpr int HH = 30; STMT; } break;            \
+        case 50: { constexpr int HH = 50; STMT; } break;            \
+        case 64: { constexpr int HH = 64; STMT; } break;            \
+        default: return fail(T2S_EINVAL, "unsupported latent width%s%s"); \
+    }
+
+void ws_offsets(int nseq, const Shape& sh, size_t off[4], size_t* total) {
     size_t p = 0;
-    const size_t ntile = (size_t)((nseq + 1) / 2) * TILES_PER_PAIR;           // pair tiles of 128 rows
+    const size_t ntile = (size_t)((nseq + 1) / 2) * sh.tiles_per_pair;         // pair tiles of 128 rows
     off[0] = p; p = align256(p + ntile * TILE_ROWS * D * 4);                   // residual stream tiles, fp32
-    off[1] = p; p = align256(p + (size_t)nseq * NHEAD * QKV_HEAD_HALVES * 2);  // q|k|v operand images, fp16
+    off[1] = p; p = align256(p + (size_t)nseq * NHEAD * sh.head_halves * 2);   // q|k|v operand images, fp16
     off[2] = p; p = align256(p + ntile * TILE_ROWS * D * 2);                   // attention-output tiles, fp16
     off[3] = p; p = align256(p + (size_t)nseq * NLAYER * MOD * 4);
     if (total) *total = p;
 }
-Workspace ws_view(void* base, int nseq) {
+Workspace ws_view(void* base, int nseq, const Shape& sh) {
     size_t off[4];
-    ws_offsets(nseq, off, nullptr);
+    ws_offsets(nseq, sh, off, nullptr);
     char* b = static_cast<char*>(base);
     return Workspace{reinterpret_cast<float*>(b + off[0]), reinterpret_cast<__half*>(b + off[1]),
                      reinterpret_cast<__half*>(b + off[2]), reinterpret_cast<float*>(b + off[3])};
 }
 
-int check_ws(const void* ws, size_t bytes, int nseq) {
+int check_ws(const void* ws, size_t bytes, int nseq, const Shape& sh) {
     if (ws == nullptr) return fail(T2S_EINVAL, "workspace is NULL%s%s");
     if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(T2S_EINVAL, "workspace must be 256-byte aligned%s%s");
-    if (bytes < t2s_dit_workspace_bytes(nseq)) return fail(T2S_EWORKSPACE, "workspace too small%s%s");
+    if (bytes < t2s_dit_workspace_bytes_h(nseq, sh.H)) return fail(T2S_EWORKSPACE, "workspace too small%s%s");
     return T2S_OK;
 }
 
-int token_grid(int nseq) {           // persistent: one CTA per SM, each looping over work items (two pair tiles)
+int token_grid(int nseq, const Shape& sh) {   // persistent: one CTA per SM, each looping over work items (two pair tiles)
     int dev = 0;
     cudaGetDevice(&dev);
-    const int items = ((nseq + 1) / 2) * (TILES_PER_PAIR / 2), sms = g_sms[dev] > 0 ? g_sms[dev] : 148;
+    const int items = ((nseq + 1) / 2) * (sh.tiles_per_pair / 2), sms = g_sms[dev] > 0 ? g_sms[dev] : 148;
     return items < sms ? items : sms;
 }
 
@@ -109,32 +133,32 @@ int launch_cond(const t2s_dit_weights* w, const float* t100, int t_stride, const
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
-int launch_embed(const t2s_dit_weights* w, const float* x, int x_shift, int nseq, const Workspace& ws, cudaStream_t st) {
+int launch_embed(const t2s_dit_weights* w, const float* x, int x_shift, int nseq, const Shape& sh, const Workspace& ws, cudaStream_t st) {
     TokArgs a = base_args(w, ws, nseq);
     a.x = x; a.x_shift = x_shift;
-    token_kernel<TOK_EMBED><<<token_grid(nseq), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
+    T2S_DISPATCH_H(sh.H, (token_kernel<TOK_EMBED, HH><<<token_grid(nseq, sh), TC_THREADS, TOK_SMEM_BYTES, st>>>(a)));
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
-int launch_attn(int nseq, const Workspace& ws, cudaStream_t st) {
-    attn_kernel<<<nseq * NHEAD, ATT_THREADS, ATT_SMEM_BYTES, st>>>(ws.qkv, ws.o, g_trace);
+int launch_attn(int nseq, const Shape& sh, const Workspace& ws, cudaStream_t st) {
+    T2S_DISPATCH_H(sh.H, (attn_kernel<HH><<<nseq * NHEAD, ATT_THREADS, AttShape<HH>::SMEM_BYTES, st>>>(ws.qkv, ws.o, g_trace)));
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
-int launch_mid(const t2s_dit_weights* w, int layer, int nseq, const Workspace& ws, cudaStream_t st) {
+int launch_mid(const t2s_dit_weights* w, int layer, int nseq, const Shape& sh, const Workspace& ws, cudaStream_t st) {
     TokArgs a = base_args(w, ws, nseq);
     a.layer = layer;
-    token_kernel<TOK_MID><<<token_grid(nseq), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
+    T2S_DISPATCH_H(sh.H, (token_kernel<TOK_MID, HH><<<token_grid(nseq, sh), TC_THREADS, TOK_SMEM_BYTES, st>>>(a)));
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
-int launch_final(const t2s_dit_weights* w, int nseq, const Workspace& ws, int out_mode, float* out, float* x_upd,
+int launch_final(const t2s_dit_weights* w, int nseq, const Shape& sh, const Workspace& ws, int out_mode, float* out, float* x_upd,
                  const float* noise, float cfg, float c1, float c2, float c3, cudaStream_t st) {
     TokArgs a = base_args(w, ws, nseq);
     a.layer = NLAYER - 1;
     a.out_mode = out_mode; a.out = out; a.x_upd = x_upd; a.noise = noise;
     a.cfg = cfg; a.c1 = c1; a.c2 = c2; a.c3 = c3;
-    token_kernel<TOK_FINAL><<<token_grid(nseq), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);
+    T2S_DISPATCH_H(sh.H, (token_kernel<TOK_FINAL, HH><<<token_grid(nseq, sh), TC_THREADS, TOK_SMEM_BYTES, st>>>(a)));
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
@@ -148,55 +172,77 @@ const char* t2s_last_error(void) { return g_err; }
 int t2s_init(void) { return ensure_init(); }
 void t2s_debug_set_phase_trace(long long* device_buf) { g_trace = device_buf; }
 
-size_t t2s_dit_workspace_bytes(int nseq) {
+size_t t2s_dit_workspace_bytes_h(int nseq, int latent_h) {
+    Shape sh;
+    if (get_shape(latent_h, &sh) != T2S_OK) return 0;
     size_t off[4], total = 0;
-    ws_offsets(nseq > 0 ? nseq : 0, off, &total);
+    ws_offsets(nseq > 0 ? nseq : 0, sh, off, &total);
     return total;
 }
-void t2s_dit_workspace_offsets(int nseq, size_t offsets[4]) { ws_offsets(nseq, offsets, nullptr); }
+size_t t2s_dit_workspace_bytes(int nseq) { return t2s_dit_workspace_bytes_h(nseq, 30); }
+int t2s_dit_workspace_offsets_h(int nseq, int latent_h, size_t offsets[4]) {
+    Shape sh;
+    TRY(get_shape(latent_h, &sh));
+    ws_offsets(nseq, sh, offsets, nullptr);
+    return T2S_OK;
+}
+void t2s_dit_workspace_offsets(int nseq, size_t offsets[4]) { t2s_dit_workspace_offsets_h(nseq, 30, offsets); }
 
 int t2s_dit_cond(const t2s_dit_weights* w, const float* t100, int t_stride, const float* emb, int cfg_pairs, int nseq,
                  void* workspace, t2s_stream_t stream) {
     if (!w || !t100 || nseq <= 0 || !workspace) return fail(T2S_EINVAL, "t2s_dit_cond: bad argument%s%s");
+    Shape sh;
+    TRY(get_shape(w->latent_h, &sh));
     TRY(ensure_init());
-    return launch_cond(w, t100, t_stride, emb, cfg_pairs ? 1 : 0, cfg_pairs, nseq, ws_view(workspace, nseq), (cudaStream_t)stream);
+    return launch_cond(w, t100, t_stride, emb, cfg_pairs ? 1 : 0, cfg_pairs, nseq, ws_view(workspace, nseq, sh), (cudaStream_t)stream);
 }
 int t2s_dit_embed_qkv(const t2s_dit_weights* w, const float* x, int x_shared, int nseq, void* workspace, t2s_stream_t stream) {
     if (!w || !x || nseq <= 0 || !workspace) return fail(T2S_EINVAL, "t2s_dit_embed_qkv: bad argument%s%s");
+    Shape sh;
+    TRY(get_shape(w->latent_h, &sh));
     TRY(ensure_init());
-    return launch_embed(w, x, x_shared ? 1 : 0, nseq, ws_view(workspace, nseq), (cudaStream_t)stream);
+    return launch_embed(w, x, x_shared ? 1 : 0, nseq, sh, ws_view(workspace, nseq, sh), (cudaStream_t)stream);
 }
-int t2s_dit_attention(int nseq, void* workspace, t2s_stream_t stream) {
+int t2s_dit_attention_h(int nseq, int latent_h, void* workspace, t2s_stream_t stream) {
     if (nseq <= 0 || !workspace) return fail(T2S_EINVAL, "t2s_dit_attention: bad argument%s%s");
+    Shape sh;
+    TRY(get_shape(latent_h, &sh));
     TRY(ensure_init());
-    return launch_attn(nseq, ws_view(workspace, nseq), (cudaStream_t)stream);
+    return launch_attn(nseq, sh, ws_view(workspace, nseq, sh), (cudaStream_t)stream);
 }
+int t2s_dit_attention(int nseq, void* workspace, t2s_stream_t stream) { return t2s_dit_attention_h(nseq, 30, workspace, stream); }
 int t2s_dit_block_post(const t2s_dit_weights* w, int layer, int nseq, void* workspace, t2s_stream_t stream) {
     if (!w || layer < 0 || layer >= NLAYER - 1 || nseq <= 0 || !workspace)
         return fail(T2S_EINVAL, "t2s_dit_block_post: bad argument (layer must be 0..2)%s%s");
+    Shape sh;
+    TRY(get_shape(w->latent_h, &sh));
     TRY(ensure_init());
-    return launch_mid(w, layer, nseq, ws_view(workspace, nseq), (cudaStream_t)stream);
+    return launch_mid(w, layer, nseq, sh, ws_view(workspace, nseq, sh), (cudaStream_t)stream);
 }
 int t2s_dit_final(const t2s_dit_weights* w, float* out, int nseq, void* workspace, t2s_stream_t stream) {
     if (!w || !out || nseq <= 0 || !workspace) return fail(T2S_EINVAL, "t2s_dit_final: bad argument%s%s");
+    Shape sh;
+    TRY(get_shape(w->latent_h, &sh));
     TRY(ensure_init());
-    return launch_final(w, nseq, ws_view(workspace, nseq), OUT_FWD, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, (cudaStream_t)stream);
+    return launch_final(w, nseq, sh, ws_view(workspace, nseq, sh), OUT_FWD, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, (cudaStream_t)stream);
 }
 
 int t2s_dit_forward(const t2s_dit_weights* w, const float* x, const float* t100, const float* emb, float* out, int nseq,
                     void* workspace, size_t workspace_bytes, t2s_stream_t stream) {
     if (!w || !x || !t100 || !out || nseq <= 0) return fail(T2S_EINVAL, "t2s_dit_forward: bad argument%s%s");
-    TRY(check_ws(workspace, workspace_bytes, nseq));
+    Shape sh;
+    TRY(get_shape(w->latent_h, &sh));
+    TRY(check_ws(workspace, workspace_bytes, nseq, sh));
     TRY(ensure_init());
     cudaStream_t st = (cudaStream_t)stream;
-    const Workspace ws = ws_view(workspace, nseq);
+    const Workspace ws = ws_view(workspace, nseq, sh);
     TRY(launch_cond(w, t100, 1, emb, 0, 0, nseq, ws, st));
-    TRY(launch_embed(w, x, 0, nseq, ws, st));
+    TRY(launch_embed(w, x, 0, nseq, sh, ws, st));
     for (int l = 0; l < NLAYER; ++l) {
-        TRY(launch_attn(nseq, ws, st));
-        if (l < NLAYER - 1) TRY(launch_mid(w, l, nseq, ws, st));
+        TRY(launch_attn(nseq, sh, ws, st));
+        if (l < NLAYER - 1) TRY(launch_mid(w, l, nseq, sh, ws, st));
     }
-    return launch_final(w, nseq, ws, OUT_FWD, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, st);
+    return launch_final(w, nseq, sh, ws, OUT_FWD, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, st);
 }
 
 int t2s_sample(const t2s_dit_weights* w, int kind, float* x, const float* emb, const float* t100, const float* coef,
@@ -206,19 +252,21 @@ int t2s_sample(const t2s_dit_weights* w, int kind, float* x, const float* emb, c
         return fail(T2S_EINVAL, "t2s_sample: bad argument%s%s");
     if (kind == 1 && !step_noise) return fail(T2S_EINVAL, "t2s_sample: DDPM needs step_noise%s%s");
     const int nseq = 2 * batch;
-    TRY(check_ws(workspace, workspace_bytes, nseq));
+    Shape sh;
+    TRY(get_shape(w->latent_h, &sh));
+    TRY(check_ws(workspace, workspace_bytes, nseq, sh));
     TRY(ensure_init());
     cudaStream_t st = (cudaStream_t)stream;
-    const Workspace ws = ws_view(workspace, nseq);
-    const size_t lat = (size_t)batch * LAT;
+    const Workspace ws = ws_view(workspace, nseq, sh);
+    const size_t lat = (size_t)batch * sh.lat;
     for (int j = 0; j < steps; ++j) {
         TRY(launch_cond(w, t100 + j, 0, emb, 1, 1, nseq, ws, st));
-        TRY(launch_embed(w, x, 1, nseq, ws, st));
+        TRY(launch_embed(w, x, 1, nseq, sh, ws, st));
         for (int l = 0; l < NLAYER; ++l) {
-            TRY(launch_attn(nseq, ws, st));
-            if (l < NLAYER - 1) TRY(launch_mid(w, l, nseq, ws, st));
+            TRY(launch_attn(nseq, sh, ws, st));
+            if (l < NLAYER - 1) TRY(launch_mid(w, l, nseq, sh, ws, st));
         }
-        TRY(launch_final(w, nseq, ws, kind == 0 ? OUT_RF : OUT_DDPM, pred_trace ? pred_trace + j * lat : nullptr, x,
+        TRY(launch_final(w, nseq, sh, ws, kind == 0 ? OUT_RF : OUT_DDPM, pred_trace ? pred_trace + j * lat : nullptr, x,
                          kind == 1 ? step_noise + j * lat : nullptr, cfg_scale, coef[3 * j], coef[3 * j + 1], coef[3 * j + 2], st));
     }
     return T2S_OK;

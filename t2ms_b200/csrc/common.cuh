@@ -9,31 +9,48 @@ namespace t2s {
 
 // Model constants (reference: model/denoiser/transformer.py:94-105,127-149)
 constexpr int D = 128;          // d_model
-constexpr int NTOK = 480;       // (30/2)*(64/2) patches
 constexpr int NHEAD = 4;
 constexpr int HD = 32;          // head dim
 constexpr int NLAYER = 4;
 constexpr int DMLP = 256;
 constexpr int LATC = 64;        // latent channels (axis 1 of the (B,64,30) latent)
-constexpr int LATP = 30;        // latent positions (axis 2)
-constexpr int LAT = LATC * LATP;
 constexpr int MOD = 6 * D;      // adaLN chunk: shift/scale/gate (msa) + shift/scale/gate (mlp)
 
-// Token-local kernels work on "pair tiles": 60 tokens of two consecutive sequences
-// (uncond/cond of one sample in CFG sampling) = rows 0..59 and 64..123 of a 128-row tile.
-constexpr int TILE_TOK = 60;
-constexpr int TILES_PER_PAIR = NTOK / TILE_TOK;   // 8
+// Token-local kernels work on "pair tiles": TILE_TOK tokens of two consecutive sequences
+// (uncond/cond of one sample in CFG sampling) = rows 0..TILE_TOK-1 and 64..64+TILE_TOK-1 of a 128-row tile.
 constexpr int TILE_ROWS = 128;
-
 constexpr int STAGE_BYTES = 32768;                // one weight stage: [128][128] fp16
 
-// q|k|v scratch: per (sequence, head) three tcgen05 operand images (layouts at attn_kernel)
-constexpr int QKV_Q_HALVES = 4 * 4 * 128 * 8;          // 16384
-constexpr int QKV_K_HALVES = 4 * NTOK * 8;             // 15360
-constexpr int QKV_V_HALVES = NTOK * HD;                // 15360
-constexpr int QKV_HEAD_HALVES = QKV_Q_HALVES + QKV_K_HALVES + QKV_V_HALVES;   // 47104 per (sequence, head)
-constexpr int QT_ROWS = 120;                           // valid query rows per q-tile
-constexpr int KCHUNK = 160;                            // keys per chunk
+// Shape of the denoiser for a latent of H positions (axis 2 of the (B,64,H) latent): H = 30 is the T2S model
+// (model/denoiser/transformer.py:132), H = 50 / 64 the fork's Transformer(dim) (model/denoiser/mytransformer.py:128-136,
+// config.yaml:46,91).  Tokens = (H/2) x 32 patches; token n = i*32 + j covers latent rows 2j, 2j+1 and positions 2i, 2i+1.
+template <int H_>
+struct DitShape {
+    static_assert(H_ == 30 || H_ == 50 || H_ == 64, "supported latent widths: 30 (T2S), 50 and 64 (fork configs)");
+    static constexpr int H = H_;
+    static constexpr int NTOK = 16 * H_;                                              // 480 | 800 | 1024
+    static constexpr int LAT = LATC * H_;
+    static constexpr int TILE_TOK = H_ == 30 ? 60 : (H_ == 50 ? 50 : 64);             // tokens per pair tile
+    static constexpr int TILES_PER_PAIR = NTOK / TILE_TOK;                            // 8 | 16 | 16 (even: work item = two tiles)
+    // attention: NQT query tiles of QT_ROWS valid rows (M = 128), NCH key chunks of KC keys
+    static constexpr int QT_ROWS = H_ == 30 ? 120 : (H_ == 50 ? 100 : 128);
+    static constexpr int NQT = NTOK / QT_ROWS;                                        // 4 | 8 | 8
+    static constexpr int KC = H_ == 30 ? 96 : (H_ == 50 ? 80 : 64);
+    static constexpr int NCH = NTOK / KC;                                             // 5 | 10 | 16
+    // q|k|v scratch: per (sequence, head) three tcgen05 operand images (layouts at attn_kernel)
+    static constexpr int Q_HALVES = NQT * 4 * 128 * 8;
+    static constexpr int K_HALVES = 4 * NTOK * 8;
+    static constexpr int V_HALVES = NTOK * HD;
+    static constexpr int HEAD_HALVES = Q_HALVES + K_HALVES + V_HALVES;
+    static_assert(TILES_PER_PAIR * TILE_TOK == NTOK && TILES_PER_PAIR % 2 == 0 && NQT * QT_ROWS == NTOK && NCH * KC == NTOK && KC % 16 == 0, "shape");
+};
+
+// The T2S shape (H = 30), used by the training path
+constexpr int NTOK = DitShape<30>::NTOK;          // (30/2)*(64/2) patches
+constexpr int LATP = 30;                          // latent positions (axis 2)
+constexpr int LAT = LATC * LATP;
+constexpr int TILE_TOK = DitShape<30>::TILE_TOK;
+constexpr int TILES_PER_PAIR = DitShape<30>::TILES_PER_PAIR;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

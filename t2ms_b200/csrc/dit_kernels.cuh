@@ -26,10 +26,11 @@ struct DitWeights {                 // device pointers; mirrors t2s_dit_weights 
     const float* b_ada;             // [4][768]
     const float* w_embed;           // [128][4]   patch_emb.weight @ conv.weight  (folded)
     const float* b_embed;           // [128]      patch_emb.weight @ conv.bias + patch_emb.bias
-    const float* pos;               // [8 tiles][32 col chunks][64 rows][4]  pos_embed in the residual tile layout
+    const float* pos;               // [tiles per pair][32 col chunks][64 rows][4]  pos_embed in the residual tile layout
     const float* w_final;           // [4][128]   linear_emb_to_patch.weight * ln.weight
     const float* b_final;           // [4]        linear_emb_to_patch.weight @ ln.bias + bias
     const float* freqs;             // [64]       10000 ** linspace(0,1,64)
+    int latent_h;                   // latent width H: 0 / 30 (T2S), 50 or 64 (fork); selects the DitShape instantiation
 };
 
 enum TokenMode { TOK_EMBED = 0, TOK_MID = 1, TOK_FINAL = 2 };
@@ -37,19 +38,19 @@ enum OutMode { OUT_FWD = 0, OUT_RF = 1, OUT_DDPM = 2 };
 
 struct TokArgs {
     DitWeights w;
-    const float* x;        // latents [(nseq >> x_shift)][64][30]
+    const float* x;        // latents [(nseq >> x_shift)][64][H]
     int x_shift;           // 1 when the two sequences of a pair share one latent (CFG), else 0
-    float* h;              // residual stream, tiled: [npair][8 tiles][32 col chunks][128 rows][4] fp32
+    float* h;              // residual stream, tiled: [npair][tiles per pair][32 col chunks][128 rows][4] fp32
     __half* qkv;           // [nseq][4 heads] x {Q, K, V tcgen05 operand images} fp16 (see attn_kernel)
-    const __half* o;       // attention output, tiled A-operand images: [npair][8 tiles][16 K chunks][16 row groups][8][8] fp16
+    const __half* o;       // attention output, tiled A-operand images: [npair][tiles per pair][16 K chunks][16 row groups][8][8] fp16
     const float* mod;      // adaLN modulation [nseq][4][768] fp32
     int nseq;
     int layer;             // block whose post-attention half runs here (MID / FINAL)
     // FINAL only
     int out_mode;
-    float* out;            // OUT_FWD: [nseq][64][30]; OUT_RF / OUT_DDPM: optional guided prediction [npair][64][30]
-    float* x_upd;          // OUT_RF / OUT_DDPM: latent updated in place [npair][64][30]
-    const float* noise;    // OUT_DDPM: [npair][64][30] for this step
+    float* out;            // OUT_FWD: [nseq][64][H]; OUT_RF / OUT_DDPM: optional guided prediction [npair][64][H]
+    float* x_upd;          // OUT_RF / OUT_DDPM: latent updated in place [npair][64][H]
+    const float* noise;    // OUT_DDPM: [npair][64][H] for this step
     float cfg, c1, c2, c3; // RF: x += pred*c1 ; DDPM: x = c1*(x - c2*pred) + c3*noise
     long long* trace;      // optional phase trace [grid][32] of clock64 stamps (tile 0, row 0), NULL = off
 };
@@ -321,9 +322,12 @@ __device__ __forceinline__ void gelu_store(uint32_t taddr, const float* __restri
     });
 }
 
-// grid = npair * 4 (two tiles per CTA), block = 576
-template <int MODE>
+// grid = min(#work items, #SMs), block = 576;  H = latent width (DitShape)
+template <int MODE, int H>
 __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
+    using S = DitShape<H>;
+    [[maybe_unused]] constexpr int NTOK = S::NTOK, TILE_TOK = S::TILE_TOK, TILES_PER_PAIR = S::TILES_PER_PAIR, LATP = S::H, LAT = S::LAT;
+    [[maybe_unused]] constexpr int QT_ROWS = S::QT_ROWS, QKV_Q_HALVES = S::Q_HALVES, QKV_K_HALVES = S::K_HALVES, QKV_HEAD_HALVES = S::HEAD_HALVES;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform
     const uint32_t sb = smem_u32(smem);
@@ -751,22 +755,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
 //   K: [d/8][key 0..479][8]             (B, K-major)         30720 B
 //   V: [key/8][d/8][key%8][8]           (B, MN-major)        30720 B
 constexpr int ATT_THREADS = 160;
-constexpr int ATT_KC = 96;                                            // keys per chunk
-constexpr int ATT_NCH = NTOK / ATT_KC;                                // 5
-constexpr int ATT_NQT = 4;                                            // q-tiles
-constexpr int ATT_SM_Q = 0, ATT_SM_K = QKV_Q_HALVES * 2, ATT_SM_V = ATT_SM_K + QKV_K_HALVES * 2;
-constexpr int ATT_SM_BAR = ATT_SM_V + QKV_V_HALVES * 2;
-constexpr int ATT_SM_TMEM = ATT_SM_BAR + 16 * 8;
-constexpr int ATT_SMEM_BYTES = ATT_SM_TMEM + 16;
-static_assert(2 * (ATT_SMEM_BYTES + 1024) <= 233472, "two attention CTAs must fit one SM");
 enum { AB_QFULL = 0, AB_KFULL = 1, AB_VFULL = 2, AB_SFULL = 3, AB_SFREE = 5, AB_PFULL = 7, AB_PVDONE = 9, AB_OFULL = 11, AB_OFREE = 12 };
-constexpr uint32_t ATT_IDESC_S = umma_idesc_f16(128, ATT_KC);
+template <int H>
+struct AttShape {
+    using S = DitShape<H>;
+    static constexpr int KC = S::KC, NCH = S::NCH, NQT = S::NQT;      // keys per chunk, chunks, q-tiles
+    static constexpr int SM_Q = 0, SM_K = S::Q_HALVES * 2, SM_V = SM_K + S::K_HALVES * 2;
+    static constexpr int SM_BAR = SM_V + S::V_HALVES * 2;
+    static constexpr int SM_TMEM = SM_BAR + 16 * 8;
+    static constexpr int SMEM_BYTES = SM_TMEM + 16;
+    static constexpr int CTAS_PER_SM = 2 * (SMEM_BYTES + 1024) <= 233472 ? 2 : 1;   // H = 30: two CTAs share an SM
+    static constexpr uint32_t IDESC_S = umma_idesc_f16(128, KC);
+    static constexpr uint32_t TCOLS = 256;                            // two S buffers (2 x KC) + O (32)
+    static constexpr uint32_t T_S = 0, T_O = 2 * KC;
+    static_assert(SMEM_BYTES <= 232448 && 2 * KC + HD <= 256, "attention kernel resources");
+};
+static_assert(AttShape<30>::CTAS_PER_SM == 2, "two attention CTAs must fit one SM for the T2S shape");
 constexpr uint32_t ATT_IDESC_PV = umma_idesc_f16(128, HD) | (1u << 16);   // B (V) is MN-major
-constexpr uint32_t ATT_TCOLS = 256;                                   // two S buffers (2 x 96) + O (32)
-constexpr uint32_t ATT_T_S = 0, ATT_T_O = 2 * ATT_KC;
 
 // grid = nseq * 4, block = 160: warps 0-3 = softmax (thread = query row = TMEM lane), warp 4 = loads + MMA issue
-__global__ void __launch_bounds__(ATT_THREADS, 2) attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ o, long long* trace) {
+template <int H>
+__global__ void __launch_bounds__(ATT_THREADS, AttShape<H>::CTAS_PER_SM) attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ o, long long* trace) {
+    using S = DitShape<H>;
+    using AS = AttShape<H>;
+    constexpr int NTOK = S::NTOK, TILE_TOK = S::TILE_TOK, TILES_PER_PAIR = S::TILES_PER_PAIR, QT_ROWS = S::QT_ROWS;
+    constexpr int QKV_Q_HALVES = S::Q_HALVES, QKV_K_HALVES = S::K_HALVES, QKV_V_HALVES = S::V_HALVES, QKV_HEAD_HALVES = S::HEAD_HALVES;
+    constexpr int ATT_KC = AS::KC, ATT_NCH = AS::NCH, ATT_NQT = AS::NQT;
+    constexpr int ATT_SM_Q = AS::SM_Q, ATT_SM_K = AS::SM_K, ATT_SM_V = AS::SM_V, ATT_SM_BAR = AS::SM_BAR, ATT_SM_TMEM = AS::SM_TMEM;
+    constexpr uint32_t ATT_IDESC_S = AS::IDESC_S, ATT_TCOLS = AS::TCOLS, ATT_T_S = AS::T_S, ATT_T_O = AS::T_O;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform
     const int seq = blockIdx.x >> 2, head = blockIdx.x & 3;
@@ -885,15 +901,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_kernel(const __half* __re
                 mbar_wait(BAR(AB_SFULL + b), (G >> 1) & 1);
                 tc_fence_after();
                 const uint32_t ts = trow + ATT_T_S + b * ATT_KC;
-                float x[32], y[32], z[32];
-                tmem_ld32(ts, x); tmem_ld32(ts + 32, y); tmem_ld32(ts + 64, z);
+                constexpr int ZN = ATT_KC - 64;                  // scores beyond the first two 32-column blocks: 32, 16 or 0
+                float x[32], y[32], z[ZN > 0 ? ZN : 1];
+                tmem_ld32(ts, x); tmem_ld32(ts + 32, y);
+                if constexpr (ZN == 32) tmem_ld32(ts + 64, *reinterpret_cast<float (*)[32]>(&z[0]));
+                if constexpr (ZN == 16) tmem_ld16(ts + 64, *reinterpret_cast<float (*)[16]>(&z[0]));
                 tmem_wait_ld();
                 float c0 = -INFINITY, c1 = -INFINITY;
 #pragma unroll
                 for (int q = 0; q < 32; q += 4) {
                     c0 = max3(c0, x[q], x[q + 1]); c1 = max3(c1, x[q + 2], x[q + 3]);
                     c0 = max3(c0, y[q], y[q + 1]); c1 = max3(c1, y[q + 2], y[q + 3]);
-                    c0 = max3(c0, z[q], z[q + 1]); c1 = max3(c1, z[q + 2], z[q + 3]);
+                    if (q < ZN) { c0 = max3(c0, z[q], z[q + 1]); c1 = max3(c1, z[q + 2], z[q + 3]); }
                 }
                 const float cm = fmaxf(c0, c1);
                 if (j == 0) {
@@ -916,20 +935,19 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_kernel(const __half* __re
                     }
                 }
                 const float nb = -mref * sc;
-                auto block = [&](const float (&v)[32], int c32) {
+                auto half = [&](const float* v, int pcol) {   // 16 scores -> 8 packed P columns
+                    uint32_t pk[8];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t pk[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float e0 = ex2_approx(fmaf(v[h * 16 + 2 * q], sc, nb)), e1 = ex2_approx(fmaf(v[h * 16 + 2 * q + 1], sc, nb));
-                            l0 += e0; l1 += e1;
-                            pk[q] = pack_h2(e0, e1);
-                        }
-                        tmem_st8(ts + c32 * 16 + h * 8, pk);  // P columns: 16 per 32 scores
+                    for (int q = 0; q < 8; ++q) {
+                        const float e0 = ex2_approx(fmaf(v[2 * q], sc, nb)), e1 = ex2_approx(fmaf(v[2 * q + 1], sc, nb));
+                        l0 += e0; l1 += e1;
+                        pk[q] = pack_h2(e0, e1);
                     }
+                    tmem_st8(ts + pcol, pk);                     // P columns: 16 per 32 scores
                 };
-                block(x, 0); block(y, 1); block(z, 2);
+                half(x, 0); half(x + 16, 8); half(y, 16); half(y + 16, 24);
+                if constexpr (ZN >= 16) half(z, 32);
+                if constexpr (ZN == 32) half(z + 16, 40);
                 if (j == 0 && qt > 0) finish(qt - 1, lprev);  // previous q-tile's O -> global before its accumulator is reused
                 tmem_wait_st();
                 tc_fence_before();

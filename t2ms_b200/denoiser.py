@@ -87,12 +87,16 @@ class Transformerlayer(nn.Module):
 
 
 class Transformer(nn.Module):
-    """Drop-in for model/denoiser/transformer.py:127-204."""
+    """Drop-in for model/denoiser/transformer.py:127-204 (``Transformer()``: H = 30, 480 tokens) and for the fork's
+    model/denoiser/mytransformer.py:127-204 (``Transformer(dim)``: H = dim; the kernels are built for dim 30, 50 and
+    64 = config.yaml:46,91 ``flow_dim``, i.e. 480 / 800 / 1024 tokens).  Latents are (B, 64, H)."""
 
-    def __init__(self):
+    def __init__(self, dim: int = 30):
         super().__init__()
+        if dim not in (30, 50, 64):
+            raise ValueError("t2ms_b200.Transformer: latent width (dim) must be 30 (T2S), 50 or 64 (fork configs)")
         self.channel = 1
-        self.H = 30
+        self.H = int(dim)
         self.W = 64
         emb_size = D_MODEL
         self.patch_size = 2
@@ -143,7 +147,7 @@ class Transformer(nn.Module):
         key = (str(device), nseq)
         ws = self._workspaces.get(key)
         if ws is None:
-            nbytes = _lib.load().t2s_dit_workspace_bytes(nseq)
+            nbytes = _lib.load().t2s_dit_workspace_bytes_h(nseq, self.H)
             ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=device)
             if len(self._workspaces) > 4:
                 self._workspaces.clear()
@@ -152,10 +156,12 @@ class Transformer(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def forward(self, input: torch.Tensor, t: torch.Tensor, text_input):
-        """input (B,64,30), t (B,) float32 or int64, text_input (B,128) or None -> (B,64,30)."""
+        """input (B,64,H), t (B,) float32 or int64, text_input (B,128) or None -> (B,64,H)."""
         if not input.is_cuda:
             raise RuntimeError("t2ms_b200.Transformer.forward needs CUDA tensors (no CPU fallback)")
         if torch.is_grad_enabled() and any(p.requires_grad for _, p in self._own_params()) and self.training:
+            if self.H != 30:
+                raise RuntimeError("t2ms_b200: the training step is built for the T2S shape (H = 30) only")
             from .training import dit_forward_autograd
             return dit_forward_autograd(self, input, t, text_input)
         return dit_forward(self, input, t, text_input)
@@ -168,7 +174,7 @@ def _aligned(ws: torch.Tensor) -> int:
 def dit_forward(model: Transformer, x: torch.Tensor, t: torch.Tensor, text: Optional[torch.Tensor]) -> torch.Tensor:
     lib = _lib.load()
     B = x.shape[0]
-    assert x.shape[1:] == (64, 30), f"latent must be (B,64,30), got {tuple(x.shape)}"
+    assert x.shape[1:] == (64, model.H), f"latent must be (B,64,{model.H}), got {tuple(x.shape)}"
     x = x.detach().to(torch.float32).contiguous()
     t100 = (t.detach() * 100.0).to(torch.float32).contiguous()          # transformer.py:31
     assert t100.shape == (B,)
@@ -180,7 +186,7 @@ def dit_forward(model: Transformer, x: torch.Tensor, t: torch.Tensor, text: Opti
     out = torch.empty_like(x)
     pk = model.packed()
     ws = model.workspace(B, x.device)
-    nbytes = lib.t2s_dit_workspace_bytes(B)
+    nbytes = lib.t2s_dit_workspace_bytes_h(B, model.H)
     with torch.cuda.device(x.device):
         rc = lib.t2s_dit_forward(pk.ref, x.data_ptr(), t100.data_ptr(), emb_ptr, out.data_ptr(), B, _aligned(ws), nbytes,
                                  torch.cuda.current_stream().cuda_stream)

@@ -25,11 +25,16 @@ def umma_stage(w: torch.Tensor) -> torch.Tensor:
     return w16.permute(2, 0, 1, 3).contiguous().reshape(-1)              # [k//8][n//8][n%8][k%8]
 
 
-def tile_rows(t: torch.Tensor) -> torch.Tensor:
-    """[480 tokens][128] fp32 -> [8 tiles][32 col chunks][64 rows][4] (60 valid rows per tile): the
+TILE_TOK = {30: 60, 50: 50, 64: 64}      # tokens per pair tile for latent width H (csrc/common.cuh: DitShape)
+
+
+def tile_rows(t: torch.Tensor, tile_tok: int = 60) -> torch.Tensor:
+    """[tokens][128] fp32 -> [tiles][32 col chunks][64 rows][4] (tile_tok valid rows per tile): the
     residual-stream tile layout, in which a warp's 32 rows x 16 B of one column chunk are contiguous."""
-    out = torch.zeros(8, 32, 64, 4, dtype=t.dtype, device=t.device)
-    out[:, :, :60, :] = t.reshape(8, 60, 32, 4).permute(0, 2, 1, 3)
+    ntile = t.shape[0] // tile_tok
+    assert ntile * tile_tok == t.shape[0]
+    out = torch.zeros(ntile, 32, 64, 4, dtype=t.dtype, device=t.device)
+    out[:, :, :tile_tok, :] = t.reshape(ntile, tile_tok, 32, 4).permute(0, 2, 1, 3)
     return out.contiguous()
 
 
@@ -64,7 +69,12 @@ class PackedDit:
         wpe, wc = g("patch_emb.weight"), g("conv.weight").reshape(4, 4)              # conv [oc][p*2+q]
         w_embed = (wpe @ wc).contiguous()                                            # [128][4]
         b_embed = (wpe @ g("conv.bias") + g("patch_emb.bias")).contiguous()
-        pos = tile_rows(g("pos_embed").reshape(480, D))
+        ntok = sd["pos_embed"].shape[-2]
+        latent_h = ntok // 16
+        if latent_h not in TILE_TOK or ntok != 16 * latent_h:
+            raise RuntimeError(f"t2ms_b200 kernels are built for latent widths {sorted(TILE_TOK)} (pos_embed has {ntok} tokens)")
+        pos = tile_rows(g("pos_embed").reshape(ntok, D), TILE_TOK[latent_h])
+        st.latent_h = latent_h
         wl = g("linear_emb_to_patch.weight")
         w_final = (wl * g("ln.weight").unsqueeze(0)).contiguous()                    # [4][128]
         b_final = (wl @ g("ln.bias") + g("linear_emb_to_patch.bias")).contiguous()
@@ -76,6 +86,7 @@ class PackedDit:
         self.ref = C.byref(st)
         self._keep = keep
         self.device = device
+        self.latent_h = latent_h
 
 
 def _conv_w(w):      # Conv1d weight [oc][ic][k] -> [ic][k][oc]

@@ -44,29 +44,30 @@ class T2SSampler:
     def sample_latent(self, emb: torch.Tensor, steps: int = 100, cfg_scale: float = 7.0, backbone: str = "flowmatching",
                       noise: Optional[torch.Tensor] = None, step_noise: Optional[torch.Tensor] = None,
                       generator: Optional[torch.Generator] = None, trace: bool = False, chunk: Optional[int] = None):
-        """emb (B,128) CUDA -> final latent (B,64,30) [, per-step guided predictions (steps,B,64,30)]."""
+        """emb (B,128) CUDA -> final latent (B,64,H) [, per-step guided predictions (steps,B,64,H)]."""
         if not emb.is_cuda:
             raise RuntimeError("T2SSampler needs CUDA tensors (no CPU fallback); use sample_host for host buffers")
         lib = _lib.load()
         kind = KIND[backbone]
         dev = emb.device
-        B = emb.shape[0]
+        B, H = emb.shape[0], self.dit.H
         emb = emb.detach().to(torch.float32).contiguous()
         if noise is None:
-            x = torch.randn(B, 64, 30, device=dev, dtype=torch.float32, generator=generator)   # infer.py:75
+            x = torch.randn(B, 64, H, device=dev, dtype=torch.float32, generator=generator)    # infer.py:75
         else:
             x = noise.detach().to(device=dev, dtype=torch.float32).clone().contiguous()
+            assert tuple(x.shape) == (B, 64, H), f"noise must be (B,64,{H})"
         if kind == 1:
             if step_noise is None:                                                         # DDPM.py:35
-                step_noise = torch.randn(steps, B, 64, 30, device=dev, dtype=torch.float32, generator=generator)
+                step_noise = torch.randn(steps, B, 64, H, device=dev, dtype=torch.float32, generator=generator)
             step_noise = step_noise.detach().to(device=dev, dtype=torch.float32).contiguous()
-            assert step_noise.shape == (steps, B, 64, 30)
-        tr = torch.empty(steps, B, 64, 30, device=dev, dtype=torch.float32) if trace else None
+            assert step_noise.shape == (steps, B, 64, H)
+        tr = torch.empty(steps, B, 64, H, device=dev, dtype=torch.float32) if trace else None
         t100, coef = self._table(kind, steps, dev)
         pk = self.dit.packed()
         chunk = B if not chunk else min(int(chunk), B)
         ws = self.dit.workspace(2 * chunk, dev)
-        nbytes = lib.t2s_dit_workspace_bytes(2 * chunk)
+        nbytes = lib.t2s_dit_workspace_bytes_h(2 * chunk, H)
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             for b0 in range(0, B, chunk):
@@ -75,7 +76,7 @@ class T2SSampler:
                 if kind == 1:
                     sn = step_noise[:, b0:b0 + nb].contiguous() if nb != B else step_noise
                 if trace:
-                    tr_c = tr if nb == B else torch.empty(steps, nb, 64, 30, device=dev, dtype=torch.float32)
+                    tr_c = tr if nb == B else torch.empty(steps, nb, 64, H, device=dev, dtype=torch.float32)
                 rc = lib.t2s_sample(pk.ref, kind, x[b0:b0 + nb].data_ptr(), emb[b0:b0 + nb].data_ptr(), t100.data_ptr(), coef,
                                     sn.data_ptr() if sn is not None else None, tr_c.data_ptr() if tr_c is not None else None,
                                     nb, steps, float(cfg_scale), _aligned(ws), nbytes, stream)
@@ -91,6 +92,8 @@ class T2SSampler:
         """Text embeddings (B,128) -> generated series (B,length) fp32 (infer.py:75-95)."""
         if self.decoder is None:
             raise RuntimeError("T2SSampler was built without an LA-VAE decoder")
+        if self.dit.H != 30:
+            raise RuntimeError("the LA-VAE decoder takes (B,64,30) latents; use sample_latent for Transformer(dim != 30)")
         z = self.sample_latent(emb, steps, cfg_scale, backbone, noise, step_noise, generator, False, chunk)
         series = torch.empty(z.shape[0], int(length), device=z.device, dtype=torch.float32)
         self.decoder.decode_into(z, int(length), series, None)

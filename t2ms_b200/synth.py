@@ -49,8 +49,9 @@ def pos_embed(num_positions: int = N_TOK, d_model: int = D) -> torch.Tensor:
     return pe.unsqueeze(0)
 
 
-def make_dit_state(seed: int = 0, adaln_std: float = 0.02, bias_std: float = 0.0) -> Dict[str, torch.Tensor]:
-    """State dict with the 55 key names / shapes of the reference ``Transformer``.
+def make_dit_state(seed: int = 0, adaln_std: float = 0.02, bias_std: float = 0.0, dim: int = 30) -> Dict[str, torch.Tensor]:
+    """State dict with the 55 key names / shapes of the reference ``Transformer``; ``dim`` = latent width
+    H of the fork's ``Transformer(dim)`` (only ``pos_embed`` (1, 16 dim, 128) depends on it; the random draws do not).
 
     ``bias_std`` > 0 additionally randomises the Linear biases and LayerNorm affine (the reference
     init leaves them 0 / 1) so that parity tests exercise every bias path of the kernels.
@@ -63,7 +64,7 @@ def make_dit_state(seed: int = 0, adaln_std: float = 0.02, bias_std: float = 0.0
             return torch.randn(n, generator=g) * bias_std
         return torch.zeros(n)
 
-    sd["pos_embed"] = pos_embed()
+    sd["pos_embed"] = pos_embed(16 * dim)
     sd["conv.weight"] = _conv_default(g, (4, 1, 2, 2), 4)
     sd["conv.bias"] = _conv_default(g, (4,), 4)
     sd["patch_emb.weight"] = _xavier(g, D, 4)
@@ -134,16 +135,16 @@ def make_text_embeddings(batch: int, seed: int = 2) -> torch.Tensor:
     return torch.nn.functional.normalize(torch.randn(batch, D, generator=g), dim=-1)
 
 
-def make_noise(batch: int, seed: int = 3) -> torch.Tensor:
-    """Initial latent replacing randn_like at infer.py:75, (B,64,30)."""
+def make_noise(batch: int, seed: int = 3, dim: int = 30) -> torch.Tensor:
+    """Initial latent replacing randn_like at infer.py:75, (B,64,dim)."""
     g = torch.Generator().manual_seed(seed)
-    return torch.randn(batch, 64, 30, generator=g)
+    return torch.randn(batch, 64, dim, generator=g)
 
 
-def make_step_noise(steps: int, batch: int, seed: int = 4) -> torch.Tensor:
+def make_step_noise(steps: int, batch: int, seed: int = 4, dim: int = 30) -> torch.Tensor:
     """Pre-drawn Gaussian noise replacing torch.randn inside DDPM.p_sample (DDPM.py:35)."""
     g = torch.Generator().manual_seed(seed)
-    return torch.randn(steps, batch, 64, 30, generator=g)
+    return torch.randn(steps, batch, 64, dim, generator=g)
 
 
 def make_series(batch: int, length: int, seed: int = 5) -> torch.Tensor:

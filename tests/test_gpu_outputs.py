@@ -45,7 +45,7 @@ def test_series_metrics_edge_cases():
 def test_run_inference_writes_reference_formats(tmp_path):
     """infer.py:66-123 on the fused sampler: two batches, saved arrays have the reference's shapes / dtypes, the
     generated series equal a direct sampler call with the same generator state, metrics equal the oracle's."""
-    dit, vae = make_dit(31), make_vae(32)
+    (dit, _), (vae, _) = make_dit(31), make_vae(32)
     smp = T2SSampler(dit, vae)
     L, steps = 48, 4
     gen = torch.Generator().manual_seed(9)

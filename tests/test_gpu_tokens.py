@@ -1,0 +1,79 @@
+"""GPU parity of the variable-width denoiser: the fork's ``Transformer(dim)``
+(model/denoiser/mytransformer.py:127-204, dim = config.yaml flow_dim 50 / 64 -> 800 / 1024 tokens) through the same
+kernels instantiated per latent width, against golden vectors generated from the fork's module and against the oracle.
+
+Tolerances as for the T2S shape (BASELINE.json north_star): single forward rel-L2 <= 2e-3, per-step guided
+velocity / epsilon rel-L2 <= 2e-3, final latent max-abs <= 1e-2."""
+import pytest
+import torch
+
+from conftest import T, load_golden
+from gpu_util import DEV, max_abs, rel_l2
+from oracle import t2s_oracle as O
+from t2ms_b200 import T2SSampler, Transformer, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(dim, seed, bias_std=0.05):
+    sd = synth.make_dit_state(seed, bias_std=bias_std, dim=dim)
+    m = Transformer(dim)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).eval(), sd
+
+
+@pytest.mark.parametrize("dim", [50, 64])
+def test_forward_matches_fork_golden(dim):
+    g = load_golden("dit_tokens.npz")
+    k = f"h{dim}/"
+    m, _ = _model(dim, 40 + dim)
+    assert m.pos_embed.shape == (1, 16 * dim, 128) and len(m.state_dict()) == 55
+    x, emb = synth.make_noise(2, seed=50 + dim, dim=dim).to(DEV), synth.make_text_embeddings(2, seed=60 + dim).to(DEV)
+    t_f, t_i = torch.tensor([0.25, 0.9], device=DEV), torch.tensor([3, 871], dtype=torch.long, device=DEV)
+    with torch.no_grad():
+        for out, key in ((m(input=x, t=t_f, text_input=emb), "cond_float"), (m(input=x, t=t_f, text_input=None), "uncond_float"),
+                         (m(input=x, t=t_i, text_input=emb), "cond_int")):
+            assert out.shape == (2, 64, dim)
+            e = rel_l2(out, T(g[k + key]))
+            print(dim, key, "rel-L2 %.2e" % e)
+            assert e < 2e-3
+
+
+@pytest.mark.parametrize("dim", [50, 64])
+def test_guided_sampling_matches_fork_golden(dim):
+    g = load_golden("dit_tokens.npz")
+    k = f"h{dim}/"
+    m, _ = _model(dim, 40 + dim)
+    smp = T2SSampler(m)
+    x, emb = synth.make_noise(2, seed=50 + dim, dim=dim).to(DEV), synth.make_text_embeddings(2, seed=60 + dim).to(DEV)
+    lat, tr = smp.sample_latent(emb, steps=3, cfg_scale=7.0, noise=x, trace=True)
+    per = [rel_l2(tr[j], T(g[k + "rf_vel"])[j]) for j in range(3)]
+    print(dim, "rf per-step", ["%.2e" % e for e in per])
+    assert max(per) < 2e-3 and max_abs(lat, T(g[k + "rf_final"])) < 1e-2
+    sn = synth.make_step_noise(3, 2, seed=70 + dim, dim=dim).to(DEV)
+    lat, tr = smp.sample_latent(emb, steps=3, cfg_scale=7.0, backbone="ddpm", noise=x, step_noise=sn, trace=True)
+    per = [rel_l2(tr[j], T(g[k + "ddpm_eps"])[j]) for j in range(3)]
+    print(dim, "ddpm per-step", ["%.2e" % e for e in per])
+    # DDPM with 3 steps amplifies the prediction error by 1/sqrt(alpha_t) ~ 7: the latent bar is relative to its scale
+    assert max(per) < 2e-3 and rel_l2(lat, T(g[k + "ddpm_final"])) < 2e-3
+    with pytest.raises(RuntimeError):
+        smp.sample(emb, 96, steps=2)                       # no LA-VAE decode for (B,64,dim != 30) latents
+
+
+@pytest.mark.parametrize("dim,B", [(50, 5), (64, 37)])
+def test_forward_odd_batches_vs_oracle(dim, B):
+    """Odd sequence counts (a half-filled last pair) and more sequences than one wave of work items."""
+    m, sd = _model(dim, 7, bias_std=0.02)
+    x, emb = synth.make_noise(B, seed=8, dim=dim), synth.make_text_embeddings(B, seed=9)
+    t = torch.linspace(0, 1, B)
+    with torch.no_grad():
+        ref = O.dit_forward(sd, x, t, emb)
+        out = m(input=x.to(DEV), t=t.to(DEV), text_input=emb.to(DEV))
+    assert rel_l2(out, ref) < 2e-3
+    per_seq = ((out.cpu().double() - ref.double()).flatten(1).norm(dim=1) / ref.double().flatten(1).norm(dim=1)).max().item()
+    assert per_seq < 3e-3
+
+
+def test_unsupported_width_raises():
+    with pytest.raises(ValueError):
+        Transformer(40)

@@ -143,3 +143,25 @@ def test_series_metrics_oracle_matches_reference_functions():
         o, x = np.transpose(g[f"{c}/ori"], (0, 2, 1)), np.transpose(g[f"{c}/gen"], (0, 2, 1))
         assert abs(O.calculate_mse(o, x) - float(g[f"{c}/mse"])) <= 1e-6 * float(g[f"{c}/mse"])
         assert abs(O.calculate_wape(o, x) - float(g[f"{c}/wape"])) <= 1e-6 * float(g[f"{c}/wape"])
+
+
+@pytest.mark.parametrize("dim", [50, 64])
+def test_variable_width_dit_oracle_matches_fork_reference(dim):
+    """oracle dit_forward on (B,64,dim) latents against the fork's model/denoiser/mytransformer.py Transformer(dim)."""
+    g = load_golden("dit_tokens.npz")
+    k = f"h{dim}/"
+    sd = synth.make_dit_state(40 + dim, bias_std=0.05, dim=dim)
+    assert synth.state_checksum(sd) == str(g[k + "checksum"])
+    x, emb = synth.make_noise(2, seed=50 + dim, dim=dim), synth.make_text_embeddings(2, seed=60 + dim)
+    t_f, t_i = torch.tensor([0.25, 0.9]), torch.tensor([3, 871], dtype=torch.long)
+    with torch.no_grad():
+        close(O.dit_forward(sd, x, t_f, emb), g[k + "cond_float"], 2e-5)
+        close(O.dit_forward(sd, x, t_f, None), g[k + "uncond_float"], 2e-5)
+        close(O.dit_forward(sd, x, t_i, emb), g[k + "cond_int"], 2e-5)
+        lat, _, vel = O.rf_sample(sd, None, x, emb, 3, 7.0, return_velocities=True)
+        close(torch.stack(vel), g[k + "rf_vel"], 1e-4)
+        close(lat, g[k + "rf_final"], 1e-4)
+        sn = synth.make_step_noise(3, 2, seed=70 + dim, dim=dim)
+        lat, _, eps = O.ddpm_sample(sd, None, x, emb, 3, 7.0, sn, return_eps=True)
+        close(torch.stack(eps), g[k + "ddpm_eps"], 1e-3, rtol=1e-5)
+        close(lat, g[k + "ddpm_final"], 1e-3, rtol=1e-5)
