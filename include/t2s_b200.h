@@ -220,6 +220,61 @@ int t2s_train_attention_forward(const float* qkv, float* o, float* nlse, int nse
 int t2s_train_attention_backward(const float* qkv, const float* o, const float* nlse, const float* dout, float* dqkv,
                                  int nseq, void* scratch, size_t scratch_bytes, t2s_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Generic LA-VAE path (the stage before the hot path): layer-wise forward with saved activations and
+ * the exact backward, fp32, reference layouts.  Covers model/pretrained/vqvae.py (in_channels 1, flow_dim 30) and the
+ * fork's multivariate model/pretrained/myvqvae.py (in_channels = input_dim, flow_dim = args.flow_dim, any length).
+ * The same struct type carries the gradient pointers (the int fields are ignored there).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int in_channels;      /* series channels: 1 (vqvae.py:114) or args.input_dim (myvqvae.py:100) */
+    int hidden;           /* args.block_hidden_size */
+    int res_hidden;       /* args.res_hidden_size */
+    int emb;              /* args.embedding_dim */
+    int n_res;            /* args.num_residual_layers (<= 4) */
+    int flow_dim;         /* latent positions: 30 (vqvae.py:70) or args.flow_dim (myvqvae.py:60) */
+    float* enc_conv1_w;   /* encoder._conv_1.weight (hidden/2, in_channels, 4) */
+    float* enc_conv1_b;
+    float* enc_conv2_w;   /* encoder._conv_2.weight (hidden, hidden/2, 4) */
+    float* enc_conv2_b;
+    float* enc_conv3_w;   /* encoder._conv_3.weight (hidden, hidden, 3) */
+    float* enc_conv3_b;
+    float* enc_res_w3[4]; /* encoder._residual_stack._layers.{i}._block.1.weight (res_hidden, hidden, 3) */
+    float* enc_res_w1[4]; /* encoder._residual_stack._layers.{i}._block.3.weight (hidden, res_hidden, 1) */
+    float* enc_pre_w;     /* encoder._pre_vq_conv.weight (emb, hidden, 1) */
+    float* enc_pre_b;
+    float* dec_conv1_w;   /* decoder._conv_1.weight (hidden, emb, 3) */
+    float* dec_conv1_b;
+    float* dec_res_w3[4];
+    float* dec_res_w1[4];
+    float* dec_ct1_w;     /* decoder._conv_trans_1.weight (hidden, hidden/2, 4) */
+    float* dec_ct1_b;
+    float* dec_ct2_w;     /* decoder._conv_trans_2.weight (hidden/2, in_channels, 4) */
+    float* dec_ct2_b;
+} t2s_lavae_params;
+
+/* Scratch (activations of every layer + gradient temporaries) for `batch` series of `length`; 0 on a bad argument. */
+size_t t2s_lavae_workspace_bytes(const t2s_lavae_params* params, int batch, int length);
+
+/* Encoder.forward (vqvae.py:57-71, myvqvae.py:49-61): x [batch][in_channels][length] -> z [batch][emb][flow_dim],
+ * before [batch][emb][n] or NULL (n = length after the two stride-2 convolutions). */
+int t2s_lavae_encode(const t2s_lavae_params* params, const float* x, float* z, float* before, int batch, int length,
+                     void* workspace, size_t workspace_bytes, t2s_stream_t stream);
+/* Decoder.forward (vqvae.py:97-105, myvqvae.py:76-86): z [batch][emb][flow_dim] -> recon [batch][in_channels][length]
+ * (incl. the final interpolation of myvqvae.py:85), after [batch][emb][length/4] or NULL. */
+int t2s_lavae_decode(const t2s_lavae_params* params, const float* z, float* recon, float* after, int batch, int length,
+                     void* workspace, size_t workspace_bytes, t2s_stream_t stream);
+/* vqvae.shared_eval (vqvae.py:118-135, myvqvae.py:116-136): encoder, decoder, recon_error = mse(recon, x),
+ * cross_loss = mse(before, after), and — when grads != NULL — the backward of loss = recon_error + cross_loss to every
+ * parameter (loss.backward(), vqvae.py:127 / myvqvae.py:127).
+ *   loss_sums [2] device floats, += { sum (recon - x)^2, sum (before - after)^2 }  (caller zeroes; the two means divide by
+ *             batch*in_channels*length and batch*emb*(length/4))
+ *   recon [batch][in_channels][length], z [batch][emb][flow_dim]: outputs, either may be NULL
+ *   grads += dL/dparam (caller zeroes); the optimizer update stays with the caller (optimizer.step(), :128). */
+int t2s_lavae_train_step(const t2s_lavae_params* params, const t2s_lavae_params* grads, const float* x, float* recon, float* z,
+                         float* loss_sums, int batch, int length, void* workspace, size_t workspace_bytes,
+                         t2s_stream_t stream);
+
 /* The tcgen05 tf32 GEMM every training Linear runs on, exported for unit tests:
  * C[m][n] (mode 0: =, 1: +=, 2: atomic +=) alpha * sum_k A(m,k) B(n,k) (+ bias[n]);  a_mn / b_mn = 1: the operand is
  * stored transposed (element (m,k) at k*ld + m). */

@@ -105,6 +105,49 @@ def make_dit_tokens(ref: str, out: str):
     np.savez_compressed(os.path.join(out, "dit_tokens.npz"), **res)
 
 
+def make_vae_train(ref: str, out: str):
+    """LA-VAE training step: vqvae.shared_eval(batch, optimizer, 'train') of model/pretrained/vqvae.py:118-135 (univariate,
+    L = 48) and of the fork's model/pretrained/myvqvae.py:116-136 (input_dim 7, flow_dim 50, L = 100 and L = 90 — the latter
+    exercises the final interpolation of myvqvae.py:85), with the reference's own optimizer (core.py:15-20 AdamW lr 1e-3,
+    weight_decay 1e-2).  Saved: losses, recon / z, every parameter's gradient norm, gradient slices, parameters after the step."""
+    from argparse import Namespace
+    from make_golden import install_shims
+    from t2ms_b200 import synth
+    install_shims(ref)
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    from model.pretrained.vqvae import vqvae as vq_uni
+    from model.pretrained.myvqvae import vqvae as vq_multi
+    res = {}
+    cases = {"uni48": (vq_uni, dict(), 1, 30, 48, 4), "multi100": (vq_multi, dict(flow_dim=50, input_dim=7), 7, 50, 100, 3),
+             "multi90": (vq_multi, dict(flow_dim=50, input_dim=7), 7, 50, 90, 2)}
+    for name, (cls, extra, cin, flow, L, B) in cases.items():
+        args = Namespace(block_hidden_size=128, num_residual_layers=2, res_hidden_size=256, embedding_dim=64, **extra)
+        m = cls(args)
+        sd = synth.make_vae_state(80 + L, in_channels=cin)
+        m.load_state_dict(sd, strict=True)
+        m.train()
+        g = torch.Generator().manual_seed(90 + L)
+        batch = torch.rand(B, L, generator=g) if cin == 1 else torch.rand(B, cin, L, generator=g)
+        opt, _ = m.configure_optimizers(lr=1e-3)
+        loss, recon_error, recon, z = m.shared_eval(batch, opt, "train")
+        k = name + "/"
+        res[k + "batch"], res[k + "loss"], res[k + "recon_error"] = batch.numpy(), np.float64(loss.item()), np.float64(recon_error.item())
+        res[k + "recon"], res[k + "z"] = recon.detach().numpy(), z.detach().numpy()
+        names = [n for n, _ in m.named_parameters()]
+        res[k + "names"] = np.array(names)
+        res[k + "grad_norms"] = np.array([float(p.grad.norm()) for _, p in m.named_parameters()])
+        for n, p in m.named_parameters():
+            res[k + "grad/" + n] = p.grad.reshape(-1)[:128].numpy().copy()
+            res[k + "after/" + n] = p.detach().reshape(-1)[:128].numpy().copy()
+        res[k + "checksum"] = np.array(synth.state_checksum(sd))
+        with torch.no_grad():
+            m.eval()
+            l2, r2, _, _ = m.shared_eval(batch, opt, "val")
+            res[k + "val_loss_after"] = np.float64(l2.item())
+    np.savez_compressed(os.path.join(out, "vae_train.npz"), **res)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -113,7 +156,7 @@ def main():
     a = ap.parse_args()
     only = set(filter(None, a.only.split(",")))
     torch.set_num_threads(8)
-    makers = {"eval": make_eval, "dit_tokens": make_dit_tokens}
+    makers = {"eval": make_eval, "dit_tokens": make_dit_tokens, "vae_train": make_vae_train}
     for name, fn in makers.items():
         if not only or name in only:
             fn(a.ref, a.out)

@@ -228,6 +228,45 @@ def vae_decode(sd: SD, z: torch.Tensor, length: int, pre: str = "decoder.") -> T
     return torch.squeeze(x), after
 
 
+def lavae_encode(sd: SD, x: torch.Tensor, flow_dim: int = 30, pre: str = "encoder.") -> Tuple[torch.Tensor, torch.Tensor]:
+    """The fork's multivariate Encoder.forward, myvqvae.py:49-61: x (B,C,L) -> z (B,E,flow_dim), before (B,E,n).
+    With C = 1 and flow_dim = 30 this is vqvae.py:57-71."""
+    n_layers = sum(1 for k in sd if k.startswith(pre + "_residual_stack._layers.") and k.endswith("_block.1.weight"))
+    x = F.relu(F.conv1d(x, sd[pre + "_conv_1.weight"], sd[pre + "_conv_1.bias"], stride=2, padding=1))
+    x = F.relu(F.conv1d(x, sd[pre + "_conv_2.weight"], sd[pre + "_conv_2.bias"], stride=2, padding=1))
+    x = F.conv1d(x, sd[pre + "_conv_3.weight"], sd[pre + "_conv_3.bias"], padding=1)
+    x = _residual_stack(sd, pre, x, n_layers)
+    before = F.conv1d(x, sd[pre + "_pre_vq_conv.weight"], sd[pre + "_pre_vq_conv.bias"])
+    return F.interpolate(before, size=flow_dim, mode="linear", align_corners=True), before
+
+
+def lavae_decode(sd: SD, z: torch.Tensor, length: int, pre: str = "decoder.") -> Tuple[torch.Tensor, torch.Tensor]:
+    """The fork's multivariate Decoder.forward, myvqvae.py:76-86: z (B,E,flow_dim) -> recon (B,C,length), after
+    (B,E,length//4); the last interpolation is the identity when 4 (length // 4) == length."""
+    n_layers = sum(1 for k in sd if k.startswith(pre + "_residual_stack._layers.") and k.endswith("_block.1.weight"))
+    x = F.interpolate(z, size=int(length / 4), mode="linear", align_corners=True)
+    after = x
+    x = F.conv1d(x, sd[pre + "_conv_1.weight"], sd[pre + "_conv_1.bias"], padding=1)
+    x = _residual_stack(sd, pre, x, n_layers)
+    x = F.relu(F.conv_transpose1d(x, sd[pre + "_conv_trans_1.weight"], sd[pre + "_conv_trans_1.bias"], stride=2, padding=1))
+    x = F.conv_transpose1d(x, sd[pre + "_conv_trans_2.weight"], sd[pre + "_conv_trans_2.bias"], stride=2, padding=1)
+    return F.interpolate(x, size=length, mode="linear", align_corners=True), after
+
+
+def lavae_train_grads(sd: SD, batch: torch.Tensor, flow_dim: int = 30):
+    """vqvae.shared_eval 'train' up to loss.backward() (vqvae.py:121-127, myvqvae.py:121-127):
+    batch (B,L) [univariate vqvae.py] or (B,C,L) [myvqvae.py] -> (loss, recon_error, recon, z, {name: grad})."""
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    x = batch.view(batch.shape[0], 1, batch.shape[-1]) if batch.dim() == 2 else batch
+    z, before = lavae_encode(p, x, flow_dim)
+    recon, after = lavae_decode(p, z, x.shape[-1])
+    data_recon = torch.squeeze(recon) if batch.dim() == 2 else recon          # vqvae.py:105
+    recon_error = F.mse_loss(data_recon, batch)
+    loss = recon_error + F.mse_loss(before, after)
+    loss.backward()
+    return loss.detach(), recon_error.detach(), data_recon.detach(), z.detach(), {k: v.grad for k, v in p.items()}
+
+
 # ----------------------------------------------------------------------------------------------
 # Sampling loops (infer.py:75-95) and the training step (train.py:66-87)
 # ----------------------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ EXPORTS = [
     "t2s_dit_cond", "t2s_dit_embed_qkv", "t2s_dit_attention", "t2s_dit_block_post", "t2s_dit_final",
     "t2s_train_workspace_bytes", "t2s_dit_train_step", "t2s_dit_train_forward", "t2s_dit_train_backward",
     "t2s_train_make_inputs", "t2s_adamw_step", "t2s_gemm_tf32",
-    "t2s_series_metrics", "t2s_train_attention_scratch_bytes", "t2s_train_attention_forward", "t2s_train_attention_backward",
+    "t2s_series_metrics", "t2s_lavae_workspace_bytes", "t2s_lavae_encode", "t2s_lavae_decode", "t2s_lavae_train_step", "t2s_train_attention_scratch_bytes", "t2s_train_attention_forward", "t2s_train_attention_backward",
 ]
 
 P = C.c_void_p
@@ -37,6 +37,16 @@ class DitParams(C.Structure):
                 ("lf_w", P), ("lf_b", P), ("freqs", P), ("qkv_w", P * 4), ("qkv_b", P * 4), ("proj_w", P * 4),
                 ("proj_b", P * 4), ("fc1_w", P * 4), ("fc1_b", P * 4), ("fc2_w", P * 4), ("fc2_b", P * 4),
                 ("ada_w", P * 4), ("ada_b", P * 4)]
+
+
+class LavaeParams(C.Structure):
+    """t2s_lavae_params: architecture ints + raw fp32 parameter (or gradient) pointers in the reference layouts."""
+    _fields_ = [("in_channels", C.c_int), ("hidden", C.c_int), ("res_hidden", C.c_int), ("emb", C.c_int), ("n_res", C.c_int),
+                ("flow_dim", C.c_int),
+                ("enc_conv1_w", P), ("enc_conv1_b", P), ("enc_conv2_w", P), ("enc_conv2_b", P), ("enc_conv3_w", P), ("enc_conv3_b", P),
+                ("enc_res_w3", P * 4), ("enc_res_w1", P * 4), ("enc_pre_w", P), ("enc_pre_b", P),
+                ("dec_conv1_w", P), ("dec_conv1_b", P), ("dec_res_w3", P * 4), ("dec_res_w1", P * 4),
+                ("dec_ct1_w", P), ("dec_ct1_b", P), ("dec_ct2_w", P), ("dec_ct2_b", P)]
 
 
 class VaeDecWeights(C.Structure):
@@ -121,6 +131,14 @@ def load() -> C.CDLL:
         lib.t2s_train_attention_backward.argtypes = [P, P, P, P, P, i, P, sz, P]
         lib.t2s_series_metrics.restype = i
         lib.t2s_series_metrics.argtypes = [P, P, i, i, P, P, P]
+        lib.t2s_lavae_workspace_bytes.restype = sz
+        lib.t2s_lavae_workspace_bytes.argtypes = [C.POINTER(LavaeParams), i, i]
+        lib.t2s_lavae_encode.restype = i
+        lib.t2s_lavae_encode.argtypes = [C.POINTER(LavaeParams), P, P, P, i, i, P, sz, P]
+        lib.t2s_lavae_decode.restype = i
+        lib.t2s_lavae_decode.argtypes = [C.POINTER(LavaeParams), P, P, P, i, i, P, sz, P]
+        lib.t2s_lavae_train_step.restype = i
+        lib.t2s_lavae_train_step.argtypes = [C.POINTER(LavaeParams), C.POINTER(LavaeParams), P, P, P, P, i, i, P, sz, P]
         _lib = lib
         return lib
 

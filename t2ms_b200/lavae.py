@@ -161,18 +161,27 @@ class vqvae(BaseModel):
         self.decoder = Decoder(args.embedding_dim, args.block_hidden_size, args.num_residual_layers, args.res_hidden_size)
 
     def shared_eval(self, batch, optimizer, mode):
-        """vqvae.py:118-135.  Only the frozen forward is on the generation path (train.py:31-33);
-        LA-VAE training is outside the scope of this package."""
+        """vqvae.py:118-135: encoder, decoder, recon_error = mse(recon, batch), cross_loss = mse(before, after),
+        loss = their sum; in 'train' mode ``optimizer.zero_grad()``, the backward (gradients written to ``param.grad``
+        by t2s_lavae_train_step) and ``optimizer.step()`` with the caller's optimizer.  Returns
+        (loss, recon_error, data_recon, z) like the reference (data_recon is torch.squeeze'd, vqvae.py:105)."""
+        from .lavae_train import LavaeEngine
+        if getattr(self, "_engine", None) is None:
+            self._engine = LavaeEngine(self, flow_dim=30)
         if mode == "train":
-            raise NotImplementedError("LA-VAE training is out of scope for t2ms_b200 (frozen in the T2S path)")
-        import torch.nn.functional as F
-        with torch.no_grad():
-            z, before = self.encoder(batch)
-            data_recon, after = self.decoder(z, length=batch.shape[-1])
-            recon_error = F.mse_loss(data_recon, batch)
-            cross_loss = F.mse_loss(before, after)
-            loss = recon_error + cross_loss
-        return loss, recon_error, data_recon, z
+            optimizer.zero_grad()
+            loss, recon_error, recon, z = self._engine.step(batch, backward=True)
+            optimizer.step()
+        elif mode in ("val", "test"):
+            loss, recon_error, recon, z = self._engine.step(batch, backward=False)
+        else:
+            raise ValueError(f"unknown mode {mode!r}")
+        return loss, recon_error, torch.squeeze(recon), z
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st.pop("_engine", None)
+        return st
 
     def forward(self, x):
         raise NotImplementedError("vqvae.forward is broken in the reference (vqvae.py:137-142 passes a tuple "

@@ -96,8 +96,9 @@ def make_dit_state(seed: int = 0, adaln_std: float = 0.02, bias_std: float = 0.0
 
 
 def make_vae_state(seed: int = 1, hidden: int = 128, res_hidden: int = 256, emb: int = 64,
-                   n_res: int = 2) -> Dict[str, torch.Tensor]:
-    """State dict with the key names / shapes of the reference ``vqvae`` (encoder.* / decoder.*)."""
+                   n_res: int = 2, in_channels: int = 1) -> Dict[str, torch.Tensor]:
+    """State dict with the key names / shapes of the reference ``vqvae`` (encoder.* / decoder.*); ``in_channels`` > 1
+    gives the fork's multivariate ``myvqvae`` (input_dim series channels)."""
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
 
@@ -112,7 +113,7 @@ def make_vae_state(seed: int = 1, hidden: int = 128, res_hidden: int = 256, emb:
         sd[name + ".weight"] = _conv_default(g, (in_c, out_c, k), fan_in)
         sd[name + ".bias"] = _conv_default(g, (out_c,), fan_in)
 
-    conv("encoder._conv_1", hidden // 2, 1, 4)
+    conv("encoder._conv_1", hidden // 2, in_channels, 4)
     conv("encoder._conv_2", hidden, hidden // 2, 4)
     conv("encoder._conv_3", hidden, hidden, 3)
     for i in range(n_res):
@@ -124,7 +125,7 @@ def make_vae_state(seed: int = 1, hidden: int = 128, res_hidden: int = 256, emb:
         conv(f"decoder._residual_stack._layers.{i}._block.1", res_hidden, hidden, 3, bias=False)
         conv(f"decoder._residual_stack._layers.{i}._block.3", hidden, res_hidden, 1, bias=False)
     convT("decoder._conv_trans_1", hidden, hidden // 2, 4)
-    convT("decoder._conv_trans_2", hidden // 2, 1, 4)
+    convT("decoder._conv_trans_2", hidden // 2, in_channels, 4)
     return sd
 
 

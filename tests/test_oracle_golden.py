@@ -165,3 +165,26 @@ def test_variable_width_dit_oracle_matches_fork_reference(dim):
         lat, _, eps = O.ddpm_sample(sd, None, x, emb, 3, 7.0, sn, return_eps=True)
         close(torch.stack(eps), g[k + "ddpm_eps"], 1e-3, rtol=1e-5)
         close(lat, g[k + "ddpm_final"], 1e-3, rtol=1e-5)
+
+
+@pytest.mark.parametrize("case,cin,flow", [("uni48", 1, 30), ("multi100", 7, 50), ("multi90", 7, 50)])
+def test_lavae_training_oracle_matches_reference(case, cin, flow):
+    """oracle lavae_train_grads (loss, recon, z, every parameter gradient, AdamW update) against
+    vqvae.shared_eval(batch, optimizer, 'train') of the reference (vqvae.py:118-135) and of the fork (myvqvae.py:116-136)."""
+    g = load_golden("vae_train.npz")
+    k = case + "/"
+    batch = T(g[k + "batch"])
+    sd = synth.make_vae_state(80 + batch.shape[-1], in_channels=cin)
+    assert synth.state_checksum(sd) == str(g[k + "checksum"])
+    loss, recon_error, recon, z, grads = O.lavae_train_grads(sd, batch, flow_dim=flow)
+    assert abs(float(loss) - float(g[k + "loss"])) <= 1e-6 and abs(float(recon_error) - float(g[k + "recon_error"])) <= 1e-6
+    close(recon, g[k + "recon"], 1e-5)
+    close(z, g[k + "z"], 1e-5)
+    names = [str(n) for n in g[k + "names"]]
+    assert sorted(names) == sorted(sd.keys())
+    for n, ref_norm in zip(names, g[k + "grad_norms"]):
+        assert abs(float(grads[n].norm()) - float(ref_norm)) <= 1e-4 * max(1.0, float(ref_norm)), n
+        close(grads[n].reshape(-1)[:128], g[k + "grad/" + n], 1e-5, rtol=1e-4)
+        # core.py:15: AdamW(lr 1e-3, weight_decay 1e-2), first step (LinearLR start_factor 0.1 -> lr 1e-4)
+        p, _, _ = O.adamw_step(sd[n].clone(), grads[n], torch.zeros_like(sd[n]), torch.zeros_like(sd[n]), 1, 1e-4, wd=1e-2)
+        close(p.reshape(-1)[:128], g[k + "after/" + n], 2e-6)
