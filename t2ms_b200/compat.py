@@ -19,6 +19,10 @@ _ALIASES = {
     "model.backbone.DDPM": ("t2ms_b200.backbone", ["DDPM", "gather"]),
     "model.pretrained.core": ("t2ms_b200.lavae", ["BaseModel"]),
     "model.pretrained.vqvae": ("t2ms_b200.lavae", ["vqvae", "Encoder", "Decoder", "Residual", "ResidualStack"]),
+    # the fork's variants (mytrain.py:8-9, myinfer.py:14-15, pretrained_mylavae.py:5)
+    "model.denoiser.mytransformer": ("t2ms_b200.denoiser", ["Transformer", "Transformerlayer", "TimeEmbedding", "modulate",
+                                                            "get_sinusoidal_positional_embeddings", "InverseLatentEmbedding"]),
+    "model.pretrained.myvqvae": ("t2ms_b200.mylavae", ["vqvae", "Encoder", "Decoder"]),
 }
 
 

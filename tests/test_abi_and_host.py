@@ -192,3 +192,27 @@ def test_compat_aliases():
     assert RT is Transformer and RD is DDPM and RV is vqvae
     v = compat.convert_reference_vae(synth.make_vae_state(5))
     assert isinstance(v, vqvae)
+
+
+def test_fork_module_aliases_and_state_dicts():
+    """The fork's module paths (mytrain.py:7-9, myinfer.py:5-6) resolve to the t2ms_b200 classes; Transformer(dim) and the
+    multivariate vqvae(args) carry the reference's parameter names / shapes (strict load of synthetic reference-shaped
+    state dicts) on CPU — only their forward needs the GPU."""
+    from argparse import Namespace
+    from t2ms_b200 import compat
+    compat.install()
+    from model.denoiser.mytransformer import Transformer as FT
+    from model.pretrained.myvqvae import vqvae as FV
+    from t2ms_b200 import mylavae
+    assert FT is Transformer and FV is mylavae.vqvae
+    for dim in (50, 64):
+        m = FT(dim)
+        m.load_state_dict(synth.make_dit_state(3, dim=dim), strict=True)
+        assert m.pos_embed.shape == (1, 16 * dim, 128) and m.patch_count == 16 * dim
+    with pytest.raises(ValueError):
+        FT(48)
+    v = FV(Namespace(block_hidden_size=128, num_residual_layers=2, res_hidden_size=256, embedding_dim=64, flow_dim=50, input_dim=7))
+    v.load_state_dict(synth.make_vae_state(4, in_channels=7), strict=True)
+    assert v.encoder._conv_1.weight.shape == (64, 7, 4) and v.decoder._conv_trans_2.weight.shape == (64, 7, 4)
+    with pytest.raises(RuntimeError):
+        v.encoder(torch.rand(2, 7, 100))                       # CPU tensors: no fallback
