@@ -22,6 +22,7 @@ int train_init() {
     CUDA_OK(cudaGetDevice(&dev));
     if (g_train_inited[dev]) return T2S_OK;
     CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(gemm_tf32_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(ta_attn_kernel<TA_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(ta_attn_kernel<TA_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(ta_attn_kernel<TA_DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM_BYTES));
@@ -63,8 +64,18 @@ struct Gemm {
         if ((a.lda & 3) || (a.ldb & 3) || (!a.a_mn && (a.K & 3)) || (!a.b_mn && (a.K & 3)) || (a.a_mn && (a.M & 3)) || (a.b_mn && (a.N & 3)))
             return fail(T2S_EINVAL, "gemm_tf32: leading dimensions / extents must be multiples of 4%s%s");
         if (((uintptr_t)a.A | (uintptr_t)a.B) & 15) return fail(T2S_EINVAL, "gemm_tf32: operands must be 16-byte aligned%s%s");
+        if ((a.mode & ~15) != 0 && (a.a_mn || batch != 1 || a.ksplit != 1 || a.N % 128 != 0 || a.M < 4 * G_BM))
+            return fail(T2S_EINVAL, "gemm_tf32: profiling mode bits apply to the persistent form only%s%s");
         if (a.mode == GEMM_ATOMIC && a.bias != nullptr) return fail(T2S_EINVAL, "gemm_tf32: bias with atomic accumulation%s%s");
         if (a.ksplit > 1 && a.mode != GEMM_ATOMIC) return fail(T2S_EINVAL, "gemm_tf32: split-K needs atomic accumulation%s%s");
+        // forward / input-gradient shapes: the persistent form (decoupled load / MMA / epilogue roles, one CTA per SM)
+        const bool vec_c = (a.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.bias == nullptr || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
+        if (!a.a_mn && batch == 1 && a.ksplit == 1 && (a.mode & 15) != GEMM_ATOMIC && a.N % 128 == 0 && a.M >= 4 * G_BM && vec_c) {
+            const int items = ((a.M + G_BM - 1) / G_BM) * (a.N / 128), sms = sm_count();
+            gemm_tf32_persistent_kernel<<<items < sms ? items : sms, P_THREADS, P_SMEM_BYTES, st>>>(a);
+            CUDA_OK(cudaGetLastError());
+            return T2S_OK;
+        }
         dim3 grid((a.M + G_BM - 1) / G_BM, (a.N + a.bn - 1) / a.bn, batch * a.ksplit);
         gemm_tf32_kernel<<<grid, G_THREADS, G_SMEM_BYTES, st>>>(a);
         CUDA_OK(cudaGetLastError());

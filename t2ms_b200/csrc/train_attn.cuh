@@ -17,9 +17,9 @@
 // (S = Q K^T with thread = query row for dQ; S^T = K Q^T with thread = key row for dK / dV), which keeps every
 // accumulation a plain "A from TMEM x B from shared memory" tcgen05.mma.
 //
-// One kernel, three modes; CTA = (sequence, head, 120-token tile) with M = 128 (8 padding rows), looping over the
-// five 96-token chunks of the other side; warps 0-3: thread = tile row = TMEM lane; warp 4: loads + MMA issue;
-// 80 KB of shared memory and 256 TMEM columns, so two CTAs share an SM.
+// One kernel, three modes; CTA = (sequence, head, 120-token tile) with M = 128 (8 padding rows), looping over chunks of
+// the other side (FWD: five of 96 tokens, DQ / DKV: ten of 48), double-buffered in TMEM; warps 0-3: thread = tile row =
+// TMEM lane; warp 4: loads + MMA issue; 80 KB of shared memory and 256 TMEM columns, so two CTAs share an SM.
 //   FWD: S = Q_t K_j^T ; P = exp2((S - m) c) -> TMEM (over S) ; O += P V_j ; O / l and the log-sum-exp are stored
 //   DQ : S = Q_t K_j^T, dP = dO_t V_j^T ; dS' = P' (dP - D) -> TMEM (over dP) ; dQ += dS' K_j
 //   DKV: S^T = K_t Q_j^T, dP^T = V_t dO_j^T ; P'^T -> TMEM (over S^T), dS'^T -> TMEM (over dP^T) ;
@@ -35,8 +35,6 @@ constexpr int TA_IMG_BYTES = TA_IMG_HALVES * 2;
 constexpr int TA_ROWS = 120;                             // valid rows per tile
 constexpr int TA_NTILE = NTOK / TA_ROWS;                 // 4
 constexpr int TA_TILE_BYTES = TA_ROWS * HD * 2;          // 7680 B copied per tile (the 8 padding rows stay undefined)
-constexpr int TA_KC = 96;                                // tokens per chunk
-constexpr int TA_NCH = NTOK / TA_KC;                     // 5
 constexpr int TA_THREADS = 160;
 constexpr float TA_PSHIFT = 4.f;                         // backward probabilities are kept as 2^4 P
 enum TaMode { TA_FWD = 0, TA_DQ = 1, TA_DKV = 2 };
@@ -48,9 +46,8 @@ constexpr int TA_SM_BAR = TA_SM_VEC + 2 * NTOK * 4;
 constexpr int TA_SM_TMEM = TA_SM_BAR + 8 * 8;
 constexpr int TA_SMEM_BYTES = TA_SM_TMEM + 16;
 static_assert(2 * (TA_SMEM_BYTES + 1024) <= 233472, "two training-attention CTAs must fit one SM");
-enum { TB_LOADED = 0, TB_SFULL = 1, TB_PFULL = 2, TB_ACC = 3 };
-constexpr uint32_t TA_T_S = 0, TA_T_DP = 96, TA_T_ACC0 = 192, TA_T_ACC1 = 224, TA_TCOLS = 256;
-constexpr uint32_t TA_IDESC_S = umma_idesc_f16(128, TA_KC);
+enum { TB_LOADED = 0, TB_SFULL = 1, TB_PFULL = 3, TB_ACC = 5 };       // SFULL / PFULL / ACC: one barrier per score buffer
+constexpr uint32_t TA_BUF = 96, TA_T_ACC0 = 192, TA_T_ACC1 = 224, TA_TCOLS = 256;   // two score buffers of 96 columns + accumulators
 constexpr uint32_t TA_IDESC_ACC = umma_idesc_f16(128, HD) | (1u << 16);     // B operand MN-major
 
 struct TaArgs {
@@ -142,9 +139,16 @@ __global__ void __launch_bounds__(512) ta_pack_do_kernel(const float* __restrict
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// grid = nseq * 4 heads * 4 tiles, block = 160
+// grid = nseq * 4 heads * 4 tiles, block = 160.  Score chunks are double-buffered in TMEM: while the row threads work on
+// chunk j (buffer j & 1) the tensor pipe has already produced the scores of chunk j + 1 and runs the accumulation of
+// chunk j - 1, so the row threads (MUFU / issue bound) never wait for an MMA in steady state.
+//   FWD     : 5 chunks of 96 keys;  TMEM  S0 [0,96) | S1 [96,192) | O [192,224)
+//   DQ / DKV: 10 chunks of 48;      TMEM  buffer b: S [96 b, +48) | dP [96 b + 48, +48) ; acc0 [192,224) | acc1 [224,256)
 template <int MODE>
 __global__ void __launch_bounds__(TA_THREADS, 2) ta_attn_kernel(const TaArgs p) {
+    constexpr int KC = MODE == TA_FWD ? 96 : 48;                    // tokens per chunk
+    constexpr int NCH = NTOK / KC;
+    constexpr uint32_t IDESC_S = umma_idesc_f16(128, KC);
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform
     const int sh = blockIdx.x >> 2, tile = blockIdx.x & 3;          // (sequence, head) index; tile of the row side
@@ -154,9 +158,11 @@ __global__ void __launch_bounds__(TA_THREADS, 2) ta_attn_kernel(const TaArgs p) 
     auto BAR = [&](int i) { return bar0 + 8u * i; };
     if (tid == 0) {
         mbar_init(BAR(TB_LOADED), 1);
-        mbar_init(BAR(TB_SFULL), 1);
-        mbar_init(BAR(TB_PFULL), 128);
-        mbar_init(BAR(TB_ACC), 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(BAR(TB_SFULL + b), 1);
+            mbar_init(BAR(TB_PFULL + b), 128);
+            mbar_init(BAR(TB_ACC + b), 1);
+        }
         mbar_fence_init();
     }
     if (warp == 4) tmem_alloc(sb + TA_SM_TMEM, TA_TCOLS);
@@ -199,54 +205,62 @@ __global__ void __launch_bounds__(TA_THREADS, 2) ta_attn_kernel(const TaArgs p) 
             }
         }
         __syncwarp();
-        mbar_wait(BAR(TB_LOADED), 0);
-        tc_fence_after();
-#pragma unroll 1
-        for (int j = 0; j < TA_NCH; ++j) {
-            if (j > 0) {                                             // the previous chunk's accumulation has consumed TMEM
-                mbar_wait(BAR(TB_ACC), (j - 1) & 1);
-                tc_fence_after();
-            }
-            // scores of chunk j (contraction over the 32 features: two K = 16 steps)
+        // scores of chunk G into buffer G & 1 (contraction over the 32 features: two K = 16 steps)
+        auto issue_scores = [&](int G) {
+            const uint32_t tb = tmem + (G & 1) * TA_BUF;
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
                 const uint64_t a0 = umma_desc(sb + TA_SM_A0 + kk * 256, 128, 512);
-                const uint64_t b0 = umma_desc(sb + TA_SM_B0 + j * (TA_KC / 8) * 512 + kk * 256, 128, 512);
-                if (lead) umma_f16(tmem + TA_T_S, a0, b0, TA_IDESC_S, kk > 0);
+                const uint64_t b0 = umma_desc(sb + TA_SM_B0 + G * (KC / 8) * 512 + kk * 256, 128, 512);
+                if (lead) umma_f16(tb, a0, b0, IDESC_S, kk > 0);
             }
             if (MODE != TA_FWD) {
 #pragma unroll
                 for (int kk = 0; kk < 2; ++kk) {
                     const uint64_t a1 = umma_desc(sb + TA_SM_A1 + kk * 256, 128, 512);
-                    const uint64_t b1 = umma_desc(sb + TA_SM_B1 + j * (TA_KC / 8) * 512 + kk * 256, 128, 512);
-                    if (lead) umma_f16(tmem + TA_T_DP, a1, b1, TA_IDESC_S, kk > 0);
+                    const uint64_t b1 = umma_desc(sb + TA_SM_B1 + G * (KC / 8) * 512 + kk * 256, 128, 512);
+                    if (lead) umma_f16(tb + KC, a1, b1, IDESC_S, kk > 0);
                 }
             }
-            if (lead) umma_commit(BAR(TB_SFULL));
+            if (lead) umma_commit(BAR(TB_SFULL + (G & 1)));
             __syncwarp();
-            mbar_wait(BAR(TB_PFULL), j & 1);                         // the fp16 A operands are in TMEM
+        };
+        mbar_wait(BAR(TB_LOADED), 0);
+        tc_fence_after();
+        issue_scores(0);
+        issue_scores(1);
+#pragma unroll 1
+        for (int j = 0; j < NCH; ++j) {
+            const int b = j & 1;
+            const uint32_t par = (j >> 1) & 1, tb = tmem + b * TA_BUF;
+            mbar_wait(BAR(TB_PFULL + b), par);                       // the fp16 A operands of chunk j are in TMEM
             tc_fence_after();
-            // accumulations over the 96 tokens of the chunk (six K = 16 steps), B operands MN-major
+            // accumulations over the KC tokens of the chunk (K = 16 per step), B operands MN-major
 #pragma unroll
-            for (int ks = 0; ks < TA_KC / 16; ++ks) {
-                const uint32_t boff = (j * (TA_KC / 8) + 2 * ks) * 512;
+            for (int ks = 0; ks < KC / 16; ++ks) {
+                const uint32_t boff = (j * (KC / 8) + 2 * ks) * 512;
                 const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
                 if (MODE == TA_FWD) {                                // O += P V
                     const uint64_t bd = umma_desc(sb + TA_SM_B1 + boff, 512, 128);
-                    if (lead) umma_f16_ts(tmem + TA_T_ACC0, tmem + TA_T_S + ks * 8, bd, TA_IDESC_ACC, acc);
+                    if (lead) umma_f16_ts(tmem + TA_T_ACC0, tb + ks * 8, bd, TA_IDESC_ACC, acc);
                 } else if (MODE == TA_DQ) {                          // dQ += dS K
                     const uint64_t bd = umma_desc(sb + TA_SM_B0 + boff, 512, 128);
-                    if (lead) umma_f16_ts(tmem + TA_T_ACC0, tmem + TA_T_DP + ks * 8, bd, TA_IDESC_ACC, acc);
+                    if (lead) umma_f16_ts(tmem + TA_T_ACC0, tb + KC + ks * 8, bd, TA_IDESC_ACC, acc);
                 } else {                                             // dV += P^T dO ; dK += dS^T Q
                     const uint64_t bd = umma_desc(sb + TA_SM_B1 + boff, 512, 128), bq = umma_desc(sb + TA_SM_B0 + boff, 512, 128);
                     if (lead) {
-                        umma_f16_ts(tmem + TA_T_ACC0, tmem + TA_T_S + ks * 8, bd, TA_IDESC_ACC, acc);
-                        umma_f16_ts(tmem + TA_T_ACC1, tmem + TA_T_DP + ks * 8, bq, TA_IDESC_ACC, acc);
+                        umma_f16_ts(tmem + TA_T_ACC0, tb + ks * 8, bd, TA_IDESC_ACC, acc);
+                        umma_f16_ts(tmem + TA_T_ACC1, tb + KC + ks * 8, bq, TA_IDESC_ACC, acc);
                     }
                 }
             }
-            if (lead) umma_commit(BAR(TB_ACC));
+            if (lead) umma_commit(BAR(TB_ACC + b));
             __syncwarp();
+            if (j + 2 < NCH) {                                       // the next scores into this buffer overwrite its A operands
+                mbar_wait(BAR(TB_ACC + b), par);
+                tc_fence_after();
+                issue_scores(j + 2);
+            }
         }
     } else {
         // ================================================================= thread = tile row
@@ -254,12 +268,14 @@ __global__ void __launch_bounds__(TA_THREADS, 2) ta_attn_kernel(const TaArgs p) 
         const int tok = tile * TA_ROWS + r;
         const bool valid = r < TA_ROWS;
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-        const uint32_t ts = trow + TA_T_S, tdp = trow + TA_T_DP;
+        constexpr int LAST = NCH - 1;                                // the final accumulation: barrier ACC[LAST & 1], phase (LAST >> 1) & 1
         if (MODE == TA_FWD) {
             float mref = 0.f, l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
-            for (int j = 0; j < TA_NCH; ++j) {
-                mbar_wait(BAR(TB_SFULL), j & 1);
+            for (int j = 0; j < NCH; ++j) {
+                const int b = j & 1;
+                const uint32_t ts = trow + b * TA_BUF;
+                mbar_wait(BAR(TB_SFULL + b), (j >> 1) & 1);
                 tc_fence_after();
                 float x[32], y[32], z[32];
                 tmem_ld32(ts, x); tmem_ld32(ts + 32, y); tmem_ld32(ts + 64, z);
@@ -275,13 +291,14 @@ __global__ void __launch_bounds__(TA_THREADS, 2) ta_attn_kernel(const TaArgs p) 
                 if (j == 0) {
                     mref = cm;
                 } else {
-                    // move the reference point only when P would exceed 2^8 (exact in fp16 below that); every earlier
-                    // P.V has completed (the scores of this chunk were issued after it)
+                    // move the reference point only when P would exceed 2^8 (exact in fp16 below that)
                     const bool need = (cm - mref) * sc > 8.f;
                     if (__any_sync(0xffffffffu, need)) {
                         const float alpha = need ? ex2_approx((mref - cm) * sc) : 1.f;
                         if (need) mref = cm;
                         l0 *= alpha; l1 *= alpha;
+                        mbar_wait(BAR(TB_ACC + (b ^ 1)), ((j - 1) >> 1) & 1);     // every earlier P.V has landed in O
+                        tc_fence_after();
                         float a0[32];
                         tmem_ld32(trow + TA_T_ACC0, a0);
                         tmem_wait_ld();
@@ -308,9 +325,9 @@ __global__ void __launch_bounds__(TA_THREADS, 2) ta_attn_kernel(const TaArgs p) 
                 block(x, 0); block(y, 1); block(z, 2);
                 tmem_wait_st();
                 tc_fence_before();
-                mbar_arrive(BAR(TB_PFULL));
+                mbar_arrive(BAR(TB_PFULL + b));
             }
-            mbar_wait(BAR(TB_ACC), (TA_NCH - 1) & 1);
+            mbar_wait(BAR(TB_ACC + (LAST & 1)), (LAST >> 1) & 1);
             tc_fence_after();
             const float l = l0 + l1, inv = 1.f / l;
             float a0[32];
@@ -330,49 +347,50 @@ __global__ void __launch_bounds__(TA_THREADS, 2) ta_attn_kernel(const TaArgs p) 
             const float* vd = vnl + NTOK;
             if (MODE == TA_DKV) mbar_wait(BAR(TB_LOADED), 0);           // the per-query vectors are in shared memory
 #pragma unroll 1
-            for (int j = 0; j < TA_NCH; ++j) {
-                mbar_wait(BAR(TB_SFULL), j & 1);
+            for (int j = 0; j < NCH; ++j) {
+                const int b = j & 1;
+                const uint32_t ts = trow + b * TA_BUF, tdp = ts + KC;
+                mbar_wait(BAR(TB_SFULL + b), (j >> 1) & 1);
                 tc_fence_after();
-#pragma unroll 1
-                for (int b = 0; b < 3; ++b) {
-                    float s[32], g[32];
-                    tmem_ld32(ts + b * 32, s);
-                    tmem_ld32(tdp + b * 32, g);
-                    tmem_wait_ld();
+                float s[48], g[48];
+                tmem_ld32(ts, *reinterpret_cast<float (*)[32]>(&s[0]));
+                tmem_ld16(ts + 32, *reinterpret_cast<float (*)[16]>(&s[32]));
+                tmem_ld32(tdp, *reinterpret_cast<float (*)[32]>(&g[0]));
+                tmem_ld16(tdp + 32, *reinterpret_cast<float (*)[16]>(&g[32]));
+                tmem_wait_ld();
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t pp[8], pd[8];
+                for (int h = 0; h < 3; ++h) {                           // 16 scores -> 8 packed columns
+                    uint32_t pp[8], pd[8];
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            float nl[4], dd[4];
-                            if (MODE == TA_DKV) {
-                                const int c = j * TA_KC + b * 32 + h * 16 + q4 * 4;
-                                const float4 n4 = *reinterpret_cast<const float4*>(vnl + c), d4 = *reinterpret_cast<const float4*>(vd + c);
-                                nl[0] = n4.x; nl[1] = n4.y; nl[2] = n4.z; nl[3] = n4.w;
-                                dd[0] = d4.x; dd[1] = d4.y; dd[2] = d4.z; dd[3] = d4.w;
-                            } else {
-                                nl[0] = nl[1] = nl[2] = nl[3] = nl_r;
-                                dd[0] = dd[1] = dd[2] = dd[3] = d_r;
-                            }
-                            float pv[4], dv[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int i = h * 16 + q4 * 4 + u;
-                                pv[u] = ex2_approx(fmaf(s[i], sc, nl[u]));
-                                dv[u] = pv[u] * (g[i] - dd[u]);
-                            }
-                            pp[q4 * 2] = pack_h2(pv[0], pv[1]); pp[q4 * 2 + 1] = pack_h2(pv[2], pv[3]);
-                            pd[q4 * 2] = pack_h2_sat(dv[0], dv[1]); pd[q4 * 2 + 1] = pack_h2_sat(dv[2], dv[3]);
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        float nl[4], dd[4];
+                        if (MODE == TA_DKV) {
+                            const int c = j * KC + h * 16 + q4 * 4;
+                            const float4 n4 = *reinterpret_cast<const float4*>(vnl + c), d4 = *reinterpret_cast<const float4*>(vd + c);
+                            nl[0] = n4.x; nl[1] = n4.y; nl[2] = n4.z; nl[3] = n4.w;
+                            dd[0] = d4.x; dd[1] = d4.y; dd[2] = d4.z; dd[3] = d4.w;
+                        } else {
+                            nl[0] = nl[1] = nl[2] = nl[3] = nl_r;
+                            dd[0] = dd[1] = dd[2] = dd[3] = d_r;
                         }
-                        if (MODE == TA_DKV) tmem_st8(ts + b * 16 + h * 8, pp);
-                        tmem_st8(tdp + b * 16 + h * 8, pd);
+                        float pv[4], dv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = h * 16 + q4 * 4 + u;
+                            pv[u] = ex2_approx(fmaf(s[i], sc, nl[u]));
+                            dv[u] = pv[u] * (g[i] - dd[u]);
+                        }
+                        pp[q4 * 2] = pack_h2(pv[0], pv[1]); pp[q4 * 2 + 1] = pack_h2(pv[2], pv[3]);
+                        pd[q4 * 2] = pack_h2_sat(dv[0], dv[1]); pd[q4 * 2 + 1] = pack_h2_sat(dv[2], dv[3]);
                     }
+                    if (MODE == TA_DKV) tmem_st8(ts + h * 8, pp);
+                    tmem_st8(tdp + h * 8, pd);
                 }
                 tmem_wait_st();
                 tc_fence_before();
-                mbar_arrive(BAR(TB_PFULL));
+                mbar_arrive(BAR(TB_PFULL + b));
             }
-            mbar_wait(BAR(TB_ACC), (TA_NCH - 1) & 1);
+            mbar_wait(BAR(TB_ACC + (LAST & 1)), (LAST >> 1) & 1);
             tc_fence_after();
             const float kscale = 0.17677669529663687f;                  // 1 / sqrt(32)
             const float base = p.dinv[sh] * 0.0625f;                     // undo the dO scale and the 2^4 of P'

@@ -40,7 +40,9 @@ def gemm(A, B, M, N, K, lda, ldb, a_mn, b_mn, bias=None, mode=0, alpha=1.0, kspl
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 128), (480, 480, 32), (480, 32, 480), (300, 256, 128), (1000, 384, 128),
-                                   (128, 256, 4096), (768, 128, 20), (4, 768, 128)])
+                                   (128, 256, 4096), (768, 128, 20), (4, 768, 128),
+                                   # persistent form (A K-major, N % 128 == 0, M >= 512): more tiles than SMs, ragged M, K = 128..384
+                                   (40000, 384, 128), (20011, 128, 256), (1536, 256, 384), (512, 128, 36)])
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
 def test_gemm_tf32(M, N, K, a_mn, b_mn):
     if (a_mn and M % 4) or (b_mn and N % 4) or ((not a_mn or not b_mn) and K % 4):
@@ -57,13 +59,14 @@ def test_gemm_tf32(M, N, K, a_mn, b_mn):
 
 def test_gemm_epilogues():
     g = torch.Generator().manual_seed(5)
-    M, N, K = 260, 384, 256
-    a, b, bias, c0 = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g), torch.randn(M, N, generator=g)
-    ref = a.double() @ b.double().t()
-    A, B = a.to(DEV), b.to(DEV)
-    assert rel(gemm(A, B, M, N, K, K, K, 0, 0, bias=bias.to(DEV), alpha=0.5), 0.5 * ref + bias.double()) < 1.5e-3
-    assert rel(gemm(A, B, M, N, K, K, K, 0, 0, mode=1, C0=c0.to(DEV)), ref + c0.double()) < 1.5e-3
-    assert rel(gemm(A, B, M, N, K, K, K, 0, 0, mode=2, ksplit=5, C0=c0.to(DEV)), ref + c0.double()) < 1.5e-3
+    for M in (260, 2600):                                  # one-tile-per-CTA form / persistent form
+        N, K = 384, 256
+        a, b, bias, c0 = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+        ref = a.double() @ b.double().t()
+        A, B = a.to(DEV), b.to(DEV)
+        assert rel(gemm(A, B, M, N, K, K, K, 0, 0, bias=bias.to(DEV), alpha=0.5), 0.5 * ref + bias.double()) < 1.5e-3
+        assert rel(gemm(A, B, M, N, K, K, K, 0, 0, mode=1, C0=c0.to(DEV)), ref + c0.double()) < 1.5e-3
+        assert rel(gemm(A, B, M, N, K, K, K, 0, 0, mode=2, ksplit=5, C0=c0.to(DEV)), ref + c0.double()) < 1.5e-3
 
 
 def _attention(qkv, dout):
