@@ -141,7 +141,7 @@ int launch_embed(const t2s_dit_weights* w, const float* x, int x_shift, int nseq
     return T2S_OK;
 }
 int launch_attn(int nseq, const Shape& sh, const Workspace& ws, cudaStream_t st) {
-    T2S_DISPATCH_H(sh.H, (attn_kernel<HH><<<nseq * NHEAD, ATT_THREADS, AttShape<HH>::SMEM_BYTES, st>>>(ws.qkv, ws.o, g_trace)));
+    T2S_DISPATCH_H(sh.H, (attn_kernel<HH><<<nseq * NHEAD, AttShape<HH>::THREADS, AttShape<HH>::SMEM_BYTES, st>>>(ws.qkv, ws.o, g_trace)));
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }

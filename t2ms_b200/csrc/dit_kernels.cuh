@@ -762,20 +762,25 @@ struct AttShape {
     static constexpr int KC = S::KC, NCH = S::NCH, NQT = S::NQT;      // keys per chunk, chunks, q-tiles
     static constexpr int SM_Q = 0, SM_K = S::Q_HALVES * 2, SM_V = SM_K + S::K_HALVES * 2;
     static constexpr int SM_BAR = SM_V + S::V_HALVES * 2;
-    static constexpr int SM_TMEM = SM_BAR + 16 * 8;
+    static constexpr int SM_TMEM = SM_BAR + 32 * 8;
     static constexpr int SMEM_BYTES = SM_TMEM + 16;
     static constexpr int CTAS_PER_SM = 2 * (SMEM_BYTES + 1024) <= 233472 ? 2 : 1;   // H = 30: two CTAs share an SM
+    // wide shapes (K / V of one head no longer fit twice): ONE CTA per SM with TWO softmax warpgroups (+ their MMA warps)
+    // working on alternate q-tiles over the shared K / V images, so one group's MMA / TMEM phases hide under the other's exps
+    static constexpr int NWG = CTAS_PER_SM == 2 ? 1 : 2;
+    static constexpr int THREADS = NWG * ATT_THREADS;
     static constexpr uint32_t IDESC_S = umma_idesc_f16(128, KC);
-    static constexpr uint32_t TCOLS = 256;                            // two S buffers (2 x KC) + O (32)
+    static constexpr uint32_t TCOLS_WG = 256;                         // per warpgroup: two S buffers (2 x KC) + O (32)
+    static constexpr uint32_t TCOLS = NWG * TCOLS_WG;
     static constexpr uint32_t T_S = 0, T_O = 2 * KC;
-    static_assert(SMEM_BYTES <= 232448 && 2 * KC + HD <= 256, "attention kernel resources");
+    static_assert(SMEM_BYTES <= 232448 && 2 * KC + HD <= 256 && NQT % NWG == 0, "attention kernel resources");
 };
 static_assert(AttShape<30>::CTAS_PER_SM == 2, "two attention CTAs must fit one SM for the T2S shape");
 constexpr uint32_t ATT_IDESC_PV = umma_idesc_f16(128, HD) | (1u << 16);   // B (V) is MN-major
 
-// grid = nseq * 4, block = 160: warps 0-3 = softmax (thread = query row = TMEM lane), warp 4 = loads + MMA issue
+// grid = nseq * 4, block = 160 per warpgroup: warps 0-3 = softmax (thread = query row = TMEM lane), warp 4 = (loads +) MMA issue
 template <int H>
-__global__ void __launch_bounds__(ATT_THREADS, AttShape<H>::CTAS_PER_SM) attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ o, long long* trace) {
+__global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM) attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ o, long long* trace) {
     using S = DitShape<H>;
     using AS = AttShape<H>;
     constexpr int NTOK = S::NTOK, TILE_TOK = S::TILE_TOK, TILES_PER_PAIR = S::TILES_PER_PAIR, QT_ROWS = S::QT_ROWS;
@@ -783,35 +788,41 @@ __global__ void __launch_bounds__(ATT_THREADS, AttShape<H>::CTAS_PER_SM) attn_ke
     constexpr int ATT_KC = AS::KC, ATT_NCH = AS::NCH, ATT_NQT = AS::NQT;
     constexpr int ATT_SM_Q = AS::SM_Q, ATT_SM_K = AS::SM_K, ATT_SM_V = AS::SM_V, ATT_SM_BAR = AS::SM_BAR, ATT_SM_TMEM = AS::SM_TMEM;
     constexpr uint32_t ATT_IDESC_S = AS::IDESC_S, ATT_TCOLS = AS::TCOLS, ATT_T_S = AS::T_S, ATT_T_O = AS::T_O;
+    constexpr int NWG = AS::NWG;
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform
+    const int tid = threadIdx.x, lane = tid & 31, warp_cta = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform
+    const int wg = warp_cta / 5, warp = warp_cta % 5;                 // warpgroup; role inside it (0-3 softmax, 4 MMA)
     const int seq = blockIdx.x >> 2, head = blockIdx.x & 3;
     const uint32_t sb = smem_u32(smem);
     const uint32_t bar0 = sb + ATT_SM_BAR;
-    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    // barriers 0-2 (Q / K / V loaded) are shared; every warpgroup owns a block of ten (AB_SFULL .. AB_OFREE)
+    auto BAR = [&](int i) { return bar0 + 8u * (i < 3 ? i : i + wg * 10); };
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) mbar_init(BAR(i), 1);
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(BAR(AB_SFULL + b), 1);
-            mbar_init(BAR(AB_SFREE + b), 128);
-            mbar_init(BAR(AB_PFULL + b), 128);
-            mbar_init(BAR(AB_PVDONE + b), 1);
+        for (int i = 0; i < 3; ++i) mbar_init(bar0 + 8u * i, 1);
+        for (int g = 0; g < NWG; ++g) {
+            const uint32_t bg = bar0 + 8u * (g * 10);
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(bg + 8u * (AB_SFULL + b), 1);
+                mbar_init(bg + 8u * (AB_SFREE + b), 128);
+                mbar_init(bg + 8u * (AB_PFULL + b), 128);
+                mbar_init(bg + 8u * (AB_PVDONE + b), 1);
+            }
+            mbar_init(bg + 8u * AB_OFULL, 1);
+            mbar_init(bg + 8u * AB_OFREE, 128);
         }
-        mbar_init(BAR(AB_OFULL), 1);
-        mbar_init(BAR(AB_OFREE), 128);
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc(sb + ATT_SM_TMEM, ATT_TCOLS);
+    if (warp_cta == 4) tmem_alloc(sb + ATT_SM_TMEM, ATT_TCOLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + ATT_SM_TMEM), 0);
-    constexpr int NG = ATT_NQT * ATT_NCH;                               // 20 score chunks: q-tile, key chunk
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + ATT_SM_TMEM), 0) + wg * AS::TCOLS_WG;
+    constexpr int NG = (ATT_NQT / NWG) * ATT_NCH;                       // score chunks of this warpgroup: (local q-tile, key chunk)
 
     if (warp == 4) {
         // ================================================================= loads + MMA issue; whole warp converged
         const bool lead = lane == 0;
-        if (lead) {
+        if (lead && wg == 0) {
             const char* src = reinterpret_cast<const char*>(qkv + (size_t)blockIdx.x * QKV_HEAD_HALVES);
             mbar_expect_tx(BAR(AB_QFULL), QKV_Q_HALVES * 2);
             bulk_g2s(sb + ATT_SM_Q, src, QKV_Q_HALVES * 2, BAR(AB_QFULL));
@@ -820,9 +831,9 @@ __global__ void __launch_bounds__(ATT_THREADS, AttShape<H>::CTAS_PER_SM) attn_ke
             mbar_expect_tx(BAR(AB_VFULL), QKV_V_HALVES * 2);
             bulk_g2s(sb + ATT_SM_V, src + (QKV_Q_HALVES + QKV_K_HALVES) * 2, QKV_V_HALVES * 2, BAR(AB_VFULL));
         }
-        // score chunk G: q-tile G/5, key chunk G%5 -> S buffer G&1
+        // score chunk G: q-tile (G / NCH) * NWG + wg, key chunk G % NCH -> S buffer G & 1
         auto issue_s = [&](int G) {
-            const int qt = G / ATT_NCH, j = G % ATT_NCH;
+            const int qt = (G / ATT_NCH) * NWG + wg, j = G % ATT_NCH;
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
                 const uint64_t ad = umma_desc(sb + ATT_SM_Q + qt * 8192 + kk * 2 * 2048, 2048, 128);
@@ -864,18 +875,18 @@ __global__ void __launch_bounds__(ATT_THREADS, AttShape<H>::CTAS_PER_SM) attn_ke
         __syncwarp();
     } else {
         // ================================================================= softmax: thread = query row
-        const int r = tid;
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const int r = (warp_cta & 3) * 32 + lane;           // TMEM lane group of a warp = its index in the CTA mod 4
+        const uint32_t trow = tmem + ((uint32_t)((warp_cta & 3) * 32) << 16);
         const float sc = 0.25503486f;                        // log2(e) / sqrt(32)
         const bool tr = trace != nullptr && tid == 0;
 #define ASTAMP(i) do { if (tr) trace[(size_t)blockIdx.x * 32 + (i)] = clock64(); } while (0)
         ASTAMP(0);
         // O / rowsum of q-tile qt -> the out-projection A-operand tile of the token kernel
-        auto finish = [&](int qt, float lsum) {
+        auto finish = [&](int ql, float lsum) {                 // ql = local q-tile index of this warpgroup
             const float inv = 1.f / lsum;
-            mbar_wait(BAR(AB_OFULL), qt & 1);
+            mbar_wait(BAR(AB_OFULL), ql & 1);
             tc_fence_after();
-            const int tok = qt * QT_ROWS + r;
+            const int tok = (ql * NWG + wg) * QT_ROWS + r;
             const int tt = tok / TILE_TOK, tilerow = (seq & 1) * 64 + (tok - tt * TILE_TOK);
             __half* dst = o + ((size_t)(seq >> 1) * TILES_PER_PAIR + tt) * (TILE_ROWS * D) + head * 4 * 1024 + tilerow * 8;
             float a0[32];
@@ -893,7 +904,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttShape<H>::CTAS_PER_SM) attn_ke
         };
         float lprev = 1.f;
 #pragma unroll 1
-        for (int qt = 0; qt < ATT_NQT; ++qt) {
+        for (int qt = 0; qt < ATT_NQT / NWG; ++qt) {            // local q-tile index (q-tile qt * NWG + wg)
             float mref = 0.f, l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
             for (int j = 0; j < ATT_NCH; ++j) {
@@ -956,12 +967,12 @@ __global__ void __launch_bounds__(ATT_THREADS, AttShape<H>::CTAS_PER_SM) attn_ke
             ASTAMP(1 + qt);
             lprev = l0 + l1;
         }
-        finish(ATT_NQT - 1, lprev);
+        finish(ATT_NQT / NWG - 1, lprev);
         ASTAMP(20);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, ATT_TCOLS);
+    if (warp_cta == 4) tmem_dealloc(tmem, ATT_TCOLS);
 }
 
 }  // namespace t2s
