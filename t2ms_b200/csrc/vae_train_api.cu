@@ -13,6 +13,19 @@ namespace {
 
 size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 constexpr int MAX_RES = 4;
+constexpr size_t LAVAE_SMEM_LIMIT = 200 * 1024;
+bool g_lavae_inited[64] = {};
+int lavae_init() {
+    TRY(ensure_init());
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    if (g_lavae_inited[dev]) return T2S_OK;
+    CUDA_OK(cudaFuncSetAttribute(conv_gather_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAVAE_SMEM_LIMIT));
+    CUDA_OK(cudaFuncSetAttribute(conv_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAVAE_SMEM_LIMIT));
+    CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAVAE_SMEM_LIMIT));
+    g_lavae_inited[dev] = true;
+    return T2S_OK;
+}
 
 struct Dims {
     int B, C, L, H, R, E, F, NR;     // batch, series channels, length, hidden, residual hidden, embedding, latent positions, residual layers
@@ -31,10 +44,12 @@ int make_dims(const t2s_lavae_params* P, int batch, int length, Dims* d) {
     // per-thread accumulator budget of conv_wgrad_kernel: 8 * Cx * k <= 4096
     const int worst = d->H * 4 > d->R ? d->H * 4 : d->R;
     if (worst > 512 || d->C * 4 > 512) return fail(T2S_EINVAL, "lavae: channel counts beyond the weight-gradient kernel's budget (Cx * k <= 512)%s%s");
-    // one sample's layer input is staged in (default-limit) shared memory
-    const size_t rows_n = (size_t)(d->H > d->R ? d->H : d->R) * (d->n > d->nd ? d->n : d->nd), rows_1 = (size_t)(d->H / 2) * (d->T1 > 2 * d->nd ? d->T1 : 2 * d->nd);
-    if (rows_n * 4 > 48 * 1024 || rows_1 * 4 > 40 * 1024 || (size_t)d->C * d->L * 4 > 40 * 1024)
-        return fail(T2S_EINVAL, "lavae: series too long for the per-sample shared-memory staging%s%s");
+    // the gather kernels stage 32 output channels' weights + one sample's layer input in shared memory
+    const int nm = d->n > d->nd ? d->n : d->nd, t1m = d->T1 > 2 * d->nd ? d->T1 : 2 * d->nd, lm = d->L > d->Lr ? d->L : d->Lr;
+    const size_t worst_n = (size_t)(d->H > d->R ? d->H : d->R) * (3 * CG_OT + nm), worst_1 = (size_t)(d->H / 2) * (4 * CG_OT + t1m),
+                 worst_0 = (size_t)d->C * (4 * CG_OT + lm);
+    if (worst_n * 4 > LAVAE_SMEM_LIMIT || worst_1 * 4 > LAVAE_SMEM_LIMIT || worst_0 * 4 > LAVAE_SMEM_LIMIT || 8 * lm > 256 * CG_MAXU)
+        return fail(T2S_EINVAL, "lavae: series too long for the shared-memory staging of the layer kernels%s%s");
     return T2S_OK;
 }
 
@@ -70,40 +85,38 @@ Acts make_acts(void* base, const Dims& d) {
 }
 
 struct Layer { int Cin, Tin, Cout, Tout, k, s, p; };
-int nsplit_for(int B, int Cout) {
-    int ns = (296 + B - 1) / B;
-    if (ns > Cout) ns = Cout;
-    return ns < 1 ? 1 : ns;
-}
 unsigned ew_grid(size_t n) { const size_t g = (n + 255) / 256; return (unsigned)(g > 2368 ? 2368 : (g < 1 ? 1 : g)); }
 
-// Conv1d forward (form A)
-int conv_fwd(const float* in, const float* w, const float* bias, const float* res, float* out, int B, const Layer& l, int relu_out, cudaStream_t st) {
-    ConvGeom g{l.Cin, l.Tin, l.Cout, l.Tout, l.k, l.s, l.p, l.Cin * l.k, l.k};
-    conv_gather_kernel<false><<<dim3(B, nsplit_for(B, l.Cout)), 256, (size_t)l.Cin * l.Tin * 4, st>>>(in, w, bias, res, out, g, 0, relu_out);
+// one gather launch: CTAs = (sample chunk, 32 output channels); samples per CTA chosen for about two waves of CTAs
+template <bool FORM_B>
+int gather_launch(const float* in, const float* w, const float* bias, const float* res, float* out, int B, int Cin, int Tin, int Cout, int Tout,
+                  int k, int s, int p, int so, int si, int relu_out, cudaStream_t st) {
+    if ((CG_OT / 4) * Tout > 256 * CG_MAXU) return fail(T2S_EINVAL, "lavae: layer too long for the gather kernel%s%s");
+    const int tiles = (Cout + CG_OT - 1) / CG_OT;
+    int chunks = (296 + tiles - 1) / tiles;
+    if (chunks > B) chunks = B;
+    const int bchunk = (B + chunks - 1) / chunks;
+    ConvGeom g{Cin, Tin, Cout, Tout, k, s, p, so, si, B, bchunk};
+    const size_t smem = ((size_t)Cin * k * CG_OT + (size_t)Cin * Tin) * 4;
+    conv_gather_kernel<FORM_B><<<dim3((B + bchunk - 1) / bchunk, tiles), 256, smem, st>>>(in, w, bias, res, out, g, 0, relu_out);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
+}
+// Conv1d forward (form A)
+int conv_fwd(const float* in, const float* w, const float* bias, const float* res, float* out, int B, const Layer& l, int relu_out, cudaStream_t st) {
+    return gather_launch<false>(in, w, bias, res, out, B, l.Cin, l.Tin, l.Cout, l.Tout, l.k, l.s, l.p, l.Cin * l.k, l.k, relu_out, st);
 }
 // Conv1d input gradient (form B): din [Cin][Tin] from dout [Cout][Tout]
 int conv_dx(const float* dout, const float* w, float* din, int B, const Layer& l, cudaStream_t st) {
-    ConvGeom g{l.Cout, l.Tout, l.Cin, l.Tin, l.k, l.s, l.p, l.k, l.Cin * l.k};
-    conv_gather_kernel<true><<<dim3(B, nsplit_for(B, l.Cin)), 256, (size_t)l.Cout * l.Tout * 4, st>>>(dout, w, nullptr, nullptr, din, g, 0, 0);
-    CUDA_OK(cudaGetLastError());
-    return T2S_OK;
+    return gather_launch<true>(dout, w, nullptr, nullptr, din, B, l.Cout, l.Tout, l.Cin, l.Tin, l.k, l.s, l.p, l.k, l.Cin * l.k, 0, st);
 }
 // ConvTranspose1d forward (form B): weight [Cin][Cout][k]
 int convT_fwd(const float* in, const float* w, const float* bias, float* out, int B, const Layer& l, int relu_out, cudaStream_t st) {
-    ConvGeom g{l.Cin, l.Tin, l.Cout, l.Tout, l.k, l.s, l.p, l.k, l.Cout * l.k};
-    conv_gather_kernel<true><<<dim3(B, nsplit_for(B, l.Cout)), 256, (size_t)l.Cin * l.Tin * 4, st>>>(in, w, bias, nullptr, out, g, 0, relu_out);
-    CUDA_OK(cudaGetLastError());
-    return T2S_OK;
+    return gather_launch<true>(in, w, bias, nullptr, out, B, l.Cin, l.Tin, l.Cout, l.Tout, l.k, l.s, l.p, l.k, l.Cout * l.k, relu_out, st);
 }
 // ConvTranspose1d input gradient (form A)
 int convT_dx(const float* dout, const float* w, float* din, int B, const Layer& l, cudaStream_t st) {
-    ConvGeom g{l.Cout, l.Tout, l.Cin, l.Tin, l.k, l.s, l.p, l.Cout * l.k, l.k};
-    conv_gather_kernel<false><<<dim3(B, nsplit_for(B, l.Cin)), 256, (size_t)l.Cout * l.Tout * 4, st>>>(dout, w, nullptr, nullptr, din, g, 0, 0);
-    CUDA_OK(cudaGetLastError());
-    return T2S_OK;
+    return gather_launch<false>(dout, w, nullptr, nullptr, din, B, l.Cout, l.Tout, l.Cin, l.Tin, l.k, l.s, l.p, l.Cout * l.k, l.k, 0, st);
 }
 int wgrad_launch(const float* Y, const float* X, float* dw, int B, int Cy, int Ty, int Cx, int Tx, int k, int s, int p, int sy, int sx, cudaStream_t st) {
     int chunks = (592 * 8 + Cy - 1) / Cy;                      // about four waves of CTAs
@@ -231,7 +244,7 @@ int t2s_lavae_encode(const t2s_lavae_params* P, const float* x, float* z, float*
     TRY(make_dims(P, batch, length, &d));
     if (!x || !z) return fail(T2S_EINVAL, "t2s_lavae_encode: bad argument%s%s");
     TRY(check_ws(workspace, workspace_bytes, make_acts(nullptr, d).total));
-    TRY(ensure_init());
+    TRY(lavae_init());
     cudaStream_t st = (cudaStream_t)stream;
     const Acts a = make_acts(workspace, d);
     TRY(enc_forward(P, x, a, d, make_layers(d), st));
@@ -245,7 +258,7 @@ int t2s_lavae_decode(const t2s_lavae_params* P, const float* z, float* recon, fl
     TRY(make_dims(P, batch, length, &d));
     if (!z || !recon) return fail(T2S_EINVAL, "t2s_lavae_decode: bad argument%s%s");
     TRY(check_ws(workspace, workspace_bytes, make_acts(nullptr, d).total));
-    TRY(ensure_init());
+    TRY(lavae_init());
     cudaStream_t st = (cudaStream_t)stream;
     const Acts a = make_acts(workspace, d);
     TRY(dec_forward(P, z, a, d, make_layers(d), st));
@@ -260,7 +273,7 @@ int t2s_lavae_train_step(const t2s_lavae_params* P, const t2s_lavae_params* G, c
     if (!x || !loss_sums) return fail(T2S_EINVAL, "t2s_lavae_train_step: bad argument%s%s");
     if (d.n != d.nd) return fail(T2S_EINVAL, "t2s_lavae_train_step: the cross loss needs equal encoder / decoder resolutions (length % 4 == 0)%s%s");
     TRY(check_ws(workspace, workspace_bytes, make_acts(nullptr, d).total));
-    TRY(ensure_init());
+    TRY(lavae_init());
     cudaStream_t st = (cudaStream_t)stream;
     const Acts a = make_acts(workspace, d);
     const Layers l = make_layers(d);
@@ -292,11 +305,8 @@ int t2s_lavae_train_step(const t2s_lavae_params* P, const t2s_lavae_params* G, c
     TRY(convT_dx(a.gT1, P->dec_ct1_w, g, d.B, l.ct1, st));
     TRY(stack_bwd(P->dec_res_w3, P->dec_res_w1, G->dec_res_w3, G->dec_res_w1, a.ds, d, d.nd, g, tmp, a.gR, st));
     TRY(conv_dw(g, a.after, G->dec_conv1_w, G->dec_conv1_b, d.B, l.dc1, st));
-    {   // d after = cross term + conv path ; d z = interp^T(d after)
-        ConvGeom cg{l.dc1.Cout, l.dc1.Tout, l.dc1.Cin, l.dc1.Tin, 3, 1, 1, 3, l.dc1.Cin * 3};
-        conv_gather_kernel<true><<<dim3(d.B, nsplit_for(d.B, d.E)), 256, (size_t)d.H * d.nd * 4, st>>>(g, P->dec_conv1_w, nullptr, a.gEn, a.gEn, cg, 0, 0);
-        CUDA_OK(cudaGetLastError());
-    }
+    // d after = cross term + conv path (res = out = gEn: every element is read and written by the same thread)
+    TRY(gather_launch<true>(g, P->dec_conv1_w, nullptr, a.gEn, a.gEn, d.B, l.dc1.Cout, l.dc1.Tout, l.dc1.Cin, l.dc1.Tin, 3, 1, 1, 3, l.dc1.Cin * 3, 0, st));
     interp_bwd_kernel<<<ew_grid(rowsE * d.F), 256, 0, st>>>(a.gEn, a.gZ, rowsE, d.F, d.nd, 0);
     // encoder: d before = cross term + interp^T(d z)
     interp_bwd_kernel<<<ew_grid(rowsE * d.n), 256, 0, st>>>(a.gZ, a.gE, rowsE, d.n, d.F, 1);
