@@ -36,8 +36,8 @@ FLOP_DECODE_96 = 15_360_000
 # fp16 attention output (480 x 128 x 2); the MID token kernel reads the residual (fp32) and the attention output,
 # writes the residual and the next block's q|k|v images
 ALGO_BYTES_PER_SEQ = {"attention": 4 * 94_208 + 480 * 128 * 2, "token_mid": 2 * 480 * 128 * 4 + 480 * 128 * 2 + 4 * 94_208}
-# DRAM bytes per launch measured by ncu at nseq = 2048 (profiles/r01_ncu_full_v9_summary.json)
-NCU_DRAM_BYTES_PER_LAUNCH = {"attention": 772_190_208 + 229_606_144, "token_mid": 904_835_840 + 1_250_365_000}
+# DRAM bytes per launch measured by ncu at nseq = 2048 (profiles/r01_ncu_full_v18_summary.json)
+NCU_DRAM_BYTES_PER_LAUNCH = {"attention": 771_782_400 + 231_961_088, "token_mid": 897_617_664 + 1_251_327_000}
 
 
 def parse():
@@ -235,7 +235,7 @@ def train_leg(a, dev, rank, world, dist):
     sps = nsteps / (ms.item() / 1e3)
     return {"metric": "t2s_dit_train_steps_per_sec", "value": sps, "unit": "optimizer steps/s", "samples_per_sec": sps * B * world,
             "ms_per_step": ms.item() / nsteps, "batch_per_gpu": B, "global_batch": B * world, "lengths": [24, 48, 96],
-            "dtype": "tf32 operands / f32 accumulate, fp32 master weights and AdamW state",
+            "dtype": "tf32 operands (Linears) and f16 operands (fused attention) / f32 accumulate, fp32 master weights and AdamW state",
             "workload": "BASELINE config 4: frozen LA-VAE encode + rectified-flow training step, mixed lengths 24/48/96, "
                         f"data-parallel x{world} (one flat-bucket NCCL all-reduce per step)",
             "tflops_algorithmic": sps * B * world * 3 * FLOP_FWD / 1e12, "final_loss": float(tr.loss_sum.item() / (B * 1920 * world))}
@@ -345,7 +345,7 @@ def main():
                          "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dom) if nseq == 2048 else None,
                          "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum at this workload size "
-                                           "(profiles/r01_ncu_full_v9_summary.json)",
+                                           "(profiles/r01_ncu_full_v18_summary.json)",
                          "algorithmic_bytes": ALGO_BYTES_PER_SEQ[dom] * nseq,
                          "co_bound": "MUFU ex2: 0.9216 M exp per sequence-block at 16/clk/SM = 0.41 ms per 2048-sequence launch "
                                      "(ncu: XU pipe 72 % busy)" if dom == "attention" else "epilogue issue + HBM",
