@@ -26,6 +26,17 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner when the box exports NCCL_DEBUG, torchrun's
+# OMP notice, ...) write to file descriptor 1 behind Python's back, so the real stdout is kept aside and fd 1 is pointed at
+# stderr for the lifetime of the process; emit() is the only writer of the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 METRIC = "t2s_dit_rf_sampled_series_per_sec"
 UNIT = "series/s"
 FLOP_FWD = 976_960_512                 # per DiT forward per sequence
@@ -150,7 +161,7 @@ def run_reference(a, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def kernel_breakdown(smp, dit, vae, a, dev):
@@ -358,7 +369,7 @@ def main():
             v, dt, threads = cpu_reference_run(a, a.cpu_sample)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{a.cpu_sample} series x {a.rf_steps} guided steps + decode in {dt:.1f} s, oracle port (torch fp32 CPU)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

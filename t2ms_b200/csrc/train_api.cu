@@ -49,6 +49,7 @@ struct Gemm {
     Gemm& amn() { a.a_mn = 1; return *this; }
     Gemm& bmn() { a.b_mn = 1; return *this; }
     Gemm& mode(int m) { a.mode = m; return *this; }
+    Gemm& qkv_images(__half* img) { a.qkv_img = img; return *this; }
     Gemm& alpha(float v) { a.alpha = v; return *this; }
     Gemm& ksplit(int k) { a.ksplit = k < 1 ? 1 : k; return *this; }
     // weight-gradient form: few output tiles, long K -> split K so that about two waves of CTAs run
@@ -66,10 +67,12 @@ struct Gemm {
         if (((uintptr_t)a.A | (uintptr_t)a.B) & 15) return fail(T2S_EINVAL, "gemm_tf32: operands must be 16-byte aligned%s%s");
         if ((a.mode & ~15) != 0 && (a.a_mn || batch != 1 || a.ksplit != 1 || a.N % 128 != 0 || a.M < 4 * G_BM))
             return fail(T2S_EINVAL, "gemm_tf32: profiling mode bits apply to the persistent form only%s%s");
+        if (a.qkv_img != nullptr && (a.a_mn || batch != 1 || a.ksplit != 1 || a.mode != GEMM_STORE || a.N != 3 * D || a.M < 4 * G_BM || a.M % NTOK != 0))
+            return fail(T2S_EINVAL, "gemm_tf32: the q|k|v image epilogue needs the persistent form with N = 384%s%s");
         if (a.mode == GEMM_ATOMIC && a.bias != nullptr) return fail(T2S_EINVAL, "gemm_tf32: bias with atomic accumulation%s%s");
         if (a.ksplit > 1 && a.mode != GEMM_ATOMIC) return fail(T2S_EINVAL, "gemm_tf32: split-K needs atomic accumulation%s%s");
         // forward / input-gradient shapes: the persistent form (decoupled load / MMA / epilogue roles, one CTA per SM)
-        const bool vec_c = (a.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.bias == nullptr || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
+        const bool vec_c = (a.qkv_img != nullptr || ((a.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0)) && (a.bias == nullptr || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
         if (!a.a_mn && batch == 1 && a.ksplit == 1 && (a.mode & 15) != GEMM_ATOMIC && a.N % 128 == 0 && a.M >= 4 * G_BM && vec_c) {
             const int items = ((a.M + G_BM - 1) / G_BM) * (a.N / 128), sms = sm_count();
             gemm_tf32_persistent_kernel<<<items < sms ? items : sms, P_THREADS, P_SMEM_BYTES, st>>>(a);
@@ -108,7 +111,8 @@ AttnScratch attn_scratch(void* base, int nseq) {
 struct TrainWs {
     float *sc, *mod, *dmod, *xp, *wemb, *bemb, *red;
     float* h[NLAYER + 1];
-    float *a1[NLAYER], *qkv[NLAYER], *o[NLAYER], *y1[NLAYER], *hm[NLAYER], *a2[NLAYER], *z1[NLAYER], *hid[NLAYER], *y2[NLAYER];
+    __half* img[NLAYER];                                // q | k | v operand images of every block (written by the QKV GEMM epilogue)
+    float *a1[NLAYER], *o[NLAYER], *y1[NLAYER], *hm[NLAYER], *a2[NLAYER], *z1[NLAYER], *hid[NLAYER], *y2[NLAYER];
     float* nlse[NLAYER];
     float *g, *g2, *d1, *d2, *dqkv, *dob;
     AttnScratch att;
@@ -124,7 +128,7 @@ TrainWs train_ws(void* base, int nseq) {
     w.xp = take(T * 4); w.wemb = take(D * 4); w.bemb = take(D); w.red = take(D * 5);
     for (int l = 0; l <= NLAYER; ++l) w.h[l] = take(T * D);
     for (int l = 0; l < NLAYER; ++l) {
-        w.a1[l] = take(T * D); w.qkv[l] = take(T * 3 * D); w.o[l] = take(T * D); w.y1[l] = take(T * D); w.hm[l] = take(T * D);
+        w.a1[l] = take(T * D); w.img[l] = reinterpret_cast<__half*>(take((size_t)nseq * NHEAD * 3 * TA_IMG_HALVES / 2 + 256)); w.o[l] = take(T * D); w.y1[l] = take(T * D); w.hm[l] = take(T * D);
         w.a2[l] = take(T * D); w.z1[l] = take(T * DMLP); w.hid[l] = take(T * DMLP); w.y2[l] = take(T * D);
     }
     w.g = take(T * D); w.g2 = take(T * D); w.d1 = take(T * D); w.d2 = take(T * DMLP); w.dqkv = take(T * 3 * D); w.dob = take(T * D);
@@ -135,29 +139,42 @@ TrainWs train_ws(void* base, int nseq) {
     return w;
 }
 
+// q | k | v rows [T][384] fp32 -> fp16 operand images (only the exported test entries and single-sequence batches need
+// it: the training step's QKV GEMM writes the images in its epilogue)
+int pack_qkv(const float* qkv, __half* img, int nseq, cudaStream_t st) {
+    const long long warps = (long long)nseq * (NTOK / 8) * 12;
+    ta_pack_qkv_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(qkv, img, nseq);
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
 // softmax(q k^T / sqrt(32)) v of every (sequence, head), keeping 4 - log2-sum-exp per row for the backward
 // (timm Attention -> F.scaled_dot_product_attention, transformer.py:116)
-int attn_forward(const float* qkv, float* o, float* nlse, const AttnScratch& a, int nseq, cudaStream_t st) {
-    const long long warps = (long long)nseq * (NTOK / 8) * 12;
-    ta_pack_qkv_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(qkv, a.img, nseq);
+int attn_forward_images(const __half* img, float* o, float* nlse, int nseq, cudaStream_t st) {
     TaArgs p{};
-    p.img = a.img; p.o = o; p.nlse = nlse;
+    p.img = img; p.o = o; p.nlse = nlse;
     ta_attn_kernel<TA_FWD><<<nseq * NHEAD * TA_NTILE, TA_THREADS, TA_SMEM_BYTES, st>>>(p);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
-// d(q | k | v) from dO, recomputing the probabilities from q, k and the saved log-sum-exp
-int attn_backward(const float* qkv, const float* o, const float* nlse, const float* dout, float* dqkv, const AttnScratch& a, int nseq,
-                  cudaStream_t st) {
-    const long long warps = (long long)nseq * (NTOK / 8) * 12;
-    ta_pack_qkv_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(qkv, a.img, nseq);
+// d(q | k | v) from dO, recomputing the probabilities from the q, k images and the saved log-sum-exp
+int attn_backward_images(const __half* img, const float* o, const float* nlse, const float* dout, float* dqkv, const AttnScratch& a, int nseq,
+                         cudaStream_t st) {
     ta_pack_do_kernel<<<nseq * NHEAD, 512, 0, st>>>(dout, o, a.doimg, a.dvec, a.dinv);
     TaArgs p{};
-    p.img = a.img; p.doimg = a.doimg; p.nlse = const_cast<float*>(nlse); p.dvec = a.dvec; p.dinv = a.dinv; p.dqkv = dqkv;
+    p.img = img; p.doimg = a.doimg; p.nlse = const_cast<float*>(nlse); p.dvec = a.dvec; p.dinv = a.dinv; p.dqkv = dqkv;
     ta_attn_kernel<TA_DQ><<<nseq * NHEAD * TA_NTILE, TA_THREADS, TA_SMEM_BYTES, st>>>(p);
     ta_attn_kernel<TA_DKV><<<nseq * NHEAD * TA_NTILE, TA_THREADS, TA_SMEM_BYTES, st>>>(p);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
+}
+int attn_forward(const float* qkv, float* o, float* nlse, const AttnScratch& a, int nseq, cudaStream_t st) {
+    TRY(pack_qkv(qkv, a.img, nseq, st));
+    return attn_forward_images(a.img, o, nlse, nseq, st);
+}
+int attn_backward(const float* qkv, const float* o, const float* nlse, const float* dout, float* dqkv, const AttnScratch& a, int nseq,
+                  cudaStream_t st) {
+    TRY(pack_qkv(qkv, a.img, nseq, st));
+    return attn_backward_images(a.img, o, nlse, dout, dqkv, a, nseq, st);
 }
 
 int colsum(const float* x, size_t rows, int ld, int cols, float* out, cudaStream_t st) {
@@ -251,8 +268,13 @@ int train_forward(const t2s_dit_params* P, const float* x_t, const float* t100, 
     for (int l = 0; l < NLAYER; ++l) {
         const int mo = l * MOD;
         ln_mod_fwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(w.h[l], w.mod, MS, mo, w.a1[l], 1e-6f);
-        TRY(Gemm(w.a1[l], P->qkv_w[l], w.qkv[l], T, 3 * D, D, D, D, 3 * D).bias(P->qkv_b[l]).launch(st));
-        TRY(attn_forward(w.qkv[l], w.o[l], w.nlse[l], w.att, nseq, st));
+        if (T >= 4 * G_BM) {                                               // q | k | v go straight out as the attention's operand images
+            TRY(Gemm(w.a1[l], P->qkv_w[l], w.dqkv, T, 3 * D, D, D, D, 3 * D).bias(P->qkv_b[l]).qkv_images(w.img[l]).launch(st));
+        } else {                                                           // a single sequence: fp32 rows (dqkv is free here), then the pack kernel
+            TRY(Gemm(w.a1[l], P->qkv_w[l], w.dqkv, T, 3 * D, D, D, D, 3 * D).bias(P->qkv_b[l]).launch(st));
+            TRY(pack_qkv(w.dqkv, w.img[l], nseq, st));
+        }
+        TRY(attn_forward_images(w.img[l], w.o[l], w.nlse[l], nseq, st));
         TRY(Gemm(w.o[l], P->proj_w[l], w.y1[l], T, D, D, D, D, D).bias(P->proj_b[l]).launch(st));
         gate_res_fwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(w.h[l], w.y1[l], w.mod, MS, mo + 2 * D, w.hm[l]);
         ln_mod_fwd_kernel<<<rgrid, ROW_THREADS, 0, st>>>(w.hm[l], w.mod, MS, mo + 3 * D, w.a2[l], 1e-6f);
@@ -288,7 +310,7 @@ int train_backward(const t2s_dit_params* P, const t2s_dit_params* Gp, const Trai
         TRY(Gemm(w.d1, w.o[l], Gp->proj_w[l], D, D, T, D, D, D).amn().bmn().wgrad().launch(st));
         TRY(Gemm(w.d1, P->proj_w[l], w.dob, T, D, D, D, D, D).bmn().launch(st));
         CUDA_OK(cudaGetLastError());
-        TRY(attn_backward(w.qkv[l], w.o[l], w.nlse[l], w.dob, w.dqkv, w.att, nseq, st));
+        TRY(attn_backward_images(w.img[l], w.o[l], w.nlse[l], w.dob, w.dqkv, w.att, nseq, st));
         TRY(colsum(w.dqkv, T, 3 * D, 3 * D, Gp->qkv_b[l], st));
         TRY(Gemm(w.dqkv, w.a1[l], Gp->qkv_w[l], 3 * D, D, T, 3 * D, D, D).amn().bmn().wgrad().launch(st));
         TRY(Gemm(w.dqkv, P->qkv_w[l], w.d1, T, D, 3 * D, 3 * D, D, D).bmn().launch(st));

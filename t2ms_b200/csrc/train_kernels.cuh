@@ -35,6 +35,9 @@ struct GemmArgs {
     int ksplit;
     int mode;
     float alpha;
+    // persistent form only: when set, C is not written; the tile (+ bias) goes out as the fp16 T8 operand images of the
+    // fused attention (train_attn.cuh): N = 384 = q | k | v, each 4 heads x 32 features; rows = sequence * 480 + token
+    __half* qkv_img;
 };
 constexpr int G_BM = 128, G_BK = 32, G_STAGES = 3, G_THREADS = 160;
 constexpr int G_STAGE_BYTES = 2 * G_BM * G_BK * 4;                     // A tile + B tile (B sized for bn = 128)
@@ -398,6 +401,27 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tf32_persistent_kernel(cons
             mbar_arrive(ACCEMPTY(ab));                           // the MMA warp may overwrite this accumulator
             __syncwarp();
             const int gn = n0 + cl;
+            if (p.qkv_img != nullptr) {
+                // thread = row: [sequence][head][q | k | v][token / 8][feature / 8][token % 8][8] fp16; for one (head, chunk) a
+                // warp writes 4 x 128 contiguous bytes
+                const int gm = m0 + wq * 32 + lane;
+                if (gm < p.M) {
+                    const int sq = gm / NTOK, tok = gm - sq * NTOK, which = n0 >> 7;
+                    __half* base = p.qkv_img + ((size_t)sq * NHEAD * 3 + which) * (NTOK * HD) + (tok >> 3) * 256 + (tok & 7) * 8;
+                    const float* srow = stg + lane * pitch;
+#pragma unroll 4
+                    for (int hc = 0; hc < 16; ++hc) {            // head hc / 4, feature chunk hc % 4
+                        const float4 a = ld4(srow + hc * 8), b = ld4(srow + hc * 8 + 4);
+                        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                        if (p.bias != nullptr) { b0 = ld4(p.bias + n0 + hc * 8); b1 = ld4(p.bias + n0 + hc * 8 + 4); }
+                        *reinterpret_cast<uint4*>(base + (size_t)(hc >> 2) * 3 * (NTOK * HD) + (hc & 3) * 64) =
+                            make_uint4(pack_h2(fmaf(a.x, p.alpha, b0.x), fmaf(a.y, p.alpha, b0.y)), pack_h2(fmaf(a.z, p.alpha, b0.z), fmaf(a.w, p.alpha, b0.w)),
+                                       pack_h2(fmaf(b.x, p.alpha, b1.x), fmaf(b.y, p.alpha, b1.y)), pack_h2(fmaf(b.z, p.alpha, b1.z), fmaf(b.w, p.alpha, b1.w)));
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias != nullptr) bv = ld4(p.bias + gn);
 #pragma unroll 4
