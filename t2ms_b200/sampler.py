@@ -21,6 +21,8 @@ KIND = {"flowmatching": 0, "rf": 0, "rectified_flow": 0, "ddpm": 1}
 
 
 class T2SSampler:
+    NOISE_WINDOW_BYTES = 1 << 30          # DDPM step noise drawn per window of steps when the caller supplies none
+
     def __init__(self, dit: Transformer, vae=None):
         self.dit = dit
         self.decoder = getattr(vae, "decoder", vae)
@@ -57,32 +59,45 @@ class T2SSampler:
         else:
             x = noise.detach().to(device=dev, dtype=torch.float32).clone().contiguous()
             assert tuple(x.shape) == (B, 64, H), f"noise must be (B,64,{H})"
-        if kind == 1:
-            if step_noise is None:                                                         # DDPM.py:35
-                step_noise = torch.randn(steps, B, 64, H, device=dev, dtype=torch.float32, generator=generator)
+        lat = 64 * H
+        if kind == 1 and step_noise is not None:
             step_noise = step_noise.detach().to(device=dev, dtype=torch.float32).contiguous()
             assert step_noise.shape == (steps, B, 64, H)
         tr = torch.empty(steps, B, 64, H, device=dev, dtype=torch.float32) if trace else None
         t100, coef = self._table(kind, steps, dev)
+        coef_p = C.cast(coef, C.c_void_p).value
         pk = self.dit.packed()
         chunk = B if not chunk else min(int(chunk), B)
         ws = self.dit.workspace(2 * chunk, dev)
         nbytes = lib.t2s_dit_workspace_bytes_h(2 * chunk, H)
         stream = torch.cuda.current_stream(dev).cuda_stream
+        # DDPM draws fresh Gaussian noise inside every p_sample (DDPM.py:35).  When the caller does not supply it, it is drawn
+        # here in windows of steps (<= NOISE_WINDOW_BYTES at a time) and the loop is enqueued window by window through the
+        # same C entry (t100 / coef offset by the window start): no host synchronisation, bounded memory at any batch size.
+        if kind == 1 and step_noise is None:
+            win = max(1, min(steps, self.NOISE_WINDOW_BYTES // (B * lat * 4)))
+        else:
+            win = steps
         with torch.cuda.device(dev):
-            for b0 in range(0, B, chunk):
-                nb = min(chunk, B - b0)
-                sn = tr_c = None
+            for j0 in range(0, steps, win):
+                nj = min(win, steps - j0)
+                sn_w = None
                 if kind == 1:
-                    sn = step_noise[:, b0:b0 + nb].contiguous() if nb != B else step_noise
-                if trace:
-                    tr_c = tr if nb == B else torch.empty(steps, nb, 64, H, device=dev, dtype=torch.float32)
-                rc = lib.t2s_sample(pk.ref, kind, x[b0:b0 + nb].data_ptr(), emb[b0:b0 + nb].data_ptr(), t100.data_ptr(), coef,
-                                    sn.data_ptr() if sn is not None else None, tr_c.data_ptr() if tr_c is not None else None,
-                                    nb, steps, float(cfg_scale), _aligned(ws), nbytes, stream)
-                _lib.check(rc, "t2s_sample")
-                if trace and nb != B:
-                    tr[:, b0:b0 + nb] = tr_c
+                    sn_w = step_noise[j0:j0 + nj] if step_noise is not None else \
+                        torch.randn(nj, B, 64, H, device=dev, dtype=torch.float32, generator=generator)
+                for b0 in range(0, B, chunk):
+                    nb = min(chunk, B - b0)
+                    sn = tr_c = None
+                    if kind == 1:
+                        sn = sn_w[:, b0:b0 + nb].contiguous() if nb != B else sn_w
+                    if trace:
+                        tr_c = tr[j0:j0 + nj] if nb == B else torch.empty(nj, nb, 64, H, device=dev, dtype=torch.float32)
+                    rc = lib.t2s_sample(pk.ref, kind, x[b0:b0 + nb].data_ptr(), emb[b0:b0 + nb].data_ptr(), t100.data_ptr() + 4 * j0,
+                                        C.cast(C.c_void_p(coef_p + 12 * j0), C.POINTER(C.c_float)), sn.data_ptr() if sn is not None else None,
+                                        tr_c.data_ptr() if tr_c is not None else None, nb, nj, float(cfg_scale), _aligned(ws), nbytes, stream)
+                    _lib.check(rc, "t2s_sample")
+                    if trace and nb != B:
+                        tr[j0:j0 + nj, b0:b0 + nb] = tr_c
         return (x, tr) if trace else x
 
     @torch.no_grad()

@@ -137,3 +137,22 @@ def test_full_size_properties():
     assert torch.equal(full[500:507], sub)
     _, ser_ref = O.rf_sample(dsd, vsd, noise[:4].cpu(), emb[:4].cpu(), steps, 7.0, 96)
     assert max_abs(full[:4], ser_ref) < TOL_SERIES
+
+
+def test_ddpm_step_noise_windows():
+    """Without caller-supplied step noise the sampler draws it per window of steps and enqueues the loop window by window
+    (t100 / coef offset into the same C entry): equal to one call with the concatenated noise of the same generator."""
+    from gpu_util import DEV, make_dit, max_abs
+    from t2ms_b200 import T2SSampler, synth
+    dit, _ = make_dit(3)
+    smp = T2SSampler(dit)
+    B, steps = 3, 7
+    emb, x0 = synth.make_text_embeddings(B, seed=5).to(DEV), synth.make_noise(B, seed=6).to(DEV)
+    smp.NOISE_WINDOW_BYTES = 3 * B * 1920 * 4                      # windows of 3, 3, 1 steps
+    g = torch.Generator(device=DEV).manual_seed(11)
+    lat, tr = smp.sample_latent(emb, steps=steps, backbone="ddpm", noise=x0, generator=g, trace=True)
+    g = torch.Generator(device=DEV).manual_seed(11)
+    sn = torch.cat([torch.randn(n, B, 64, 30, device=DEV, generator=g) for n in (3, 3, 1)])
+    smp.NOISE_WINDOW_BYTES = 1 << 30
+    lat2, tr2 = smp.sample_latent(emb, steps=steps, backbone="ddpm", noise=x0, step_noise=sn, trace=True)
+    assert max_abs(lat, lat2) == 0.0 and max_abs(tr, tr2) == 0.0
