@@ -29,12 +29,24 @@ sys.path.insert(0, ROOT)
 # The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner when the box exports NCCL_DEBUG, torchrun's
 # OMP notice, ...) write to file descriptor 1 behind Python's back, so the real stdout is kept aside and fd 1 is pointed at
 # stderr for the lifetime of the process; emit() is the only writer of the real stdout.
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+_REAL_STDOUT = None
+
+
+def capture_stdout() -> None:
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit(obj) -> None:
-    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 METRIC = "t2s_dit_rf_sampled_series_per_sec"
@@ -254,6 +266,7 @@ def train_leg(a, dev, rank, world, dist):
 
 def main():
     a = parse()
+    capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -10,7 +10,6 @@ import argparse
 import json
 import os
 import sys
-import time
 
 import torch
 
@@ -74,21 +73,17 @@ def main():
                              "series_per_s": round(B * world / (ms.item() / 1e3), 2)})
     cpu = []
     if rank == 0 and a.cpu_budget_s > 0:
-        from oracle import t2s_oracle as O
-        threads = os.cpu_count() or 1
-        torch.set_num_threads(threads)
-        dsd, vsd = synth.make_dit_state(0), synth.make_vae_state(1)
+        # the CPU reference legs are bench.py's own cpu_baseline leg (the oracle port of infer.py:75-95 on all host cores)
+        import bench
+        from argparse import Namespace
         spent = 0.0
         for B, L, steps in ((1, 24, 10), (8, 24, 10), (8, 96, 10), (8, 24, 50), (8, 96, 100), (64, 96, 10)):
             if spent > a.cpu_budget_s:
                 break
-            emb, noise = synth.make_text_embeddings(B), synth.make_noise(B)
-            t0 = time.perf_counter()
-            O.rf_sample(dsd, vsd, noise, emb, steps, a.cfg, L)
-            dt = time.perf_counter() - t0
+            v, dt, threads = bench.cpu_reference_run(Namespace(backbone=a.backbone, rf_steps=steps, cfg=a.cfg, length=L), B)
             spent += dt
-            cpu.append({"batch": B, "length": L, "steps": steps, "s": round(dt, 3), "series_per_s": round(B / dt, 3), "cores": threads,
-                        "kind": "port (oracle restatement of infer.py:75-95, torch fp32 CPU)"})
+            cpu.append({"batch": B, "length": L, "steps": steps, "s": round(dt, 3), "series_per_s": round(v, 3), "cores": threads,
+                        "kind": "port (bench.py cpu_baseline leg: oracle restatement of infer.py:75-95, torch fp32 CPU)"})
     if rank == 0:
         out = {"workload": "BASELINE config 5: guided RF sampling sweep, host buffers in/out (e2e), CFG %g" % a.cfg, "n_gpus": world,
                "gpu": rows, "cpu_reference": cpu}
