@@ -141,7 +141,18 @@ int launch_embed(const t2s_dit_weights* w, const float* x, int x_shift, int nseq
     return T2S_OK;
 }
 int launch_attn(int nseq, const Shape& sh, const Workspace& ws, cudaStream_t st) {
-    T2S_DISPATCH_H(sh.H, (attn_kernel<HH><<<nseq * NHEAD, AttShape<HH>::THREADS, AttShape<HH>::SMEM_BYTES, st>>>(ws.qkv, ws.o, g_trace)));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int sms = g_sms[dev] > 0 ? g_sms[dev] : 148;
+    // fewer (sequence, head) CTAs than resident slots: one CTA per q-tile (group) instead, for latency
+#define T2S_ATTN_LAUNCH(HH_)                                                                                                     \
+    {                                                                                                                            \
+        const int full = AttShape<HH_>::NQT / AttShape<HH_>::NWG;                                                                \
+        const int npart = nseq * NHEAD < sms * AttShape<HH_>::CTAS_PER_SM / 2 ? full : 1;                                        \
+        attn_kernel<HH_><<<nseq * NHEAD * npart, AttShape<HH_>::THREADS, AttShape<HH_>::SMEM_BYTES, st>>>(ws.qkv, ws.o, g_trace, npart); \
+    }
+    T2S_DISPATCH_H(sh.H, T2S_ATTN_LAUNCH(HH));
+#undef T2S_ATTN_LAUNCH
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }

@@ -780,7 +780,7 @@ constexpr uint32_t ATT_IDESC_PV = umma_idesc_f16(128, HD) | (1u << 16);   // B (
 
 // grid = nseq * 4, block = 160 per warpgroup: warps 0-3 = softmax (thread = query row = TMEM lane), warp 4 = (loads +) MMA issue
 template <int H>
-__global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM) attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ o, long long* trace) {
+__global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM) attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ o, long long* trace, int npart) {
     using S = DitShape<H>;
     using AS = AttShape<H>;
     constexpr int NTOK = S::NTOK, TILE_TOK = S::TILE_TOK, TILES_PER_PAIR = S::TILES_PER_PAIR, QT_ROWS = S::QT_ROWS;
@@ -792,7 +792,10 @@ __global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp_cta = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform
     const int wg = warp_cta / 5, warp = warp_cta % 5;                 // warpgroup; role inside it (0-3 softmax, 4 MMA)
-    const int seq = blockIdx.x >> 2, head = blockIdx.x & 3;
+    // npart = 1: one CTA per (sequence, head) walks over all q-tiles.  npart = NQT / NWG (small batches: too few (sequence,
+    // head) pairs to fill the GPU): one CTA per q-tile (group), K / V are re-read from L2 by every part.
+    const int sh = blockIdx.x / npart, part = blockIdx.x - sh * npart;
+    const int seq = sh >> 2, head = sh & 3;
     const uint32_t sb = smem_u32(smem);
     const uint32_t bar0 = sb + ATT_SM_BAR;
     // barriers 0-2 (Q / K / V loaded) are shared; every warpgroup owns a block of ten (AB_SFULL .. AB_OFREE)
@@ -817,15 +820,22 @@ __global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + ATT_SM_TMEM), 0) + wg * AS::TCOLS_WG;
-    constexpr int NG = (ATT_NQT / NWG) * ATT_NCH;                       // score chunks of this warpgroup: (local q-tile, key chunk)
+    const int nql = ATT_NQT / NWG / npart;                              // q-tiles of this warpgroup in this CTA
+    const int NG = nql * ATT_NCH;                                       // its score chunks: (local q-tile, key chunk)
+    auto q_tile = [&](int ql) { return (ql * npart + part) * NWG + wg; };
 
     if (warp == 4) {
         // ================================================================= loads + MMA issue; whole warp converged
         const bool lead = lane == 0;
         if (lead && wg == 0) {
-            const char* src = reinterpret_cast<const char*>(qkv + (size_t)blockIdx.x * QKV_HEAD_HALVES);
-            mbar_expect_tx(BAR(AB_QFULL), QKV_Q_HALVES * 2);
-            bulk_g2s(sb + ATT_SM_Q, src, QKV_Q_HALVES * 2, BAR(AB_QFULL));
+            const char* src = reinterpret_cast<const char*>(qkv + (size_t)sh * QKV_HEAD_HALVES);
+            if (npart == 1) {
+                mbar_expect_tx(BAR(AB_QFULL), QKV_Q_HALVES * 2);
+                bulk_g2s(sb + ATT_SM_Q, src, QKV_Q_HALVES * 2, BAR(AB_QFULL));
+            } else {                                             // only this part's NWG q-tiles (adjacent 8 KB images)
+                mbar_expect_tx(BAR(AB_QFULL), NWG * 8192);
+                bulk_g2s(sb + ATT_SM_Q + part * NWG * 8192, src + part * NWG * 8192, NWG * 8192, BAR(AB_QFULL));
+            }
             mbar_expect_tx(BAR(AB_KFULL), QKV_K_HALVES * 2);
             bulk_g2s(sb + ATT_SM_K, src + QKV_Q_HALVES * 2, QKV_K_HALVES * 2, BAR(AB_KFULL));
             mbar_expect_tx(BAR(AB_VFULL), QKV_V_HALVES * 2);
@@ -833,7 +843,7 @@ __global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM
         }
         // score chunk G: q-tile (G / NCH) * NWG + wg, key chunk G % NCH -> S buffer G & 1
         auto issue_s = [&](int G) {
-            const int qt = (G / ATT_NCH) * NWG + wg, j = G % ATT_NCH;
+            const int qt = q_tile(G / ATT_NCH), j = G % ATT_NCH;
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
                 const uint64_t ad = umma_desc(sb + ATT_SM_Q + qt * 8192 + kk * 2 * 2048, 2048, 128);
@@ -878,7 +888,7 @@ __global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM
         const int r = (warp_cta & 3) * 32 + lane;           // TMEM lane group of a warp = its index in the CTA mod 4
         const uint32_t trow = tmem + ((uint32_t)((warp_cta & 3) * 32) << 16);
         const float sc = 0.25503486f;                        // log2(e) / sqrt(32)
-        const bool tr = trace != nullptr && tid == 0;
+        const bool tr = trace != nullptr && tid == 0 && npart == 1;
 #define ASTAMP(i) do { if (tr) trace[(size_t)blockIdx.x * 32 + (i)] = clock64(); } while (0)
         ASTAMP(0);
         // O / rowsum of q-tile qt -> the out-projection A-operand tile of the token kernel
@@ -886,7 +896,7 @@ __global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM
             const float inv = 1.f / lsum;
             mbar_wait(BAR(AB_OFULL), ql & 1);
             tc_fence_after();
-            const int tok = (ql * NWG + wg) * QT_ROWS + r;
+            const int tok = q_tile(ql) * QT_ROWS + r;
             const int tt = tok / TILE_TOK, tilerow = (seq & 1) * 64 + (tok - tt * TILE_TOK);
             __half* dst = o + ((size_t)(seq >> 1) * TILES_PER_PAIR + tt) * (TILE_ROWS * D) + head * 4 * 1024 + tilerow * 8;
             float a0[32];
@@ -904,7 +914,7 @@ __global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM
         };
         float lprev = 1.f;
 #pragma unroll 1
-        for (int qt = 0; qt < ATT_NQT / NWG; ++qt) {            // local q-tile index (q-tile qt * NWG + wg)
+        for (int qt = 0; qt < nql; ++qt) {                       // local q-tile index (q-tile q_tile(qt))
             float mref = 0.f, l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
             for (int j = 0; j < ATT_NCH; ++j) {
@@ -967,7 +977,7 @@ __global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM
             ASTAMP(1 + qt);
             lprev = l0 + l1;
         }
-        finish(ATT_NQT / NWG - 1, lprev);
+        finish(nql - 1, lprev);
         ASTAMP(20);
     }
     tc_fence_before();
