@@ -23,10 +23,13 @@ KIND = {"flowmatching": 0, "rf": 0, "rectified_flow": 0, "ddpm": 1}
 class T2SSampler:
     NOISE_WINDOW_BYTES = 1 << 30          # DDPM step noise drawn per window of steps when the caller supplies none
 
+    GRAPH_MAX_BATCH = 64                  # sample_host replays a captured CUDA graph up to this batch (launch-gap bound regime)
+
     def __init__(self, dit: Transformer, vae=None):
         self.dit = dit
         self.decoder = getattr(vae, "decoder", vae)
         self._tables = {}
+        self._graphs = {}
 
     def _table(self, kind: int, steps: int, device) -> Tuple[torch.Tensor, C.Array]:
         key = (kind, steps, str(device))
@@ -115,12 +118,53 @@ class T2SSampler:
         return (series, z) if return_latent else series
 
     @torch.no_grad()
-    def sample_host(self, emb_host: torch.Tensor, length: int, out_host: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
+    def sample_graph(self, emb: torch.Tensor, length: int, steps: int = 100, cfg_scale: float = 7.0, noise=None, generator=None):
+        """Rectified-flow `sample` through a captured CUDA graph (one graph per (batch, length, steps, cfg, weights)): the
+        ~10 launches per step are replayed without per-launch gaps, which is what bounds small batches (B = 1: 15.3 -> 13.7 ms
+        per 100 steps).  The loop only enqueues kernels (no allocation, no host sync), so capture needs nothing special;
+        inputs go through static buffers, the result is copied out of the graph's memory."""
+        if self.decoder is None or self.dit.H != 30:
+            raise RuntimeError("sample_graph needs the LA-VAE decoder and the T2S shape")
+        dev, B = emb.device, emb.shape[0]
+        key = (str(dev), B, int(length), int(steps), float(cfg_scale), id(self.dit.packed()), id(self.decoder._packed_weights()))
+        ent = self._graphs.get(key)
+        if ent is None:
+            s_emb = torch.empty(B, 128, device=dev, dtype=torch.float32)
+            s_x0 = torch.empty(B, 64, 30, device=dev, dtype=torch.float32)
+            s_emb.copy_(emb)
+            s_x0.normal_()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                       # warm-up outside the capture: workspace, tables, allocator
+                self.sample(s_emb, length, steps=steps, cfg_scale=cfg_scale, noise=s_x0)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                s_out = self.sample(s_emb, length, steps=steps, cfg_scale=cfg_scale, noise=s_x0)
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            ent = self._graphs[key] = (g, s_emb, s_x0, s_out)
+        g, s_emb, s_x0, s_out = ent
+        s_emb.copy_(emb.detach().to(torch.float32), non_blocking=True)
+        if noise is None:
+            s_x0.normal_(generator=generator)                    # infer.py:75
+        else:
+            s_x0.copy_(noise, non_blocking=True)
+        g.replay()
+        return s_out.clone()
+
+    @torch.no_grad()
+    def sample_host(self, emb_host: torch.Tensor, length: int, out_host: Optional[torch.Tensor] = None, graph="auto", **kw) -> torch.Tensor:
         """End-to-end call with HOST buffers: H2D copy of the (pinned) text embeddings, the fused loop,
-        D2H copy of the series.  Returns the host tensor after synchronising the stream."""
+        D2H copy of the series.  Returns the host tensor after synchronising the stream.  Small rectified-flow batches
+        (<= GRAPH_MAX_BATCH) replay a captured CUDA graph (`graph="auto"`; pass False to force plain enqueueing)."""
         dev = next(self.dit.parameters()).device
         emb = emb_host.to(dev, non_blocking=True)
-        series = self.sample(emb, length, **kw)
+        plain = set(kw) <= {"steps", "cfg_scale", "noise", "generator", "backbone"} and KIND[kw.get("backbone", "flowmatching")] == 0
+        if graph and plain and emb.shape[0] <= self.GRAPH_MAX_BATCH and self.dit.H == 30 and self.decoder is not None:
+            series = self.sample_graph(emb, length, **{k: v for k, v in kw.items() if k != "backbone"})
+        else:
+            series = self.sample(emb, length, **kw)
         if out_host is None:
             out_host = torch.empty(series.shape, dtype=torch.float32, pin_memory=True)
         out_host.copy_(series, non_blocking=True)

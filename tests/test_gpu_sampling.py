@@ -186,3 +186,24 @@ def test_sampling_loop_is_cuda_graph_capturable():
     torch.cuda.synchronize()
     ref2 = smp.sample(static_emb, L, steps=steps, noise=static_x0)
     assert max_abs(out, ref2) == 0.0
+
+
+def test_sample_graph_and_host_entry_match_eager():
+    """`sample_graph` (captured graph, static buffers) and the host-buffer entry that uses it for small batches return
+    what the plain enqueueing path returns; a weight update invalidates the cached graph."""
+    from gpu_util import DEV, make_dit, make_vae, max_abs
+    from t2ms_b200 import T2SSampler, synth
+    (dit, _), (vae, _) = make_dit(3), make_vae(4)
+    smp = T2SSampler(dit, vae)
+    B, steps, L = 4, 5, 24
+    emb, x0 = synth.make_text_embeddings(B, seed=5), synth.make_noise(B, seed=6).to(DEV)
+    eager = smp.sample(emb.to(DEV), L, steps=steps, noise=x0)
+    for _ in range(2):                                              # capture, then a pure replay
+        assert max_abs(smp.sample_graph(emb.to(DEV), L, steps=steps, noise=x0), eager) == 0.0
+    host = smp.sample_host(emb.pin_memory(), L, steps=steps, noise=x0)
+    assert not host.is_cuda and max_abs(host, eager) == 0.0
+    assert max_abs(smp.sample_host(emb.pin_memory(), L, steps=steps, noise=x0, graph=False), eager) == 0.0
+    with torch.no_grad():
+        dit.ln.bias.add_(0.1)                                       # new weights -> new packed object -> new graph
+    eager2 = smp.sample(emb.to(DEV), L, steps=steps, noise=x0)
+    assert max_abs(eager2, eager) > 0 and max_abs(smp.sample_graph(emb.to(DEV), L, steps=steps, noise=x0), eager2) == 0.0
