@@ -43,6 +43,9 @@ int t2s_api::ensure_init() {
     CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_EMBED, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));       \
     CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_MID, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));         \
     CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_FINAL, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));       \
+    CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_EMBED, HH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));    \
+    CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_MID, HH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));      \
+    CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_FINAL, HH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));    \
     CUDA_OK(cudaFuncSetAttribute(attn_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttShape<HH>::SMEM_BYTES));
     T2S_SET_ATTRS(30)
     T2S_SET_ATTRS(50)
@@ -110,12 +113,26 @@ int check_ws(const void* ws, size_t bytes, int nseq, const Shape& sh) {
     return T2S_OK;
 }
 
-int token_grid(int nseq, const Shape& sh) {   // persistent: one CTA per SM, each looping over work items (two pair tiles)
+// persistent: one CTA per SM, each looping over work items of `ne` pair tiles; small batches (all single-tile items fit
+// one wave of CTAs) use single-tile items: twice the CTAs, shorter items
+int token_ne(int nseq, const Shape& sh) {
     int dev = 0;
     cudaGetDevice(&dev);
-    const int items = ((nseq + 1) / 2) * (sh.tiles_per_pair / 2), sms = g_sms[dev] > 0 ? g_sms[dev] : 148;
+    const int sms = g_sms[dev] > 0 ? g_sms[dev] : 148;
+    return ((nseq + 1) / 2) * sh.tiles_per_pair <= sms ? 1 : 2;
+}
+int token_grid(int nseq, const Shape& sh, int ne) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int items = ((nseq + 1) / 2) * (sh.tiles_per_pair / ne), sms = g_sms[dev] > 0 ? g_sms[dev] : 148;
     return items < sms ? items : sms;
 }
+#define T2S_TOKEN_LAUNCH(MODE_, HH_)                                                                                  \
+    {                                                                                                                 \
+        const int ne = token_ne(nseq, sh);                                                                            \
+        if (ne == 2) token_kernel<MODE_, HH_, 2><<<token_grid(nseq, sh, 2), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);     \
+        else token_kernel<MODE_, HH_, 1><<<token_grid(nseq, sh, 1), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);             \
+    }
 
 TokArgs base_args(const t2s_dit_weights* w, const Workspace& ws, int nseq) {
     TokArgs a;
@@ -136,7 +153,7 @@ int launch_cond(const t2s_dit_weights* w, const float* t100, int t_stride, const
 int launch_embed(const t2s_dit_weights* w, const float* x, int x_shift, int nseq, const Shape& sh, const Workspace& ws, cudaStream_t st) {
     TokArgs a = base_args(w, ws, nseq);
     a.x = x; a.x_shift = x_shift;
-    T2S_DISPATCH_H(sh.H, (token_kernel<TOK_EMBED, HH><<<token_grid(nseq, sh), TC_THREADS, TOK_SMEM_BYTES, st>>>(a)));
+    T2S_DISPATCH_H(sh.H, T2S_TOKEN_LAUNCH(TOK_EMBED, HH));
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
@@ -159,7 +176,7 @@ int launch_attn(int nseq, const Shape& sh, const Workspace& ws, cudaStream_t st)
 int launch_mid(const t2s_dit_weights* w, int layer, int nseq, const Shape& sh, const Workspace& ws, cudaStream_t st) {
     TokArgs a = base_args(w, ws, nseq);
     a.layer = layer;
-    T2S_DISPATCH_H(sh.H, (token_kernel<TOK_MID, HH><<<token_grid(nseq, sh), TC_THREADS, TOK_SMEM_BYTES, st>>>(a)));
+    T2S_DISPATCH_H(sh.H, T2S_TOKEN_LAUNCH(TOK_MID, HH));
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
@@ -169,7 +186,7 @@ int launch_final(const t2s_dit_weights* w, int nseq, const Shape& sh, const Work
     a.layer = NLAYER - 1;
     a.out_mode = out_mode; a.out = out; a.x_upd = x_upd; a.noise = noise;
     a.cfg = cfg; a.c1 = c1; a.c2 = c2; a.c3 = c3;
-    T2S_DISPATCH_H(sh.H, (token_kernel<TOK_FINAL, HH><<<token_grid(nseq, sh), TC_THREADS, TOK_SMEM_BYTES, st>>>(a)));
+    T2S_DISPATCH_H(sh.H, T2S_TOKEN_LAUNCH(TOK_FINAL, HH));
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }

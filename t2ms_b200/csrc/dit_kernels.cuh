@@ -323,7 +323,9 @@ __device__ __forceinline__ void gelu_store(uint32_t taddr, const float* __restri
 }
 
 // grid = min(#work items, #SMs), block = 576;  H = latent width (DitShape)
-template <int MODE, int H>
+// NE = pair tiles per work item: 2 (tiles alternate on the tensor pipe: throughput) or 1 (small batches: twice the CTAs,
+// shorter items; the second tile's epilogue warps idle)
+template <int MODE, int H, int NE = 2>
 __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
     using S = DitShape<H>;
     [[maybe_unused]] constexpr int NTOK = S::NTOK, TILE_TOK = S::TILE_TOK, TILES_PER_PAIR = S::TILES_PER_PAIR, LATP = S::H, LAT = S::LAT;
@@ -337,12 +339,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
     const int l = p.layer;                                         // block whose second half runs here (MID / FINAL)
     const int ln = (MODE == TOK_EMBED) ? 0 : l + 1;                // block whose QKV is produced here (EMBED / MID)
     constexpr int N_STAGES = (MODE == TOK_EMBED) ? 3 : (MODE == TOK_MID ? 8 : 5);
-    const int n_items = ((p.nseq + 1) / 2) * (TILES_PER_PAIR / 2);  // work item = two consecutive pair tiles
+    const int n_items = ((p.nseq + 1) / 2) * (TILES_PER_PAIR / NE);  // work item = NE consecutive pair tiles
 
     if (tid == 0) {
         for (int i = 0; i < B_VFREE; ++i) mbar_init(BAR(i), 1);                  // WFULL, WEMPTY, VFULL
-        for (int i = 0; i < 2; ++i) mbar_init(BAR(B_VFREE + i), 512);
-        for (int e = 0; e < 2; ++e) {
+        for (int i = 0; i < 2; ++i) mbar_init(BAR(B_VFREE + i), 256 * NE);
+        for (int e = 0; e < NE; ++e) {
             mbar_init(TBAR(e, T_OFULL), 1);
             for (int i = T_A2; i <= T_DONE; ++i) mbar_init(TBAR(e, i), 256);
             mbar_init(TBAR(e, T_HAFREE), 1);
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
         // inputs of work item `item` (iteration it): per-pair vectors into vector buffer it & 1, the two
         // attention-output tiles into the HA buffers, the residual tiles towards L2
         auto fetch_inputs = [&](int it, int item) {
-            const int pair = item / (TILES_PER_PAIR / 2), vb = it & 1;
+            const int pair = item / (TILES_PER_PAIR / NE), vb = it & 1;
             if (it >= 2) mbar_wait(BAR(B_VFREE + vb), ((it >> 1) - 1) & 1);     // the item two back has released this buffer
             const int sq0 = min(2 * pair, p.nseq - 1), sq1 = min(2 * pair + 1, p.nseq - 1);
             const uint32_t vdst = sb + TC_SM_VEC + vb * (V_FLOATS * 4), vbar = BAR(B_VFULL + vb);
@@ -393,13 +395,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             if (MODE == TOK_FINAL) { cp(V_WFIN, p.w.w_final, 4 * D); cp(V_BFIN, p.w.b_final, 4); }
             if (bytes != VBYTES) __trap();
             if (MODE != TOK_EMBED) {
-                if (lead) prefetch_l2(p.h + (size_t)item * 2 * (TILE_ROWS * D), 2 * TILE_ROWS * D * 4);
+                if (lead) prefetch_l2(p.h + (size_t)item * NE * (TILE_ROWS * D), NE * TILE_ROWS * D * 4);
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
+                for (int e = 0; e < NE; ++e) {
                     if (it >= 1) mbar_wait(TBAR(e, T_HAFREE), (it - 1) & 1);     // fc2's first K half of the previous item has read HA
                     if (lead) {
                         mbar_expect_tx(TBAR(e, T_OFULL), STAGE_BYTES);
-                        bulk_g2s(sb + TC_SM_HA + e * STAGE_BYTES, reinterpret_cast<const char*>(p.o) + ((size_t)item * 2 + e) * STAGE_BYTES,
+                        bulk_g2s(sb + TC_SM_HA + e * STAGE_BYTES, reinterpret_cast<const char*>(p.o) + ((size_t)item * NE + e) * STAGE_BYTES,
                                  STAGE_BYTES, TBAR(e, T_OFULL));
                     }
                 }
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             if (MODE != TOK_EMBED) {
                 wfull(gs);                                               // proj (o tile sits in HA) -> X
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
+                for (int e = 0; e < NE; ++e) {
                     if (it > 0) mbar_wait(TBAR(e, T_DONE), (it - 1) & 1);   // the previous item has drained this region
                     mbar_wait(TBAR(e, T_OFULL), par);
                     tc_fence_after();
@@ -455,7 +457,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 wdone(gs); ++gs;
                 wfull(gs);                                               // fc1 cols 0..127 -> Y
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
+                for (int e = 0; e < NE; ++e) {
                     mbar_wait(TBAR(e, T_A2), par);
                     tc_fence_after();
                     tc_gemm(A_(e), wslot(gs), D_(e, Y), false, lead);
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 wdone(gs); ++gs;
                 wfull(gs);                                               // fc1 cols 128..255 -> Y (hidden-a done: Y drained)
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
+                for (int e = 0; e < NE; ++e) {
                     mbar_wait(TBAR(e, T_HA), par);
                     tc_fence_after();
                     tc_gemm(A_(e), wslot(gs), D_(e, Y), false, lead);
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 wdone(gs); ++gs;
                 wfull(gs); wfull(gs + 1);                                // fc2, both K halves -> Y (hidden-b done: Y drained)
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
+                for (int e = 0; e < NE; ++e) {
                     mbar_wait(TBAR(e, T_HB), par);
                     tc_fence_after();
                     tc_gemm(HA_(e), wslot(gs), D_(e, Y), false, lead);
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             if (MODE != TOK_FINAL) {
                 wfull(gs); wfull(gs + 1);                                // q -> X, k -> Y
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
+                for (int e = 0; e < NE; ++e) {
                     mbar_wait(TBAR(e, T_A3), par);
                     tc_fence_after();
                     tc_gemm(A_(e), wslot(gs), D_(e, X), false, lead);
@@ -497,7 +499,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 wdone(gs); wdone(gs + 1); gs += 2;
                 wfull(gs);                                               // v -> X (after the q epilogue has drained X)
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
+                for (int e = 0; e < NE; ++e) {
                     mbar_wait(TBAR(e, T_XFREE), par);
                     tc_fence_after();
                     tc_gemm(A_(e), wslot(gs), D_(e, X), false, lead);
@@ -521,16 +523,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
         const bool tr = p.trace != nullptr && e == 0 && r == 0 && hh == 0;
 #define STAMP(i) do { if (tr) p.trace[(size_t)blockIdx.x * 32 + (i)] = clock64(); } while (0)
 #pragma unroll 1
-        for (int it = 0, item = blockIdx.x; item < n_items; ++it, item += gridDim.x) {
+        for (int it = 0, item = blockIdx.x; item < n_items && e < NE; ++it, item += gridDim.x) {
         const uint32_t par = it & 1;
         const uint32_t X = (it & 1) * 128, Y = 128 - X;                 // the two TMEM regions swap roles every item
-        const int pair = item / (TILES_PER_PAIR / 2), tt = (item % (TILES_PER_PAIR / 2)) * 2 + e;
+        const int pair = item / (TILES_PER_PAIR / NE), tt = (item % (TILES_PER_PAIR / NE)) * NE + e;
         const int seq = 2 * pair + branch;
         const bool valid = tl < TILE_TOK && seq < p.nseq;
         const int tok = tt * TILE_TOK + tl;
         const float* vec = reinterpret_cast<const float*>(smem + TC_SM_VEC) + (it & 1) * V_FLOATS;
         const float* modb = vec + V_MOD + branch * MOD;
-        float* htile = p.h + ((size_t)item * 2 + e) * (TILE_ROWS * D);  // [32 col chunks][128 rows][4]
+        float* htile = p.h + ((size_t)item * NE + e) * (TILE_ROWS * D);  // [32 col chunks][128 rows][4]
         const float* hrow_c = htile + (c0 / 4) * TILE_ROWS * 4 + r * 4; // + c4 * TILE_ROWS * 4
         float* hrow = htile + (c0 / 4) * TILE_ROWS * 4 + r * 4;
         STAMP(0);
