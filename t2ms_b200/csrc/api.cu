@@ -145,8 +145,11 @@ TokArgs base_args(const t2s_dit_weights* w, const Workspace& ws, int nseq) {
 
 int launch_cond(const t2s_dit_weights* w, const float* t100, int t_stride, const float* emb, int emb_shift, int cfg_pairs,
                 int nseq, const Workspace& ws, cudaStream_t st) {
-    dim3 grid((nseq + 7) / 8, NLAYER * 3);
-    cond_kernel<<<grid, 256, 0, st>>>(ws.mod, t100, t_stride, emb, emb_shift, cfg_pairs, w->freqs, w->w_ada_t, w->b_ada, nseq);
+    if (nseq <= 64)
+        cond_split_kernel<<<dim3((nseq + 7) / 8, NLAYER * 3), 256, 0, st>>>(ws.mod, t100, t_stride, emb, emb_shift, cfg_pairs, w->freqs, w->w_ada_t,
+                                                                           w->b_ada, nseq);
+    else
+        cond_kernel<<<dim3((nseq + 7) / 8, NLAYER), 256, 0, st>>>(ws.mod, t100, t_stride, emb, emb_shift, cfg_pairs, w->freqs, w->w_ada_t, w->b_ada, nseq);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }

@@ -57,10 +57,59 @@ struct TokArgs {
 
 // =================================================================================== cond
 // mod[seq][l][:] = Linear_l( SiLU( temb(t) (+ text) ) )      transformer.py:30-40,106-109,115,174-178
-// grid (ceil(nseq/8), 4 blocks x 3 column groups), block 256: a thread owns one of the 768 outputs of one block for 8
-// sequences (the weight column is read once, coalesced across the warp, 8 loads in flight).  Splitting the columns over
-// CTAs keeps the kernel short at small batches, where it used to be a quarter of a sampling step.
+// grid (ceil(nseq/8), 4), block 256
 __global__ void __launch_bounds__(256) cond_kernel(float* __restrict__ mod, const float* __restrict__ t100, int t_stride,
+                                                   const float* __restrict__ emb, int emb_shift, int cfg_pairs,
+                                                   const float* __restrict__ freqs, const float* __restrict__ w_ada_t,
+                                                   const float* __restrict__ b_ada, int nseq) {
+    __shared__ float sc[8][D];
+    const int s0 = blockIdx.x * 8, l = blockIdx.y, tid = threadIdx.x;
+    for (int i = tid; i < 8 * D; i += 256) {
+        const int si = i >> 7, f = i & 127, seq = s0 + si;
+        float v = 0.f;
+        if (seq < nseq) {
+            const float arg = __fdiv_rn(t100[(size_t)seq * t_stride], freqs[f & 63]);
+            float c = (f < 64) ? sinf(arg) : cosf(arg);
+            if (emb != nullptr && (!cfg_pairs || (seq & 1))) c = c + emb[(size_t)(seq >> emb_shift) * D + f];
+            v = c / (1.0f + expf(-c));
+        }
+        sc[si][f] = v;
+    }
+    __syncthreads();
+    float acc[3][8];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int s = 0; s < 8; ++s) acc[a][s] = 0.f;
+    const float* w = w_ada_t + (size_t)l * D * MOD;
+#pragma unroll 4
+    for (int k = 0; k < D; ++k) {
+        const float w0 = w[k * MOD + tid], w1 = w[k * MOD + 256 + tid], w2 = w[k * MOD + 512 + tid];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const float c = sc[s][k];
+            acc[0][s] = fmaf(w0, c, acc[0][s]);
+            acc[1][s] = fmaf(w1, c, acc[1][s]);
+            acc[2][s] = fmaf(w2, c, acc[2][s]);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const int seq = s0 + s;
+        if (seq < nseq) {
+            float* dst = mod + ((size_t)seq * NLAYER + l) * MOD;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) dst[a * 256 + tid] = acc[a][s] + b_ada[l * MOD + a * 256 + tid];
+        }
+    }
+}
+
+// ----- small batches: the same computation with the 768 outputs of a block split over three CTAs
+// grid (ceil(nseq/8), 4 blocks x 3 column groups), block 256: a thread owns one of the 768 outputs of one block for 8
+// sequences (8 weight loads in flight).  Three times the CTAs and a third of the serial work per thread: at batch 1 the
+// one-CTA-per-block form was a quarter of a sampling step; at large batches the form above is faster (the prologue is
+// not repeated per column group).
+__global__ void __launch_bounds__(256) cond_split_kernel(float* __restrict__ mod, const float* __restrict__ t100, int t_stride,
                                                    const float* __restrict__ emb, int emb_shift, int cfg_pairs,
                                                    const float* __restrict__ freqs, const float* __restrict__ w_ada_t,
                                                    const float* __restrict__ b_ada, int nseq) {
