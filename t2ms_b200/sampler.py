@@ -110,11 +110,13 @@ class T2SSampler:
         """Text embeddings (B,128) -> generated series (B,length) fp32 (infer.py:75-95)."""
         if self.decoder is None:
             raise RuntimeError("T2SSampler was built without an LA-VAE decoder")
-        if self.dit.H != 30:
-            raise RuntimeError("the LA-VAE decoder takes (B,64,30) latents; use sample_latent for Transformer(dim != 30)")
         z = self.sample_latent(emb, steps, cfg_scale, backbone, noise, step_noise, generator, False, chunk)
-        series = torch.empty(z.shape[0], int(length), device=z.device, dtype=torch.float32)
-        self.decoder.decode_into(z, int(length), series, None)
+        if self.dit.H == 30 and hasattr(self.decoder, "decode_into"):
+            series = torch.empty(z.shape[0], int(length), device=z.device, dtype=torch.float32)
+            self.decoder.decode_into(z, int(length), series, None)          # fused single-kernel T2S decoder
+        else:
+            # the fork's multivariate LA-VAE (mylavae.Decoder, myinfer.py:147): (B, 64, flow_dim) -> (B, input_dim, length)
+            series = self.decoder(z, int(length))[0]
         return (series, z) if return_latent else series
 
     @torch.no_grad()

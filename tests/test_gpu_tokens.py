@@ -57,7 +57,7 @@ def test_guided_sampling_matches_fork_golden(dim):
     # DDPM with 3 steps amplifies the prediction error by 1/sqrt(alpha_t) ~ 7: the latent bar is relative to its scale
     assert max(per) < 2e-3 and rel_l2(lat, T(g[k + "ddpm_final"])) < 2e-3
     with pytest.raises(RuntimeError):
-        smp.sample(emb, 96, steps=2)                       # no LA-VAE decode for (B,64,dim != 30) latents
+        smp.sample(emb, 96, steps=2)                       # built without a decoder
 
 
 @pytest.mark.parametrize("dim,B", [(50, 5), (64, 37)])
@@ -77,3 +77,26 @@ def test_forward_odd_batches_vs_oracle(dim, B):
 def test_unsupported_width_raises():
     with pytest.raises(ValueError):
         Transformer(40)
+
+
+def test_fork_generation_loop_with_multivariate_lavae():
+    """The fork's generation loop (myinfer.py:116-147): Transformer(flow_dim) guided sampling + the multivariate LA-VAE
+    decoder, through T2SSampler.sample, against the oracle (rf_sample on (B,64,50) latents + lavae_decode)."""
+    from argparse import Namespace
+    from t2ms_b200.mylavae import vqvae as vq_multi
+    m, sd = _model(50, 21, bias_std=0.02)
+    vae = vq_multi(Namespace(block_hidden_size=128, num_residual_layers=2, res_hidden_size=256, embedding_dim=64, flow_dim=50, input_dim=7))
+    vsd = synth.make_vae_state(22, in_channels=7)
+    vae.load_state_dict(vsd, strict=True)
+    vae = vae.to(DEV).eval()
+    m.encoder = vae.encoder                                 # myinfer.py:133
+    assert len([n for n, _ in m._own_params()]) == 55
+    B, L, steps = 3, 100, 4
+    x0, emb = synth.make_noise(B, seed=23, dim=50), synth.make_text_embeddings(B, seed=24)
+    series, z = T2SSampler(m, vae).sample(emb.to(DEV), L, steps=steps, cfg_scale=7.0, noise=x0.to(DEV), return_latent=True)
+    lat_ref, _ = O.rf_sample(sd, None, x0, emb, steps, 7.0)
+    ser_ref, _ = O.lavae_decode(vsd, lat_ref, L)
+    assert series.shape == (B, 7, L) and max_abs(z, lat_ref) < 1e-2 and max_abs(series, ser_ref) < 1e-2
+    with torch.no_grad():
+        z_enc, _ = m.encoder(torch.rand(B, 7, L, device=DEV))   # the attached encoder still runs (myinfer.py:117)
+    assert z_enc.shape == (B, 64, 50)
