@@ -149,8 +149,14 @@ def cpu_reference_run(a, n_series: int, repeats: int = 1):
 
 def workload_name(a):
     kind = "rectified-flow" if a.backbone == "flowmatching" else "DDPM"
+    if a.backbone == "flowmatching" and (a.length, a.batch, a.rf_steps) == (96, 1024, 100):
+        tag = "BASELINE config 2"
+    elif a.backbone == "ddpm" and (a.length, a.rf_steps) == (48, 1000):
+        tag = "BASELINE config 3: batch 512 sharded over the GPUs" if a.batch * max(a.gpus, 1) == 512 else "BASELINE config 3 shape"
+    else:
+        tag = "BASELINE config 5 sweep point"
     return (f"T2S-DiT {kind} sampling length {a.length} with CFG {a.cfg:g}, batch {a.batch}/GPU, {a.rf_steps} steps, "
-            f"LA-VAE decode (BASELINE config 2)")
+            f"LA-VAE decode ({tag})")
 
 
 def run_reference(a, rank, world):
