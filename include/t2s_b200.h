@@ -172,10 +172,13 @@ typedef struct {
     float* fc2_b[4];   /* (128) */
     float* ada_w[4];   /* layers.{l}.adaLN_modulation.1.weight (768,128) */
     float* ada_b[4];   /* (768) */
+    int latent_h;      /* latent width H: 0 / 30 = T2S (pos_embed (1,480,128), latents (B,64,30)); 50 / 64 = the fork's
+                        * Transformer(dim) trained by mytrain.py:23 (pos_embed (1,16 H,128), latents (B,64,H)) */
 } t2s_dit_params;
 
 /* Scratch for a training step over `nseq` sequences (saved activations of every block + backward temporaries). */
-size_t t2s_train_workspace_bytes(int nseq);
+size_t t2s_train_workspace_bytes(int nseq);                        /* H = 30 */
+size_t t2s_train_workspace_bytes_h(int nseq, int latent_h);        /* 0 when latent_h is unsupported */
 
 /* pred = Transformer.forward(x_t, t, emb | None) (transformer.py:158-193), loss = F.mse_loss(pred, target)
  * (rectified_flow.py:13-16 / DDPM.py:37-38), backward to every trainable parameter (train.py:83-85).
@@ -202,7 +205,9 @@ int t2s_dit_train_backward(const t2s_dit_params* params, const t2s_dit_params* g
  * kind 1: DDPM.q_sample (DDPM.py:19-27), target = eps (train.py:74-76): x_t = ca x1 + cb eps with
  *   ca = sqrt(alpha_bar_t), cb = sqrt(1 - alpha_bar_t) per sample.   x1, noise, x_t, target: [batch][64][30]. */
 int t2s_train_make_inputs(int kind, const float* x1, const float* noise, const float* ca, const float* cb, float* x_t,
-                          float* target, int batch, t2s_stream_t stream);
+                          float* target, int batch, t2s_stream_t stream);                       /* latents (B,64,30) */
+int t2s_train_make_inputs_h(int kind, const float* x1, const float* noise, const float* ca, const float* cb, float* x_t,
+                            float* target, int batch, int latent_h, t2s_stream_t stream);       /* latents (B,64,H) */
 
 /* torch.optim.AdamW single step over a flat fp32 buffer (train.py:37: lr 1e-4, betas (0.9, 0.999), eps 1e-8, wd 0):
  * g is multiplied by grad_scale first (1/world_size after a SUM all-reduce).  step counts from 1. */

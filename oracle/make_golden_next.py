@@ -105,6 +105,45 @@ def make_dit_tokens(ref: str, out: str):
     np.savez_compressed(os.path.join(out, "dit_tokens.npz"), **res)
 
 
+def make_dit_tokens_train(ref: str, out: str):
+    """One rectified-flow training step of the fork's variable-width denoiser (mytrain.py:66-87 around
+    model/denoiser/mytransformer.py Transformer(dim), dim = 50 and 64): loss and every parameter gradient (norms + slices)
+    on synthetic latents (the multivariate LA-VAE encoder is exercised separately)."""
+    from make_golden import install_shims
+    from t2ms_b200 import synth
+    install_shims(ref)
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    from model.denoiser.mytransformer import Transformer
+    from model.backbone.rectified_flow import RectifiedFlow
+    res = {}
+    for dim in (50, 64):
+        sd = synth.make_dit_state(140 + dim, bias_std=0.02, dim=dim)
+        m = Transformer(dim)
+        m.load_state_dict(sd, strict=True)
+        m.train()
+        B = 3
+        x1, x0 = synth.make_noise(B, seed=150 + dim, dim=dim), synth.make_noise(B, seed=160 + dim, dim=dim)
+        emb = synth.make_text_embeddings(B, seed=170 + dim)
+        t = torch.tensor([0.2, 0.55, 0.9])
+        rf = RectifiedFlow()
+        x_t = t[:, None, None] * x1 + (1 - t[:, None, None]) * x0           # create_flow with the noise fixed (rectified_flow.py:8-12)
+        target = x1 - x0
+        pred = m(input=x_t, t=t, text_input=emb)
+        loss = rf.loss(pred, target)
+        loss.backward()
+        k = f"h{dim}/"
+        res[k + "loss"] = np.float64(loss.item())
+        res[k + "pred"] = pred.detach().numpy()
+        names = [n for n, p in m.named_parameters() if p.grad is not None]
+        res[k + "names"] = np.array(names)
+        res[k + "grad_norms"] = np.array([float(dict(m.named_parameters())[n].grad.norm()) for n in names])
+        for n in names:
+            res[k + "grad/" + n] = dict(m.named_parameters())[n].grad.reshape(-1)[:128].numpy().copy()
+        res[k + "checksum"] = np.array(synth.state_checksum(sd))
+    np.savez_compressed(os.path.join(out, "dit_tokens_train.npz"), **res)
+
+
 def make_vae_train(ref: str, out: str):
     """LA-VAE training step: vqvae.shared_eval(batch, optimizer, 'train') of model/pretrained/vqvae.py:118-135 (univariate,
     L = 48) and of the fork's model/pretrained/myvqvae.py:116-136 (input_dim 7, flow_dim 50, L = 100 and L = 90 — the latter
@@ -156,7 +195,7 @@ def main():
     a = ap.parse_args()
     only = set(filter(None, a.only.split(",")))
     torch.set_num_threads(8)
-    makers = {"eval": make_eval, "dit_tokens": make_dit_tokens, "vae_train": make_vae_train}
+    makers = {"eval": make_eval, "dit_tokens": make_dit_tokens, "dit_tokens_train": make_dit_tokens_train, "vae_train": make_vae_train}
     for name, fn in makers.items():
         if not only or name in only:
             fn(a.ref, a.out)

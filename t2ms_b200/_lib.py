@@ -17,7 +17,7 @@ EXPORTS = [
     "t2s_dit_workspace_bytes_h", "t2s_dit_workspace_offsets_h", "t2s_dit_attention_h",
     "t2s_dit_forward", "t2s_sample", "t2s_vae_decode", "t2s_vae_encode",
     "t2s_dit_cond", "t2s_dit_embed_qkv", "t2s_dit_attention", "t2s_dit_block_post", "t2s_dit_final",
-    "t2s_train_workspace_bytes", "t2s_dit_train_step", "t2s_dit_train_forward", "t2s_dit_train_backward",
+    "t2s_train_workspace_bytes", "t2s_train_workspace_bytes_h", "t2s_train_make_inputs_h", "t2s_dit_train_step", "t2s_dit_train_forward", "t2s_dit_train_backward",
     "t2s_train_make_inputs", "t2s_adamw_step", "t2s_gemm_tf32",
     "t2s_series_metrics", "t2s_lavae_workspace_bytes", "t2s_lavae_encode", "t2s_lavae_decode", "t2s_lavae_train_step", "t2s_train_attention_scratch_bytes", "t2s_train_attention_forward", "t2s_train_attention_backward",
 ]
@@ -36,7 +36,7 @@ class DitParams(C.Structure):
     _fields_ = [("conv_w", P), ("conv_b", P), ("pe_w", P), ("pe_b", P), ("pos", P), ("ln_w", P), ("ln_b", P),
                 ("lf_w", P), ("lf_b", P), ("freqs", P), ("qkv_w", P * 4), ("qkv_b", P * 4), ("proj_w", P * 4),
                 ("proj_b", P * 4), ("fc1_w", P * 4), ("fc1_b", P * 4), ("fc2_w", P * 4), ("fc2_b", P * 4),
-                ("ada_w", P * 4), ("ada_b", P * 4)]
+                ("ada_w", P * 4), ("ada_b", P * 4), ("latent_h", C.c_int)]
 
 
 class LavaeParams(C.Structure):
@@ -111,6 +111,10 @@ def load() -> C.CDLL:
         d = C.c_double
         lib.t2s_train_workspace_bytes.restype = sz
         lib.t2s_train_workspace_bytes.argtypes = [i]
+        lib.t2s_train_workspace_bytes_h.restype = sz
+        lib.t2s_train_workspace_bytes_h.argtypes = [i, i]
+        lib.t2s_train_make_inputs_h.restype = i
+        lib.t2s_train_make_inputs_h.argtypes = [i, P, P, P, P, P, P, i, i, P]
         lib.t2s_dit_train_step.restype = i
         lib.t2s_dit_train_step.argtypes = [C.POINTER(DitParams), C.POINTER(DitParams), P, P, P, P, P, P, i, d, P, sz, P]
         lib.t2s_dit_train_forward.restype = i

@@ -30,22 +30,32 @@
 
 namespace t2s {
 
-constexpr int TA_IMG_HALVES = NTOK * HD;                 // 15360 halves = 30720 B per T8 image
-constexpr int TA_IMG_BYTES = TA_IMG_HALVES * 2;
-constexpr int TA_ROWS = 120;                             // valid rows per tile
-constexpr int TA_NTILE = NTOK / TA_ROWS;                 // 4
-constexpr int TA_TILE_BYTES = TA_ROWS * HD * 2;          // 7680 B copied per tile (the 8 padding rows stay undefined)
 constexpr int TA_THREADS = 160;
 constexpr float TA_PSHIFT = 4.f;                         // backward probabilities are kept as 2^4 P
 enum TaMode { TA_FWD = 0, TA_DQ = 1, TA_DKV = 2 };
 
-constexpr int TA_SM_A0 = 0, TA_SM_A1 = 8192;             // two 128-row operand tiles
-constexpr int TA_SM_B0 = 16384, TA_SM_B1 = TA_SM_B0 + TA_IMG_BYTES;   // two full images
-constexpr int TA_SM_VEC = TA_SM_B1 + TA_IMG_BYTES;       // DKV: [2][480] fp32 (4 - lse2 | D) of the query side
-constexpr int TA_SM_BAR = TA_SM_VEC + 2 * NTOK * 4;
-constexpr int TA_SM_TMEM = TA_SM_BAR + 8 * 8;
-constexpr int TA_SMEM_BYTES = TA_SM_TMEM + 16;
-static_assert(2 * (TA_SMEM_BYTES + 1024) <= 233472, "two training-attention CTAs must fit one SM");
+// Shape of the training attention for a latent of H positions (16 H tokens; H = 30: T2S, 50 / 64: the fork's
+// Transformer(dim)): tile rows, chunk widths and the shared-memory map.  H = 30 fits two CTAs per SM; the wide shapes keep
+// two full images of 51 / 64 KB resident and run one CTA per SM.
+template <int H>
+struct TaShape {
+    static constexpr int NTOK = 16 * H;
+    static constexpr int IMG_HALVES = NTOK * HD;             // one T8 image
+    static constexpr int IMG_BYTES = IMG_HALVES * 2;
+    static constexpr int ROWS = H == 64 ? 128 : 120;         // valid rows per tile (a multiple of 8); the last tile may be partial
+    static constexpr int NTILE = (NTOK + ROWS - 1) / ROWS;   // 4 | 7 | 8
+    static constexpr int KC_FWD = H == 30 ? 96 : (H == 50 ? 80 : 64);
+    static constexpr int KC_BWD = H == 30 ? 48 : 32;
+    static constexpr int SM_A0 = 0, SM_A1 = 8192;            // two 128-row operand tiles
+    static constexpr int SM_B0 = 16384, SM_B1 = SM_B0 + IMG_BYTES;   // two full images
+    static constexpr int SM_VEC = SM_B1 + IMG_BYTES;         // DKV: [2][NTOK] fp32 (4 - lse2 | D) of the query side
+    static constexpr int SM_BAR = SM_VEC + 2 * NTOK * 4;
+    static constexpr int SM_TMEM = SM_BAR + 8 * 8;
+    static constexpr int SMEM_BYTES = SM_TMEM + 16;
+    static constexpr int CTAS_PER_SM = 2 * (SMEM_BYTES + 1024) <= 233472 ? 2 : 1;
+    static_assert(SMEM_BYTES <= 232448 && NTOK % KC_FWD == 0 && NTOK % KC_BWD == 0 && ROWS % 8 == 0 && (NTOK % ROWS) % 8 == 0, "training attention shape");
+};
+static_assert(TaShape<30>::CTAS_PER_SM == 2, "two training-attention CTAs must fit one SM for the T2S shape");
 enum { TB_LOADED = 0, TB_SFULL = 1, TB_PFULL = 3, TB_ACC = 5 };       // SFULL / PFULL / ACC: one barrier per score buffer
 constexpr uint32_t TA_BUF = 96, TA_T_ACC0 = 192, TA_T_ACC1 = 224, TA_TCOLS = 256;   // two score buffers of 96 columns + accumulators
 constexpr uint32_t TA_IDESC_ACC = umma_idesc_f16(128, HD) | (1u << 16);     // B operand MN-major
@@ -70,7 +80,8 @@ __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
 // q | k | v rows [T][384] fp32 -> T8 fp16 images.  One warp = 8 consecutive tokens of one (which, head): lane =
 // (feature chunk, token % 8) reads 32 contiguous bytes and writes one 16-byte core-matrix row; a warp writes 512
 // contiguous bytes.
-__global__ void __launch_bounds__(256) ta_pack_qkv_kernel(const float* __restrict__ qkv, __half* __restrict__ img, int nseq) {
+__global__ void __launch_bounds__(256) ta_pack_qkv_kernel(const float* __restrict__ qkv, __half* __restrict__ img, int nseq, int ntok) {
+    const int NTOK = ntok, TA_IMG_HALVES = ntok * HD;
     const int lane = threadIdx.x & 31;
     const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const long long nw = (long long)nseq * (NTOK / 8) * 12;
@@ -86,18 +97,20 @@ __global__ void __launch_bounds__(256) ta_pack_qkv_kernel(const float* __restric
 }
 
 // dO [T][128] fp32 (+ O) -> per (sequence, head): power-of-two scale s with max |s dO| in [0.5, 1), the T8 image of
-// s dO, D = rowsum(s dO . O) and 1 / s.   grid = nseq * 4, block = 512 (16 warps x up to 4 token groups).
+// s dO, D = rowsum(s dO . O) and 1 / s.   grid = nseq * 4, block = 512 (16 warps x up to NG 8-token groups each).
+template <int NG>
 __global__ void __launch_bounds__(512) ta_pack_do_kernel(const float* __restrict__ dout, const float* __restrict__ o,
-                                                         __half* __restrict__ doimg, float* __restrict__ dvec, float* __restrict__ dinv) {
+                                                         __half* __restrict__ doimg, float* __restrict__ dvec, float* __restrict__ dinv, int ntok) {
+    const int NTOK = ntok, TA_IMG_HALVES = ntok * HD;
     __shared__ float red[16];
     const int seq = blockIdx.x >> 2, head = blockIdx.x & 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int dc = lane >> 3, t8 = lane & 7;
-    float4 v[4][2];
-    float dsum[4];
+    float4 v[NG][2];
+    float dsum[NG];
     float amax = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NG; ++i) {
         const int g = warp + 16 * i;
         dsum[i] = 0.f;
         v[i][0] = v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -124,7 +137,7 @@ __global__ void __launch_bounds__(512) ta_pack_do_kernel(const float* __restrict
     const float s = ldexpf(1.f, -e);
     if (threadIdx.x == 0) dinv[blockIdx.x] = ldexpf(1.f, e);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NG; ++i) {
         const int g = warp + 16 * i;
         float dsm = dsum[i];
         dsm += __shfl_xor_sync(0xffffffffu, dsm, 8);
@@ -139,20 +152,26 @@ __global__ void __launch_bounds__(512) ta_pack_do_kernel(const float* __restrict
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// grid = nseq * 4 heads * 4 tiles, block = 160.  Score chunks are double-buffered in TMEM: while the row threads work on
+// grid = nseq * 4 heads * NTILE tiles, block = 160.  Score chunks are double-buffered in TMEM: while the row threads work on
 // chunk j (buffer j & 1) the tensor pipe has already produced the scores of chunk j + 1 and runs the accumulation of
 // chunk j - 1, so the row threads (MUFU / issue bound) never wait for an MMA in steady state.
-//   FWD     : 5 chunks of 96 keys;  TMEM  S0 [0,96) | S1 [96,192) | O [192,224)
-//   DQ / DKV: 10 chunks of 48;      TMEM  buffer b: S [96 b, +48) | dP [96 b + 48, +48) ; acc0 [192,224) | acc1 [224,256)
-template <int MODE>
-__global__ void __launch_bounds__(TA_THREADS, 2) ta_attn_kernel(const TaArgs p) {
-    constexpr int KC = MODE == TA_FWD ? 96 : 48;                    // tokens per chunk
+//   FWD     : chunks of KC = 96 | 80 | 64 keys (H = 30 | 50 | 64);  TMEM  S0 [0,KC) | S1 [96,96+KC) | O [192,224)
+//   DQ / DKV: chunks of KC = 48 | 32 | 32;   TMEM  buffer b: S [96 b, +KC) | dP [96 b + KC, +KC) ; acc0 [192,224) | acc1 [224,256)
+template <int MODE, int H = 30>
+__global__ void __launch_bounds__(TA_THREADS, TaShape<H>::CTAS_PER_SM) ta_attn_kernel(const TaArgs p) {
+    using TS = TaShape<H>;
+    constexpr int NTOK = TS::NTOK, TA_IMG_BYTES = TS::IMG_BYTES, TA_ROWS = TS::ROWS, TA_NTILE = TS::NTILE;
+    constexpr int TA_SM_A0 = TS::SM_A0, TA_SM_A1 = TS::SM_A1, TA_SM_B0 = TS::SM_B0, TA_SM_B1 = TS::SM_B1, TA_SM_VEC = TS::SM_VEC;
+    constexpr int TA_SM_BAR = TS::SM_BAR, TA_SM_TMEM = TS::SM_TMEM;
+    constexpr int KC = MODE == TA_FWD ? TS::KC_FWD : TS::KC_BWD;    // tokens per chunk
     constexpr int NCH = NTOK / KC;
     constexpr uint32_t IDESC_S = umma_idesc_f16(128, KC);
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform
-    const int sh = blockIdx.x >> 2, tile = blockIdx.x & 3;          // (sequence, head) index; tile of the row side
+    const int sh = blockIdx.x / TA_NTILE, tile = blockIdx.x - sh * TA_NTILE;   // (sequence, head) index; tile of the row side
     const int seq = sh >> 2, head = sh & 3;
+    const int nrow = min(TA_ROWS, NTOK - tile * TA_ROWS);           // valid rows of this tile (the last one may be partial)
+    const uint32_t TA_TILE_BYTES = (uint32_t)nrow * HD * 2;
     const uint32_t sb = smem_u32(smem);
     const uint32_t bar0 = sb + TA_SM_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * i; };
@@ -179,7 +198,7 @@ __global__ void __launch_bounds__(TA_THREADS, 2) ta_attn_kernel(const TaArgs p) 
             const char* q = reinterpret_cast<const char*>(p.img) + (size_t)sh * 3 * TA_IMG_BYTES;
             const char* k = q + TA_IMG_BYTES;
             const char* v = k + TA_IMG_BYTES;
-            const size_t toff = (size_t)tile * TA_TILE_BYTES;
+            const size_t toff = (size_t)tile * TA_ROWS * HD * 2;
             if (MODE == TA_FWD) {
                 mbar_expect_tx(BAR(TB_LOADED), TA_TILE_BYTES + 2 * TA_IMG_BYTES);
                 bulk_g2s(sb + TA_SM_A0, q + toff, TA_TILE_BYTES, BAR(TB_LOADED));
@@ -266,7 +285,7 @@ __global__ void __launch_bounds__(TA_THREADS, 2) ta_attn_kernel(const TaArgs p) 
         // ================================================================= thread = tile row
         const int r = tid;
         const int tok = tile * TA_ROWS + r;
-        const bool valid = r < TA_ROWS;
+        const bool valid = r < nrow;
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
         constexpr int LAST = NCH - 1;                                // the final accumulation: barrier ACC[LAST & 1], phase (LAST >> 1) & 1
         if (MODE == TA_FWD) {
@@ -277,15 +296,18 @@ __global__ void __launch_bounds__(TA_THREADS, 2) ta_attn_kernel(const TaArgs p) 
                 const uint32_t ts = trow + b * TA_BUF;
                 mbar_wait(BAR(TB_SFULL + b), (j >> 1) & 1);
                 tc_fence_after();
-                float x[32], y[32], z[32];
-                tmem_ld32(ts, x); tmem_ld32(ts + 32, y); tmem_ld32(ts + 64, z);
+                constexpr int ZN = KC - 64;                      // scores beyond the first two 32-column blocks: 32, 16 or 0
+                float x[32], y[32], z[ZN > 0 ? ZN : 1];
+                tmem_ld32(ts, x); tmem_ld32(ts + 32, y);
+                if constexpr (ZN == 32) tmem_ld32(ts + 64, *reinterpret_cast<float (*)[32]>(&z[0]));
+                if constexpr (ZN == 16) tmem_ld16(ts + 64, *reinterpret_cast<float (*)[16]>(&z[0]));
                 tmem_wait_ld();
                 float c0 = -INFINITY, c1 = -INFINITY;
 #pragma unroll
                 for (int q = 0; q < 32; q += 4) {
                     c0 = max3(c0, x[q], x[q + 1]); c1 = max3(c1, x[q + 2], x[q + 3]);
                     c0 = max3(c0, y[q], y[q + 1]); c1 = max3(c1, y[q + 2], y[q + 3]);
-                    c0 = max3(c0, z[q], z[q + 1]); c1 = max3(c1, z[q + 2], z[q + 3]);
+                    if (q < ZN) { c0 = max3(c0, z[q], z[q + 1]); c1 = max3(c1, z[q + 2], z[q + 3]); }
                 }
                 const float cm = fmaxf(c0, c1);
                 if (j == 0) {
@@ -309,20 +331,19 @@ __global__ void __launch_bounds__(TA_THREADS, 2) ta_attn_kernel(const TaArgs p) 
                     }
                 }
                 const float nb = -mref * sc;
-                auto block = [&](const float (&v)[32], int c32) {
+                auto half = [&](const float* v, int pcol) {   // 16 scores -> 8 packed P columns
+                    uint32_t pk[8];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t pk[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float e0 = ex2_approx(fmaf(v[h * 16 + 2 * q], sc, nb)), e1 = ex2_approx(fmaf(v[h * 16 + 2 * q + 1], sc, nb));
-                            l0 += e0; l1 += e1;
-                            pk[q] = pack_h2(e0, e1);
-                        }
-                        tmem_st8(ts + c32 * 16 + h * 8, pk);
+                    for (int q = 0; q < 8; ++q) {
+                        const float e0 = ex2_approx(fmaf(v[2 * q], sc, nb)), e1 = ex2_approx(fmaf(v[2 * q + 1], sc, nb));
+                        l0 += e0; l1 += e1;
+                        pk[q] = pack_h2(e0, e1);
                     }
+                    tmem_st8(ts + pcol, pk);
                 };
-                block(x, 0); block(y, 1); block(z, 2);
+                half(x, 0); half(x + 16, 8); half(y, 16); half(y + 16, 24);
+                if constexpr (ZN >= 16) half(z, 32);
+                if constexpr (ZN == 32) half(z + 16, 40);
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(BAR(TB_PFULL + b));
@@ -352,14 +373,14 @@ __global__ void __launch_bounds__(TA_THREADS, 2) ta_attn_kernel(const TaArgs p) 
                 const uint32_t ts = trow + b * TA_BUF, tdp = ts + KC;
                 mbar_wait(BAR(TB_SFULL + b), (j >> 1) & 1);
                 tc_fence_after();
-                float s[48], g[48];
+                float s[KC], g[KC];
                 tmem_ld32(ts, *reinterpret_cast<float (*)[32]>(&s[0]));
-                tmem_ld16(ts + 32, *reinterpret_cast<float (*)[16]>(&s[32]));
+                if constexpr (KC == 48) tmem_ld16(ts + 32, *reinterpret_cast<float (*)[16]>(&s[32]));
                 tmem_ld32(tdp, *reinterpret_cast<float (*)[32]>(&g[0]));
-                tmem_ld16(tdp + 32, *reinterpret_cast<float (*)[16]>(&g[32]));
+                if constexpr (KC == 48) tmem_ld16(tdp + 32, *reinterpret_cast<float (*)[16]>(&g[32]));
                 tmem_wait_ld();
 #pragma unroll
-                for (int h = 0; h < 3; ++h) {                           // 16 scores -> 8 packed columns
+                for (int h = 0; h < KC / 16; ++h) {                     // 16 scores -> 8 packed columns
                     uint32_t pp[8], pd[8];
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {

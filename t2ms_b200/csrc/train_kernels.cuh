@@ -38,6 +38,7 @@ struct GemmArgs {
     // persistent form only: when set, C is not written; the tile (+ bias) goes out as the fp16 T8 operand images of the
     // fused attention (train_attn.cuh): N = 384 = q | k | v, each 4 heads x 32 features; rows = sequence * 480 + token
     __half* qkv_img;
+    int img_ntok;       // tokens per sequence of those images (480 | 800 | 1024)
 };
 constexpr int G_BM = 128, G_BK = 32, G_STAGES = 3, G_THREADS = 160;
 constexpr int G_STAGE_BYTES = 2 * G_BM * G_BK * 4;                     // A tile + B tile (B sized for bn = 128)
@@ -406,15 +407,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_tf32_persistent_kernel(cons
                 // warp writes 4 x 128 contiguous bytes
                 const int gm = m0 + wq * 32 + lane;
                 if (gm < p.M) {
-                    const int sq = gm / NTOK, tok = gm - sq * NTOK, which = n0 >> 7;
-                    __half* base = p.qkv_img + ((size_t)sq * NHEAD * 3 + which) * (NTOK * HD) + (tok >> 3) * 256 + (tok & 7) * 8;
+                    const int ntok = p.img_ntok, sq = gm / ntok, tok = gm - sq * ntok, which = n0 >> 7;
+                    __half* base = p.qkv_img + ((size_t)sq * NHEAD * 3 + which) * ((size_t)ntok * HD) + (tok >> 3) * 256 + (tok & 7) * 8;
                     const float* srow = stg + lane * pitch;
 #pragma unroll 4
                     for (int hc = 0; hc < 16; ++hc) {            // head hc / 4, feature chunk hc % 4
                         const float4 a = ld4(srow + hc * 8), b = ld4(srow + hc * 8 + 4);
                         float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
                         if (p.bias != nullptr) { b0 = ld4(p.bias + n0 + hc * 8); b1 = ld4(p.bias + n0 + hc * 8 + 4); }
-                        *reinterpret_cast<uint4*>(base + (size_t)(hc >> 2) * 3 * (NTOK * HD) + (hc & 3) * 64) =
+                        *reinterpret_cast<uint4*>(base + (size_t)(hc >> 2) * 3 * ((size_t)ntok * HD) + (hc & 3) * 64) =
                             make_uint4(pack_h2(fmaf(a.x, p.alpha, b0.x), fmaf(a.y, p.alpha, b0.y)), pack_h2(fmaf(a.z, p.alpha, b0.z), fmaf(a.w, p.alpha, b0.w)),
                                        pack_h2(fmaf(b.x, p.alpha, b1.x), fmaf(b.y, p.alpha, b1.y)), pack_h2(fmaf(b.z, p.alpha, b1.z), fmaf(b.w, p.alpha, b1.w)));
                     }
@@ -455,10 +456,11 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 __device__ __forceinline__ float4 round4(float4 v) { return make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w)); }
 
-// Row kernels over [T][128] buffers use: grid (nseq, 8), block 256 = 8 warps; a CTA owns 60 tokens of one sequence,
+// Row kernels over [T][128] buffers use: grid (nseq, tokens / rc), block 256 = 8 warps; a CTA owns rc tokens of one sequence
+// (rc = 60 | 50 | 64 for the 480 | 800 | 1024-token shapes; the token count is gridDim.y * rc),
 // a warp walks rows, a lane owns 4 consecutive features (float4).  Per-sequence / per-feature sums are reduced
 // across the CTA's warps in shared memory and added to the global accumulators with one atomic per feature.
-constexpr int ROW_THREADS = 256, ROW_CHUNK = 60;
+constexpr int ROW_THREADS = 256;
 __device__ __forceinline__ void cta_feature_atomic(float4 acc, float* __restrict__ dst, float (*sm)[D]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     st4(&sm[warp][lane * 4], acc);
@@ -487,15 +489,17 @@ __global__ void cond_act_kernel(float* __restrict__ sc, const float* __restrict_
 // ---- patchify + conv + patch_emb + pos_embed (transformer.py:166-172): h0 [T][128], xp [T][4] (patch pixels)
 __global__ void __launch_bounds__(ROW_THREADS) embed_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w_embed,
                                                                const float* __restrict__ b_embed, const float* __restrict__ pos,
-                                                               float* __restrict__ h0, float* __restrict__ xp, int nseq) {
+                                                               float* __restrict__ h0, float* __restrict__ xp, int nseq, int rc) {
+    [[maybe_unused]] const int ntok = gridDim.y * rc, latp = ntok >> 4, lat = LATC * latp;   // tokens per sequence, latent width
+
     const int seq = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float* xs = x + (size_t)seq * LAT;
-    for (int tl = warp; tl < ROW_CHUNK; tl += ROW_THREADS / 32) {
-        const int n = blockIdx.y * ROW_CHUNK + tl, i = n >> 5, j = n & 31;
+    const float* xs = x + (size_t)seq * lat;
+    for (int tl = warp; tl < rc; tl += ROW_THREADS / 32) {
+        const int n = blockIdx.y * rc + tl, i = n >> 5, j = n & 31;
         float xv[4];
 #pragma unroll
-        for (int pq = 0; pq < 4; ++pq) xv[pq] = xs[(2 * j + (pq & 1)) * LATP + 2 * i + (pq >> 1)];
-        const size_t row = (size_t)seq * NTOK + n;
+        for (int pq = 0; pq < 4; ++pq) xv[pq] = xs[(2 * j + (pq & 1)) * latp + 2 * i + (pq >> 1)];
+        const size_t row = (size_t)seq * ntok + n;
         if (lane == 0) st4(xp + row * 4, make_float4(xv[0], xv[1], xv[2], xv[3]));
         float r[4];
 #pragma unroll
@@ -510,12 +514,14 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_fwd_kernel(const float* __r
 
 // ---- a = LN(h; eps, no affine) * (1 + scale) + shift    (transformer.py:7-8,102-103,116-117)
 __global__ void __launch_bounds__(ROW_THREADS) ln_mod_fwd_kernel(const float* __restrict__ h, const float* __restrict__ mod, int mod_stride,
-                                                                int shift_off, float* __restrict__ a, float eps) {
+                                                                int shift_off, float* __restrict__ a, float eps, int rc) {
+    [[maybe_unused]] const int ntok = gridDim.y * rc, latp = ntok >> 4, lat = LATC * latp;   // tokens per sequence, latent width
+
     const int seq = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float4 sh = ld4(mod + (size_t)seq * mod_stride + shift_off + lane * 4);
     const float4 sc = ld4(mod + (size_t)seq * mod_stride + shift_off + D + lane * 4);
-    for (int tl = warp; tl < ROW_CHUNK; tl += ROW_THREADS / 32) {
-        const size_t row = (size_t)seq * NTOK + blockIdx.y * ROW_CHUNK + tl;
+    for (int tl = warp; tl < rc; tl += ROW_THREADS / 32) {
+        const size_t row = (size_t)seq * ntok + blockIdx.y * rc + tl;
         const float4 v = ld4(h + row * D + lane * 4);
         const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.f / D);
         const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
@@ -528,13 +534,15 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_mod_fwd_kernel(const float* __
 // ---- backward of the above: da -> dshift, dscale (per sequence), dh_out = dh_in + LN'(da * (1 + scale))
 __global__ void __launch_bounds__(ROW_THREADS) ln_mod_bwd_kernel(const float* __restrict__ da, const float* __restrict__ h,
                                                                 const float* __restrict__ mod, float* __restrict__ dmod, int mod_stride,
-                                                                int shift_off, const float* __restrict__ dh_in, float* __restrict__ dh_out, float eps) {
+                                                                int shift_off, const float* __restrict__ dh_in, float* __restrict__ dh_out, float eps, int rc) {
+    [[maybe_unused]] const int ntok = gridDim.y * rc, latp = ntok >> 4, lat = LATC * latp;   // tokens per sequence, latent width
+
     __shared__ float sm[ROW_THREADS / 32][D];
     const int seq = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float4 sc = ld4(mod + (size_t)seq * mod_stride + shift_off + D + lane * 4);
     float4 dsh = make_float4(0.f, 0.f, 0.f, 0.f), dsc = dsh;
-    for (int tl = warp; tl < ROW_CHUNK; tl += ROW_THREADS / 32) {
-        const size_t row = (size_t)seq * NTOK + blockIdx.y * ROW_CHUNK + tl;
+    for (int tl = warp; tl < rc; tl += ROW_THREADS / 32) {
+        const size_t row = (size_t)seq * ntok + blockIdx.y * rc + tl;
         const float4 v = ld4(h + row * D + lane * 4), g = ld4(da + row * D + lane * 4);
         const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.f / D);
         const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
@@ -558,11 +566,13 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_mod_bwd_kernel(const float* __
 // ---- h_out = h_in + gate * y     (transformer.py:116-117)
 __global__ void __launch_bounds__(ROW_THREADS) gate_res_fwd_kernel(const float* __restrict__ h_in, const float* __restrict__ y,
                                                                   const float* __restrict__ mod, int mod_stride, int gate_off,
-                                                                  float* __restrict__ h_out) {
+                                                                  float* __restrict__ h_out, int rc) {
+    [[maybe_unused]] const int ntok = gridDim.y * rc, latp = ntok >> 4, lat = LATC * latp;   // tokens per sequence, latent width
+
     const int seq = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float4 g = ld4(mod + (size_t)seq * mod_stride + gate_off + lane * 4);
-    for (int tl = warp; tl < ROW_CHUNK; tl += ROW_THREADS / 32) {
-        const size_t o = ((size_t)seq * NTOK + blockIdx.y * ROW_CHUNK + tl) * D + lane * 4;
+    for (int tl = warp; tl < rc; tl += ROW_THREADS / 32) {
+        const size_t o = ((size_t)seq * ntok + blockIdx.y * rc + tl) * D + lane * 4;
         const float4 a = ld4(h_in + o), b = ld4(y + o);
         st4(h_out + o, make_float4(fmaf(g.x, b.x, a.x), fmaf(g.y, b.y, a.y), fmaf(g.z, b.z, a.z), fmaf(g.w, b.w, a.w)));
     }
@@ -570,13 +580,15 @@ __global__ void __launch_bounds__(ROW_THREADS) gate_res_fwd_kernel(const float* 
 // backward: dgate[seq] += sum_n dh * y ; dy = dh * gate ; dbias += sum_rows dy
 __global__ void __launch_bounds__(ROW_THREADS) gate_res_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ y,
                                                                   const float* __restrict__ mod, float* __restrict__ dmod, int mod_stride,
-                                                                  int gate_off, float* __restrict__ dy, float* __restrict__ dbias) {
+                                                                  int gate_off, float* __restrict__ dy, float* __restrict__ dbias, int rc) {
+    [[maybe_unused]] const int ntok = gridDim.y * rc, latp = ntok >> 4, lat = LATC * latp;   // tokens per sequence, latent width
+
     __shared__ float sm[ROW_THREADS / 32][D];
     const int seq = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float4 g = ld4(mod + (size_t)seq * mod_stride + gate_off + lane * 4);
     float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
-    for (int tl = warp; tl < ROW_CHUNK; tl += ROW_THREADS / 32) {
-        const size_t o = ((size_t)seq * NTOK + blockIdx.y * ROW_CHUNK + tl) * D + lane * 4;
+    for (int tl = warp; tl < rc; tl += ROW_THREADS / 32) {
+        const size_t o = ((size_t)seq * ntok + blockIdx.y * rc + tl) * D + lane * 4;
         const float4 a = ld4(dh + o), b = ld4(y + o);
         dg.x = fmaf(a.x, b.x, dg.x); dg.y = fmaf(a.y, b.y, dg.y); dg.z = fmaf(a.z, b.z, dg.z); dg.w = fmaf(a.w, b.w, dg.w);
         const float4 r = make_float4(a.x * g.x, a.y * g.y, a.z * g.z, a.w * g.w);
@@ -640,7 +652,9 @@ __global__ void __launch_bounds__(ROW_THREADS) final_kernel(const float* __restr
                                                            const float* __restrict__ target, const float* __restrict__ dpred, float dscale,
                                                            float* __restrict__ loss_sum,
                                                            float* __restrict__ dh, float* __restrict__ dlnw, float* __restrict__ dlnb,
-                                                           float* __restrict__ dwf, float* __restrict__ dbf) {
+                                                           float* __restrict__ dwf, float* __restrict__ dbf, int rc) {
+    [[maybe_unused]] const int ntok = gridDim.y * rc, latp = ntok >> 4, lat = LATC * latp;   // tokens per sequence, latent width
+
     __shared__ float sm[ROW_THREADS / 32][D];
     const int seq = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float4 w4 = ld4(lnw + lane * 4), b4 = ld4(lnb + lane * 4);
@@ -649,9 +663,9 @@ __global__ void __launch_bounds__(ROW_THREADS) final_kernel(const float* __restr
     for (int c = 0; c < 4; ++c) wfr[c] = ld4(wf + c * D + lane * 4);
     float4 a_lnw = make_float4(0.f, 0.f, 0.f, 0.f), a_lnb = a_lnw, a_wf[4] = {a_lnw, a_lnw, a_lnw, a_lnw};
     float a_bf[4] = {0.f, 0.f, 0.f, 0.f}, a_loss = 0.f;
-    for (int tl = warp; tl < ROW_CHUNK; tl += ROW_THREADS / 32) {
-        const int n = blockIdx.y * ROW_CHUNK + tl, i = n >> 5, j = n & 31;
-        const size_t row = (size_t)seq * NTOK + n;
+    for (int tl = warp; tl < rc; tl += ROW_THREADS / 32) {
+        const int n = blockIdx.y * rc + tl, i = n >> 5, j = n & 31;
+        const size_t row = (size_t)seq * ntok + n;
         const float4 v = ld4(h + row * D + lane * 4);
         const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.f / D);
         const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
@@ -662,7 +676,7 @@ __global__ void __launch_bounds__(ROW_THREADS) final_kernel(const float* __restr
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             o4[c] = warp_sum(y.x * wfr[c].x + y.y * wfr[c].y + y.z * wfr[c].z + y.w * wfr[c].w) + bf[c];
-            const size_t xi = (size_t)seq * LAT + (2 * j + (c & 1)) * LATP + 2 * i + (c >> 1);
+            const size_t xi = (size_t)seq * lat + (2 * j + (c & 1)) * latp + 2 * i + (c >> 1);
             if (lane == 0 && pred != nullptr) pred[xi] = o4[c];
             d4[c] = 0.f;
             if (target != nullptr) {
@@ -720,14 +734,16 @@ __global__ void __launch_bounds__(ROW_THREADS) final_kernel(const float* __restr
 
 // ---- patch-embedding backward reductions: m4[c][pq] += sum_rows dh0[row][c] * xp[row][pq] ; s[c] += sum_rows dh0[row][c]
 // out: [128][5] (m4 | s)
-__global__ void __launch_bounds__(ROW_THREADS) embed_bwd_kernel(const float* __restrict__ dh0, const float* __restrict__ xp, float* __restrict__ out) {
+__global__ void __launch_bounds__(ROW_THREADS) embed_bwd_kernel(const float* __restrict__ dh0, const float* __restrict__ xp, float* __restrict__ out, int rc) {
+    [[maybe_unused]] const int ntok = gridDim.y * rc, latp = ntok >> 4, lat = LATC * latp;   // tokens per sequence, latent width
+
     __shared__ float sm[ROW_THREADS / 32][D];
     const int seq = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 acc[5];
 #pragma unroll
     for (int q = 0; q < 5; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int tl = warp; tl < ROW_CHUNK; tl += ROW_THREADS / 32) {
-        const size_t row = (size_t)seq * NTOK + blockIdx.y * ROW_CHUNK + tl;
+    for (int tl = warp; tl < rc; tl += ROW_THREADS / 32) {
+        const size_t row = (size_t)seq * ntok + blockIdx.y * rc + tl;
         const float4 g = ld4(dh0 + row * D + lane * 4), x4 = ld4(xp + row * 4);
         const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
@@ -780,9 +796,10 @@ __global__ void embed_bwd_finish_kernel(const float* __restrict__ red, const flo
 // ---- training inputs: rectified-flow interpolation (rectified_flow.py:8-12, train.py:69-71) and DDPM q_sample
 // (DDPM.py:19-27, train.py:73-75).  kind 0: x_t = t x1 + (1-t) x0, target = x1 - x0;  kind 1: x_t = ca[b] x1 + cb[b] eps, target = eps
 __global__ void make_train_inputs_kernel(int kind, const float* __restrict__ x1, const float* __restrict__ nz, const float* __restrict__ ca,
-                                         const float* __restrict__ cb, float* __restrict__ xt, float* __restrict__ target, size_t n) {
+                                         const float* __restrict__ cb, float* __restrict__ xt, float* __restrict__ target, size_t n, int lat) {
+
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = i / LAT;
+        const size_t b = i / lat;
         const float a = x1[i], z = nz[i];
         if (kind == 0) {
             const float t = ca[b];

@@ -160,8 +160,6 @@ class Transformer(nn.Module):
         if not input.is_cuda:
             raise RuntimeError("t2ms_b200.Transformer.forward needs CUDA tensors (no CPU fallback)")
         if torch.is_grad_enabled() and any(p.requires_grad for _, p in self._own_params()) and self.training:
-            if self.H != 30:
-                raise RuntimeError("t2ms_b200: the training step is built for the T2S shape (H = 30) only")
             from .training import dit_forward_autograd
             return dit_forward_autograd(self, input, t, text_input)
         return dit_forward(self, input, t, text_input)

@@ -38,8 +38,9 @@ def trainable_names() -> List[str]:
     return names
 
 
-def _struct(tensors: Dict[str, torch.Tensor], pos: Optional[torch.Tensor], freqs: Optional[torch.Tensor]) -> _lib.DitParams:
+def _struct(tensors: Dict[str, torch.Tensor], pos: Optional[torch.Tensor], freqs: Optional[torch.Tensor], latent_h: int = 30) -> _lib.DitParams:
     st = _lib.DitParams()
+    st.latent_h = int(latent_h)
     for name, field in _TOP.items():
         setattr(st, field, tensors[name].data_ptr())
     for l in range(N_LAYER):
@@ -69,10 +70,12 @@ class _Workspace:
         self.buf = None
         self.nseq = 0
 
-    def get(self, nseq: int, device) -> Tuple[int, int]:
+    def get(self, nseq: int, device, latent_h: int = 30) -> Tuple[int, int]:
         lib = _lib.load()
-        nbytes = lib.t2s_train_workspace_bytes(nseq)
-        if self.buf is None or self.nseq < nseq or self.buf.device != device:
+        nbytes = lib.t2s_train_workspace_bytes_h(nseq, latent_h)
+        if nbytes == 0:
+            raise RuntimeError("t2s_train_workspace_bytes_h: " + lib.t2s_last_error().decode(errors="replace"))
+        if self.buf is None or self.buf.numel() < nbytes + 256 or self.buf.device != device:
             self.buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
             self.nseq = nseq
         return _aligned_ptr(self.buf), nbytes
@@ -110,11 +113,11 @@ def _own_trainable(model) -> Dict[str, torch.nn.Parameter]:
     return {n: named[n] for n in trainable_names()}
 
 
-def _prep_inputs(x, t, text):
+def _prep_inputs(x, t, text, latent_h: int = 30):
     if not x.is_cuda:
         raise RuntimeError("t2ms_b200 training needs CUDA tensors (no CPU / PyTorch fallback)")
     B = x.shape[0]
-    assert tuple(x.shape[1:]) == (64, 30), f"latent must be (B,64,30), got {tuple(x.shape)}"
+    assert tuple(x.shape[1:]) == (64, latent_h), f"latent must be (B,64,{latent_h}), got {tuple(x.shape)}"
     x = x.detach().to(torch.float32).contiguous()
     t100 = (t.detach() * 100.0).to(device=x.device, dtype=torch.float32).contiguous()       # transformer.py:31
     assert t100.shape == (B,)
@@ -136,9 +139,9 @@ class _DitFunction(torch.autograd.Function):
             if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
                 raise RuntimeError(f"parameter {n} must be a contiguous fp32 CUDA tensor")
         dev = x.device
-        st = _struct(tensors, model.pos_embed.detach(), _freqs(dev))
+        st = _struct(tensors, model.pos_embed.detach(), _freqs(dev), model.H)
         ws = _module_ws(model)
-        ptr, nbytes = ws.get(x.shape[0], dev)
+        ptr, nbytes = ws.get(x.shape[0], dev, model.H)
         pred = torch.empty_like(x)
         with torch.cuda.device(dev):
             rc = lib.t2s_dit_train_forward(C.byref(st), x.data_ptr(), t100.data_ptr(), text.data_ptr() if text is not None else None,
@@ -156,9 +159,9 @@ class _DitFunction(torch.autograd.Function):
             raise RuntimeError("the training workspace was reused by another forward before backward() ran")
         dev = dpred.device
         gbuf = FlatBuffer(ctx.shapes, dev)
-        gst = _struct(gbuf.views(), None, None)
+        gst = _struct(gbuf.views(), None, None, model.H)
         dpred = dpred.to(torch.float32).contiguous()
-        ptr, nbytes = _module_ws(model).get(ctx.nseq, dev)
+        ptr, nbytes = _module_ws(model).get(ctx.nseq, dev, model.H)
         with torch.cuda.device(dev):
             rc = lib.t2s_dit_train_backward(C.byref(ctx.st), C.byref(gst), dpred.data_ptr(), ctx.nseq, ptr, nbytes,
                                             torch.cuda.current_stream().cuda_stream)
@@ -168,7 +171,7 @@ class _DitFunction(torch.autograd.Function):
 
 def dit_forward_autograd(model, x, t, text):
     """Transformer.forward in training mode (called from t2ms_b200.denoiser.Transformer.forward)."""
-    x, t100, text = _prep_inputs(x, t, text)
+    x, t100, text = _prep_inputs(x, t, text, model.H)
     params = [p for p in _own_trainable(model).values()]
     return _DitFunction.apply(model, x, t100, text, *params)
 
@@ -198,8 +201,10 @@ class DitTrainer:
                 v.copy_(p.data)
                 p.data = v
                 p.grad = self.grads.view(n)
-        self._pst = _struct(self.params.views(), model.pos_embed.detach(), _freqs(dev))
-        self._gst = _struct(self.grads.views(), None, None)
+        self.H = int(getattr(model, "H", 30))
+        self.lat = 64 * self.H
+        self._pst = _struct(self.params.views(), model.pos_embed.detach(), _freqs(dev), self.H)
+        self._gst = _struct(self.grads.views(), None, None, self.H)
         self.ws = _Workspace()
         self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_count = 0
@@ -212,11 +217,11 @@ class DitTrainer:
     def forward_backward(self, x_t, t, emb, target, loss_numel: Optional[float] = None, backward: bool = True, pred=None):
         """Accumulates dL/dparam into ``self.grads`` and sum((pred-target)^2) into ``self.loss_sum``."""
         lib = _lib.load()
-        x_t, t100, emb = _prep_inputs(x_t, t, emb)
+        x_t, t100, emb = _prep_inputs(x_t, t, emb, self.H)
         target = target.detach().to(torch.float32).contiguous()
         B = x_t.shape[0]
-        numel = float(loss_numel if loss_numel is not None else B * 1920)
-        ptr, nbytes = self.ws.get(B, self.device)
+        numel = float(loss_numel if loss_numel is not None else B * self.lat)
+        ptr, nbytes = self.ws.get(B, self.device, self.H)
         with torch.cuda.device(self.device):
             rc = lib.t2s_dit_train_step(C.byref(self._pst), C.byref(self._gst) if backward else None, x_t.data_ptr(), t100.data_ptr(),
                                         emb.data_ptr() if emb is not None else None, target.data_ptr(), self.loss_sum.data_ptr(),
@@ -256,8 +261,8 @@ class DitTrainer:
             ab = ddpm.alpha_bar.to(x1.device).gather(-1, t.to(x1.device))
             kind, ca, cb = 1, (ab ** 0.5).contiguous(), ((1 - ab) ** 0.5).contiguous()
         with torch.cuda.device(x1.device):
-            rc = lib.t2s_train_make_inputs(kind, x1.data_ptr(), noise.data_ptr(), ca.data_ptr(), cb.data_ptr() if cb is not None else None,
-                                           xt.data_ptr(), target.data_ptr(), x1.shape[0], torch.cuda.current_stream().cuda_stream)
+            rc = lib.t2s_train_make_inputs_h(kind, x1.data_ptr(), noise.data_ptr(), ca.data_ptr(), cb.data_ptr() if cb is not None else None,
+                                             xt.data_ptr(), target.data_ptr(), x1.shape[0], self.H, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "t2s_train_make_inputs")
         return xt, target
 
@@ -267,7 +272,7 @@ class DitTrainer:
         import torch.distributed as dist
         world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
         B = x_t.shape[0]
-        numel = float(B * 1920 * world)                                  # global mean (equal shards)
+        numel = float(B * self.lat * world)                              # global mean (equal shards)
         self.zero_grad()
         mb = B if not micro_batch else min(int(micro_batch), B)
         for b0 in range(0, B, mb):
@@ -284,12 +289,14 @@ class DitTrainer:
         """One optimizer step exactly as the reference loop does it for a length-grouped sub-batch:
         frozen LA-VAE encoder (train.py:66), t / noise draws and create_flow | q_sample (:68-76), the per-BATCH
         classifier-free-guidance dropout coin (:80-82, shared by all data-parallel ranks), forward, MSE, backward,
-        gradient all-reduce, AdamW (:83-87).  ``series`` (B,L) or an already encoded latent (B,64,30)."""
+        gradient all-reduce, AdamW (:83-87).  ``series`` (B,L) [or (B,input_dim,L) with the fork's multivariate encoder,
+        mytrain.py] or an already encoded latent (B,64,H)."""
         import torch.distributed as dist
         dev = self.device
         enc = encoder if encoder is not None else getattr(self.model, "encoder", None)
         with torch.no_grad():
-            x1 = series if series.dim() == 3 else enc(series.to(dev))[0]
+            is_latent = series.dim() == 3 and tuple(series.shape[1:]) == (64, self.H)
+            x1 = series if is_latent else enc(series.to(dev))[0]
         B = x1.shape[0]
         if backbone in ("flowmatching", "rf", "rectified_flow"):
             t = torch.round(torch.rand(B, device=dev, generator=generator) * total_step) / total_step          # train.py:69

@@ -100,3 +100,64 @@ def test_fork_generation_loop_with_multivariate_lavae():
     with torch.no_grad():
         z_enc, _ = m.encoder(torch.rand(B, 7, L, device=DEV))   # the attached encoder still runs (myinfer.py:117)
     assert z_enc.shape == (B, 64, 50)
+
+
+@pytest.mark.parametrize("dim", [50, 64])
+def test_wide_training_step_matches_fork_golden(dim):
+    """Training step of the fork's Transformer(dim) (mytrain.py:66-87): prediction, loss and every parameter gradient
+    against golden vectors from model/denoiser/mytransformer.py.  Same tolerances as the T2S shape
+    (tests/test_gpu_train.py): prediction rel-L2 2e-3, loss 2e-3 relative, gradients rel-L2 1e-2 (tf32 / fp16 operands)."""
+    from t2ms_b200.training import DitTrainer, trainable_names
+    g = load_golden("dit_tokens_train.npz")
+    k = f"h{dim}/"
+    sd = synth.make_dit_state(140 + dim, bias_std=0.02, dim=dim)
+    m = Transformer(dim)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).train()
+    x1, x0 = synth.make_noise(3, seed=150 + dim, dim=dim), synth.make_noise(3, seed=160 + dim, dim=dim)
+    emb, t = synth.make_text_embeddings(3, seed=170 + dim), torch.tensor([0.2, 0.55, 0.9])
+    tr = DitTrainer(m)
+    x_t, target = tr.make_inputs("flowmatching", x1.to(DEV), x0.to(DEV), t.to(DEV))
+    assert max_abs(x_t, O.rf_create_flow(x1, t, x0)) < 1e-6 and max_abs(target, x1 - x0) < 1e-6
+    tr.zero_grad()
+    pred = torch.empty(3, 64, dim, device=DEV)
+    tr.forward_backward(x_t, t.to(DEV), emb.to(DEV), target, pred=pred)
+    torch.cuda.synchronize()
+    assert rel_l2(pred, T(g[k + "pred"])) < 2e-3
+    loss = tr.loss_sum.item() / (3 * 64 * dim)
+    assert abs(loss - float(g[k + "loss"])) <= 2e-3 * float(g[k + "loss"])
+    worst = 0.0
+    for n, ref_norm in zip([str(x) for x in g[k + "names"]], g[k + "grad_norms"]):
+        gr = tr.grads.view(n)
+        assert abs(gr.norm().item() - float(ref_norm)) <= 1e-2 * float(ref_norm), (n, gr.norm().item(), float(ref_norm))
+        e = rel_l2(gr.reshape(-1)[:128], T(g[k + "grad/" + n]))
+        worst = max(worst, e)
+        assert e < 1e-2, (n, e)
+    assert sorted(str(x) for x in g[k + "names"]) == sorted(trainable_names())
+    print(dim, "worst gradient-slice rel-L2 %.2e" % worst)
+
+
+def test_wide_training_through_autograd_and_optimizer():
+    """The reference-style loop of mytrain.py (model(...), loss.backward(), optimizer.step()) on Transformer(64) in training
+    mode: gradients equal the oracle's, a step changes the parameters."""
+    dim, B = 64, 5
+    sd = synth.make_dit_state(9, bias_std=0.02, dim=dim)
+    m = Transformer(dim)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).train()
+    x1, x0 = synth.make_noise(B, seed=1, dim=dim), synth.make_noise(B, seed=2, dim=dim)
+    emb, t = synth.make_text_embeddings(B, seed=3), torch.linspace(0.05, 0.95, B)
+    x_t, target = O.rf_create_flow(x1, t, x0), x1 - x0
+    opt = torch.optim.AdamW([p for n, p in m.named_parameters() if p.requires_grad], lr=1e-4, weight_decay=0)
+    pred = m(input=x_t.to(DEV), t=t.to(DEV), text_input=emb.to(DEV))
+    loss = torch.nn.functional.mse_loss(pred, target.to(DEV))
+    opt.zero_grad()
+    loss.backward()
+    loss_ref, grads = O.train_step_grads(sd, x_t, t, emb, target)
+    assert abs(loss.item() - loss_ref.item()) <= 2e-3 * loss_ref.item()
+    named = dict(m.named_parameters())
+    for n in ("layers.0.attn.qkv.weight", "layers.3.mlp.fc2.weight", "patch_emb.weight", "layers.2.adaLN_modulation.1.bias", "ln.weight"):
+        assert rel_l2(named[n].grad, grads[n]) < 1e-2, n
+    before = named["layers.1.attn.proj.weight"].detach().clone()
+    opt.step()
+    assert (named["layers.1.attn.proj.weight"] - before).abs().max().item() > 0

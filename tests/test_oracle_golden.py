@@ -188,3 +188,21 @@ def test_lavae_training_oracle_matches_reference(case, cin, flow):
         # core.py:15: AdamW(lr 1e-3, weight_decay 1e-2), first step (LinearLR start_factor 0.1 -> lr 1e-4)
         p, _, _ = O.adamw_step(sd[n].clone(), grads[n], torch.zeros_like(sd[n]), torch.zeros_like(sd[n]), 1, 1e-4, wd=1e-2)
         close(p.reshape(-1)[:128], g[k + "after/" + n], 2e-6)
+
+
+@pytest.mark.parametrize("dim", [50, 64])
+def test_variable_width_training_oracle_matches_fork_reference(dim):
+    """oracle train_step_grads on (B,64,dim) latents against one rectified-flow training step of the fork's
+    Transformer(dim) (mytrain.py:66-87, model/denoiser/mytransformer.py)."""
+    g = load_golden("dit_tokens_train.npz")
+    k = f"h{dim}/"
+    sd = synth.make_dit_state(140 + dim, bias_std=0.02, dim=dim)
+    assert synth.state_checksum(sd) == str(g[k + "checksum"])
+    x1, x0 = synth.make_noise(3, seed=150 + dim, dim=dim), synth.make_noise(3, seed=160 + dim, dim=dim)
+    emb, t = synth.make_text_embeddings(3, seed=170 + dim), torch.tensor([0.2, 0.55, 0.9])
+    x_t, target = O.rf_create_flow(x1, t, x0), x1 - x0
+    loss, grads = O.train_step_grads(sd, x_t, t, emb, target)
+    assert abs(float(loss) - float(g[k + "loss"])) <= 1e-5 * float(g[k + "loss"])
+    for n, ref_norm in zip([str(x) for x in g[k + "names"]], g[k + "grad_norms"]):
+        assert abs(float(grads[n].norm()) - float(ref_norm)) <= 2e-4 * max(float(ref_norm), 1e-8), n
+        close(grads[n].reshape(-1)[:128], g[k + "grad/" + n], 1e-7, rtol=2e-4)

@@ -37,7 +37,7 @@ def test_flat_buffer_layout_and_param_struct():
         assert off % 64 == 0 and fb.view(n).shape == s
     assert fb.flat.numel() >= 925_592
     st = _struct(fb.views(), None, None)
-    assert ctypes.sizeof(_lib.DitParams) == (10 + 10 * 4) * 8
+    assert ctypes.sizeof(_lib.DitParams) == (10 + 10 * 4) * 8 + 8      # 50 pointers + latent_h (padded)
     assert st.qkv_w[3] == fb.view("layers.3.attn.qkv.weight").data_ptr() and st.lf_b == fb.view("linear_emb_to_patch.bias").data_ptr()
 
 
