@@ -83,6 +83,29 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// Packed fp32 arithmetic (SASS FFMA2 / FADD2): two independent fp32 operations per issue slot.
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    unsigned long long a, b, c, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    unsigned long long a, b, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    unsigned long long a, b, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
 __device__ __forceinline__ float tanh_approx(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -98,6 +121,22 @@ __device__ __forceinline__ float gelu_tanh(float x) {
     float t = tanh_approx(u);
 #endif
     return 0.5f * x * (1.0f + t);
+}
+
+// two GELU(tanh) values with packed fp32 arithmetic: 0.5 x (1 + tanh(x (k0 + k0 k1 x^2)))
+__device__ __forceinline__ void gelu_tanh2(float& y0, float& y1, float x0, float x1) {
+    const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+    float s0, s1, p0, p1, u0, u1, h0, h1;
+    mul2(s0, s1, x0, x1, x0, x1);
+    fma2(p0, p1, s0, s1, k01, k01, k0, k0);
+    mul2(u0, u1, p0, p1, x0, x1);
+#ifdef T2S_PRECISE_GELU
+    const float t0 = tanhf(u0), t1 = tanhf(u1);
+#else
+    const float t0 = tanh_approx(u0), t1 = tanh_approx(u1);
+#endif
+    mul2(h0, h1, x0, x1, 0.5f, 0.5f);
+    fma2(y0, y1, h0, h1, t0, t1, h0, h1);
 }
 
 // ---------------------------------------------------------------- async copies

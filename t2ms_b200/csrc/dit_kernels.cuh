@@ -238,10 +238,13 @@ __device__ __forceinline__ void for_blocks16(uint32_t taddr, F&& body) {
 //                    (element (col chunk c4, this row) at +c4*TILE_ROWS*4 floats).
 __device__ __forceinline__ void block_stats(const float (&a)[16], float shift, float& sum, float& sq) {
     float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+    const float ns = -shift;
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-        const float d0 = a[j] - shift, d1 = a[j + 1] - shift;
-        s0 += d0; s1 += d1; q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
+    for (int j = 0; j < 16; j += 2) {                       // packed fp32: three issue slots per pair
+        float d0, d1;
+        add2(d0, d1, a[j], a[j + 1], ns, ns);
+        add2(s0, s1, s0, s1, d0, d1);
+        fma2(q0, q1, d0, d1, d0, d1, q0, q1);
     }
     sum += s0 + s1; sq += q0 + q1;
 }
@@ -263,10 +266,11 @@ __device__ __forceinline__ HalfStats resid_pass_regs(uint32_t tacc, const float*
         for (int q = 0; q < 4; ++q) {
             const float4 g4 = *reinterpret_cast<const float4*>(gate + cb * 16 + q * 4);
             const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 16 + q * 4);
-            a[q * 4 + 0] = fmaf(g4.x, a[q * 4 + 0] + b4.x, hq[cb * 4 + q].x);
-            a[q * 4 + 1] = fmaf(g4.y, a[q * 4 + 1] + b4.y, hq[cb * 4 + q].y);
-            a[q * 4 + 2] = fmaf(g4.z, a[q * 4 + 2] + b4.z, hq[cb * 4 + q].z);
-            a[q * 4 + 3] = fmaf(g4.w, a[q * 4 + 3] + b4.w, hq[cb * 4 + q].w);
+            float t0, t1, t2, t3;
+            add2(t0, t1, a[q * 4 + 0], a[q * 4 + 1], b4.x, b4.y);
+            add2(t2, t3, a[q * 4 + 2], a[q * 4 + 3], b4.z, b4.w);
+            fma2(a[q * 4 + 0], a[q * 4 + 1], g4.x, g4.y, t0, t1, hq[cb * 4 + q].x, hq[cb * 4 + q].y);
+            fma2(a[q * 4 + 2], a[q * 4 + 3], g4.z, g4.w, t2, t3, hq[cb * 4 + q].z, hq[cb * 4 + q].w);
         }
         if (cb == 0) shift = a[0];
         block_stats(a, shift, sum, sq);
@@ -289,10 +293,11 @@ __device__ __forceinline__ HalfStats resid_pass_tmem(uint32_t tacc, uint32_t thi
         for (int q = 0; q < 4; ++q) {
             const float4 g4 = *reinterpret_cast<const float4*>(gate + cb * 16 + q * 4);
             const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 16 + q * 4);
-            a[q * 4 + 0] = fmaf(g4.x, a[q * 4 + 0] + b4.x, h[q * 4 + 0]);
-            a[q * 4 + 1] = fmaf(g4.y, a[q * 4 + 1] + b4.y, h[q * 4 + 1]);
-            a[q * 4 + 2] = fmaf(g4.z, a[q * 4 + 2] + b4.z, h[q * 4 + 2]);
-            a[q * 4 + 3] = fmaf(g4.w, a[q * 4 + 3] + b4.w, h[q * 4 + 3]);
+            float t0, t1, t2, t3;
+            add2(t0, t1, a[q * 4 + 0], a[q * 4 + 1], b4.x, b4.y);
+            add2(t2, t3, a[q * 4 + 2], a[q * 4 + 3], b4.z, b4.w);
+            fma2(a[q * 4 + 0], a[q * 4 + 1], g4.x, g4.y, t0, t1, h[q * 4 + 0], h[q * 4 + 1]);
+            fma2(a[q * 4 + 2], a[q * 4 + 3], g4.z, g4.w, t2, t3, h[q * 4 + 2], h[q * 4 + 3]);
         }
         if (cb < 3) tmem_ld16(thin + (cb + 1) * 16, h);
         if (cb == 0) shift = a[0];
@@ -325,15 +330,22 @@ __device__ __forceinline__ RowStats merge_stats(HalfStats hs, float2* slot, int 
 // packed to fp16 and stored as the next GEMM's A operand image.  kc0 = first 8-column K chunk of the half (8 hh).
 __device__ __forceinline__ void ln_mod_store(uint32_t trow, RowStats st, const float* __restrict__ shift, const float* __restrict__ scale,
                                              uint8_t* abuf, int r, int kc0) {
+    const float nmean = -st.mean;
     for_blocks16<4>(trow, [&](int cb, float (&a)[16]) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 sc = *reinterpret_cast<const float4*>(scale + cb * 16 + q * 4);
             const float4 sh = *reinterpret_cast<const float4*>(shift + cb * 16 + q * 4);
-            a[q * 4 + 0] = fmaf((a[q * 4 + 0] - st.mean) * st.rstd, 1.f + sc.x, sh.x);
-            a[q * 4 + 1] = fmaf((a[q * 4 + 1] - st.mean) * st.rstd, 1.f + sc.y, sh.y);
-            a[q * 4 + 2] = fmaf((a[q * 4 + 2] - st.mean) * st.rstd, 1.f + sc.z, sh.z);
-            a[q * 4 + 3] = fmaf((a[q * 4 + 3] - st.mean) * st.rstd, 1.f + sc.w, sh.w);
+            // ((a - mean) * rstd) * (1 + scale) + shift, packed: three issue slots per pair
+            float d0, d1, d2, d3, n0, n1, n2, n3, s0, s1, s2, s3;
+            add2(d0, d1, a[q * 4 + 0], a[q * 4 + 1], nmean, nmean);
+            add2(d2, d3, a[q * 4 + 2], a[q * 4 + 3], nmean, nmean);
+            mul2(n0, n1, d0, d1, st.rstd, st.rstd);
+            mul2(n2, n3, d2, d3, st.rstd, st.rstd);
+            add2(s0, s1, sc.x, sc.y, 1.f, 1.f);
+            add2(s2, s3, sc.z, sc.w, 1.f, 1.f);
+            fma2(a[q * 4 + 0], a[q * 4 + 1], n0, n1, s0, s1, sh.x, sh.y);
+            fma2(a[q * 4 + 2], a[q * 4 + 3], n2, n3, s2, s3, sh.z, sh.w);
         }
 #pragma unroll
         for (int c8 = 0; c8 < 2; ++c8)
@@ -350,10 +362,11 @@ __device__ __forceinline__ void gelu_store(uint32_t taddr, const float* __restri
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 16 + q * 4);
-            v[q * 4 + 0] = gelu_tanh(v[q * 4 + 0] + b4.x);
-            v[q * 4 + 1] = gelu_tanh(v[q * 4 + 1] + b4.y);
-            v[q * 4 + 2] = gelu_tanh(v[q * 4 + 2] + b4.z);
-            v[q * 4 + 3] = gelu_tanh(v[q * 4 + 3] + b4.w);
+            float x0, x1, x2, x3;
+            add2(x0, x1, v[q * 4 + 0], v[q * 4 + 1], b4.x, b4.y);
+            add2(x2, x3, v[q * 4 + 2], v[q * 4 + 3], b4.z, b4.w);
+            gelu_tanh2(v[q * 4 + 0], v[q * 4 + 1], x0, x1);
+            gelu_tanh2(v[q * 4 + 2], v[q * 4 + 3], x2, x3);
         }
 #pragma unroll
         for (int c8 = 0; c8 < 2; ++c8)
@@ -693,9 +706,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                             const float4 b0 = *reinterpret_cast<const float4*>(bq + cb * 16 + c * 8);
                             const float4 b1 = *reinterpret_cast<const float4*>(bq + cb * 16 + c * 8 + 4);
                             const float* x = v + c * 8;
-                            *reinterpret_cast<uint4*>(hb + c * dstride) =
-                                make_uint4(pack_h2(x[0] + b0.x, x[1] + b0.y), pack_h2(x[2] + b0.z, x[3] + b0.w),
-                                           pack_h2(x[4] + b1.x, x[5] + b1.y), pack_h2(x[6] + b1.z, x[7] + b1.w));
+                            float y0, y1, y2, y3, y4, y5, y6, y7;
+                            add2(y0, y1, x[0], x[1], b0.x, b0.y); add2(y2, y3, x[2], x[3], b0.z, b0.w);
+                            add2(y4, y5, x[4], x[5], b1.x, b1.y); add2(y6, y7, x[6], x[7], b1.z, b1.w);
+                            *reinterpret_cast<uint4*>(hb + c * dstride) = make_uint4(pack_h2(y0, y1), pack_h2(y2, y3), pack_h2(y4, y5), pack_h2(y6, y7));
                         }
                     }
                 });
@@ -714,8 +728,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             for_blocks16<4>(trow + HREG, [&](int cb, float (&a)[16]) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
-                    const float y0 = (a[j] - st.mean) * st.rstd, y1 = (a[j + 1] - st.mean) * st.rstd;
-                    const float y2 = (a[j + 2] - st.mean) * st.rstd, y3 = (a[j + 3] - st.mean) * st.rstd;
+                    float y0, y1, y2, y3;
+                    add2(y0, y1, a[j], a[j + 1], -st.mean, -st.mean); add2(y2, y3, a[j + 2], a[j + 3], -st.mean, -st.mean);
+                    mul2(y0, y1, y0, y1, st.rstd, st.rstd); mul2(y2, y3, y2, y3, st.rstd, st.rstd);
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const float4 w = *reinterpret_cast<const float4*>(vec + V_WFIN + c4 * D + c0 + cb * 16 + j);
@@ -1002,9 +1017,11 @@ __global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM
                 auto half = [&](const float* v, int pcol) {   // 16 scores -> 8 packed P columns
                     uint32_t pk[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float e0 = ex2_approx(fmaf(v[2 * q], sc, nb)), e1 = ex2_approx(fmaf(v[2 * q + 1], sc, nb));
-                        l0 += e0; l1 += e1;
+                    for (int q = 0; q < 8; ++q) {                 // packed fp32 (FFMA2 / FADD2): one issue slot per pair
+                        float t0, t1;
+                        fma2(t0, t1, v[2 * q], v[2 * q + 1], sc, sc, nb, nb);
+                        const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+                        add2(l0, l1, l0, l1, e0, e1);
                         pk[q] = pack_h2(e0, e1);
                     }
                     tmem_st8(ts + pcol, pk);                     // P columns: 16 per 32 scores
