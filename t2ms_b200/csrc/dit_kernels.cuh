@@ -965,9 +965,12 @@ __global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM
             if (r < QT_ROWS) {
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8)
-                    *reinterpret_cast<uint4*>(dst + c8 * 1024) =
-                        make_uint4(pack_h2(a0[c8 * 8 + 0] * inv, a0[c8 * 8 + 1] * inv), pack_h2(a0[c8 * 8 + 2] * inv, a0[c8 * 8 + 3] * inv),
-                                   pack_h2(a0[c8 * 8 + 4] * inv, a0[c8 * 8 + 5] * inv), pack_h2(a0[c8 * 8 + 6] * inv, a0[c8 * 8 + 7] * inv));
+                {
+                    float y[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) mul2(y[u], y[u + 1], a0[c8 * 8 + u], a0[c8 * 8 + u + 1], inv, inv);
+                    *reinterpret_cast<uint4*>(dst + c8 * 1024) = make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7]));
+                }
             }
         };
         float lprev = 1.f;

@@ -334,9 +334,11 @@ __global__ void __launch_bounds__(TA_THREADS, TaShape<H>::CTAS_PER_SM) ta_attn_k
                 auto half = [&](const float* v, int pcol) {   // 16 scores -> 8 packed P columns
                     uint32_t pk[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float e0 = ex2_approx(fmaf(v[2 * q], sc, nb)), e1 = ex2_approx(fmaf(v[2 * q + 1], sc, nb));
-                        l0 += e0; l1 += e1;
+                    for (int q = 0; q < 8; ++q) {                 // packed fp32 (FFMA2 / FADD2): one issue slot per pair
+                        float t0, t1;
+                        fma2(t0, t1, v[2 * q], v[2 * q + 1], sc, sc, nb, nb);
+                        const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+                        add2(l0, l1, l0, l1, e0, e1);
                         pk[q] = pack_h2(e0, e1);
                     }
                     tmem_st8(ts + pcol, pk);
@@ -396,10 +398,13 @@ __global__ void __launch_bounds__(TA_THREADS, TaShape<H>::CTAS_PER_SM) ta_attn_k
                         }
                         float pv[4], dv[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < 4; u += 2) {             // packed fp32: scale, difference and product per pair
                             const int i = h * 16 + q4 * 4 + u;
-                            pv[u] = ex2_approx(fmaf(s[i], sc, nl[u]));
-                            dv[u] = pv[u] * (g[i] - dd[u]);
+                            float t0, t1, d0, d1;
+                            fma2(t0, t1, s[i], s[i + 1], sc, sc, nl[u], nl[u + 1]);
+                            pv[u] = ex2_approx(t0); pv[u + 1] = ex2_approx(t1);
+                            add2(d0, d1, g[i], g[i + 1], -dd[u], -dd[u + 1]);
+                            mul2(dv[u], dv[u + 1], pv[u], pv[u + 1], d0, d1);
                         }
                         pp[q4 * 2] = pack_h2(pv[0], pv[1]); pp[q4 * 2 + 1] = pack_h2(pv[2], pv[3]);
                         pd[q4 * 2] = pack_h2_sat(dv[0], dv[1]); pd[q4 * 2 + 1] = pack_h2_sat(dv[2], dv[3]);
