@@ -1,5 +1,5 @@
-// Shared device helpers for the T2S sm_100a kernels: PTX wrappers (ldmatrix / mma.sync /
-// cp.async / bulk async copy + mbarrier), fragment packing and fast math.
+// Shared device helpers for the T2S sm_100a kernels: PTX wrappers (tcgen05 / TMEM, bulk async copy + mbarrier,
+// cp.async, packed fp32 arithmetic) and fast math.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -56,22 +56,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-// ---------------------------------------------------------------- tensor-core fragments
-__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-// D(16x8,f32) += A(16x16,f16,row) * B(16x8,f16,col)
-__device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                        uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -111,19 +95,9 @@ __device__ __forceinline__ float tanh_approx(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// GELU(tanh), timm Mlp act (model/denoiser/transformer.py:99)
-__device__ __forceinline__ float gelu_tanh(float x) {
-    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-    float u = k0 * (x + k1 * x * x * x);
-#ifdef T2S_PRECISE_GELU
-    float t = tanhf(u);
-#else
-    float t = tanh_approx(u);
-#endif
-    return 0.5f * x * (1.0f + t);
-}
 
-// two GELU(tanh) values with packed fp32 arithmetic: 0.5 x (1 + tanh(x (k0 + k0 k1 x^2)))
+// GELU(tanh), timm Mlp act (model/denoiser/transformer.py:99): two values with packed fp32 arithmetic,
+// 0.5 x (1 + tanh(x (k0 + k0 k1 x^2)))
 __device__ __forceinline__ void gelu_tanh2(float& y0, float& y1, float x0, float x1) {
     const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
     float s0, s1, p0, p1, u0, u1, h0, h1;
@@ -140,11 +114,7 @@ __device__ __forceinline__ void gelu_tanh2(float& y0, float& y1, float x0, float
 }
 
 // ---------------------------------------------------------------- async copies
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(dst), "l"(src) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // mbarrier + bulk async copy (the TMA engine without a tensor map: SASS UBLKCP)
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -266,15 +236,5 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
     return r;
 }
 
-__device__ __forceinline__ float quad_sum(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    return v;
-}
-__device__ __forceinline__ float quad_max(float v) {
-    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
-    return v;
-}
 
 }  // namespace t2s
