@@ -311,10 +311,11 @@ int t2s_vae_decode(const t2s_vae_dec_weights* w, const float* z, float* series, 
     memcpy(&dw, w, sizeof(dw));
     cudaStream_t st = (cudaStream_t)stream;
     const int smem = VAE_DEC_SMEM_FLOATS * 4;
+    const int nt = batch <= 148 ? 1024 : 256;          // fewer series than SMs: more threads per series
     switch (length) {
-        case 24: vae_decode_kernel<6><<<batch, 256, smem, st>>>(dw, z, series, after); break;
-        case 48: vae_decode_kernel<12><<<batch, 256, smem, st>>>(dw, z, series, after); break;
-        case 96: vae_decode_kernel<24><<<batch, 256, smem, st>>>(dw, z, series, after); break;
+        case 24: vae_decode_kernel<6><<<batch, nt, smem, st>>>(dw, z, series, after); break;
+        case 48: vae_decode_kernel<12><<<batch, nt, smem, st>>>(dw, z, series, after); break;
+        case 96: vae_decode_kernel<24><<<batch, nt, smem, st>>>(dw, z, series, after); break;
         default: return fail(T2S_EINVAL, "t2s_vae_decode: length must be 24, 48 or 96%s%s");
     }
     CUDA_OK(cudaGetLastError());
@@ -329,10 +330,11 @@ int t2s_vae_encode(const t2s_vae_enc_weights* w, const float* x, float* z, float
     memcpy(&ew, w, sizeof(ew));
     cudaStream_t st = (cudaStream_t)stream;
     const int smem = VAE_ENC_SMEM_FLOATS * 4;
+    const int nt = batch <= 148 ? 1024 : 256;
     switch (length) {
-        case 24: vae_encode_kernel<6><<<batch, 256, smem, st>>>(ew, x, z, before); break;
-        case 48: vae_encode_kernel<12><<<batch, 256, smem, st>>>(ew, x, z, before); break;
-        case 96: vae_encode_kernel<24><<<batch, 256, smem, st>>>(ew, x, z, before); break;
+        case 24: vae_encode_kernel<6><<<batch, nt, smem, st>>>(ew, x, z, before); break;
+        case 48: vae_encode_kernel<12><<<batch, nt, smem, st>>>(ew, x, z, before); break;
+        case 96: vae_encode_kernel<24><<<batch, nt, smem, st>>>(ew, x, z, before); break;
         default: return fail(T2S_EINVAL, "t2s_vae_encode: length must be 24, 48 or 96%s%s");
     }
     CUDA_OK(cudaGetLastError());

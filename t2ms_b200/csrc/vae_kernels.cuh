@@ -144,9 +144,9 @@ constexpr int VAE_LD_MAX = 24 + 2;
 constexpr int VAE_DEC_SMEM_FLOATS = LATC * LATP + VH * VAE_LD_MAX + VR * VAE_LD_MAX + VE * (2 * 24 + 2);
 constexpr int VAE_ENC_SMEM_FLOATS = (96 + 2) + VE * (2 * 24 + 2) + VH * VAE_LD_MAX + VR * VAE_LD_MAX + VH * VAE_LD_MAX;
 
-// Decoder.forward (vqvae.py:97-105).  grid = B, block = 256.  z [B][64][30] -> series [B][4*L4], after [B][64][L4]
+// Decoder.forward (vqvae.py:97-105).  grid = B, block = 256 (1024 for small batches: one series per CTA, latency-bound).  z [B][64][30] -> series [B][4*L4], after [B][64][L4]
 template <int L4>
-__global__ void __launch_bounds__(256) vae_decode_kernel(const VaeDecWeights w, const float* __restrict__ z, float* __restrict__ series,
+__global__ void __launch_bounds__(1024) vae_decode_kernel(const VaeDecWeights w, const float* __restrict__ z, float* __restrict__ series,
                                                          float* __restrict__ after) {
     extern __shared__ __align__(16) float sm[];
     constexpr int LD = L4 + 2, NP = 6;
@@ -155,25 +155,25 @@ __global__ void __launch_bounds__(256) vae_decode_kernel(const VaeDecWeights w, 
     float* hid = xa + VH * LD;               // [256][LD]
     float* ct = hid + VR * LD;               // [64][2*L4+2]
     const int b = blockIdx.x, tid = threadIdx.x;
-    for (int i = tid; i < LATC * LATP; i += 256) zs[i] = z[(size_t)b * LAT + i];
-    for (int i = tid; i < VR * LD; i += 256) hid[i] = 0.f;
-    for (int i = tid; i < VH * LD; i += 256) xa[i] = 0.f;
-    for (int i = tid; i < VE * (2 * L4 + 2); i += 256) ct[i] = 0.f;
+    for (int i = tid; i < LATC * LATP; i += blockDim.x) zs[i] = z[(size_t)b * LAT + i];
+    for (int i = tid; i < VR * LD; i += blockDim.x) hid[i] = 0.f;
+    for (int i = tid; i < VH * LD; i += blockDim.x) xa[i] = 0.f;
+    for (int i = tid; i < VE * (2 * L4 + 2); i += blockDim.x) ct[i] = 0.f;
     __syncthreads();
     // interpolate 30 -> L4 into hid[0..63] (halo 1) and emit `after`
     interp_rows(zs, LATP, LATP, hid, LD, 1, L4, LATC);
     __syncthreads();
     if (after)
-        for (int i = tid; i < LATC * L4; i += 256) after[(size_t)b * LATC * L4 + i] = hid[(i / L4) * LD + 1 + (i % L4)];
+        for (int i = tid; i < LATC * L4; i += blockDim.x) after[(size_t)b * LATC * L4 + i] = hid[(i / L4) * LD + 1 + (i % L4)];
     conv_rows<3, 1, NP>(hid, LD, LATC, w.conv1_w, w.conv1_b, VH, L4, xa, LD, 1, false, nullptr, 0, 0);
     __syncthreads();
-    for (int i = tid; i < LATC * LD; i += 256) hid[i] = 0.f;   // restore halo/zero state of the scratch rows
+    for (int i = tid; i < LATC * LD; i += blockDim.x) hid[i] = 0.f;   // restore halo/zero state of the scratch rows
     __syncthreads();
     residual_stack<NP>(xa, hid, LD, L4, w.res_w3, w.res_w1);
     convT_rows<NP>(xa, LD, VH, w.ct1_w, w.ct1_b, VE, L4, ct, 2 * L4 + 2, 1, true);
     __syncthreads();
     // conv_trans_2: 64 -> 1, out length 4*L4
-    for (int o = tid; o < 4 * L4; o += 256) {
+    for (int o = tid; o < 4 * L4; o += blockDim.x) {
         const int m = o >> 1;
         float acc = w.ct2_b[0];
         if ((o & 1) == 0) {
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) vae_decode_kernel(const VaeDecWeights w, 
 
 // Encoder.forward (vqvae.py:57-71).  x [B][4*L4] -> z [B][64][30], before [B][64][L4]
 template <int L4>
-__global__ void __launch_bounds__(256) vae_encode_kernel(const VaeEncWeights w, const float* __restrict__ x, float* __restrict__ z,
+__global__ void __launch_bounds__(1024) vae_encode_kernel(const VaeEncWeights w, const float* __restrict__ x, float* __restrict__ z,
                                                          float* __restrict__ before) {
     extern __shared__ __align__(16) float sm[];
     constexpr int L = 4 * L4, L2 = 2 * L4, LD = L4 + 2, NP = 6;
@@ -199,9 +199,9 @@ __global__ void __launch_bounds__(256) vae_encode_kernel(const VaeEncWeights w, 
     float* hid = xa + VH * VAE_LD_MAX;      // [256][LD]
     float* xb = hid + VR * VAE_LD_MAX;      // [128][LD]
     const int b = blockIdx.x, tid = threadIdx.x;
-    for (int i = tid; i < VAE_ENC_SMEM_FLOATS; i += 256) sm[i] = 0.f;
+    for (int i = tid; i < VAE_ENC_SMEM_FLOATS; i += blockDim.x) sm[i] = 0.f;
     __syncthreads();
-    for (int i = tid; i < L; i += 256) xs[1 + i] = x[(size_t)b * L + i];
+    for (int i = tid; i < L; i += blockDim.x) xs[1 + i] = x[(size_t)b * L + i];
     __syncthreads();
     conv_rows<4, 2, NP>(xs, 0, 1, w.conv1_w, w.conv1_b, VE, L2, c1, L2 + 2, 1, true, nullptr, 0, 0);
     __syncthreads();
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) vae_encode_kernel(const VaeEncWeights w, 
     conv_rows<1, 1, NP>(xa + 1, LD, VH, w.pre_w, w.pre_b, VE, L4, xb, LD, 0, false, nullptr, 0, 0);
     __syncthreads();
     if (before)
-        for (int i = tid; i < VE * L4; i += 256) before[(size_t)b * VE * L4 + i] = xb[(i / L4) * LD + (i % L4)];
+        for (int i = tid; i < VE * L4; i += blockDim.x) before[(size_t)b * VE * L4 + i] = xb[(i / L4) * LD + (i % L4)];
     interp_rows(xb, LD, L4, z + (size_t)b * LAT, LATP, 0, LATP, VE);
 }
 
