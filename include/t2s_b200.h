@@ -114,6 +114,15 @@ int t2s_sample(const t2s_dit_weights* w, int kind, float* x, const float* emb, c
                const float* step_noise, float* pred_trace, int batch, int steps, float cfg_scale,
                void* workspace, size_t workspace_bytes, t2s_stream_t stream);
 
+/* The DDPM loop of t2s_sample with the Gaussian noise of DDPM.p_sample (model/backbone/DDPM.py:35) generated inside the
+ * update kernel: Philox4x32-10 keyed by `seed` on the counter (element index in [batch][64][H], step j, 0, 0), first two
+ * words -> u1 = ((w0 >> 8) + 1) 2^-24, u2 = (w1 >> 8) 2^-24 -> sqrt(-2 ln u1) cos(2 pi u2).  No noise tensor, no RNG
+ * kernel between steps.  The element index is local to the call: callers that split a batch over calls / ranks give
+ * every part its own seed. */
+int t2s_sample_ddpm_seeded(const t2s_dit_weights* w, float* x, const float* emb, const float* t100, const float* coef,
+                           unsigned long long seed, float* pred_trace, int batch, int steps, float cfg_scale,
+                           void* workspace, size_t workspace_bytes, t2s_stream_t stream);
+
 /* Decoder.forward (model/pretrained/vqvae.py:97-105): z [batch][64][30] -> series [batch][length]
  * (length in {24,48,96}), after [batch][64][length/4] or NULL. */
 int t2s_vae_decode(const t2s_vae_dec_weights* w, const float* z, float* series, float* after, int batch, int length,

@@ -364,3 +364,35 @@ def calculate_wape(ori_data, gen_data) -> float:
     den = np.abs(ori).reshape(ori.shape[0], -1).sum(axis=1)
     ratio = np.where(den != 0, num / np.where(den != 0, den, 1.0), np.nan)
     return float(np.nanmean(ratio)) if np.any(den != 0) else float("nan")
+
+
+# ---------------------------------------------------------------------------------- counter-based DDPM noise
+def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11; Random123):
+    counter words c0..c3 (uint64 arrays holding 32-bit values), key (k0, k1) -> four 32-bit output words.  Pinned by the
+    Random123 known-answer vectors in tests/test_oracle_golden.py."""
+    import numpy as np
+    m32 = np.uint64(0xFFFFFFFF)
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) for c in (c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0 & 0xFFFFFFFF), np.uint64(k1 & 0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = np.uint64(0xD2511F53) * c0, np.uint64(0xCD9E8D57) * c2
+        h0, l0, h1, l1 = p0 >> np.uint64(32), p0 & m32, p1 >> np.uint64(32), p1 & m32
+        c0, c1, c2, c3 = h1 ^ c1 ^ k0, l1, h0 ^ c3 ^ k1, l0
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & m32, (k1 + np.uint64(0xBB67AE85)) & m32
+    return c0, c1, c2, c3
+
+
+def philox_normal(seed: int, step: int, n_elements: int):
+    """numpy restatement of the in-kernel noise of t2s_sample_ddpm_seeded (csrc/common.cuh: philox_normal): Philox4x32-10
+    keyed by `seed` (low word, high word) on the counter (element, element >> 32, step, 0); u1 = ((w0 >> 8) + 1) 2^-24,
+    u2 = (w1 >> 8) 2^-24; z = sqrt(-2 ln u1) cos(2 pi u2).  Returns float32 [n_elements].  It stands in for the torch.randn
+    drawn inside DDPM.p_sample (DDPM.py:35), which no implementation can reproduce bit for bit on another generator."""
+    import numpy as np
+    el = np.arange(n_elements, dtype=np.uint64)
+    w0, w1, _, _ = philox4x32_10(el & np.uint64(0xFFFFFFFF), el >> np.uint64(32), np.full(n_elements, step, dtype=np.uint64),
+                                 np.zeros(n_elements, dtype=np.uint64), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    u1 = ((w0 >> np.uint64(8)).astype(np.float32) + np.float32(1.0)) * np.float32(2.0 ** -24)
+    u2 = (w1 >> np.uint64(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    r = np.sqrt(np.float32(-2.0) * np.log(u1)).astype(np.float32)
+    return (r * np.cos(2.0 * np.pi * u2.astype(np.float64)).astype(np.float32)).astype(np.float32)

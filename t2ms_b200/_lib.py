@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libt2s_b200.so")
 EXPORTS = [
     "t2s_version", "t2s_last_error", "t2s_init", "t2s_debug_set_phase_trace", "t2s_dit_workspace_bytes", "t2s_dit_workspace_offsets",
     "t2s_dit_workspace_bytes_h", "t2s_dit_workspace_offsets_h", "t2s_dit_attention_h",
-    "t2s_dit_forward", "t2s_sample", "t2s_vae_decode", "t2s_vae_encode",
+    "t2s_dit_forward", "t2s_sample", "t2s_sample_ddpm_seeded", "t2s_vae_decode", "t2s_vae_encode",
     "t2s_dit_cond", "t2s_dit_embed_qkv", "t2s_dit_attention", "t2s_dit_block_post", "t2s_dit_final",
     "t2s_train_workspace_bytes", "t2s_train_workspace_bytes_h", "t2s_train_make_inputs_h", "t2s_dit_train_step", "t2s_dit_train_forward", "t2s_dit_train_backward",
     "t2s_train_make_inputs", "t2s_adamw_step", "t2s_gemm_tf32",
@@ -94,6 +94,8 @@ def load() -> C.CDLL:
         lib.t2s_dit_forward.argtypes = [C.POINTER(DitWeights), P, P, P, P, i, P, sz, P]
         lib.t2s_sample.restype = i
         lib.t2s_sample.argtypes = [C.POINTER(DitWeights), i, P, P, P, C.POINTER(f), P, P, i, i, f, P, sz, P]
+        lib.t2s_sample_ddpm_seeded.restype = i
+        lib.t2s_sample_ddpm_seeded.argtypes = [C.POINTER(DitWeights), P, P, P, C.POINTER(f), C.c_ulonglong, P, i, i, f, P, sz, P]
         lib.t2s_vae_decode.restype = i
         lib.t2s_vae_decode.argtypes = [C.POINTER(VaeDecWeights), P, P, P, i, i, P]
         lib.t2s_vae_encode.restype = i

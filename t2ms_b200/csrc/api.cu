@@ -184,10 +184,10 @@ int launch_mid(const t2s_dit_weights* w, int layer, int nseq, const Shape& sh, c
     return T2S_OK;
 }
 int launch_final(const t2s_dit_weights* w, int nseq, const Shape& sh, const Workspace& ws, int out_mode, float* out, float* x_upd,
-                 const float* noise, float cfg, float c1, float c2, float c3, cudaStream_t st) {
+                 const float* noise, float cfg, float c1, float c2, float c3, cudaStream_t st, unsigned long long seed = 0, unsigned int step = 0) {
     TokArgs a = base_args(w, ws, nseq);
     a.layer = NLAYER - 1;
-    a.out_mode = out_mode; a.out = out; a.x_upd = x_upd; a.noise = noise;
+    a.out_mode = out_mode; a.out = out; a.x_upd = x_upd; a.noise = noise; a.seed = seed; a.step = step;
     a.cfg = cfg; a.c1 = c1; a.c2 = c2; a.c3 = c3;
     T2S_DISPATCH_H(sh.H, T2S_TOKEN_LAUNCH(TOK_FINAL, HH));
     CUDA_OK(cudaGetLastError());
@@ -276,12 +276,10 @@ int t2s_dit_forward(const t2s_dit_weights* w, const float* x, const float* t100,
     return launch_final(w, nseq, sh, ws, OUT_FWD, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, st);
 }
 
-int t2s_sample(const t2s_dit_weights* w, int kind, float* x, const float* emb, const float* t100, const float* coef,
-               const float* step_noise, float* pred_trace, int batch, int steps, float cfg_scale, void* workspace,
-               size_t workspace_bytes, t2s_stream_t stream) {
-    if (!w || !x || !emb || !t100 || !coef || batch <= 0 || steps <= 0 || (kind != 0 && kind != 1))
-        return fail(T2S_EINVAL, "t2s_sample: bad argument%s%s");
-    if (kind == 1 && !step_noise) return fail(T2S_EINVAL, "t2s_sample: DDPM needs step_noise%s%s");
+namespace {
+int sample_impl(const t2s_dit_weights* w, int kind, float* x, const float* emb, const float* t100, const float* coef,
+                const float* step_noise, unsigned long long seed, unsigned int step0, float* pred_trace, int batch, int steps, float cfg_scale,
+                void* workspace, size_t workspace_bytes, t2s_stream_t stream) {
     const int nseq = 2 * batch;
     Shape sh;
     TRY(get_shape(w->latent_h, &sh));
@@ -298,9 +296,27 @@ int t2s_sample(const t2s_dit_weights* w, int kind, float* x, const float* emb, c
             if (l < NLAYER - 1) TRY(launch_mid(w, l, nseq, sh, ws, st));
         }
         TRY(launch_final(w, nseq, sh, ws, kind == 0 ? OUT_RF : OUT_DDPM, pred_trace ? pred_trace + j * lat : nullptr, x,
-                         kind == 1 ? step_noise + j * lat : nullptr, cfg_scale, coef[3 * j], coef[3 * j + 1], coef[3 * j + 2], st));
+                         (kind == 1 && step_noise) ? step_noise + j * lat : nullptr, cfg_scale, coef[3 * j], coef[3 * j + 1], coef[3 * j + 2], st, seed,
+                         step0 + (unsigned int)j));
     }
     return T2S_OK;
+}
+}  // namespace
+
+int t2s_sample(const t2s_dit_weights* w, int kind, float* x, const float* emb, const float* t100, const float* coef,
+               const float* step_noise, float* pred_trace, int batch, int steps, float cfg_scale, void* workspace,
+               size_t workspace_bytes, t2s_stream_t stream) {
+    if (!w || !x || !emb || !t100 || !coef || batch <= 0 || steps <= 0 || (kind != 0 && kind != 1))
+        return fail(T2S_EINVAL, "t2s_sample: bad argument%s%s");
+    if (kind == 1 && !step_noise) return fail(T2S_EINVAL, "t2s_sample: DDPM needs step_noise (or t2s_sample_ddpm_seeded)%s%s");
+    return sample_impl(w, kind, x, emb, t100, coef, step_noise, 0ull, 0u, pred_trace, batch, steps, cfg_scale, workspace, workspace_bytes, stream);
+}
+
+int t2s_sample_ddpm_seeded(const t2s_dit_weights* w, float* x, const float* emb, const float* t100, const float* coef, unsigned long long seed,
+                           float* pred_trace, int batch, int steps, float cfg_scale, void* workspace, size_t workspace_bytes,
+                           t2s_stream_t stream) {
+    if (!w || !x || !emb || !t100 || !coef || batch <= 0 || steps <= 0) return fail(T2S_EINVAL, "t2s_sample_ddpm_seeded: bad argument%s%s");
+    return sample_impl(w, 1, x, emb, t100, coef, nullptr, seed, 0u, pred_trace, batch, steps, cfg_scale, workspace, workspace_bytes, stream);
 }
 
 int t2s_vae_decode(const t2s_vae_dec_weights* w, const float* z, float* series, float* after, int batch, int length,

@@ -113,6 +113,27 @@ __device__ __forceinline__ void gelu_tanh2(float& y0, float& y1, float x0, float
     fma2(y0, y1, h0, h1, t0, t1, h0, h1);
 }
 
+// ---------------------------------------------------------------- counter-based Gaussian noise
+// Philox4x32-10 (Salmon et al., SC'11) keyed by a 64-bit seed on the counter (element index, step), followed by one
+// Box-Muller transform: a standard normal per (seed, step, element), stateless and order-independent, so the DDPM
+// ancestral update (DDPM.py:35 draws torch.randn inside p_sample) needs no noise tensor and no RNG kernel between steps.
+// tests/ restate it in numpy (oracle.philox_normal) and feed those values to the CPU oracle as the step noise.
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned int step, unsigned long long element) {
+    uint32_t c0 = (uint32_t)element, c1 = (uint32_t)(element >> 32), c2 = step, c3 = 0u;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const float u1 = ((float)(c0 >> 8) + 1.0f) * 5.9604644775390625e-8f;     // (0, 1]   (24 bits)
+    const float u2 = (float)(c1 >> 8) * 5.9604644775390625e-8f;              // [0, 1)
+    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
 // ---------------------------------------------------------------- async copies
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 

@@ -50,7 +50,9 @@ struct TokArgs {
     int out_mode;
     float* out;            // OUT_FWD: [nseq][64][H]; OUT_RF / OUT_DDPM: optional guided prediction [npair][64][H]
     float* x_upd;          // OUT_RF / OUT_DDPM: latent updated in place [npair][64][H]
-    const float* noise;    // OUT_DDPM: [npair][64][H] for this step
+    const float* noise;    // OUT_DDPM: [npair][64][H] for this step, or NULL = in-kernel Philox noise (seed, step)
+    unsigned long long seed;
+    unsigned int step;
     float cfg, c1, c2, c3; // RF: x += pred*c1 ; DDPM: x = c1*(x - c2*pred) + c3*noise
     long long* trace;      // optional phase trace [grid][32] of clock64 stamps (tile 0, row 0), NULL = off
 };
@@ -777,7 +779,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                         xn = xo + pred * p.c1;
                     } else {
                         const float mean2 = p.c1 * (xo - p.c2 * pred);
-                        xn = mean2 + p.c3 * p.noise[xi];
+                        xn = mean2 + p.c3 * (p.noise != nullptr ? p.noise[xi] : philox_normal(p.seed, p.step, xi));
                     }
                     p.x_upd[xi] = xn;
                 }

@@ -48,8 +48,14 @@ class T2SSampler:
     @torch.no_grad()
     def sample_latent(self, emb: torch.Tensor, steps: int = 100, cfg_scale: float = 7.0, backbone: str = "flowmatching",
                       noise: Optional[torch.Tensor] = None, step_noise: Optional[torch.Tensor] = None,
-                      generator: Optional[torch.Generator] = None, trace: bool = False, chunk: Optional[int] = None):
-        """emb (B,128) CUDA -> final latent (B,64,H) [, per-step guided predictions (steps,B,64,H)]."""
+                      generator: Optional[torch.Generator] = None, trace: bool = False, chunk: Optional[int] = None,
+                      noise_source: str = "philox", seed: Optional[int] = None):
+        """emb (B,128) CUDA -> final latent (B,64,H) [, per-step guided predictions (steps,B,64,H)].
+
+        DDPM draws Gaussian noise inside every p_sample (DDPM.py:35).  ``step_noise`` (steps,B,64,H) supplies it explicitly
+        (parity tests); otherwise ``noise_source="philox"`` (default) generates it inside the update kernel from ``seed``
+        (drawn from ``generator`` / torch's global RNG when None) — one enqueue for the whole loop, no noise tensor — and
+        ``noise_source="torch"`` draws it with ``torch.randn`` per window of steps."""
         if not emb.is_cuda:
             raise RuntimeError("T2SSampler needs CUDA tensors (no CPU fallback); use sample_host for host buffers")
         lib = _lib.load()
@@ -77,7 +83,13 @@ class T2SSampler:
         # DDPM draws fresh Gaussian noise inside every p_sample (DDPM.py:35).  When the caller does not supply it, it is drawn
         # here in windows of steps (<= NOISE_WINDOW_BYTES at a time) and the loop is enqueued window by window through the
         # same C entry (t100 / coef offset by the window start): no host synchronisation, bounded memory at any batch size.
-        if kind == 1 and step_noise is None:
+        philox = kind == 1 and step_noise is None and noise_source == "philox"
+        if kind == 1 and step_noise is None and noise_source not in ("philox", "torch"):
+            raise ValueError("noise_source must be 'philox' or 'torch'")
+        if philox and seed is None:
+            gdev = generator.device if generator is not None else "cpu"
+            seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator, device=gdev).item())
+        if kind == 1 and step_noise is None and not philox:
             win = max(1, min(steps, self.NOISE_WINDOW_BYTES // (B * lat * 4)))
         else:
             win = steps
@@ -85,16 +97,26 @@ class T2SSampler:
             for j0 in range(0, steps, win):
                 nj = min(win, steps - j0)
                 sn_w = None
-                if kind == 1:
+                if kind == 1 and not philox:
                     sn_w = step_noise[j0:j0 + nj] if step_noise is not None else \
                         torch.randn(nj, B, 64, H, device=dev, dtype=torch.float32, generator=generator)
                 for b0 in range(0, B, chunk):
                     nb = min(chunk, B - b0)
                     sn = tr_c = None
-                    if kind == 1:
+                    if kind == 1 and not philox:
                         sn = sn_w[:, b0:b0 + nb].contiguous() if nb != B else sn_w
                     if trace:
                         tr_c = tr[j0:j0 + nj] if nb == B else torch.empty(nj, nb, 64, H, device=dev, dtype=torch.float32)
+                    if philox:
+                        # every batch chunk gets its own key so that element indices (local to a call) never repeat a stream
+                        rc = lib.t2s_sample_ddpm_seeded(pk.ref, x[b0:b0 + nb].data_ptr(), emb[b0:b0 + nb].data_ptr(), t100.data_ptr(), coef,
+                                                        C.c_ulonglong((seed + 0x9E3779B97F4A7C15 * (b0 // chunk)) & (2 ** 64 - 1)),
+                                                        tr_c.data_ptr() if tr_c is not None else None, nb, steps, float(cfg_scale),
+                                                        _aligned(ws), nbytes, stream)
+                        _lib.check(rc, "t2s_sample_ddpm_seeded")
+                        if trace and nb != B:
+                            tr[:, b0:b0 + nb] = tr_c
+                        continue
                     rc = lib.t2s_sample(pk.ref, kind, x[b0:b0 + nb].data_ptr(), emb[b0:b0 + nb].data_ptr(), t100.data_ptr() + 4 * j0,
                                         C.cast(C.c_void_p(coef_p + 12 * j0), C.POINTER(C.c_float)), sn.data_ptr() if sn is not None else None,
                                         tr_c.data_ptr() if tr_c is not None else None, nb, nj, float(cfg_scale), _aligned(ws), nbytes, stream)

@@ -150,7 +150,7 @@ def test_ddpm_step_noise_windows():
     emb, x0 = synth.make_text_embeddings(B, seed=5).to(DEV), synth.make_noise(B, seed=6).to(DEV)
     smp.NOISE_WINDOW_BYTES = 3 * B * 1920 * 4                      # windows of 3, 3, 1 steps
     g = torch.Generator(device=DEV).manual_seed(11)
-    lat, tr = smp.sample_latent(emb, steps=steps, backbone="ddpm", noise=x0, generator=g, trace=True)
+    lat, tr = smp.sample_latent(emb, steps=steps, backbone="ddpm", noise=x0, generator=g, trace=True, noise_source="torch")
     g = torch.Generator(device=DEV).manual_seed(11)
     sn = torch.cat([torch.randn(n, B, 64, 30, device=DEV, generator=g) for n in (3, 3, 1)])
     smp.NOISE_WINDOW_BYTES = 1 << 30
@@ -207,3 +207,29 @@ def test_sample_graph_and_host_entry_match_eager():
         dit.ln.bias.add_(0.1)                                       # new weights -> new packed object -> new graph
     eager2 = smp.sample(emb.to(DEV), L, steps=steps, noise=x0)
     assert max_abs(eager2, eager) > 0 and max_abs(smp.sample_graph(emb.to(DEV), L, steps=steps, noise=x0), eager2) == 0.0
+
+
+def test_ddpm_in_kernel_philox_noise_matches_its_restatement():
+    """DDPM with the ancestral noise generated inside the update kernel (t2s_sample_ddpm_seeded): the whole 6-step guided loop
+    equals the CPU oracle fed with the numpy restatement of the same counter-based generator (oracle.philox_normal), the
+    noise is standard normal, and a second call with the same seed reproduces the result bit for bit."""
+    import numpy as np
+    from gpu_util import DEV, make_dit, max_abs, rel_l2
+    from t2ms_b200 import T2SSampler, synth
+    dit, dsd = make_dit(3)
+    smp = T2SSampler(dit)
+    B, steps, seed = 3, 6, 0x1234_5678_9ABC_DEF1
+    emb, x0 = synth.make_text_embeddings(B, seed=5), synth.make_noise(B, seed=6)
+    lat, tr = smp.sample_latent(emb.to(DEV), steps=steps, backbone="ddpm", noise=x0.to(DEV), trace=True, seed=seed)
+    lat2 = smp.sample_latent(emb.to(DEV), steps=steps, backbone="ddpm", noise=x0.to(DEV), seed=seed)
+    assert max_abs(lat, lat2) == 0.0
+    sn = torch.from_numpy(np.stack([O.philox_normal(seed, j, B * 1920) for j in range(steps)])).reshape(steps, B, 64, 30)
+    assert abs(sn.mean().item()) < 0.02 and abs(sn.std().item() - 1.0) < 0.02
+    ref, _, eps = O.ddpm_sample(dsd, None, x0, emb, steps, 7.0, sn, return_eps=True)
+    per = [rel_l2(tr[j], eps[j]) for j in range(steps)]
+    assert max(per) < 2e-3, per
+    assert rel_l2(lat, ref) < 2e-3
+    other = smp.sample_latent(emb.to(DEV), steps=steps, backbone="ddpm", noise=x0.to(DEV), seed=seed + 1)
+    assert max_abs(other, lat) > 1e-3                               # another seed, another trajectory
+    default = smp.sample_latent(emb.to(DEV), steps=2, backbone="ddpm", noise=x0.to(DEV))   # seed drawn from torch's RNG
+    assert torch.isfinite(default).all()

@@ -206,3 +206,17 @@ def test_variable_width_training_oracle_matches_fork_reference(dim):
     for n, ref_norm in zip([str(x) for x in g[k + "names"]], g[k + "grad_norms"]):
         assert abs(float(grads[n].norm()) - float(ref_norm)) <= 2e-4 * max(float(ref_norm), 1e-8), n
         close(grads[n].reshape(-1)[:128], g[k + "grad/" + n], 1e-7, rtol=2e-4)
+
+
+def test_philox_known_answer_vectors():
+    """Philox4x32-10 against the published Random123 known-answer vectors (kat_vectors: philox4x32 10): the generator behind
+    the in-kernel DDPM noise (t2s_sample_ddpm_seeded) and its numpy restatement."""
+    f = 0xFFFFFFFF
+    for ctr, key, expect in (((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+                             ((f, f, f, f), (f, f), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+                             ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))):
+        out = O.philox4x32_10(*[np.array([c], dtype=np.uint64) for c in ctr], *key)
+        assert tuple(int(w[0]) for w in out) == expect
+    z = O.philox_normal(987654321, 7, 400_000)
+    assert abs(float(z.mean())) < 0.01 and abs(float(z.std()) - 1.0) < 0.01 and np.isfinite(z).all()
+    assert not np.array_equal(z[:1000], O.philox_normal(987654321, 8, 1000))           # the step is part of the counter
