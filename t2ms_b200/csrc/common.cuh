@@ -117,7 +117,7 @@ __device__ __forceinline__ void gelu_tanh2(float& y0, float& y1, float x0, float
 // Philox4x32-10 (Salmon et al., SC'11) keyed by a 64-bit seed on the counter (element index, step), followed by one
 // Box-Muller transform: a standard normal per (seed, step, element), stateless and order-independent, so the DDPM
 // ancestral update (DDPM.py:35 draws torch.randn inside p_sample) needs no noise tensor and no RNG kernel between steps.
-// tests/ restate it in numpy (oracle.philox_normal) and feed those values to the CPU oracle as the step noise.
+// The parity tests restate it in numpy and feed those values to the CPU reference loop as the step noise.
 __device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned int step, unsigned long long element) {
     uint32_t c0 = (uint32_t)element, c1 = (uint32_t)(element >> 32), c2 = step, c3 = 0u;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
