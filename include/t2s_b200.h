@@ -39,7 +39,7 @@ typedef struct {
     const float* b_fc2[4];  /* [128] */
     const float* w_ada_t;   /* [4][128][768]  adaLN_modulation.1.weight transposed */
     const float* b_ada;     /* [4][768] */
-    const float* w_embed;   /* [128][4]  patch_emb.weight @ conv.weight.view(4,4) */
+    const float* w_embed;   /* [4][128]  (patch_emb.weight @ conv.weight.view(4,4))^T: pixel-major */
     const float* b_embed;   /* [128]     patch_emb.weight @ conv.bias + patch_emb.bias */
     const float* pos;       /* [tiles][32 col chunks][64 rows][4] pos_embed in the residual tile layout (8 tiles of 60 tokens for H = 30) */
     const float* w_final;   /* [4][128]  linear_emb_to_patch.weight * ln.weight */

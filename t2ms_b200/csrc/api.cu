@@ -53,11 +53,17 @@ int t2s_api::ensure_init() {
 #undef T2S_SET_ATTRS
     const int dec = VAE_DEC_SMEM_FLOATS * 4, enc = VAE_ENC_SMEM_FLOATS * 4;
     CUDA_OK(cudaFuncSetAttribute(vae_decode_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec));
+    CUDA_OK(cudaFuncSetAttribute(vae_decode_kernel<6, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec));
     CUDA_OK(cudaFuncSetAttribute(vae_decode_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec));
+    CUDA_OK(cudaFuncSetAttribute(vae_decode_kernel<12, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec));
     CUDA_OK(cudaFuncSetAttribute(vae_decode_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec));
+    CUDA_OK(cudaFuncSetAttribute(vae_decode_kernel<24, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec));
     CUDA_OK(cudaFuncSetAttribute(vae_encode_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc));
+    CUDA_OK(cudaFuncSetAttribute(vae_encode_kernel<6, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc));
     CUDA_OK(cudaFuncSetAttribute(vae_encode_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc));
+    CUDA_OK(cudaFuncSetAttribute(vae_encode_kernel<12, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc));
     CUDA_OK(cudaFuncSetAttribute(vae_encode_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc));
+    CUDA_OK(cudaFuncSetAttribute(vae_encode_kernel<24, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc));
     CUDA_OK(cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev));
     g_inited[dev] = true;
     return T2S_OK;
@@ -327,11 +333,14 @@ int t2s_vae_decode(const t2s_vae_dec_weights* w, const float* z, float* series, 
     memcpy(&dw, w, sizeof(dw));
     cudaStream_t st = (cudaStream_t)stream;
     const int smem = VAE_DEC_SMEM_FLOATS * 4;
-    const int nt = batch <= 148 ? 1024 : 256;          // fewer series than SMs: more threads per series
+    const bool wide = batch <= 148;                    // fewer series than SMs: 1024 threads per series (latency), else 256
+#define T2S_VAE_LAUNCH(KERNEL, L4_, ...)                                                       \
+    if (wide) KERNEL<L4_, 1024><<<batch, 1024, smem, st>>>(__VA_ARGS__);                       \
+    else KERNEL<L4_, 256><<<batch, 256, smem, st>>>(__VA_ARGS__)
     switch (length) {
-        case 24: vae_decode_kernel<6><<<batch, nt, smem, st>>>(dw, z, series, after); break;
-        case 48: vae_decode_kernel<12><<<batch, nt, smem, st>>>(dw, z, series, after); break;
-        case 96: vae_decode_kernel<24><<<batch, nt, smem, st>>>(dw, z, series, after); break;
+        case 24: T2S_VAE_LAUNCH(vae_decode_kernel, 6, dw, z, series, after); break;
+        case 48: T2S_VAE_LAUNCH(vae_decode_kernel, 12, dw, z, series, after); break;
+        case 96: T2S_VAE_LAUNCH(vae_decode_kernel, 24, dw, z, series, after); break;
         default: return fail(T2S_EINVAL, "t2s_vae_decode: length must be 24, 48 or 96%s%s");
     }
     CUDA_OK(cudaGetLastError());
@@ -346,11 +355,11 @@ int t2s_vae_encode(const t2s_vae_enc_weights* w, const float* x, float* z, float
     memcpy(&ew, w, sizeof(ew));
     cudaStream_t st = (cudaStream_t)stream;
     const int smem = VAE_ENC_SMEM_FLOATS * 4;
-    const int nt = batch <= 148 ? 1024 : 256;
+    const bool wide = batch <= 148;
     switch (length) {
-        case 24: vae_encode_kernel<6><<<batch, nt, smem, st>>>(ew, x, z, before); break;
-        case 48: vae_encode_kernel<12><<<batch, nt, smem, st>>>(ew, x, z, before); break;
-        case 96: vae_encode_kernel<24><<<batch, nt, smem, st>>>(ew, x, z, before); break;
+        case 24: T2S_VAE_LAUNCH(vae_encode_kernel, 6, ew, x, z, before); break;
+        case 48: T2S_VAE_LAUNCH(vae_encode_kernel, 12, ew, x, z, before); break;
+        case 96: T2S_VAE_LAUNCH(vae_encode_kernel, 24, ew, x, z, before); break;
         default: return fail(T2S_EINVAL, "t2s_vae_encode: length must be 24, 48 or 96%s%s");
     }
     CUDA_OK(cudaGetLastError());

@@ -24,7 +24,7 @@ struct DitWeights {                 // device pointers; mirrors t2s_dit_weights 
     const float* b_fc2[NLAYER];     // [128]
     const float* w_ada_t;           // [4][128 k][768 o]  (adaLN Linear weight, transposed)
     const float* b_ada;             // [4][768]
-    const float* w_embed;           // [128][4]   patch_emb.weight @ conv.weight  (folded)
+    const float* w_embed;           // [4][128]   (patch_emb.weight @ conv.weight)^T  (folded, pixel-major)
     const float* b_embed;           // [128]      patch_emb.weight @ conv.bias + patch_emb.bias
     const float* pos;               // [tiles per pair][32 col chunks][64 rows][4]  pos_embed in the residual tile layout
     const float* w_final;           // [4][128]   linear_emb_to_patch.weight * ln.weight
@@ -179,7 +179,7 @@ constexpr int TC_SM_VEC = TC_SM_W + TC_NSTAGE * STAGE_BYTES;     // [2 buffers] 
 constexpr int V_MOD = 0;        // [2 branches][768]  adaLN chunk of block l
 constexpr int V_MODN = 1536;    // [2][256]           shift_msa | scale_msa of the next block
 constexpr int V_BPROJ = 2048, V_B1 = 2176, V_B2 = 2432, V_BQKV = 2560;
-constexpr int V_WEMB = 0;       // [128][4]   EMBED only: aliases the V_MOD area it does not use
+constexpr int V_WEMB = 0;       // [4][128]   EMBED only: aliases the V_MOD area it does not use
 constexpr int V_BEMB = 512;     // [128]
 constexpr int V_WFIN = 1536;    // [4][128]   FINAL only: aliases the V_MODN area it does not use
 constexpr int V_BFIN = 2560;    // [4]        FINAL only: aliases V_BQKV
@@ -611,19 +611,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             for (int cb = 0; cb < 4; ++cb) {
                 float a[16];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 4; ++q) {                    // four columns: bias + pos, then the 4-pixel dot products, packed fp32
+                    const int c = c0 + cb * 16 + q * 4;
                     const float4 pe = valid ? *reinterpret_cast<const float4*>(pos + (cb * 4 + q) * 64 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float pev[4] = {pe.x, pe.y, pe.z, pe.w};
+                    const float4 b4 = *reinterpret_cast<const float4*>(vec + V_BEMB + c);
+                    float y0, y1, y2, y3;
+                    add2(y0, y1, b4.x, b4.y, pe.x, pe.y);
+                    add2(y2, y3, b4.z, b4.w, pe.z, pe.w);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int c = c0 + cb * 16 + q * 4 + u;
-                        const float4 w4 = *reinterpret_cast<const float4*>(vec + V_WEMB + c * 4);
-                        a[q * 4 + u] = valid ? (w4.x * xv[0] + w4.y * xv[1] + w4.z * xv[2] + w4.w * xv[3] + vec[V_BEMB + c] + pev[u]) : 0.f;
+                    for (int pq = 0; pq < 4; ++pq) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(vec + V_WEMB + pq * D + c);   // [4 pixels][128 columns]
+                        fma2(y0, y1, w4.x, w4.y, xv[pq], xv[pq], y0, y1);
+                        fma2(y2, y3, w4.z, w4.w, xv[pq], xv[pq], y2, y3);
                     }
+                    a[q * 4 + 0] = valid ? y0 : 0.f; a[q * 4 + 1] = valid ? y1 : 0.f;
+                    a[q * 4 + 2] = valid ? y2 : 0.f; a[q * 4 + 3] = valid ? y3 : 0.f;
                 }
                 if (cb == 0) shift = a[0];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { const float d = a[j] - shift; sum += d; sq = fmaf(d, d, sq); }
+                block_stats(a, shift, sum, sq);
                 tmem_st16(trow + X + cb * 16, a);
                 if (valid) {
 #pragma unroll

@@ -145,8 +145,8 @@ constexpr int VAE_DEC_SMEM_FLOATS = LATC * LATP + VH * VAE_LD_MAX + VR * VAE_LD_
 constexpr int VAE_ENC_SMEM_FLOATS = (96 + 2) + VE * (2 * 24 + 2) + VH * VAE_LD_MAX + VR * VAE_LD_MAX + VH * VAE_LD_MAX;
 
 // Decoder.forward (vqvae.py:97-105).  grid = B, block = 256 (1024 for small batches: one series per CTA, latency-bound).  z [B][64][30] -> series [B][4*L4], after [B][64][L4]
-template <int L4>
-__global__ void __launch_bounds__(1024) vae_decode_kernel(const VaeDecWeights w, const float* __restrict__ z, float* __restrict__ series,
+template <int L4, int NT = 256>
+__global__ void __launch_bounds__(NT) vae_decode_kernel(const VaeDecWeights w, const float* __restrict__ z, float* __restrict__ series,
                                                          float* __restrict__ after) {
     extern __shared__ __align__(16) float sm[];
     constexpr int LD = L4 + 2, NP = 6;
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(1024) vae_decode_kernel(const VaeDecWeights w,
 }
 
 // Encoder.forward (vqvae.py:57-71).  x [B][4*L4] -> z [B][64][30], before [B][64][L4]
-template <int L4>
-__global__ void __launch_bounds__(1024) vae_encode_kernel(const VaeEncWeights w, const float* __restrict__ x, float* __restrict__ z,
+template <int L4, int NT = 256>
+__global__ void __launch_bounds__(NT) vae_encode_kernel(const VaeEncWeights w, const float* __restrict__ x, float* __restrict__ z,
                                                          float* __restrict__ before) {
     extern __shared__ __align__(16) float sm[];
     constexpr int L = 4 * L4, L2 = 2 * L4, LD = L4 + 2, NP = 6;

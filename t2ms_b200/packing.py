@@ -67,7 +67,7 @@ class PackedDit:
         w_ada_t = torch.stack([g(f"layers.{l}.adaLN_modulation.1.weight").t().contiguous() for l in range(4)]).contiguous()
         b_ada = torch.stack([g(f"layers.{l}.adaLN_modulation.1.bias") for l in range(4)]).contiguous()
         wpe, wc = g("patch_emb.weight"), g("conv.weight").reshape(4, 4)              # conv [oc][p*2+q]
-        w_embed = (wpe @ wc).contiguous()                                            # [128][4]
+        w_embed = (wpe @ wc).t().contiguous()                                        # [4][128] (pixel-major)
         b_embed = (wpe @ g("conv.bias") + g("patch_emb.bias")).contiguous()
         ntok = sd["pos_embed"].shape[-2]
         latent_h = ntok // 16
