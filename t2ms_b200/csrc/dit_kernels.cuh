@@ -990,19 +990,14 @@ __global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM
                 mbar_wait(BAR(AB_SFULL + b), (G >> 1) & 1);
                 tc_fence_after();
                 const uint32_t ts = trow + ATT_T_S + b * ATT_KC;
-                constexpr int ZN = ATT_KC - 64;                  // scores beyond the first two 32-column blocks: 32, 16 or 0
-                float x[32], y[32], z[ZN > 0 ? ZN : 1];
-                tmem_ld32(ts, x); tmem_ld32(ts + 32, y);
-                if constexpr (ZN == 32) tmem_ld32(ts + 64, *reinterpret_cast<float (*)[32]>(&z[0]));
-                if constexpr (ZN == 16) tmem_ld16(ts + 64, *reinterpret_cast<float (*)[16]>(&z[0]));
+                float v[ATT_KC];                                 // the score chunk: 32-column loads + a 16-column remainder
+#pragma unroll
+                for (int c = 0; c + 32 <= ATT_KC; c += 32) tmem_ld32(ts + c, *reinterpret_cast<float (*)[32]>(&v[c]));
+                if constexpr (ATT_KC % 32 == 16) tmem_ld16(ts + ATT_KC - 16, *reinterpret_cast<float (*)[16]>(&v[ATT_KC - 16]));
                 tmem_wait_ld();
                 float c0 = -INFINITY, c1 = -INFINITY;
 #pragma unroll
-                for (int q = 0; q < 32; q += 4) {
-                    c0 = max3(c0, x[q], x[q + 1]); c1 = max3(c1, x[q + 2], x[q + 3]);
-                    c0 = max3(c0, y[q], y[q + 1]); c1 = max3(c1, y[q + 2], y[q + 3]);
-                    if (q < ZN) { c0 = max3(c0, z[q], z[q + 1]); c1 = max3(c1, z[q + 2], z[q + 3]); }
-                }
+                for (int q = 0; q < ATT_KC; q += 4) { c0 = max3(c0, v[q], v[q + 1]); c1 = max3(c1, v[q + 2], v[q + 3]); }
                 const float cm = fmaxf(c0, c1);
                 if (j == 0) {
                     mref = cm;
@@ -1024,21 +1019,19 @@ __global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM
                     }
                 }
                 const float nb = -mref * sc;
-                auto half = [&](const float* v, int pcol) {   // 16 scores -> 8 packed P columns
+#pragma unroll
+                for (int hb = 0; hb < ATT_KC / 16; ++hb) {       // 16 scores -> 8 packed P columns
                     uint32_t pk[8];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {                 // packed fp32 (FFMA2 / FADD2): one issue slot per pair
                         float t0, t1;
-                        fma2(t0, t1, v[2 * q], v[2 * q + 1], sc, sc, nb, nb);
+                        fma2(t0, t1, v[hb * 16 + 2 * q], v[hb * 16 + 2 * q + 1], sc, sc, nb, nb);
                         const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
                         add2(l0, l1, l0, l1, e0, e1);
                         pk[q] = pack_h2(e0, e1);
                     }
-                    tmem_st8(ts + pcol, pk);                     // P columns: 16 per 32 scores
-                };
-                half(x, 0); half(x + 16, 8); half(y, 16); half(y + 16, 24);
-                if constexpr (ZN >= 16) half(z, 32);
-                if constexpr (ZN == 32) half(z + 16, 40);
+                    tmem_st8(ts + hb * 8, pk);
+                }
                 if (j == 0 && qt > 0) finish(qt - 1, lprev);  // previous q-tile's O -> global before its accumulator is reused
                 tmem_wait_st();
                 tc_fence_before();
