@@ -182,6 +182,21 @@ def test_train_step_gradients_match_oracle(with_text):
                 assert rel(got, T(g[key])) < GRAD_TOL, key
 
 
+def test_single_sequence_step_uses_the_pack_path():
+    """One sequence (480 rows: below the persistent GEMM's threshold) takes the fp32 q|k|v + pack-kernel path instead of the
+    GEMM's image epilogue: same gradients."""
+    g, dsd, x1, x0, t, emb = _golden_case()
+    x_t, target = O.rf_create_flow(x1, t, x0)[:1], (x1 - x0)[:1]
+    loss_ref, grads_ref = O.train_step_grads(dsd, x_t, t[:1], emb[:1], target)
+    m, tr = _trainer(dsd)
+    tr.zero_grad()
+    tr.forward_backward(x_t.to(DEV), t[:1].to(DEV), emb[:1].to(DEV), target.to(DEV))
+    torch.cuda.synchronize()
+    assert abs(tr.loss_sum.item() / 1920 - loss_ref.item()) / loss_ref.item() < LOSS_TOL
+    bad = {n: rel(tr.grads.view(n), grads_ref[n]) for n in trainable_names() if not rel(tr.grads.view(n), grads_ref[n]) < GRAD_TOL}
+    assert not bad, bad
+
+
 def test_adamw_matches_reference_update():
     g, dsd, x1, x0, t, emb = _golden_case()
     x_t, target = O.rf_create_flow(x1, t, x0), x1 - x0
