@@ -75,7 +75,7 @@ def parse():
     ap.add_argument("--cfg", type=float, default=7.0)
     ap.add_argument("--backbone", default="flowmatching", choices=["flowmatching", "ddpm"])
     ap.add_argument("--chunk", type=int, default=0, help="samples per launch wave (0 = whole batch)")
-    ap.add_argument("--cpu-sample", type=int, default=8, help="series in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=24, help="series in the bounded CPU-baseline sample (~10-15 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-batch", type=int, default=256, help="latents per GPU per optimizer step of the training leg (0 = skip)")
     return ap.parse_args()
