@@ -159,9 +159,12 @@ int launch_cond(const t2s_dit_weights* w, const float* t100, int t_stride, const
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
-int launch_embed(const t2s_dit_weights* w, const float* x, int x_shift, int nseq, const Shape& sh, const Workspace& ws, cudaStream_t st) {
+// fused = inside t2s_dit_forward / t2s_sample: the residual stream entering block 0 is not materialised (EMBED skips the
+// store, the MID kernel of block 0 recomputes it from x); the stage-wise test entries keep it in the workspace
+int launch_embed(const t2s_dit_weights* w, const float* x, int x_shift, int nseq, const Shape& sh, const Workspace& ws, cudaStream_t st,
+                 bool fused = false) {
     TokArgs a = base_args(w, ws, nseq);
-    a.x = x; a.x_shift = x_shift;
+    a.x = x; a.x_shift = x_shift; a.skip_h_store = fused ? 1 : 0;
     T2S_DISPATCH_H(sh.H, T2S_TOKEN_LAUNCH(TOK_EMBED, HH));
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
@@ -182,9 +185,11 @@ int launch_attn(int nseq, const Shape& sh, const Workspace& ws, cudaStream_t st)
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
-int launch_mid(const t2s_dit_weights* w, int layer, int nseq, const Shape& sh, const Workspace& ws, cudaStream_t st) {
+int launch_mid(const t2s_dit_weights* w, int layer, int nseq, const Shape& sh, const Workspace& ws, cudaStream_t st,
+               const float* x = nullptr, int x_shift = 0) {
     TokArgs a = base_args(w, ws, nseq);
     a.layer = layer;
+    if (layer == 0 && x != nullptr) { a.recompute_h0 = 1; a.x = x; a.x_shift = x_shift; }
     T2S_DISPATCH_H(sh.H, T2S_TOKEN_LAUNCH(TOK_MID, HH));
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
@@ -274,10 +279,10 @@ int t2s_dit_forward(const t2s_dit_weights* w, const float* x, const float* t100,
     cudaStream_t st = (cudaStream_t)stream;
     const Workspace ws = ws_view(workspace, nseq, sh);
     TRY(launch_cond(w, t100, 1, emb, 0, 0, nseq, ws, st));
-    TRY(launch_embed(w, x, 0, nseq, sh, ws, st));
+    TRY(launch_embed(w, x, 0, nseq, sh, ws, st, true));
     for (int l = 0; l < NLAYER; ++l) {
         TRY(launch_attn(nseq, sh, ws, st));
-        if (l < NLAYER - 1) TRY(launch_mid(w, l, nseq, sh, ws, st));
+        if (l < NLAYER - 1) TRY(launch_mid(w, l, nseq, sh, ws, st, x, 0));
     }
     return launch_final(w, nseq, sh, ws, OUT_FWD, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, st);
 }
@@ -296,10 +301,10 @@ int sample_impl(const t2s_dit_weights* w, int kind, float* x, const float* emb, 
     const size_t lat = (size_t)batch * sh.lat;
     for (int j = 0; j < steps; ++j) {
         TRY(launch_cond(w, t100 + j, 0, emb, 1, 1, nseq, ws, st));
-        TRY(launch_embed(w, x, 1, nseq, sh, ws, st));
+        TRY(launch_embed(w, x, 1, nseq, sh, ws, st, true));
         for (int l = 0; l < NLAYER; ++l) {
             TRY(launch_attn(nseq, sh, ws, st));
-            if (l < NLAYER - 1) TRY(launch_mid(w, l, nseq, sh, ws, st));
+            if (l < NLAYER - 1) TRY(launch_mid(w, l, nseq, sh, ws, st, x, 1));
         }
         TRY(launch_final(w, nseq, sh, ws, kind == 0 ? OUT_RF : OUT_DDPM, pred_trace ? pred_trace + j * lat : nullptr, x,
                          (kind == 1 && step_noise) ? step_noise + j * lat : nullptr, cfg_scale, coef[3 * j], coef[3 * j + 1], coef[3 * j + 2], st, seed,

@@ -55,6 +55,10 @@ struct TokArgs {
     unsigned int step;
     float cfg, c1, c2, c3; // RF: x += pred*c1 ; DDPM: x = c1*(x - c2*pred) + c3*noise
     long long* trace;      // optional phase trace [grid][32] of clock64 stamps (tile 0, row 0), NULL = off
+    // The residual stream entering block 0 is a 4-pixel affine map of the latent plus pos_embed: the fused loops do not
+    // materialise it.  EMBED skips its store (skip_h_store) and the MID kernel of block 0 recomputes its rows from x with the
+    // same instruction sequence (recompute_h0; needs x, x_shift): 240 KB per sequence less written and read per step.
+    int skip_h_store, recompute_h0;
 };
 
 // =================================================================================== cond
@@ -188,7 +192,8 @@ constexpr int TC_SM_VB = TC_SM_VEC + 2 * V_FLOATS * 4;           // [2 tiles][12
 constexpr int TC_SM_ST = TC_SM_VB + 2 * TILE_ROWS * 4 * 4;        // [2 tiles][2 halves][128] float2 LayerNorm statistics exchange
 constexpr int TC_SM_BAR = TC_SM_ST + 2 * 2 * TILE_ROWS * 8;
 constexpr int TC_SM_TMEM = TC_SM_BAR + 48 * 8;
-constexpr int TOK_SMEM_BYTES = TC_SM_TMEM + 16;
+constexpr int TC_SM_EMB = TC_SM_TMEM + 16;                        // [4][128] folded patch-embed weight + [128] bias (recompute_h0)
+constexpr int TOK_SMEM_BYTES = TC_SM_EMB + 5 * D * 4;
 static_assert(TOK_SMEM_BYTES <= 232448, "token kernel shared memory exceeds 227 KB");
 // barrier ids
 enum { B_WFULL = 0, B_WEMPTY = 2, B_VFULL = 4, B_VFREE = 6, B_TILE = 8 };
@@ -409,6 +414,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
         mbar_fence_init();
     }
     if (warp == 16) tmem_alloc(sb + TC_SM_TMEM, 512);
+    if (MODE == TOK_MID && p.recompute_h0) {
+        float* semb = reinterpret_cast<float*>(smem + TC_SM_EMB);
+        for (int i = tid; i < 5 * D; i += TC_THREADS) semb[i] = i < 4 * D ? p.w.w_embed[i] : p.w.b_embed[i - 4 * D];
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -451,7 +460,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             if (MODE == TOK_FINAL) { cp(V_WFIN, p.w.w_final, 4 * D); cp(V_BFIN, p.w.b_final, 4); }
             if (bytes != VBYTES) __trap();
             if (MODE != TOK_EMBED) {
-                if (lead) prefetch_l2(p.h + (size_t)item * NE * (TILE_ROWS * D), NE * TILE_ROWS * D * 4);
+                if (lead && !(MODE == TOK_MID && p.recompute_h0)) prefetch_l2(p.h + (size_t)item * NE * (TILE_ROWS * D), NE * TILE_ROWS * D * 4);
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
                     if (it >= 1) mbar_wait(TBAR(e, T_HAFREE), (it - 1) & 1);     // fc2's first K half of the previous item has read HA
@@ -630,7 +639,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 if (cb == 0) shift = a[0];
                 block_stats(a, shift, sum, sq);
                 tmem_st16(trow + X + cb * 16, a);
-                if (valid) {
+                if (valid && !p.skip_h_store) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         *reinterpret_cast<float4*>(hrow + (cb * 4 + q) * TILE_ROWS * 4) = make_float4(a[q * 4], a[q * 4 + 1], a[q * 4 + 2], a[q * 4 + 3]);
@@ -645,7 +654,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             // x = x + gate_msa * (o Wproj^T + b)        (transformer.py:116); x stays parked in X until the MLP branch adds to it
             float4 hq[16];                                               // this thread's 64 residual values, in flight during the wait
 #pragma unroll
-            for (int c4 = 0; c4 < 16; ++c4) hq[c4] = valid ? *reinterpret_cast<const float4*>(hrow_c + c4 * TILE_ROWS * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c4 = 0; c4 < 16; ++c4) hq[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE == TOK_MID && p.recompute_h0) {
+                // block 0: the residual input is patch-embed(x) + pos (transformer.py:166-172), recomputed exactly as EMBED formed it
+                if (valid) {
+                    const float* xs = p.x + (size_t)(seq >> p.x_shift) * LAT;
+                    const int i = tok >> 5, j = tok & 31;
+                    float xv[4];
+#pragma unroll
+                    for (int pq = 0; pq < 4; ++pq) xv[pq] = xs[(2 * j + (pq & 1)) * LATP + 2 * i + (pq >> 1)];
+                    const float* pos = p.w.pos + ((size_t)tt * 32 * 64 + tl) * 4 + (c0 / 4) * 64 * 4;
+                    const float* semb = reinterpret_cast<const float*>(smem + TC_SM_EMB);
+#pragma unroll
+                    for (int c4 = 0; c4 < 16; ++c4) {
+                        const int c = c0 + c4 * 4;
+                        const float4 pe = *reinterpret_cast<const float4*>(pos + c4 * 64 * 4);
+                        const float4 b4 = *reinterpret_cast<const float4*>(semb + 4 * D + c);
+                        float y0, y1, y2, y3;
+                        add2(y0, y1, b4.x, b4.y, pe.x, pe.y);
+                        add2(y2, y3, b4.z, b4.w, pe.z, pe.w);
+#pragma unroll
+                        for (int pq = 0; pq < 4; ++pq) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(semb + pq * D + c);
+                            fma2(y0, y1, w4.x, w4.y, xv[pq], xv[pq], y0, y1);
+                            fma2(y2, y3, w4.z, w4.w, xv[pq], xv[pq], y2, y3);
+                        }
+                        hq[c4] = make_float4(y0, y1, y2, y3);
+                    }
+                }
+            } else if (valid) {
+#pragma unroll
+                for (int c4 = 0; c4 < 16; ++c4) hq[c4] = *reinterpret_cast<const float4*>(hrow_c + c4 * TILE_ROWS * 4);
+            }
             mbar_wait(TBAR(e, T_ACC + 0), par);
             tc_fence_after();
             STAMP(3);
