@@ -844,8 +844,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
 // softmax(q k^T / sqrt(32)) v for one (sequence, head) per CTA (timm Attention -> F.scaled_dot_product_attention).
 // The 480 queries form four 120-row q-tiles (M = 128 with 8 padding rows), the 480 keys five 96-key chunks.
 // Single pass, thread per query row (= TMEM lane), a 96-key score chunk held in registers:
-//   S_j = Q_tile K_j^T (tcgen05.mma M128 N96 K16 x2, double-buffered in TMEM) is read ONCE (the TMEM read port, not
-//   the tensor pipe, is the scarce resource next to the MUFU); the row maximum of the chunk is taken with FMNMX3;
+//   S_j = Q_tile K_j^T (tcgen05.mma M128 N96 K16 x2, double-buffered in TMEM) is read ONCE (a second pass over S
+//   costs the softmax warps another dependent round of loads); the row maximum of the chunk is taken with FMNMX3;
 //   P_j = exp2((S_j - m) * log2e/sqrt(32)) is packed to fp16 and written back over the first 48 columns of its own
 //   S buffer (tcgen05.st); O += P_j V_j is a tcgen05.mma with the A operand read from TMEM (M128 N32 K16 x6, V as
 //   MN-major B operand) accumulating over the chunks in one 32-column accumulator; O / rowsum is written straight
