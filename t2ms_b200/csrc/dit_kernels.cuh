@@ -62,6 +62,9 @@ struct TokArgs {
 };
 
 // =================================================================================== cond
+// The modulation table holds, per (sequence, block), shift_msa | 1 + scale_msa | gate_msa | shift_mlp | 1 + scale_mlp |
+// gate_mlp: the token kernel's normalise-modulate is then two fused multiply-adds per element.
+__device__ __forceinline__ bool mod_is_scale(int col) { return (col >> 7) == 1 || (col >> 7) == 4; }
 // mod[seq][l][:] = Linear_l( SiLU( temb(t) (+ text) ) )      transformer.py:30-40,106-109,115,174-178
 // grid (ceil(nseq/8), 4), block 256
 __global__ void __launch_bounds__(256) cond_kernel(float* __restrict__ mod, const float* __restrict__ t100, int t_stride,
@@ -105,7 +108,8 @@ __global__ void __launch_bounds__(256) cond_kernel(float* __restrict__ mod, cons
         if (seq < nseq) {
             float* dst = mod + ((size_t)seq * NLAYER + l) * MOD;
 #pragma unroll
-            for (int a = 0; a < 3; ++a) dst[a * 256 + tid] = acc[a][s] + b_ada[l * MOD + a * 256 + tid];
+            for (int a = 0; a < 3; ++a)                      // the scale slices hold 1 + scale (see ln_mod_store)
+                dst[a * 256 + tid] = acc[a][s] + (b_ada[l * MOD + a * 256 + tid] + (mod_is_scale(a * 256 + tid) ? 1.f : 0.f));
         }
     }
 }
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(256) cond_split_kernel(float* __restrict__ mod
 #pragma unroll
         for (int s = 0; s < 8; ++s) acc[s] = fmaf(wv, sc[s][k], acc[s]);
     }
-    const float bv = b_ada[l * MOD + col];
+    const float bv = b_ada[l * MOD + col] + (mod_is_scale(col) ? 1.f : 0.f);
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
         const int seq = s0 + s;
@@ -335,24 +339,20 @@ __device__ __forceinline__ RowStats merge_stats(HalfStats hs, float2* slot, int 
 
 // pass 2 over this thread's 64 columns: LayerNorm (no affine) + modulate x*(1+scale)+shift (transformer.py:7-8,102-103),
 // packed to fp16 and stored as the next GEMM's A operand image.  kc0 = first 8-column K chunk of the half (8 hh).
-__device__ __forceinline__ void ln_mod_store(uint32_t trow, RowStats st, const float* __restrict__ shift, const float* __restrict__ scale,
+__device__ __forceinline__ void ln_mod_store(uint32_t trow, RowStats st, const float* __restrict__ shift, const float* __restrict__ scale1,
                                              uint8_t* abuf, int r, int kc0) {
-    const float nmean = -st.mean;
+    const float rs = st.rstd, nm = -st.mean * st.rstd;
     for_blocks16<4>(trow, [&](int cb, float (&a)[16]) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float4 sc = *reinterpret_cast<const float4*>(scale + cb * 16 + q * 4);
+            const float4 sc = *reinterpret_cast<const float4*>(scale1 + cb * 16 + q * 4);   // 1 + scale
             const float4 sh = *reinterpret_cast<const float4*>(shift + cb * 16 + q * 4);
-            // ((a - mean) * rstd) * (1 + scale) + shift, packed: three issue slots per pair
-            float d0, d1, d2, d3, n0, n1, n2, n3, s0, s1, s2, s3;
-            add2(d0, d1, a[q * 4 + 0], a[q * 4 + 1], nmean, nmean);
-            add2(d2, d3, a[q * 4 + 2], a[q * 4 + 3], nmean, nmean);
-            mul2(n0, n1, d0, d1, st.rstd, st.rstd);
-            mul2(n2, n3, d2, d3, st.rstd, st.rstd);
-            add2(s0, s1, sc.x, sc.y, 1.f, 1.f);
-            add2(s2, s3, sc.z, sc.w, 1.f, 1.f);
-            fma2(a[q * 4 + 0], a[q * 4 + 1], n0, n1, s0, s1, sh.x, sh.y);
-            fma2(a[q * 4 + 2], a[q * 4 + 3], n2, n3, s2, s3, sh.z, sh.w);
+            // ((a - mean) * rstd) * (1 + scale) + shift as two packed fused multiply-adds per pair
+            float n0, n1, n2, n3;
+            fma2(n0, n1, a[q * 4 + 0], a[q * 4 + 1], rs, rs, nm, nm);
+            fma2(n2, n3, a[q * 4 + 2], a[q * 4 + 3], rs, rs, nm, nm);
+            fma2(a[q * 4 + 0], a[q * 4 + 1], n0, n1, sc.x, sc.y, sh.x, sh.y);
+            fma2(a[q * 4 + 2], a[q * 4 + 3], n2, n3, sc.z, sc.w, sh.z, sh.w);
         }
 #pragma unroll
         for (int c8 = 0; c8 < 2; ++c8)

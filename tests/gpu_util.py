@@ -81,7 +81,11 @@ class Workspace:
         return self._tiles(raw.permute(0, 1, 3, 4, 2, 5).reshape(npair, 8, 128, 128)).float()
 
     def mod(self):
-        return self._view(3, self.nseq * 4 * 768 * 4, torch.float32, (self.nseq, 4, 768))
+        """adaLN table as the reference lays it out (the kernels keep 1 + scale in the two scale slices)."""
+        m = self._view(3, self.nseq * 4 * 768 * 4, torch.float32, (self.nseq, 4, 768)).clone()
+        m[..., 128:256] -= 1.0
+        m[..., 512:640] -= 1.0
+        return m
 
 
 def stream():
