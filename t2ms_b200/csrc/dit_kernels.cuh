@@ -905,8 +905,25 @@ __global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM
     const uint32_t bar0 = sb + ATT_SM_BAR;
     // barriers 0-2 (Q / K / V loaded) are shared; every warpgroup owns a block of ten (AB_SFULL .. AB_OFREE)
     auto BAR = [&](int i) { return bar0 + 8u * (i < 3 ? i : i + wg * 10); };
-    if (tid == 0) {
+    if (warp_cta == 4 && lane == 0) {
+        // the operand loads go out first: their latency overlaps the TMEM allocation, the remaining barrier set-up and
+        // the CTA-wide synchronisation
         for (int i = 0; i < 3; ++i) mbar_init(bar0 + 8u * i, 1);
+        mbar_fence_init();
+        const char* src = reinterpret_cast<const char*>(qkv + (size_t)sh * QKV_HEAD_HALVES);
+        if (npart == 1) {
+            mbar_expect_tx(bar0 + 8u * AB_QFULL, QKV_Q_HALVES * 2);
+            bulk_g2s(sb + ATT_SM_Q, src, QKV_Q_HALVES * 2, bar0 + 8u * AB_QFULL);
+        } else {                                                 // only this part's NWG q-tiles (adjacent 8 KB images)
+            mbar_expect_tx(bar0 + 8u * AB_QFULL, NWG * 8192);
+            bulk_g2s(sb + ATT_SM_Q + part * NWG * 8192, src + part * NWG * 8192, NWG * 8192, bar0 + 8u * AB_QFULL);
+        }
+        mbar_expect_tx(bar0 + 8u * AB_KFULL, QKV_K_HALVES * 2);
+        bulk_g2s(sb + ATT_SM_K, src + QKV_Q_HALVES * 2, QKV_K_HALVES * 2, bar0 + 8u * AB_KFULL);
+        mbar_expect_tx(bar0 + 8u * AB_VFULL, QKV_V_HALVES * 2);
+        bulk_g2s(sb + ATT_SM_V, src + (QKV_Q_HALVES + QKV_K_HALVES) * 2, QKV_V_HALVES * 2, bar0 + 8u * AB_VFULL);
+    }
+    if (tid == 0) {
         for (int g = 0; g < NWG; ++g) {
             const uint32_t bg = bar0 + 8u * (g * 10);
             for (int b = 0; b < 2; ++b) {
@@ -920,7 +937,7 @@ __global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM
         }
         mbar_fence_init();
     }
-    if (warp_cta == 4) tmem_alloc(sb + ATT_SM_TMEM, ATT_TCOLS);
+    if (warp_cta == 4) { __syncwarp(); tmem_alloc(sb + ATT_SM_TMEM, ATT_TCOLS); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -932,20 +949,6 @@ __global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM
     if (warp == 4) {
         // ================================================================= loads + MMA issue; whole warp converged
         const bool lead = lane == 0;
-        if (lead && wg == 0) {
-            const char* src = reinterpret_cast<const char*>(qkv + (size_t)sh * QKV_HEAD_HALVES);
-            if (npart == 1) {
-                mbar_expect_tx(BAR(AB_QFULL), QKV_Q_HALVES * 2);
-                bulk_g2s(sb + ATT_SM_Q, src, QKV_Q_HALVES * 2, BAR(AB_QFULL));
-            } else {                                             // only this part's NWG q-tiles (adjacent 8 KB images)
-                mbar_expect_tx(BAR(AB_QFULL), NWG * 8192);
-                bulk_g2s(sb + ATT_SM_Q + part * NWG * 8192, src + part * NWG * 8192, NWG * 8192, BAR(AB_QFULL));
-            }
-            mbar_expect_tx(BAR(AB_KFULL), QKV_K_HALVES * 2);
-            bulk_g2s(sb + ATT_SM_K, src + QKV_Q_HALVES * 2, QKV_K_HALVES * 2, BAR(AB_KFULL));
-            mbar_expect_tx(BAR(AB_VFULL), QKV_V_HALVES * 2);
-            bulk_g2s(sb + ATT_SM_V, src + (QKV_Q_HALVES + QKV_K_HALVES) * 2, QKV_V_HALVES * 2, BAR(AB_VFULL));
-        }
         // score chunk G: q-tile (G / NCH) * NWG + wg, key chunk G % NCH -> S buffer G & 1
         auto issue_s = [&](int G) {
             const int qt = q_tile(G / ATT_NCH), j = G % ATT_NCH;
