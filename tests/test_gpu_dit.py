@@ -168,15 +168,15 @@ def test_errors_are_loud():
         model(input=torch.zeros(1, 30, 64, device=DEV), t=torch.zeros(1, device=DEV), text_input=None)
 
 
-@pytest.mark.parametrize("boost", [1.0, 6.0])
-def test_attention_kernel_against_exact_softmax(boost):
+@pytest.mark.parametrize("boost,nseq", [(1.0, 3), (6.0, 3), (1.0, 150), (6.0, 150)])
+def test_attention_kernel_against_exact_softmax(boost, nseq):
     """attn_kernel alone on crafted q|k|v: with boost > 1 the keys of the later chunks score far above the first
-    chunk's maximum, which drives many (not all) rows through the reference-point move + O rescale path."""
+    chunk's maximum, which drives many (not all) rows through the reference-point move + O rescale path.
+    nseq = 150: 600 CTAs on 296 resident slots (CTAs start while their SM neighbour is mid-way)."""
     from gpu_util import DEV, Workspace, make_dit, pack_qkv_images, stream
     from t2ms_b200 import _lib
     lib = _lib.load()
     model, _ = make_dit(3)
-    nseq = 3
     g = torch.Generator().manual_seed(17)
     q, k, v = (torch.randn(nseq, 4, 480, 32, generator=g) for _ in range(3))
     k[:, :, 200:] *= boost
