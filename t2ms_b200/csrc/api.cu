@@ -46,7 +46,8 @@ int t2s_api::ensure_init() {
     CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_EMBED, HH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));    \
     CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_MID, HH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));      \
     CUDA_OK(cudaFuncSetAttribute(token_kernel<TOK_FINAL, HH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));    \
-    CUDA_OK(cudaFuncSetAttribute(attn_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttShape<HH>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(attn_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttShape<HH>::SMEM_BYTES));       \
+    CUDA_OK(cudaFuncSetAttribute(attn_kernel<HH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttShape<HH, true>::SMEM_BYTES));
     T2S_SET_ATTRS(30)
     T2S_SET_ATTRS(50)
     T2S_SET_ATTRS(64)
@@ -176,9 +177,13 @@ int launch_attn(int nseq, const Shape& sh, const Workspace& ws, cudaStream_t st)
     // fewer (sequence, head) CTAs than resident slots: one CTA per q-tile (group) instead, for latency
 #define T2S_ATTN_LAUNCH(HH_)                                                                                                     \
     {                                                                                                                            \
-        const int full = AttShape<HH_>::NQT / AttShape<HH_>::NWG;                                                                \
-        const int npart = nseq * NHEAD < sms * AttShape<HH_>::CTAS_PER_SM / 2 ? full : 1;                                        \
-        attn_kernel<HH_><<<nseq * NHEAD * npart, AttShape<HH_>::THREADS, AttShape<HH_>::SMEM_BYTES, st>>>(ws.qkv, ws.o, g_trace, npart); \
+        using LS = AttShape<HH_, true>;                                                                                          \
+        if (nseq * NHEAD < sms * LS::CTAS_PER_SM / 2) {                                                                          \
+            const int npart = LS::NQT / LS::NWG;                                                                                 \
+            attn_kernel<HH_, true><<<nseq * NHEAD * npart, LS::THREADS, LS::SMEM_BYTES, st>>>(ws.qkv, ws.o, g_trace, npart);     \
+        } else {                                                                                                                 \
+            attn_kernel<HH_><<<nseq * NHEAD, AttShape<HH_>::THREADS, AttShape<HH_>::SMEM_BYTES, st>>>(ws.qkv, ws.o, g_trace, 1); \
+        }                                                                                                                        \
     }
     T2S_DISPATCH_H(sh.H, T2S_ATTN_LAUNCH(HH));
 #undef T2S_ATTN_LAUNCH

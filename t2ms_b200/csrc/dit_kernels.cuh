@@ -842,40 +842,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
 
 // =================================================================================== attention (tcgen05)
 // softmax(q k^T / sqrt(32)) v for one (sequence, head) per CTA (timm Attention -> F.scaled_dot_product_attention).
-// The 480 queries form four 120-row q-tiles (M = 128 with 8 padding rows), the 480 keys five 96-key chunks.
-// Single pass, thread per query row (= TMEM lane), a 96-key score chunk held in registers:
-//   S_j = Q_tile K_j^T (tcgen05.mma M128 N96 K16 x2, double-buffered in TMEM) is read ONCE (a second pass over S
+// The 480 queries form four 120-row q-tiles (M = 128 with 8 padding rows), the 480 keys ten 48-key chunks.
+// Single pass, thread per query row (= TMEM lane), a 48-key score chunk held in registers:
+//   S_j = Q_tile K_j^T (tcgen05.mma M128 N48 K16 x2, double-buffered in TMEM) is read ONCE (a second pass over S
 //   costs the softmax warps another dependent round of loads); the row maximum of the chunk is taken with FMNMX3;
-//   P_j = exp2((S_j - m) * log2e/sqrt(32)) is packed to fp16 and written back over the first 48 columns of its own
-//   S buffer (tcgen05.st); O += P_j V_j is a tcgen05.mma with the A operand read from TMEM (M128 N32 K16 x6, V as
+//   P_j = exp2((S_j - m) * log2e/sqrt(32)) is packed to fp16 and written back over the first 24 columns of its own
+//   S buffer (tcgen05.st); O += P_j V_j is a tcgen05.mma with the A operand read from TMEM (M128 N32 K16 x3, V as
 //   MN-major B operand) accumulating over the chunks in one 32-column accumulator; O / rowsum is written straight
 //   into the out-projection's A-operand tile.
 //   The reference point m is the maximum of the first chunk and is only moved when a later chunk exceeds it by more
 //   than 2^8 in the exp2 domain (P <= 256 stays exact in fp16, sums are fp32): then the row sum and the O row are
 //   rescaled (rare; taken warp-uniformly after the previous P.V has completed).  The result is the exact softmax.
-// CTA = one softmax warpgroup (thread = query row) + one MMA/load warp, 92 KB of shared memory and 256 TMEM
-// columns, so TWO CTAs share an SM: one CTA's loads, pass A and epilogue hide under the other's exp pass.
+// CTA = TWO softmax warpgroups (thread = query row), each with its own MMA warp, barriers and 128 TMEM columns
+// (two 48-column S buffers + the 32-column O), on alternate q-tiles over the shared Q / K / V images; 92 KB of shared
+// memory, so TWO CTAs share an SM = FOUR softmax warps per scheduler.  The kernel sits on the MUFU; a softmax warp's
+// chunk is a serial load -> max -> exp -> store -> arrive chain, and with only two such warps per scheduler (one
+// warpgroup per CTA, 96-key chunks: the previous form) the MUFU idled whenever both were outside their exp loop
+// (0.636 -> 0.597 ms per 2048-sequence launch).  The wide shapes (K / V of one head no longer fit twice) run ONE such
+// CTA per SM with 256 TMEM columns per warpgroup.
 // Q, K, V arrive by bulk async copies: the token kernel stores them directly as tcgen05 operand images
 //   Q: [q-tile][d/8][row 0..127][8]     (A, K-major)         32768 B
 //   K: [d/8][key 0..479][8]             (B, K-major)         30720 B
 //   V: [key/8][d/8][key%8][8]           (B, MN-major)        30720 B
 constexpr int ATT_THREADS = 160;
 enum { AB_QFULL = 0, AB_KFULL = 1, AB_VFULL = 2, AB_SFULL = 3, AB_SFREE = 5, AB_PFULL = 7, AB_PVDONE = 9, AB_OFULL = 11, AB_OFREE = 12 };
-template <int H>
+// LAT: the small-batch form of the T2S shape (one CTA per q-tile, see attn_kernel): ONE warpgroup and 96-key chunks, the
+// shortest serial chain for a single q-tile when there is nothing to overlap it with
+template <int H, bool LAT = false>
 struct AttShape {
     using S = DitShape<H>;
-    static constexpr int KC = S::KC, NCH = S::NCH, NQT = S::NQT;      // keys per chunk, chunks, q-tiles
+    static constexpr bool ONE_WG = LAT && H == 30;
+    static constexpr int KC = ONE_WG ? 96 : S::KC, NCH = S::NTOK / KC, NQT = S::NQT;      // keys per chunk, chunks, q-tiles
     static constexpr int SM_Q = 0, SM_K = S::Q_HALVES * 2, SM_V = SM_K + S::K_HALVES * 2;
     static constexpr int SM_BAR = SM_V + S::V_HALVES * 2;
     static constexpr int SM_TMEM = SM_BAR + 32 * 8;
     static constexpr int SMEM_BYTES = SM_TMEM + 16;
     static constexpr int CTAS_PER_SM = 2 * (SMEM_BYTES + 1024) <= 233472 ? 2 : 1;   // H = 30: two CTAs share an SM
-    // wide shapes (K / V of one head no longer fit twice): ONE CTA per SM with TWO softmax warpgroups (+ their MMA warps)
-    // working on alternate q-tiles over the shared K / V images, so one group's MMA / TMEM phases hide under the other's exps
-    static constexpr int NWG = CTAS_PER_SM == 2 ? 1 : 2;
+    // TWO softmax warpgroups (+ their MMA warps) per CTA on alternate q-tiles over the shared K / V images, so one group's
+    // MMA / TMEM phases hide under the other's exps
+    static constexpr int NWG = ONE_WG ? 1 : 2;
     static constexpr int THREADS = NWG * ATT_THREADS;
     static constexpr uint32_t IDESC_S = umma_idesc_f16(128, KC);
-    static constexpr uint32_t TCOLS_WG = 256;                         // per warpgroup: two S buffers (2 x KC) + O (32)
+    static constexpr uint32_t TCOLS_WG = 2 * KC + HD <= 128 ? 128 : 256;   // per warpgroup: two S buffers (2 x KC) + O (32)
     static constexpr uint32_t TCOLS = NWG * TCOLS_WG;
     static constexpr uint32_t T_S = 0, T_O = 2 * KC;
     static_assert(SMEM_BYTES <= 232448 && 2 * KC + HD <= 256 && NQT % NWG == 0, "attention kernel resources");
@@ -884,10 +892,10 @@ static_assert(AttShape<30>::CTAS_PER_SM == 2, "two attention CTAs must fit one S
 constexpr uint32_t ATT_IDESC_PV = umma_idesc_f16(128, HD) | (1u << 16);   // B (V) is MN-major
 
 // grid = nseq * 4, block = 160 per warpgroup: warps 0-3 = softmax (thread = query row = TMEM lane), warp 4 = (loads +) MMA issue
-template <int H>
-__global__ void __launch_bounds__(AttShape<H>::THREADS, AttShape<H>::CTAS_PER_SM) attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ o, long long* trace, int npart) {
+template <int H, bool LAT = false>
+__global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::CTAS_PER_SM) attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ o, long long* trace, int npart) {
     using S = DitShape<H>;
-    using AS = AttShape<H>;
+    using AS = AttShape<H, LAT>;
     constexpr int NTOK = S::NTOK, TILE_TOK = S::TILE_TOK, TILES_PER_PAIR = S::TILES_PER_PAIR, QT_ROWS = S::QT_ROWS;
     constexpr int QKV_Q_HALVES = S::Q_HALVES, QKV_K_HALVES = S::K_HALVES, QKV_V_HALVES = S::V_HALVES, QKV_HEAD_HALVES = S::HEAD_HALVES;
     constexpr int ATT_KC = AS::KC, ATT_NCH = AS::NCH, ATT_NQT = AS::NQT;

@@ -117,8 +117,9 @@ def test_rf_sampling_vs_oracle_config1():
 
 def test_full_size_properties():
     """BASELINE config 2 size (B=1024, L=96) through size-independent properties: samples are independent,
-    so any sub-batch / chunking reproduces the same series bit-for-bit; duplicates of one prompt+noise
-    produce identical rows; and a small slice matches the oracle."""
+    so any chunking reproduces the same series bit-for-bit; duplicates of one prompt+noise produce identical rows;
+    a sub-batch small enough for the latency kernels (attention with 96-key instead of 48-key chunks: another summation
+    order) agrees to the attention kernel's own accuracy; and a small slice matches the oracle."""
     from gpu_util import DEV, make_dit, make_vae, max_abs
     from t2ms_b200 import T2SSampler, synth
     dit, dsd = make_dit(61)
@@ -134,7 +135,9 @@ def test_full_size_properties():
     chunked = smp.sample(emb, 96, steps=steps, noise=noise, chunk=37)
     assert torch.equal(full, chunked)
     sub = smp.sample(emb[500:507], 96, steps=steps, noise=noise[500:507])
-    assert torch.equal(full[500:507], sub)
+    assert max_abs(full[500:507], sub) < TOL_SERIES / 5
+    sub = smp.sample(emb[500:580], 96, steps=steps, noise=noise[500:580])            # large enough for the throughput kernels
+    assert torch.equal(full[500:580], sub)
     _, ser_ref = O.rf_sample(dsd, vsd, noise[:4].cpu(), emb[:4].cpu(), steps, 7.0, 96)
     assert max_abs(full[:4], ser_ref) < TOL_SERIES
 
