@@ -35,8 +35,8 @@ struct DitShape {
     // attention: NQT query tiles of QT_ROWS valid rows (M = 128), NCH key chunks of KC keys
     static constexpr int QT_ROWS = H_ == 30 ? 120 : (H_ == 50 ? 100 : 128);
     static constexpr int NQT = NTOK / QT_ROWS;                                        // 4 | 8 | 8
-    static constexpr int KC = H_ == 30 ? 48 : (H_ == 50 ? 80 : 64);
-    static constexpr int NCH = NTOK / KC;                                             // 10 | 10 | 16
+    static constexpr int KC = H_ == 30 ? 48 : 32;        // two S buffers + O in 128 TMEM columns: four softmax warpgroups per SM
+    static constexpr int NCH = NTOK / KC;                                             // 10 | 25 | 32
     // q|k|v scratch: per (sequence, head) three tcgen05 operand images (layouts at attn_kernel)
     static constexpr int Q_HALVES = NQT * 4 * 128 * 8;
     static constexpr int K_HALVES = 4 * NTOK * 8;

@@ -858,8 +858,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
 // memory, so TWO CTAs share an SM = FOUR softmax warps per scheduler.  The kernel sits on the MUFU; a softmax warp's
 // chunk is a serial load -> max -> exp -> store -> arrive chain, and with only two such warps per scheduler (one
 // warpgroup per CTA, 96-key chunks: the previous form) the MUFU idled whenever both were outside their exp loop
-// (0.636 -> 0.597 ms per 2048-sequence launch).  The wide shapes (K / V of one head no longer fit twice) run ONE such
-// CTA per SM with 256 TMEM columns per warpgroup.
+// (0.636 -> 0.597 ms per 2048-sequence launch).  The wide shapes (K / V of one head no longer fit twice) run ONE CTA
+// per SM with FOUR warpgroups on 32-key chunks (H = 64: 8.36 -> 7.55 ms per guided step at batch 512).
 // Q, K, V arrive by bulk async copies: the token kernel stores them directly as tcgen05 operand images
 //   Q: [q-tile][d/8][row 0..127][8]     (A, K-major)         32768 B
 //   K: [d/8][key 0..479][8]             (B, K-major)         30720 B
@@ -875,12 +875,12 @@ struct AttShape {
     static constexpr int KC = ONE_WG ? 96 : S::KC, NCH = S::NTOK / KC, NQT = S::NQT;      // keys per chunk, chunks, q-tiles
     static constexpr int SM_Q = 0, SM_K = S::Q_HALVES * 2, SM_V = SM_K + S::K_HALVES * 2;
     static constexpr int SM_BAR = SM_V + S::V_HALVES * 2;
-    static constexpr int SM_TMEM = SM_BAR + 32 * 8;
+    static constexpr int SM_TMEM = SM_BAR + 48 * 8;
     static constexpr int SMEM_BYTES = SM_TMEM + 16;
     static constexpr int CTAS_PER_SM = 2 * (SMEM_BYTES + 1024) <= 233472 ? 2 : 1;   // H = 30: two CTAs share an SM
     // TWO softmax warpgroups (+ their MMA warps) per CTA on alternate q-tiles over the shared K / V images, so one group's
-    // MMA / TMEM phases hide under the other's exps
-    static constexpr int NWG = ONE_WG ? 1 : 2;
+    // MMA / TMEM phases hide under the other's exps; FOUR (32-key chunks) where only one CTA fits an SM (wide shapes)
+    static constexpr int NWG = ONE_WG ? 1 : (CTAS_PER_SM == 2 ? 2 : 4);   // four softmax warpgroups per SM either way
     static constexpr int THREADS = NWG * ATT_THREADS;
     static constexpr uint32_t IDESC_S = umma_idesc_f16(128, KC);
     static constexpr uint32_t TCOLS_WG = 2 * KC + HD <= 128 ? 128 : 256;   // per warpgroup: two S buffers (2 x KC) + O (32)
