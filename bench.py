@@ -49,6 +49,8 @@ def emit(obj) -> None:
         os.write(_REAL_STDOUT, data)
 
 
+BASELINE_WHAT = {"reference": "unmodified reference modules from baseline/_ref (torch fp32 CPU, timm Attention -> SDPA)",
+                 "port": "oracle port (torch fp32 CPU); baseline/_ref not staged"}
 METRIC = "t2s_dit_rf_sampled_series_per_sec"
 UNIT = "series/s"
 FLOP_FWD = 976_960_512                 # per DiT forward per sequence
@@ -78,6 +80,7 @@ def parse():
     ap.add_argument("--chunk", type=int, default=0, help="samples per launch wave (0 = whole batch)")
     ap.add_argument("--cpu-sample", type=int, default=24, help="series in the bounded CPU-baseline sample (~10-15 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-PyTorch-eager-on-this-GPU baseline leg")
     ap.add_argument("--train-batch", type=int, default=256, help="latents per GPU per optimizer step of the training leg (0 = skip)")
     return ap.parse_args()
 
@@ -128,24 +131,101 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _reference_objects(device="cpu"):
+    """The unmodified reference modules staged in baseline/_ref (oracle/ref_install.py), or None when they are not there."""
+    from oracle import ref_install as R
+    from t2ms_b200 import synth
+    if not R.available():
+        return None
+    ref = R.load()
+    dit, vae = R.build_reference_models(ref, synth.make_dit_state(0), synth.make_vae_state(1), device)
+    return R, ref, dit, vae
+
+
 def cpu_reference_run(a, n_series: int, repeats: int = 1):
-    """The oracle port of the reference loop (infer.py:75-95) on the host cores; returns (series/s, seconds, threads)."""
+    """The reference loop (infer.py:75-95) on the host cores: the UNMODIFIED reference modules from baseline/_ref
+    (kind "reference"), or the oracle port when they are not staged (kind "port").
+    Returns (series/s, seconds, threads, kind)."""
     from oracle import t2s_oracle as O
     from t2ms_b200 import synth
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    dsd, vsd = synth.make_dit_state(0), synth.make_vae_state(1)
     emb, noise = synth.make_text_embeddings(n_series), synth.make_noise(n_series)
+    objs = _reference_objects("cpu")
+    if objs is not None:
+        R, ref, rdit, rvae = objs
+        run = lambda: R.reference_sample(ref, rdit, rvae, emb, noise, a.rf_steps, a.cfg, a.length, a.backbone)
+        kind = "reference"
+    else:
+        dsd, vsd = synth.make_dit_state(0), synth.make_vae_state(1)
+        if a.backbone == "flowmatching":
+            run = lambda: O.rf_sample(dsd, vsd, noise, emb, a.rf_steps, a.cfg, a.length)
+        else:
+            sn = synth.make_step_noise(a.rf_steps, n_series)
+            run = lambda: O.ddpm_sample(dsd, vsd, noise, emb, a.rf_steps, a.cfg, sn, a.length)
+        kind = "port"
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        if a.backbone == "flowmatching":
-            O.rf_sample(dsd, vsd, noise, emb, a.rf_steps, a.cfg, a.length)
-        else:
-            O.ddpm_sample(dsd, vsd, noise, emb, a.rf_steps, a.cfg, synth.make_step_noise(a.rf_steps, n_series), a.length)
+        run()
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return n_series / best, best, threads
+    return n_series / best, best, threads, kind
+
+
+def gpu_eager_baseline(a, dev):
+    """the reference PyTorch-eager on the B200 itself — the same unmodified modules from baseline/_ref moved to
+    the GPU, fp32, stock settings (torch's default: no TF32 matmuls), the loop of infer.py:75-95 at the bench workload, device
+    resident inputs, CUDA events.  Also with TF32 matmuls allowed, and the kernel launches per guided step (torch.profiler)."""
+    objs = _reference_objects(dev)
+    if objs is None:
+        return {"unavailable": "baseline/_ref is not staged (run oracle/ref_install.py where /root/reference is mounted)"}
+    R, ref, rdit, rvae = objs
+    from t2ms_b200 import synth
+    B = a.batch
+    emb = synth.make_text_embeddings(B).to(dev)
+    noise = torch.randn(B, 64, 30, device=dev)
+    res = {"kind": "reference modules (baseline/_ref) on cuda, torch eager fp32", "batch": B, "denoise_steps": a.rf_steps, "unit": UNIT}
+
+    def timed(steps):
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        R.reference_sample(ref, rdit, rvae, emb, noise, steps, a.cfg, a.length, a.backbone)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1)
+
+    prev = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    try:
+        for allow in (False, True):
+            torch.backends.cuda.matmul.allow_tf32 = allow
+            timed(3)                                                    # warm-up: cuBLAS / cuDNN / SDPA heuristics, allocator
+            ms3 = timed(3)
+            # bounded: the whole loop when it fits ~20 s, else extrapolated from a measured prefix of the steps (same per-step work)
+            steps = a.rf_steps if ms3 / 3 * a.rf_steps < 20000 else max(3, int(20000 / (ms3 / 3)))
+            ms = timed(steps)
+            if steps != a.rf_steps:
+                ms = ms * a.rf_steps / steps
+            key = "value" if not allow else "value_tf32_allowed"
+            res[key] = B / (ms / 1e3)
+            res["ms_per_batch" if not allow else "ms_per_batch_tf32_allowed"] = ms
+            res["measured_steps" if not allow else "measured_steps_tf32_allowed"] = steps
+        res["tf32_allowed"] = False
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            R.reference_sample(ref, rdit, rvae, emb[:8], noise[:8], 2, a.cfg, a.length, a.backbone)
+            torch.cuda.synchronize(dev)
+        n = sum(1 for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "memcpy" not in e.name.lower()
+                and "memset" not in e.name.lower())
+        res["launches_per_step"] = n // 2
+    except Exception as exc:                                            # CUPTI may be unavailable on the box
+        res["launches_per_step"] = None
+        res["launches_note"] = f"torch.profiler unavailable: {type(exc).__name__}"
+    return res
 
 
 def workload_name(a):
@@ -166,7 +246,7 @@ def run_reference(a, rank, world):
     n = a.cpu_sample
     times = []
     for i in range(a.warmup + a.steps):
-        v, dt, threads = cpu_reference_run(a, n)
+        v, dt, threads, kind = cpu_reference_run(a, n)
         if i >= a.warmup:
             times.append(dt)
     total = sum(times)
@@ -175,8 +255,8 @@ def run_reference(a, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": workload_name(a), "sample": f"{n} series per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n} series x {a.rf_steps} guided steps + decode per step, oracle port (torch fp32 CPU)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{n} series x {a.rf_steps} guided steps + decode per step, " + BASELINE_WHAT[kind]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -386,9 +466,13 @@ def main():
         }
         line["train"] = train
         if not a.no_cpu_baseline and world == 1:       # reported at N=1 only (host cores are shared by the ranks otherwise)
-            v, dt, threads = cpu_reference_run(a, a.cpu_sample)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{a.cpu_sample} series x {a.rf_steps} guided steps + decode in {dt:.1f} s, oracle port (torch fp32 CPU)"}
+            v, dt, threads, kind = cpu_reference_run(a, a.cpu_sample)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                                    "sample": f"{a.cpu_sample} series x {a.rf_steps} guided steps + decode in {dt:.1f} s, " + BASELINE_WHAT[kind]}
+        if not a.no_gpu_eager and world == 1:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(a, dev)
+            if line["gpu_eager_baseline"].get("value"):
+                line["gpu_eager_baseline"]["ours_over_eager"] = value / line["gpu_eager_baseline"]["value"]
         emit(line)
     if world > 1:
         dist.barrier()

@@ -295,15 +295,28 @@ def rf_sample(dit: SD, vae: Optional[SD], noise: torch.Tensor, emb: torch.Tensor
     return (x_t, series, vel) if return_velocities else (x_t, series)
 
 
+class _Indexable:
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __getitem__(self, j):
+        return self.fn(j)
+
+
 @torch.no_grad()
 def ddpm_sample(dit: SD, vae: Optional[SD], noise: torch.Tensor, emb: torch.Tensor, steps: int,
                 cfg_scale: float, step_noise: torch.Tensor, length: Optional[int] = None,
-                return_eps: bool = False):
-    """infer.py:83-88 (+ :95).  ``step_noise`` (steps,B,64,30) replaces the torch.randn drawn inside
-    DDPM.p_sample (DDPM.py:35)."""
+                return_eps: bool = False, keep_states: Optional[dict] = None):
+    """infer.py:83-88 (+ :95).  ``step_noise`` (steps,B,64,30) — a tensor, or a callable j -> (B,64,30) for long
+    schedules — replaces the torch.randn drawn inside DDPM.p_sample (DDPM.py:35).  ``keep_states``: a dict whose keys are
+    loop indices j; it is filled with (x_t entering step j, guided epsilon of step j) for teacher-forced comparisons."""
     sched = ddpm_schedule(steps)
     x_t = noise.clone()
     eps_l = []
+    if not callable(step_noise):
+        _sn = step_noise
+        step_noise = lambda j: _sn[j]
+    step_noise = _Indexable(step_noise)
     for j in range(steps):
         t = torch.full((x_t.size(0),), math.floor(steps - 1 - j), dtype=torch.long)
         u = dit_forward(dit, x_t, t, None)
@@ -311,6 +324,8 @@ def ddpm_sample(dit: SD, vae: Optional[SD], noise: torch.Tensor, emb: torch.Tens
         pred = u + cfg_scale * (c - u)
         if return_eps:
             eps_l.append(pred)
+        if keep_states is not None and j in keep_states:
+            keep_states[j] = (x_t.clone(), pred.clone())
         x_t = ddpm_p_sample(x_t, pred, t, step_noise[j], sched)
     series = vae_decode(vae, x_t, length)[0] if (vae is not None and length) else None
     return (x_t, series, eps_l) if return_eps else (x_t, series)

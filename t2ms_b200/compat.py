@@ -27,12 +27,28 @@ _ALIASES = {
 
 
 def install(force: bool = False) -> None:
+    """Alias the B200 implementations under the reference's module paths.  When the reference's own ``model`` package is
+    importable (an untouched infer.py / train.py run from the reference checkout), the REAL packages stay in place and only
+    the hot-path submodules are overridden in ``sys.modules`` — ``from model.denoiser.mlp import MLP`` (infer.py:4, train.py:9)
+    and every other real submodule keep importing.  Otherwise empty namespace packages stand in."""
     import importlib
+    import importlib.util
     for pkg in ("model", "model.denoiser", "model.backbone", "model.pretrained"):
-        if pkg not in sys.modules or force:
+        if pkg in sys.modules and not force:
+            continue
+        real = None
+        try:
+            if importlib.util.find_spec(pkg) is not None:
+                real = importlib.import_module(pkg)
+        except (ImportError, ValueError):
+            real = None
+        if real is None:
             m = types.ModuleType(pkg)
             m.__path__ = []
             sys.modules[pkg] = m
+            parent, _, leaf = pkg.rpartition(".")
+            if parent:
+                setattr(sys.modules[parent], leaf, m)
     for alias, (target, names) in _ALIASES.items():
         if alias in sys.modules and not force:
             continue

@@ -56,9 +56,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// fp32 pair -> packed fp16, round-to-nearest, SATURATING: a value beyond the fp16 range becomes +-65504 instead of inf,
+// so an out-of-range activation (LN-modulated input, GELU output, q|k|v, attention output) degrades accuracy instead of
+// poisoning the sequence with inf / NaN (tests/test_gpu_config_parity.py: fp16 range stress).  One F2FP either way.
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
-    __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 
 // ---------------------------------------------------------------- fast math (MUFU)

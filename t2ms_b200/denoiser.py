@@ -113,7 +113,9 @@ class Transformer(nn.Module):
         self.initialize_weights()
         self._packed: Optional[PackedDit] = None
         self._packed_key = None
+        self._pack_generation = 0          # bumped by every re-pack: cache keys use it, never id() of a freed object
         self._workspaces = {}
+        self._warned_no_grad = False
 
     def initialize_weights(self):
         """model/denoiser/transformer.py:194-204 (xavier Linear weights, zero biases, zero adaLN)."""
@@ -141,6 +143,8 @@ class Transformer(nn.Module):
             with torch.no_grad():
                 self._packed = PackedDit({n: p for n, p in params}, dev)
             self._packed_key = key
+            self._pack_generation += 1
+            self._packed.generation = self._pack_generation
         return self._packed
 
     def workspace(self, nseq: int, device) -> torch.Tensor:
@@ -149,9 +153,12 @@ class Transformer(nn.Module):
         if ws is None:
             nbytes = _lib.load().t2s_dit_workspace_bytes_h(nseq, self.H)
             ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=device)
-            if len(self._workspaces) > 4:
-                self._workspaces.clear()
+            # small LRU; an evicted buffer is only freed once nothing else (a cached CUDA graph of T2SSampler) holds it
+            while len(self._workspaces) >= 4:
+                self._workspaces.pop(next(iter(self._workspaces)))
             self._workspaces[key] = ws
+        else:
+            self._workspaces[key] = self._workspaces.pop(key)           # most recently used last
         return ws
 
     # ------------------------------------------------------------------ forward
@@ -162,6 +169,13 @@ class Transformer(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for _, p in self._own_params()) and self.training:
             from .training import dit_forward_autograd
             return dit_forward_autograd(self, input, t, text_input)
+        if torch.is_grad_enabled() and not self._warned_no_grad and (input.requires_grad or (text_input is not None and text_input.requires_grad)
+                                                                    or any(p.requires_grad for _, p in self._own_params())):
+            import warnings
+            self._warned_no_grad = True
+            warnings.warn("t2ms_b200.Transformer.forward in eval() mode (or with frozen parameters) returns a tensor WITHOUT a grad_fn; "
+                          "gradients w.r.t. `input` / `text_input` are never produced.  Call .train() for the training path, or wrap "
+                          "inference in torch.no_grad() as infer.py:65 does.", stacklevel=2)
         return dit_forward(self, input, t, text_input)
 
 

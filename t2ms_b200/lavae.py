@@ -71,6 +71,8 @@ class _PackedMixin:
             with torch.no_grad():
                 self._pk = type(self)._packer({n: p for n, p in params}, dev)
             self._pk_key = key
+            self._pk_generation = getattr(self, "_pk_generation", 0) + 1
+            self._pk.generation = self._pk_generation
         return self._pk
 
     def __getstate__(self):

@@ -150,7 +150,13 @@ class T2SSampler:
         if self.decoder is None or self.dit.H != 30:
             raise RuntimeError("sample_graph needs the LA-VAE decoder and the T2S shape")
         dev, B = emb.device, emb.shape[0]
-        key = (str(dev), B, int(length), int(steps), float(cfg_scale), id(self.dit.packed()), id(self.decoder._packed_weights()))
+        pk, dpk = self.dit.packed(), self.decoder._packed_weights()
+        # a captured graph holds RAW device pointers (workspace, packed weights of both models): the cache entry keeps those
+        # objects alive for as long as the graph exists, and the key uses their monotonically increasing pack generations
+        # (an id() can be reused by a new object once the old pack is freed)
+        key = (str(dev), B, int(length), int(steps), float(cfg_scale), pk.generation, dpk.generation)
+        for k in [k for k in self._graphs if k[0] == key[0] and k[5:] != key[5:]]:
+            del self._graphs[k]                                     # weights changed: graphs of the old packs can never be replayed
         ent = self._graphs.get(key)
         if ent is None:
             s_emb = torch.empty(B, 128, device=dev, dtype=torch.float32)
@@ -167,8 +173,8 @@ class T2SSampler:
                 s_out = self.sample(s_emb, length, steps=steps, cfg_scale=cfg_scale, noise=s_x0)
             if len(self._graphs) >= 8:
                 self._graphs.pop(next(iter(self._graphs)))
-            ent = self._graphs[key] = (g, s_emb, s_x0, s_out)
-        g, s_emb, s_x0, s_out = ent
+            ent = self._graphs[key] = (g, s_emb, s_x0, s_out, (self.dit.workspace(2 * B, dev), pk, dpk))
+        g, s_emb, s_x0, s_out, _keepalive = ent
         s_emb.copy_(emb.detach().to(torch.float32), non_blocking=True)
         if noise is None:
             s_x0.normal_(generator=generator)                    # infer.py:75

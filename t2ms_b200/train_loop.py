@@ -100,11 +100,20 @@ def save_checkpoint(path: str, trainer: DitTrainer, epoch: int, loss_list: List[
     torch.save(dict(model=trainer.model.state_dict(), optimizer=optimizer_state_dict(trainer), epoch=epoch, loss_list=loss_list), path)
 
 
-def load_checkpoint(path: str, trainer: DitTrainer, map_location=None):
-    """train.py:42-47 -> (start_epoch, loss_list)."""
+def load_checkpoint(path: str, trainer: DitTrainer, map_location=None, strict: bool = True):
+    """train.py:42-47 -> (start_epoch, loss_list).  Like the reference's ``model.load_state_dict(ckpt['model'])`` (strict), a
+    checkpoint with missing or unexpected keys raises; ``strict=False`` returns after reporting them with a warning."""
     ck = torch.load(path, map_location=map_location or trainer.device)
     with torch.no_grad():
-        own = dict(trainer.model.named_parameters())
+        own = dict(trainer.model.state_dict(keep_vars=True))
+        missing = sorted(k for k in own if k not in ck["model"])
+        unexpected = sorted(k for k in ck["model"] if k not in own)
+        if missing or unexpected:
+            msg = f"checkpoint {path}: missing keys {missing}, unexpected keys {unexpected}"
+            if strict:
+                raise RuntimeError(msg)
+            import warnings
+            warnings.warn(msg)
         for k, v in ck["model"].items():
             if k in own:
                 own[k].data.copy_(v)                      # in place: the parameters are views of the flat buffer

@@ -69,6 +69,7 @@ class _Workspace:
     def __init__(self):
         self.buf = None
         self.nseq = 0
+        self.generation = 0          # bumped by every training-mode forward: backward() checks it still owns the activations
 
     def get(self, nseq: int, device, latent_h: int = 30) -> Tuple[int, int]:
         lib = _lib.load()
@@ -93,12 +94,13 @@ def _module_ws(model) -> _Workspace:
 class FlatBuffer:
     """One contiguous fp32 buffer holding every trainable tensor at a 256-byte aligned offset."""
 
-    def __init__(self, shapes: Dict[str, torch.Size], device):
+    def __init__(self, shapes: Dict[str, torch.Size], device, tail: int = 0):
         self.offsets, off = {}, 0
         for n, s in shapes.items():
             self.offsets[n] = (off, s)
             off += (s.numel() + 63) // 64 * 64
-        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.numel = off                                  # elements holding tensors; `tail` extra fp32 slots follow
+        self.flat = torch.zeros(off + tail, dtype=torch.float32, device=device)
 
     def view(self, name: str) -> torch.Tensor:
         off, s = self.offsets[name]
@@ -147,7 +149,11 @@ class _DitFunction(torch.autograd.Function):
             rc = lib.t2s_dit_train_forward(C.byref(st), x.data_ptr(), t100.data_ptr(), text.data_ptr() if text is not None else None,
                                            pred.data_ptr(), x.shape[0], ptr, nbytes, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "t2s_dit_train_forward")
+        ws.generation += 1
         ctx.model, ctx.st, ctx.nseq, ctx.keep = model, st, x.shape[0], (tensors, ws.buf)
+        ctx.generation = ws.generation
+        ctx.versions = tuple(p._version for p in params)
+        ctx.params = params
         ctx.shapes = {n: p.shape for n, p in tensors.items()}
         return pred
 
@@ -155,8 +161,14 @@ class _DitFunction(torch.autograd.Function):
     def backward(ctx, dpred):
         lib = _lib.load()
         model = ctx.model
-        if ctx.keep[1] is not _module_ws(model).buf:
-            raise RuntimeError("the training workspace was reused by another forward before backward() ran")
+        ws = _module_ws(model)
+        if ctx.keep[1] is not ws.buf or ctx.generation != ws.generation:
+            raise RuntimeError("t2ms_b200.Transformer keeps the activations of ONE training-mode forward per module: another "
+                               "forward ran before this backward() (e.g. (loss1 + loss2).backward() over two forwards, or gradient "
+                               "accumulation without a backward in between).  Call backward() after each forward, or use "
+                               "DitTrainer(micro_batch=...) for accumulation.")
+        if tuple(p._version for p in ctx.params) != ctx.versions:
+            raise RuntimeError("a parameter of t2ms_b200.Transformer was modified in place between forward and backward()")
         dev = dpred.device
         gbuf = FlatBuffer(ctx.shapes, dev)
         gst = _struct(gbuf.views(), None, None, model.H)
@@ -185,7 +197,8 @@ class DitTrainer:
     kernel / one collective over 3.7 MB.
     """
 
-    def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, group=None):
+    def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, group=None,
+                 coin_seed: int = 0):
         params = _own_trainable(model)
         dev = next(iter(params.values())).device
         if dev.type != "cuda":
@@ -193,7 +206,8 @@ class DitTrainer:
         self.model, self.device, self.group = model, dev, group
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         shapes = {n: p.shape for n, p in params.items()}
-        self.params, self.grads = FlatBuffer(shapes, dev), FlatBuffer(shapes, dev)
+        # the gradient bucket carries the loss sum in its tail: the data-parallel exchange is ONE all_reduce
+        self.params, self.grads = FlatBuffer(shapes, dev), FlatBuffer(shapes, dev, tail=64)
         self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.params.flat), torch.zeros_like(self.params.flat)
         with torch.no_grad():
             for n, p in params.items():
@@ -206,13 +220,15 @@ class DitTrainer:
         self._pst = _struct(self.params.views(), model.pos_embed.detach(), _freqs(dev), self.H)
         self._gst = _struct(self.grads.views(), None, None, self.H)
         self.ws = _Workspace()
-        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.loss_sum = self.grads.flat[self.grads.numel:self.grads.numel + 1]       # [sum of squared errors]
         self.step_count = 0
+        # the per-batch CFG-dropout coin (train.py:80, CPU RNG): with data parallelism every rank draws it from an identically
+        # seeded CPU generator — no broadcast, no device round trip; a single process keeps the reference's global-RNG draw
+        self._coin_gen = torch.Generator().manual_seed(int(coin_seed))
 
     # ------------------------------------------------------------------ pieces
     def zero_grad(self):
-        self.grads.flat.zero_()
-        self.loss_sum.zero_()
+        self.grads.flat.zero_()                           # gradients + loss sum + element count (the bucket's tail)
 
     def forward_backward(self, x_t, t, emb, target, loss_numel: Optional[float] = None, backward: bool = True, pred=None):
         """Accumulates dL/dparam into ``self.grads`` and sum((pred-target)^2) into ``self.loss_sum``."""
@@ -230,11 +246,10 @@ class DitTrainer:
         _lib.check(rc, "t2s_dit_train_step")
 
     def allreduce_grads(self):
-        """Data-parallel exchange: one SUM all-reduce of the flat gradient bucket (+ the loss sum)."""
+        """Data-parallel exchange: ONE SUM all-reduce of the flat gradient bucket, whose tail carries the loss sum."""
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.group)
-            dist.all_reduce(self.loss_sum, op=dist.ReduceOp.SUM, group=self.group)
 
     def optimizer_step(self, lr: Optional[float] = None, grad_scale: float = 1.0):
         lib = _lib.load()
@@ -245,7 +260,7 @@ class DitTrainer:
                                     float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                     float(grad_scale), torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "t2s_adamw_step")
-        self.model._packed = None                     # inference weight images are stale now
+        self.model._packed = None                     # inference weight images are stale now (packed() re-packs, new generation)
 
     # ------------------------------------------------------------------ inputs (train.py:68-76)
     def make_inputs(self, backbone: str, x1, noise, t, ddpm=None):
@@ -267,12 +282,15 @@ class DitTrainer:
         return xt, target
 
     # ------------------------------------------------------------------ one optimizer step
-    def step(self, x_t, t, emb, target, lr: Optional[float] = None, micro_batch: Optional[int] = None) -> torch.Tensor:
+    def step(self, x_t, t, emb, target, lr: Optional[float] = None, micro_batch: Optional[int] = None,
+             global_batch: Optional[int] = None) -> torch.Tensor:
         """One optimizer step on (x_t, t, emb | None, target); returns the (global) loss as a device scalar."""
         import torch.distributed as dist
         world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
         B = x_t.shape[0]
-        numel = float(B * self.lat * world)                              # global mean (equal shards)
+        # equal shards (the data-parallel contract of bench.py / train_loop.py): the global element count is known on the host.
+        # `global_batch` overrides it for uneven shards (every rank passes the same total).
+        numel = float((global_batch if global_batch else B * world) * self.lat)
         self.zero_grad()
         mb = B if not micro_batch else min(int(micro_batch), B)
         for b0 in range(0, B, mb):
@@ -285,7 +303,7 @@ class DitTrainer:
     # ------------------------------------------------------------------ train.py:60-87 for one (sub-)batch
     def train_batch(self, series, emb, backbone: str = "flowmatching", total_step: int = 100, p_uncond: float = 0.3,
                     encoder=None, ddpm=None, lr: Optional[float] = None, generator: Optional[torch.Generator] = None,
-                    micro_batch: Optional[int] = None) -> torch.Tensor:
+                    micro_batch: Optional[int] = None, global_batch: Optional[int] = None) -> torch.Tensor:
         """One optimizer step exactly as the reference loop does it for a length-grouped sub-batch:
         frozen LA-VAE encoder (train.py:66), t / noise draws and create_flow | q_sample (:68-76), the per-BATCH
         classifier-free-guidance dropout coin (:80-82, shared by all data-parallel ranks), forward, MSE, backward,
@@ -304,10 +322,10 @@ class DitTrainer:
             t = torch.floor(torch.rand(B, device=dev, generator=generator) * total_step).long()               # train.py:73
         noise = torch.randn(x1.shape, device=dev, generator=generator)
         x_t, target = self.make_inputs(backbone, x1, noise, t, ddpm)
-        coin = torch.rand(1)                                                                                   # CPU RNG, train.py:80
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            c = coin.to(dev)
-            dist.broadcast(c, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
-            coin = c.cpu()
+            coin = torch.rand(1, generator=self._coin_gen)          # same stream on every rank: no collective, no host sync
+        else:
+            coin = torch.rand(1)                                    # CPU RNG, train.py:80
         text = None if coin.item() < p_uncond else emb
-        return self.step(x_t, t.to(torch.float32) if t.dtype != torch.float32 else t, text, target, lr=lr, micro_batch=micro_batch)
+        return self.step(x_t, t.to(torch.float32) if t.dtype != torch.float32 else t, text, target, lr=lr, micro_batch=micro_batch,
+                         global_batch=global_batch)

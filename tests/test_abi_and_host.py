@@ -194,6 +194,41 @@ def test_compat_aliases():
     assert isinstance(v, vqvae)
 
 
+_COMPAT_CHECKOUT = r'''
+import sys
+sys.path.insert(0, sys.argv[1])          # the repo
+sys.path.insert(0, sys.argv[2])          # a reference-style checkout: model/ is a real (namespace) package with other submodules
+from t2ms_b200 import compat
+compat.install()                         # INTEGRATION.md 2(a): first line of an untouched infer.py / train.py
+# the import lines of infer.py:4-8 / train.py:6-11
+from model.denoiser.mlp import MLP
+from model.denoiser.transformer import Transformer
+from model.backbone.rectified_flow import RectifiedFlow
+from model.backbone.DDPM import DDPM
+import t2ms_b200
+assert MLP.marker == "real reference submodule"
+assert Transformer is t2ms_b200.Transformer and RectifiedFlow is t2ms_b200.RectifiedFlow and DDPM is t2ms_b200.DDPM
+import model.pretrained.vqvae as V
+assert V.vqvae is t2ms_b200.vqvae          # the class path the pickled LA-VAE resolves (infer.py:39-41)
+print("ok")
+'''
+
+
+def test_compat_install_keeps_real_reference_submodules_importable(tmp_path):
+    """ADVICE r1: install() must not hide the reference's other submodules (model.denoiser.mlp, infer.py:4) behind empty
+    fake packages when the scripts run from a reference checkout."""
+    co = tmp_path / "checkout"
+    (co / "model" / "denoiser").mkdir(parents=True)
+    (co / "model" / "backbone").mkdir()
+    (co / "model" / "pretrained").mkdir()
+    (co / "model" / "denoiser" / "mlp.py").write_text("class MLP:\n    marker = 'real reference submodule'\n")
+    (co / "model" / "denoiser" / "transformer.py").write_text("raise ImportError('the reference denoiser must not be imported')\n")
+    script = tmp_path / "c.py"
+    script.write_text(_COMPAT_CHECKOUT)
+    r = subprocess.run([sys.executable, str(script), ROOT, str(co)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_fork_module_aliases_and_state_dicts():
     """The fork's module paths (mytrain.py:7-9, myinfer.py:5-6) resolve to the t2ms_b200 classes; Transformer(dim) and the
     multivariate vqvae(args) carry the reference's parameter names / shapes (strict load of synthetic reference-shaped

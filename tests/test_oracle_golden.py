@@ -1,6 +1,7 @@
 """The CPU oracle (oracle/t2s_oracle.py) against outputs of the unmodified reference
 (tests/golden/*.npz, written by oracle/make_golden.py)."""
 import math
+import sys
 
 import numpy as np
 import pytest
@@ -220,3 +221,25 @@ def test_philox_known_answer_vectors():
     z = O.philox_normal(987654321, 7, 400_000)
     assert abs(float(z.mean())) < 0.01 and abs(float(z.std()) - 1.0) < 0.01 and np.isfinite(z).all()
     assert not np.array_equal(z[:1000], O.philox_normal(987654321, 8, 1000))           # the step is part of the counter
+
+
+def test_staged_reference_modules_agree_with_the_oracle():
+    """baseline/_ref (the unmodified reference files staged by oracle/ref_install.py for the bench baselines) drives the
+    same loop as the oracle: equal to fp32 rounding.  Skipped where the reference was never mounted."""
+    from oracle import ref_install as R
+    if not R.available():
+        pytest.skip("baseline/_ref is not staged")
+    from t2ms_b200 import synth
+    ref = R.load()
+    dsd, vsd = synth.make_dit_state(0), synth.make_vae_state(1)
+    dit, vae = R.build_reference_models(ref, dsd, vsd)
+    emb, noise = synth.make_text_embeddings(3), synth.make_noise(3)
+    s = R.reference_sample(ref, dit, vae, emb, noise, 3, 7.0, 48)
+    _, so = O.rf_sample(dsd, vsd, noise, emb, 3, 7.0, 48)
+    assert (s - so).abs().max().item() < 1e-5
+    sn = synth.make_step_noise(3, 3)
+    s = R.reference_sample(ref, dit, vae, emb, noise, 3, 7.0, 24, backbone="ddpm", step_noise=sn)
+    _, so = O.ddpm_sample(dsd, vsd, noise, emb, 3, 7.0, sn, 24)
+    assert (s - so).abs().max().item() < 1e-5
+    for m in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
+        del sys.modules[m]                       # leave no reference modules behind for the compat-alias tests

@@ -85,14 +85,18 @@ for n in g:
     dist.all_reduce(buf, op=dist.ReduceOp.SUM)
     err = ((buf - full[n]).norm() / full[n].norm()).item()
     assert err < 1e-5, (n, err)
-# the shared classifier-free-guidance coin (train.py:80-82): rank 0's draw wins on every rank
+# the shared classifier-free-guidance coin (train.py:80-82): every rank draws it from an identically seeded CPU generator
+# (DitTrainer(coin_seed=...)), whatever its global RNG state is: no broadcast, no device round trip
 torch.manual_seed(100 + rank)
-coin = torch.rand(1)
-dist.broadcast(coin, src=0)
-ref = torch.tensor([0.0]); 
-if rank == 0: ref = coin.clone()
-dist.broadcast(ref, src=0)
-assert torch.equal(coin, ref)
+gen = torch.Generator().manual_seed(0)
+coins = torch.cat([torch.rand(1, generator=gen) for _ in range(16)])
+got = [torch.empty_like(coins) for _ in range(world)]
+dist.all_gather(got, coins)
+assert all(torch.equal(g, got[0]) for g in got)
+# ONE all_reduce carries the gradients and the loss sum (the bucket's tail)
+flat = torch.cat([torch.full((8,), float(rank + 1)), torch.tensor([0.5 * (rank + 1)])])
+dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+assert flat[0].item() == 3.0 and flat[-1].item() == 1.5
 dist.destroy_process_group()
 print("ok", rank)
 '''
