@@ -50,6 +50,14 @@ typedef struct {
      * pos is [16 H / T tiles][32][64][4] with T = 60 | 50 | 64 tokens per tile; every latent buffer of the calls
      * below is [..][64][H]. */
     int latent_h;
+    /* The same fp16 weights cut into 16 KB HALF stages [64 n][128 k] — element (n,k) at byte
+     * (k/8)*1024 + (n/8)*128 + (n%8)*16 + (k%8)*2 — for the fused per-step kernel (t2s_dit_fused_step, H = 30), whose
+     * three-slot weight ring holds half stages.  NULL = not packed: the fused kernel is not used.
+     *   w_qkv_half[l]:  6 halves: q rows 0..63 | q rows 64..127 | k 0..63 | k 64..127 | v 0..63 | v 64..127
+     *   w_post_half[l]: 10 halves: proj h0 h1 | fc1 rows 0..127 h0 h1 | fc1 rows 128..255 h0 h1 |
+     *                   fc2 (cols 0..127, h0) (cols 128..255, h0) (cols 0..127, h1) (cols 128..255, h1)      */
+    const void* w_qkv_half[4];
+    const void* w_post_half[4];
 } t2s_dit_weights;
 
 /* LA-VAE decoder / encoder weights (model/pretrained/vqvae.py:36-105), fp32, [ic][k][oc] layouts. */
@@ -82,6 +90,14 @@ const char* t2s_last_error(void);
 
 /* Sets kernel attributes for the current device; call once per device before stream capture. */
 int t2s_init(void);
+
+/* The fused per-step kernel (one persistent cooperative launch per guided step, csrc/dit_fused.cuh) serves the T2S shape
+ * from `min_pairs` sequence pairs on (default 40; -1 = never: the per-phase kernels run instead); `inflight` bounds the
+ * pairs admitted and not yet finished (0 = no limit).  Process-wide tuning knobs, not needed for correctness. */
+void t2s_set_fused(int min_pairs, int inflight);
+/* Profiling aid: when non-NULL, every CTA of the fused kernel writes device_buf[blockIdx.x*8 + {0: token items, 1: token
+ * scheduler-starved cycles, 2: attention units, 3: attention starved cycles, 4: total cycles}]. */
+void t2s_debug_set_fused_stats(long long* device_buf);
 
 /* Profiling aid: when non-NULL, every token-block CTA writes clock64() stamps of its phase boundaries to
  * device_buf[blockIdx.x*32 + i] (see tools/phase_trace.py).  NULL (default) switches it off. */

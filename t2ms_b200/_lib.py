@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libt2s_b200.so")
 
 EXPORTS = [
-    "t2s_version", "t2s_last_error", "t2s_init", "t2s_debug_set_phase_trace", "t2s_dit_workspace_bytes", "t2s_dit_workspace_offsets",
+    "t2s_version", "t2s_last_error", "t2s_init", "t2s_debug_set_phase_trace", "t2s_set_fused", "t2s_debug_set_fused_stats", "t2s_dit_workspace_bytes", "t2s_dit_workspace_offsets",
     "t2s_dit_workspace_bytes_h", "t2s_dit_workspace_offsets_h", "t2s_dit_attention_h",
     "t2s_dit_forward", "t2s_sample", "t2s_sample_ddpm_seeded", "t2s_vae_decode", "t2s_vae_encode",
     "t2s_dit_cond", "t2s_dit_embed_qkv", "t2s_dit_attention", "t2s_dit_block_post", "t2s_dit_final",
@@ -28,7 +28,7 @@ P = C.c_void_p
 class DitWeights(C.Structure):
     _fields_ = [("w_qkv", P * 4), ("w_post", P * 4), ("b_qkv", P * 4), ("b_proj", P * 4), ("b_fc1", P * 4),
                 ("b_fc2", P * 4), ("w_ada_t", P), ("b_ada", P), ("w_embed", P), ("b_embed", P), ("pos", P),
-                ("w_final", P), ("b_final", P), ("freqs", P), ("latent_h", C.c_int)]
+                ("w_final", P), ("b_final", P), ("freqs", P), ("latent_h", C.c_int), ("w_qkv_half", P * 4), ("w_post_half", P * 4)]
 
 
 class DitParams(C.Structure):
@@ -80,6 +80,10 @@ def load() -> C.CDLL:
         lib.t2s_init.restype = i
         lib.t2s_debug_set_phase_trace.restype = None
         lib.t2s_debug_set_phase_trace.argtypes = [P]
+        lib.t2s_set_fused.restype = None
+        lib.t2s_set_fused.argtypes = [i, i]
+        lib.t2s_debug_set_fused_stats.restype = None
+        lib.t2s_debug_set_fused_stats.argtypes = [P]
         lib.t2s_dit_workspace_bytes.restype = sz
         lib.t2s_dit_workspace_bytes.argtypes = [i]
         lib.t2s_dit_workspace_offsets.restype = None

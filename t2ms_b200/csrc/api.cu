@@ -4,6 +4,7 @@
 
 #include "../../include/t2s_b200.h"
 #include "dit_kernels.cuh"
+#include "dit_fused.cuh"
 #include "vae_kernels.cuh"
 #include "eval_kernels.cuh"
 
@@ -26,6 +27,11 @@ using namespace t2s_api;
 
 namespace {
 long long* g_trace = nullptr;   // t2s_debug_set_phase_trace
+long long* g_fused_stats = nullptr;   // t2s_debug_set_fused_stats
+// fused per-step kernel (dit_fused.cuh): used for the T2S shape from this many sequence pairs on (fewer pairs cannot fill
+// both halves of 148 SMs: the per-phase kernels with their small-batch forms stay faster); -1 = never
+int g_fused_min_pairs = 40;
+int g_fused_inflight = 0;       // pairs admitted and not yet finished (0 = no limit)
 constexpr int MAX_DEV = 64;
 bool g_inited[MAX_DEV] = {};
 int g_sms[MAX_DEV] = {};
@@ -52,6 +58,7 @@ int t2s_api::ensure_init() {
     T2S_SET_ATTRS(50)
     T2S_SET_ATTRS(64)
 #undef T2S_SET_ATTRS
+    CUDA_OK(cudaFuncSetAttribute(fused_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES));
     const int dec = VAE_DEC_SMEM_FLOATS * 4, enc = VAE_ENC_SMEM_FLOATS * 4;
     CUDA_OK(cudaFuncSetAttribute(vae_decode_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec));
     CUDA_OK(cudaFuncSetAttribute(vae_decode_kernel<6, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec));
@@ -75,7 +82,7 @@ namespace {
 size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 struct Workspace {
-    float* h; __half* qkv; __half* o; float* mod;
+    float* h; __half* qkv; __half* o; float* mod; int* sched;
 };
 // run-time view of DitShape<H>
 struct Shape { int H, ntok, tiles_per_pair, head_halves, lat; };
@@ -96,21 +103,22 @@ int get_shape(int latent_h, Shape* s) {
         default: return fail(T2S_EINVAL, "unsupported latent width%s%s"); \
     }
 
-void ws_offsets(int nseq, const Shape& sh, size_t off[4], size_t* total) {
+void ws_offsets(int nseq, const Shape& sh, size_t off[5], size_t* total) {
     size_t p = 0;
     const size_t ntile = (size_t)((nseq + 1) / 2) * sh.tiles_per_pair;         // pair tiles of 128 rows
     off[0] = p; p = align256(p + ntile * TILE_ROWS * D * 4);                   // residual stream tiles, fp32
     off[1] = p; p = align256(p + (size_t)nseq * NHEAD * sh.head_halves * 2);   // q|k|v operand images, fp16
     off[2] = p; p = align256(p + ntile * TILE_ROWS * D * 2);                   // attention-output tiles, fp16
     off[3] = p; p = align256(p + (size_t)nseq * NLAYER * MOD * 4);
+    off[4] = p; p = align256(p + fused_sched_ints((nseq + 1) / 2) * 4);          // dataflow scheduler state of the fused step kernel
     if (total) *total = p;
 }
 Workspace ws_view(void* base, int nseq, const Shape& sh) {
-    size_t off[4];
+    size_t off[5];
     ws_offsets(nseq, sh, off, nullptr);
     char* b = static_cast<char*>(base);
     return Workspace{reinterpret_cast<float*>(b + off[0]), reinterpret_cast<__half*>(b + off[1]),
-                     reinterpret_cast<__half*>(b + off[2]), reinterpret_cast<float*>(b + off[3])};
+                     reinterpret_cast<__half*>(b + off[2]), reinterpret_cast<float*>(b + off[3]), reinterpret_cast<int*>(b + off[4])};
 }
 
 int check_ws(const void* ws, size_t bytes, int nseq, const Shape& sh) {
@@ -210,11 +218,47 @@ int launch_final(const t2s_dit_weights* w, int nseq, const Shape& sh, const Work
     return T2S_OK;
 }
 
+// ---- the fused per-step kernel (dit_fused.cuh): one cooperative persistent launch for everything after the conditioning
+bool use_fused(const t2s_dit_weights* w, int nseq, const Shape& sh) {
+    return sh.H == 30 && g_fused_min_pairs >= 0 && (nseq + 1) / 2 >= g_fused_min_pairs && w->w_qkv_half[0] != nullptr &&
+           w->w_post_half[0] != nullptr;
+}
+int launch_fused(const t2s_dit_weights* w, const float* x, int x_shift, int nseq, const Workspace& ws, int out_mode, float* out,
+                 float* x_upd, const float* noise, float cfg, float c1, float c2, float c3, cudaStream_t st, unsigned long long seed = 0,
+                 unsigned int step = 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    FusedArgs a;
+    memset(&a, 0, sizeof(a));
+    memcpy(&a.w, w, sizeof(DitWeights));
+    a.x = x; a.x_shift = x_shift; a.h = ws.h; a.qkv = ws.qkv; a.o = ws.o; a.mod = ws.mod; a.nseq = nseq;
+    a.out_mode = out_mode; a.out = out; a.x_upd = x_upd; a.noise = noise; a.seed = seed; a.step = step;
+    a.cfg = cfg; a.c1 = c1; a.c2 = c2; a.c3 = c3;
+    a.sched = ws.sched; a.inflight = g_fused_inflight; a.stats = g_fused_stats;
+    CUDA_OK(cudaMemsetAsync(ws.sched, 0, fused_sched_ints((nseq + 1) / 2) * 4, st));
+    // the CTAs wait on one another through the scheduler flags: a cooperative launch guarantees that all of them are resident
+    cudaLaunchConfig_t cfgl;
+    memset(&cfgl, 0, sizeof(cfgl));
+    cfgl.gridDim = dim3(g_sms[dev] > 0 ? g_sms[dev] : 148);
+    cfgl.blockDim = dim3(FS_THREADS);
+    cfgl.dynamicSmemBytes = FS_SMEM_BYTES;
+    cfgl.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfgl.attrs = attr;
+    cfgl.numAttrs = 1;
+    CUDA_OK(cudaLaunchKernelEx(&cfgl, fused_step_kernel, a));
+    return T2S_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
-int t2s_version(void) { return 100; }
+int t2s_version(void) { return 200; }
+void t2s_set_fused(int min_pairs, int inflight) { g_fused_min_pairs = min_pairs; g_fused_inflight = inflight; }
+void t2s_debug_set_fused_stats(long long* device_buf) { g_fused_stats = device_buf; }
 const char* t2s_last_error(void) { return g_err; }
 int t2s_init(void) { return ensure_init(); }
 void t2s_debug_set_phase_trace(long long* device_buf) { g_trace = device_buf; }
@@ -222,7 +266,7 @@ void t2s_debug_set_phase_trace(long long* device_buf) { g_trace = device_buf; }
 size_t t2s_dit_workspace_bytes_h(int nseq, int latent_h) {
     Shape sh;
     if (get_shape(latent_h, &sh) != T2S_OK) return 0;
-    size_t off[4], total = 0;
+    size_t off[5], total = 0;
     ws_offsets(nseq > 0 ? nseq : 0, sh, off, &total);
     return total;
 }
@@ -230,7 +274,9 @@ size_t t2s_dit_workspace_bytes(int nseq) { return t2s_dit_workspace_bytes_h(nseq
 int t2s_dit_workspace_offsets_h(int nseq, int latent_h, size_t offsets[4]) {
     Shape sh;
     TRY(get_shape(latent_h, &sh));
-    ws_offsets(nseq, sh, offsets, nullptr);
+    size_t off[5];
+    ws_offsets(nseq, sh, off, nullptr);
+    for (int i = 0; i < 4; ++i) offsets[i] = off[i];
     return T2S_OK;
 }
 void t2s_dit_workspace_offsets(int nseq, size_t offsets[4]) { t2s_dit_workspace_offsets_h(nseq, 30, offsets); }
@@ -284,6 +330,7 @@ int t2s_dit_forward(const t2s_dit_weights* w, const float* x, const float* t100,
     cudaStream_t st = (cudaStream_t)stream;
     const Workspace ws = ws_view(workspace, nseq, sh);
     TRY(launch_cond(w, t100, 1, emb, 0, 0, nseq, ws, st));
+    if (use_fused(w, nseq, sh)) return launch_fused(w, x, 0, nseq, ws, OUT_FWD, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, st);
     TRY(launch_embed(w, x, 0, nseq, sh, ws, st, true));
     for (int l = 0; l < NLAYER; ++l) {
         TRY(launch_attn(nseq, sh, ws, st));
@@ -304,8 +351,17 @@ int sample_impl(const t2s_dit_weights* w, int kind, float* x, const float* emb, 
     cudaStream_t st = (cudaStream_t)stream;
     const Workspace ws = ws_view(workspace, nseq, sh);
     const size_t lat = (size_t)batch * sh.lat;
+    const bool fused = use_fused(w, nseq, sh);
     for (int j = 0; j < steps; ++j) {
         TRY(launch_cond(w, t100 + j, 0, emb, 1, 1, nseq, ws, st));
+        if (fused) {
+            // one persistent launch per guided step: patch-embed, the four blocks (attention and token work of different
+            // sequence pairs overlapped on every SM), final projection, guidance mix and the Euler / ancestral update
+            TRY(launch_fused(w, x, 1, nseq, ws, kind == 0 ? OUT_RF : OUT_DDPM, pred_trace ? pred_trace + j * lat : nullptr, x,
+                             (kind == 1 && step_noise) ? step_noise + j * lat : nullptr, cfg_scale, coef[3 * j], coef[3 * j + 1],
+                             coef[3 * j + 2], st, seed, step0 + (unsigned int)j));
+            continue;
+        }
         TRY(launch_embed(w, x, 1, nseq, sh, ws, st, true));
         for (int l = 0; l < NLAYER; ++l) {
             TRY(launch_attn(nseq, sh, ws, st));

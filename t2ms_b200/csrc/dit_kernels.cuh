@@ -31,6 +31,9 @@ struct DitWeights {                 // device pointers; mirrors t2s_dit_weights 
     const float* b_final;           // [4]        linear_emb_to_patch.weight @ ln.bias + bias
     const float* freqs;             // [64]       10000 ** linspace(0,1,64)
     int latent_h;                   // latent width H: 0 / 30 (T2S), 50 or 64 (fork); selects the DitShape instantiation
+    // the same fp16 weights as 16 KB HALF stages [64 n][128 k] (K-chunk stride 1024 B) for the fused step kernel, or NULL:
+    const __half* w_qkv_half[NLAYER];   // 6 halves:  q n 0..63 | q n 64..127 | k .. | k .. | v .. | v ..
+    const __half* w_post_half[NLAYER];  // 10 halves: proj h0 h1 | fc1[0:128] h0 h1 | fc1[128:256] h0 h1 | fc2 (k0,h0) (k1,h0) (k0,h1) (k1,h1)
 };
 
 enum TokenMode { TOK_EMBED = 0, TOK_MID = 1, TOK_FINAL = 2 };
@@ -221,6 +224,13 @@ __device__ __forceinline__ void tc_gemm(uint32_t a_smem, uint32_t w_smem, uint32
 // in TMEM, which serves as the row buffer for the LayerNorm's second pass.  LayerNorm statistics of the two halves
 // are merged through shared memory (Chan's parallel-variance formula) behind a 256-thread named barrier.
 struct RowStats { float mean, rstd; };
+// per-column constants (biases): from shared memory (token_kernel stages them per item) or, GB = true, straight from global
+// memory through the read-only path (the fused step kernel: a warp-uniform address, one L1 sector per load)
+template <bool GB>
+__device__ __forceinline__ float4 ldv4(const float* p) {
+    if constexpr (GB) return __ldg(reinterpret_cast<const float4*>(p));
+    else return *reinterpret_cast<const float4*>(p);
+}
 struct HalfStats { float mean, m2; };
 
 // pipelined walk over NB 16-column blocks of a TMEM region (NB even)
@@ -265,6 +275,7 @@ __device__ __forceinline__ HalfStats half_stats(float shift, float sum, float sq
     st.m2 = fmaxf(sq - sum * sum * (1.f / 64), 0.f);
     return st;
 }
+template <bool GB = false>
 __device__ __forceinline__ HalfStats resid_pass_regs(uint32_t tacc, const float* __restrict__ gate, const float* __restrict__ bias,
                                                      const float4 (&hq)[16]) {
     float sum = 0.f, sq = 0.f, shift = 0.f;
@@ -276,7 +287,7 @@ __device__ __forceinline__ HalfStats resid_pass_regs(uint32_t tacc, const float*
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 g4 = *reinterpret_cast<const float4*>(gate + cb * 16 + q * 4);
-            const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 16 + q * 4);
+            const float4 b4 = ldv4<GB>(bias + cb * 16 + q * 4);
             float t0, t1, t2, t3;
             add2(t0, t1, a[q * 4 + 0], a[q * 4 + 1], b4.x, b4.y);
             add2(t2, t3, a[q * 4 + 2], a[q * 4 + 3], b4.z, b4.w);
@@ -290,7 +301,7 @@ __device__ __forceinline__ HalfStats resid_pass_regs(uint32_t tacc, const float*
     tmem_wait_st();
     return half_stats(shift, sum, sq);
 }
-template <bool STORE>
+template <bool STORE, bool GB = false>
 __device__ __forceinline__ HalfStats resid_pass_tmem(uint32_t tacc, uint32_t thin, const float* __restrict__ gate, const float* __restrict__ bias,
                                                      float* __restrict__ hdst, bool valid) {
     float sum = 0.f, sq = 0.f, shift = 0.f;
@@ -303,7 +314,7 @@ __device__ __forceinline__ HalfStats resid_pass_tmem(uint32_t tacc, uint32_t thi
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 g4 = *reinterpret_cast<const float4*>(gate + cb * 16 + q * 4);
-            const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 16 + q * 4);
+            const float4 b4 = ldv4<GB>(bias + cb * 16 + q * 4);
             float t0, t1, t2, t3;
             add2(t0, t1, a[q * 4 + 0], a[q * 4 + 1], b4.x, b4.y);
             add2(t2, t3, a[q * 4 + 2], a[q * 4 + 3], b4.z, b4.w);
@@ -364,11 +375,12 @@ __device__ __forceinline__ void ln_mod_store(uint32_t trow, RowStats st, const f
 
 // hidden = GELU_tanh(acc + b1) over this thread's 64 columns, packed to fp16 into an A operand image (timm Mlp,
 // transformer.py:99,105)
+template <bool GB = false>
 __device__ __forceinline__ void gelu_store(uint32_t taddr, const float* __restrict__ bias, uint8_t* abuf, int r, int kc0) {
     for_blocks16<4>(taddr, [&](int cb, float (&v)[16]) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bias + cb * 16 + q * 4);
+            const float4 b4 = ldv4<GB>(bias + cb * 16 + q * 4);
             float x0, x1, x2, x3;
             add2(x0, x1, v[q * 4 + 0], v[q * 4 + 1], b4.x, b4.y);
             add2(x2, x3, v[q * 4 + 2], v[q * 4 + 3], b4.z, b4.w);

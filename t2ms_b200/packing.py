@@ -25,6 +25,15 @@ def umma_stage(w: torch.Tensor) -> torch.Tensor:
     return w16.permute(2, 0, 1, 3).contiguous().reshape(-1)              # [k//8][n//8][n%8][k%8]
 
 
+def umma_half_stages(w: torch.Tensor) -> torch.Tensor:
+    """[128 n][128 k] weight block -> two fp16 HALF-stage images [64 n][128 k] (rows 0..63, rows 64..127), each in the
+    tcgen05 no-swizzle K-major canonical layout with a K-chunk stride of 1024 B: element (n,k) of a half at byte
+    (k//8)*1024 + (n//8)*128 + (n%8)*16 + (k%8)*2 (t2ms_b200/csrc/dit_fused.cuh: fs_gemm_half, LBO=1024, SBO=128)."""
+    assert tuple(w.shape) == (128, 128)
+    w16 = w.detach().to(torch.float16).reshape(2, 8, 8, 16, 8)          # [half][n//8][n%8][k//8][k%8]
+    return w16.permute(0, 3, 1, 2, 4).contiguous().reshape(-1)            # [half][k//8][n//8][n%8][k%8]
+
+
 TILE_TOK = {30: 60, 50: 50, 64: 64}      # tokens per pair tile for latent width H (csrc/common.cuh: DitShape)
 
 
@@ -59,6 +68,14 @@ class PackedDit:
                     umma_stage(w2[:, :D].contiguous()), umma_stage(w2[:, D:].contiguous())]
             post = torch.cat(post)
             assert qkv.numel() * 2 == 3 * 32768 and post.numel() * 2 == 5 * 32768
+            if sd["pos_embed"].shape[-2] == 480:                                    # T2S shape: half stages for the fused step kernel
+                qkv_h = torch.cat([umma_half_stages(wq[i * D:(i + 1) * D]) for i in range(3)])
+                f2a, f2b = umma_half_stages(w2[:, :D].contiguous()).reshape(2, -1), umma_half_stages(w2[:, D:].contiguous()).reshape(2, -1)
+                post_h = torch.cat([umma_half_stages(g(p + "attn.proj.weight")), umma_half_stages(w1[:D]), umma_half_stages(w1[D:]),
+                                    f2a[0], f2b[0], f2a[1], f2b[1]])
+                assert qkv_h.numel() * 2 == 6 * 16384 and post_h.numel() * 2 == 10 * 16384
+                keep += [qkv_h, post_h]
+                st.w_qkv_half[l], st.w_post_half[l] = _ptr(qkv_h), _ptr(post_h)
             bq, bp = g(p + "attn.qkv.bias").contiguous(), g(p + "attn.proj.bias").contiguous()
             b1, b2 = g(p + "mlp.fc1.bias").contiguous(), g(p + "mlp.fc2.bias").contiguous()
             keep += [qkv, post, bq, bp, b1, b2]

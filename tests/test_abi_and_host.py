@@ -33,7 +33,7 @@ def test_header_symbols_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/t2s_b200.h but not exported"
     assert sorted(declared) == sorted(_lib.EXPORTS)
-    assert lib.t2s_version() == 100
+    assert lib.t2s_version() == 200
 
 
 def test_workspace_sizes(lib):
