@@ -91,13 +91,17 @@ const char* t2s_last_error(void);
 /* Sets kernel attributes for the current device; call once per device before stream capture. */
 int t2s_init(void);
 
-/* The fused per-step kernel (one persistent cooperative launch per guided step, csrc/dit_fused.cuh) serves the T2S shape
- * from `min_pairs` sequence pairs on (default 40; -1 = never: the per-phase kernels run instead); `inflight` bounds the
- * pairs admitted and not yet finished (0 = no limit).  Process-wide tuning knobs, not needed for correctness. */
+/* The fused per-step kernel (one persistent cooperative launch per guided step: attention and token work of different
+ * sequence pairs co-resident on every SM, coupled by a dataflow scheduler; csrc/dit_fused.cuh) serves the T2S shape from
+ * `min_pairs` sequence pairs on; -1 (the default) = never: the per-phase kernels run, which measured faster (DESIGN.md
+ * §4.9).  `inflight` bounds the pairs admitted and not yet finished (0 = no limit).  Process-wide switches; results are
+ * the same either way (tests/test_gpu_fused.py). */
 void t2s_set_fused(int min_pairs, int inflight);
 /* Profiling aid: when non-NULL, every CTA of the fused kernel writes device_buf[blockIdx.x*8 + {0: token items, 1: token
  * scheduler-starved cycles, 2: attention units, 3: attention starved cycles, 4: total cycles}]. */
 void t2s_debug_set_fused_stats(long long* device_buf);
+/* ... and device_buf[(blockIdx.x*16 + item)*32 + i] = clock64() at phase boundary i of its first 16 token items (slot 31: mode*16 + layer + 1). */
+void t2s_debug_set_fused_trace(long long* device_buf);
 
 /* Profiling aid: when non-NULL, every token-block CTA writes clock64() stamps of its phase boundaries to
  * device_buf[blockIdx.x*32 + i] (see tools/phase_trace.py).  NULL (default) switches it off. */
@@ -148,6 +152,17 @@ int t2s_vae_decode(const t2s_vae_dec_weights* w, const float* z, float* series, 
  * before [batch][64][length/4] or NULL. */
 int t2s_vae_encode(const t2s_vae_enc_weights* w, const float* x, float* z, float* before, int batch, int length,
                    t2s_stream_t stream);
+
+/* Step-wise process maths for loops that call the backbone classes once per step (infer.py:82,88), element-wise, every
+ * operation rounded like the reference's torch expression:
+ *   t2s_rf_euler       RectifiedFlow.euler (model/backbone/rectified_flow.py:5-7): out = x + v * dt, n elements
+ *   t2s_ddpm_p_sample  DDPM.p_sample (model/backbone/DDPM.py:28-36): out = c1[b] * (xt - c2[b] * eps_hat) + c3[b] * noise with
+ *                      c1 = 1/sqrt(alpha_t), c2 = (1-alpha_t)/sqrt(1-alpha_bar_t), c3 = sqrt(beta_t) gathered per sample
+ *                      ([batch] device arrays), noise = the torch.randn of DDPM.py:35; [batch][elems_per_sample] tensors.
+ * (RectifiedFlow.create_flow and DDPM.q_sample are t2s_train_make_inputs.) */
+int t2s_rf_euler(const float* x, const float* v, float dt, float* out, size_t n, t2s_stream_t stream);
+int t2s_ddpm_p_sample(const float* xt, const float* eps_hat, const float* noise, const float* c1, const float* c2, const float* c3,
+                      float* out, int batch, int elems_per_sample, t2s_stream_t stream);
 
 /* Evaluation of generated series on the device (the step after the path): evaluation.py:166-181 calculate_mse and
  * evaluation.py:184-206 calculate_wape on univariate series (the (N, L, 1) arrays written at infer.py:117-121).

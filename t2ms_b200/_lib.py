@@ -13,13 +13,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libt2s_b200.so")
 
 EXPORTS = [
-    "t2s_version", "t2s_last_error", "t2s_init", "t2s_debug_set_phase_trace", "t2s_set_fused", "t2s_debug_set_fused_stats", "t2s_dit_workspace_bytes", "t2s_dit_workspace_offsets",
+    "t2s_version", "t2s_last_error", "t2s_init", "t2s_debug_set_phase_trace", "t2s_set_fused", "t2s_debug_set_fused_stats", "t2s_debug_set_fused_trace", "t2s_dit_workspace_bytes", "t2s_dit_workspace_offsets",
     "t2s_dit_workspace_bytes_h", "t2s_dit_workspace_offsets_h", "t2s_dit_attention_h",
     "t2s_dit_forward", "t2s_sample", "t2s_sample_ddpm_seeded", "t2s_vae_decode", "t2s_vae_encode",
     "t2s_dit_cond", "t2s_dit_embed_qkv", "t2s_dit_attention", "t2s_dit_block_post", "t2s_dit_final",
     "t2s_train_workspace_bytes", "t2s_train_workspace_bytes_h", "t2s_train_make_inputs_h", "t2s_dit_train_step", "t2s_dit_train_forward", "t2s_dit_train_backward",
     "t2s_train_make_inputs", "t2s_adamw_step", "t2s_gemm_tf32",
-    "t2s_series_metrics", "t2s_lavae_workspace_bytes", "t2s_lavae_encode", "t2s_lavae_decode", "t2s_lavae_train_step", "t2s_train_attention_scratch_bytes", "t2s_train_attention_forward", "t2s_train_attention_backward",
+    "t2s_series_metrics", "t2s_rf_euler", "t2s_ddpm_p_sample", "t2s_lavae_workspace_bytes", "t2s_lavae_encode", "t2s_lavae_decode", "t2s_lavae_train_step", "t2s_train_attention_scratch_bytes", "t2s_train_attention_forward", "t2s_train_attention_backward",
 ]
 
 P = C.c_void_p
@@ -84,6 +84,8 @@ def load() -> C.CDLL:
         lib.t2s_set_fused.argtypes = [i, i]
         lib.t2s_debug_set_fused_stats.restype = None
         lib.t2s_debug_set_fused_stats.argtypes = [P]
+        lib.t2s_debug_set_fused_trace.restype = None
+        lib.t2s_debug_set_fused_trace.argtypes = [P]
         lib.t2s_dit_workspace_bytes.restype = sz
         lib.t2s_dit_workspace_bytes.argtypes = [i]
         lib.t2s_dit_workspace_offsets.restype = None
@@ -139,6 +141,10 @@ def load() -> C.CDLL:
         lib.t2s_train_attention_forward.argtypes = [P, P, P, i, P, sz, P]
         lib.t2s_train_attention_backward.restype = i
         lib.t2s_train_attention_backward.argtypes = [P, P, P, P, P, i, P, sz, P]
+        lib.t2s_rf_euler.restype = i
+        lib.t2s_rf_euler.argtypes = [P, P, f, P, sz, P]
+        lib.t2s_ddpm_p_sample.restype = i
+        lib.t2s_ddpm_p_sample.argtypes = [P, P, P, P, P, P, P, i, i, P]
         lib.t2s_series_metrics.restype = i
         lib.t2s_series_metrics.argtypes = [P, P, i, i, P, P, P]
         lib.t2s_lavae_workspace_bytes.restype = sz

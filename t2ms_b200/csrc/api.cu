@@ -7,6 +7,7 @@
 #include "dit_fused.cuh"
 #include "vae_kernels.cuh"
 #include "eval_kernels.cuh"
+#include "backbone_kernels.cuh"
 
 using namespace t2s;
 
@@ -28,9 +29,10 @@ using namespace t2s_api;
 namespace {
 long long* g_trace = nullptr;   // t2s_debug_set_phase_trace
 long long* g_fused_stats = nullptr;   // t2s_debug_set_fused_stats
-// fused per-step kernel (dit_fused.cuh): used for the T2S shape from this many sequence pairs on (fewer pairs cannot fill
-// both halves of 148 SMs: the per-phase kernels with their small-batch forms stay faster); -1 = never
-int g_fused_min_pairs = 40;
+long long* g_fused_trace = nullptr;   // t2s_debug_set_fused_trace
+// fused per-step kernel (dit_fused.cuh): used for the T2S shape from this many sequence pairs on; -1 = never (the default:
+// measured slower than the per-phase kernels at every batch size; t2s_set_fused switches it on)
+int g_fused_min_pairs = -1;
 int g_fused_inflight = 0;       // pairs admitted and not yet finished (0 = no limit)
 constexpr int MAX_DEV = 64;
 bool g_inited[MAX_DEV] = {};
@@ -234,7 +236,7 @@ int launch_fused(const t2s_dit_weights* w, const float* x, int x_shift, int nseq
     a.x = x; a.x_shift = x_shift; a.h = ws.h; a.qkv = ws.qkv; a.o = ws.o; a.mod = ws.mod; a.nseq = nseq;
     a.out_mode = out_mode; a.out = out; a.x_upd = x_upd; a.noise = noise; a.seed = seed; a.step = step;
     a.cfg = cfg; a.c1 = c1; a.c2 = c2; a.c3 = c3;
-    a.sched = ws.sched; a.inflight = g_fused_inflight; a.stats = g_fused_stats;
+    a.sched = ws.sched; a.inflight = g_fused_inflight; a.stats = g_fused_stats; a.trace = g_fused_trace;
     CUDA_OK(cudaMemsetAsync(ws.sched, 0, fused_sched_ints((nseq + 1) / 2) * 4, st));
     // the CTAs wait on one another through the scheduler flags: a cooperative launch guarantees that all of them are resident
     cudaLaunchConfig_t cfgl;
@@ -259,6 +261,7 @@ extern "C" {
 int t2s_version(void) { return 200; }
 void t2s_set_fused(int min_pairs, int inflight) { g_fused_min_pairs = min_pairs; g_fused_inflight = inflight; }
 void t2s_debug_set_fused_stats(long long* device_buf) { g_fused_stats = device_buf; }
+void t2s_debug_set_fused_trace(long long* device_buf) { g_fused_trace = device_buf; }
 const char* t2s_last_error(void) { return g_err; }
 int t2s_init(void) { return ensure_init(); }
 void t2s_debug_set_phase_trace(long long* device_buf) { g_trace = device_buf; }
@@ -428,6 +431,27 @@ int t2s_vae_encode(const t2s_vae_enc_weights* w, const float* x, float* z, float
         case 96: T2S_VAE_LAUNCH(vae_encode_kernel, 24, ew, x, z, before); break;
         default: return fail(T2S_EINVAL, "t2s_vae_encode: length must be 24, 48 or 96%s%s");
     }
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+
+int t2s_rf_euler(const float* x, const float* v, float dt, float* out, size_t n, t2s_stream_t stream) {
+    if (!x || !v || !out || n == 0) return fail(T2S_EINVAL, "t2s_rf_euler: bad argument%s%s");
+    TRY(ensure_init());
+    const size_t blocks = (n + 255) / 256;
+    rf_euler_kernel<<<(unsigned)(blocks > 4736 ? 4736 : blocks), 256, 0, (cudaStream_t)stream>>>(x, v, dt, out, n);
+    CUDA_OK(cudaGetLastError());
+    return T2S_OK;
+}
+
+int t2s_ddpm_p_sample(const float* xt, const float* eps_hat, const float* noise, const float* c1, const float* c2, const float* c3,
+                      float* out, int batch, int elems_per_sample, t2s_stream_t stream) {
+    if (!xt || !eps_hat || !noise || !c1 || !c2 || !c3 || !out || batch <= 0 || elems_per_sample <= 0)
+        return fail(T2S_EINVAL, "t2s_ddpm_p_sample: bad argument%s%s");
+    TRY(ensure_init());
+    const size_t n = (size_t)batch * elems_per_sample, blocks = (n + 255) / 256;
+    ddpm_p_sample_kernel<<<(unsigned)(blocks > 4736 ? 4736 : blocks), 256, 0, (cudaStream_t)stream>>>(xt, eps_hat, noise, c1, c2, c3, out, n,
+                                                                                                   elems_per_sample);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }

@@ -177,6 +177,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar) : "memory");
 }
+// One arrival per WARP instead of one per thread: every arrival on an mbarrier wakes its suspended waiters (the MMA issuer
+// spun ~550 times per 128-arrival phase, each spin an MIO instruction queued in front of the compute warps' TMEM traffic).
+// Call with the whole warp converged, after each lane's own fences; the barrier's count is the number of WARPS.
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM (5th-gen tensor cores)

@@ -416,10 +416,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
 
     if (tid == 0) {
         for (int i = 0; i < B_VFREE; ++i) mbar_init(BAR(i), 1);                  // WFULL, WEMPTY, VFULL
-        for (int i = 0; i < 2; ++i) mbar_init(BAR(B_VFREE + i), 256 * NE);
+        for (int i = 0; i < 2; ++i) mbar_init(BAR(B_VFREE + i), 8 * NE);          // one arrival per epilogue WARP (mbar_arrive_warp)
         for (int e = 0; e < NE; ++e) {
             mbar_init(TBAR(e, T_OFULL), 1);
-            for (int i = T_A2; i <= T_DONE; ++i) mbar_init(TBAR(e, i), 256);
+            for (int i = T_A2; i <= T_DONE; ++i) mbar_init(TBAR(e, i), 8);
             mbar_init(TBAR(e, T_HAFREE), 1);
             for (int i = T_ACC; i < T_COUNT; ++i) mbar_init(TBAR(e, i), 1);
         }
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             ln_mod_store(trow + X, st, modb + 3 * D + c0, modb + 4 * D + c0, abuf, r, kc0);
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(TBAR(e, T_A2));
+            mbar_arrive_warp(TBAR(e, T_A2));
             STAMP(4);
             // hidden = GELU(fc1)                         (transformer.py:117)
             mbar_wait(TBAR(e, T_ACC + 1), par);
@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             gelu_store(trow + Y, vec + V_B1 + c0, habuf, r, kc0);
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(TBAR(e, T_HA));
+            mbar_arrive_warp(TBAR(e, T_HA));
             STAMP(6);
             mbar_wait(TBAR(e, T_ACC + 2), par);
             tc_fence_after();
@@ -723,7 +723,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             gelu_store(trow + Y, vec + V_B1 + D + c0, abuf, r, kc0);
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(TBAR(e, T_HB));
+            mbar_arrive_warp(TBAR(e, T_HB));
             STAMP(8);
             // x = x + gate_mlp * (hidden W2^T + b): X (parked x) + gate * Y -> Y
             mbar_wait(TBAR(e, T_ACC + 3), par);
@@ -740,7 +740,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             ln_mod_store(trow + HREG, st, modn + c0, modn + D + c0, abuf, r, kc0);
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(TBAR(e, T_A3));
+            mbar_arrive_warp(TBAR(e, T_A3));
             STAMP(11);
             // q | k | v = a' W^T + b, stored fp16 in the attention kernel's smem image layout
 #pragma unroll 1
@@ -775,10 +775,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 STAMP(13 + 2 * which);
                 if (which == 0) {                                        // X drained: the v chunk may overwrite it
                     tc_fence_before();
-                    mbar_arrive(TBAR(e, T_XFREE));
+                    mbar_arrive_warp(TBAR(e, T_XFREE));
                 } else if (which == 1 && MODE == TOK_MID) {              // Y drained: the next item's proj may overwrite it
                     tc_fence_before();
-                    mbar_arrive(TBAR(e, T_DONE));
+                    mbar_arrive_warp(TBAR(e, T_DONE));
                 }
             }
         } else {
@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 }
             });
             tc_fence_before();
-            mbar_arrive(TBAR(e, T_DONE));                                // Y drained: the next item's proj may overwrite it
+            mbar_arrive_warp(TBAR(e, T_DONE));                                // Y drained: the next item's proj may overwrite it
             float* vb = reinterpret_cast<float*>(smem + TC_SM_VB) + e * TILE_ROWS * 4;
             float4* px = reinterpret_cast<float4*>(stx);                 // the statistics exchange is idle now: partial sums of half 1
             asm volatile("bar.sync %0, 256;\n" :: "r"(1 + e) : "memory");  // ... once every thread has read its merge partner
@@ -843,7 +843,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             }
         }
         // item done: this vector buffer may be reused (the producer's copies for the item after next wait on it)
-        mbar_arrive(BAR(B_VFREE + (it & 1)));
+        mbar_arrive_warp(BAR(B_VFREE + (it & 1)));
         STAMP(18);
         }
     }
@@ -949,11 +949,11 @@ __global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::C
             for (int b = 0; b < 2; ++b) {
                 mbar_init(bg + 8u * (AB_SFULL + b), 1);
                 mbar_init(bg + 8u * (AB_SFREE + b), 128);
-                mbar_init(bg + 8u * (AB_PFULL + b), 128);
+                mbar_init(bg + 8u * (AB_PFULL + b), 4);            // one arrival per softmax WARP (mbar_arrive_warp)
                 mbar_init(bg + 8u * (AB_PVDONE + b), 1);
             }
             mbar_init(bg + 8u * AB_OFULL, 1);
-            mbar_init(bg + 8u * AB_OFREE, 128);
+            mbar_init(bg + 8u * AB_OFREE, 4);
         }
         mbar_fence_init();
     }
@@ -1031,7 +1031,7 @@ __global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::C
             tmem_ld32(trow + ATT_T_O, a0);
             tmem_wait_ld();
             tc_fence_before();
-            mbar_arrive(BAR(AB_OFREE));
+            mbar_arrive_warp(BAR(AB_OFREE));
             if (r < QT_ROWS) {
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8)
@@ -1098,7 +1098,7 @@ __global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::C
                 if (j == 0 && qt > 0) finish(qt - 1, lprev);  // previous q-tile's O -> global before its accumulator is reused
                 tmem_wait_st();
                 tc_fence_before();
-                mbar_arrive(BAR(AB_PFULL + b));
+                mbar_arrive_warp(BAR(AB_PFULL + b));
             }
             ASTAMP(1 + qt);
             lprev = l0 + l1;

@@ -184,23 +184,15 @@ def _aligned(ws: torch.Tensor) -> int:
 
 
 def dit_forward(model: Transformer, x: torch.Tensor, t: torch.Tensor, text: Optional[torch.Tensor]) -> torch.Tensor:
-    lib = _lib.load()
+    """Transformer.forward through the custom op ``t2s_b200::dit_forward`` (t2ms_b200/ops.py -> t2s_dit_forward)."""
+    from . import ops
     B = x.shape[0]
     assert x.shape[1:] == (64, model.H), f"latent must be (B,64,{model.H}), got {tuple(x.shape)}"
     x = x.detach().to(torch.float32).contiguous()
     t100 = (t.detach() * 100.0).to(torch.float32).contiguous()          # transformer.py:31
     assert t100.shape == (B,)
-    emb_ptr = None
     if text is not None:
         text = text.detach().to(torch.float32).contiguous()
         assert text.shape == (B, D_MODEL)
-        emb_ptr = text.data_ptr()
-    out = torch.empty_like(x)
     pk = model.packed()
-    ws = model.workspace(B, x.device)
-    nbytes = lib.t2s_dit_workspace_bytes_h(B, model.H)
-    with torch.cuda.device(x.device):
-        rc = lib.t2s_dit_forward(pk.ref, x.data_ptr(), t100.data_ptr(), emb_ptr, out.data_ptr(), B, _aligned(ws), nbytes,
-                                 torch.cuda.current_stream().cuda_stream)
-    _lib.check(rc, "t2s_dit_forward")
-    return out
+    return ops.dit_forward(x, t100, text, model.workspace(B, x.device), pk.handle, model.H)

@@ -109,15 +109,9 @@ class Encoder(_PackedMixin, nn.Module):
         B, L = inputs.shape[0], inputs.shape[-1]
         if L not in LENGTHS:
             raise ValueError(f"series length must be one of {LENGTHS}, got {L}")
+        from . import ops
         x = inputs.detach().reshape(B, L).to(torch.float32).contiguous()
-        z = torch.empty(B, 64, 30, device=x.device, dtype=torch.float32)
-        before = torch.empty(B, 64, L // 4, device=x.device, dtype=torch.float32)
-        pk = self._packed_weights()
-        with torch.cuda.device(x.device):
-            rc = _lib.load().t2s_vae_encode(pk.ref, x.data_ptr(), z.data_ptr(), before.data_ptr(), B, L,
-                                            torch.cuda.current_stream().cuda_stream)
-        _lib.check(rc, "t2s_vae_encode")
-        return z, before
+        return ops.vae_encode(x, self._packed_weights().handle)          # custom op t2s_b200::vae_encode -> t2s_vae_encode
 
 
 class Decoder(_PackedMixin, nn.Module):
@@ -133,11 +127,10 @@ class Decoder(_PackedMixin, nn.Module):
         self._conv_trans_2 = nn.ConvTranspose1d(num_hiddens // 2, 1, kernel_size=4, stride=2, padding=1)
 
     def decode_into(self, z: torch.Tensor, length: int, series: torch.Tensor, after=None):
-        pk = self._packed_weights()
-        with torch.cuda.device(z.device):
-            rc = _lib.load().t2s_vae_decode(pk.ref, z.data_ptr(), series.data_ptr(), after.data_ptr() if after is not None else None,
-                                            z.shape[0], int(length), torch.cuda.current_stream().cuda_stream)
-        _lib.check(rc, "t2s_vae_decode")
+        """Decode into a caller-owned (B, length) buffer (custom op t2s_b200::vae_decode_into)."""
+        from . import ops
+        assert after is None and series.shape[1] == int(length)
+        ops.vae_decode_into(z, series, self._packed_weights().handle)
 
     def forward(self, inputs, length):
         if not inputs.is_cuda:
@@ -147,11 +140,9 @@ class Decoder(_PackedMixin, nn.Module):
             raise ValueError(f"series length must be one of {LENGTHS}, got {length}")
         z = inputs.detach().to(torch.float32).contiguous()
         assert z.shape[1:] == (64, 30), f"latent must be (B,64,30), got {tuple(z.shape)}"
-        B = z.shape[0]
-        series = torch.empty(B, 1, length, device=z.device, dtype=torch.float32)
-        after = torch.empty(B, 64, length // 4, device=z.device, dtype=torch.float32)
-        self.decode_into(z, length, series, after)
-        return torch.squeeze(series), after          # vqvae.py:105 (drops the batch dim at B == 1)
+        from . import ops
+        series, after = ops.vae_decode(z, length, self._packed_weights().handle)      # custom op -> t2s_vae_decode
+        return torch.squeeze(series.unsqueeze(1)), after          # vqvae.py:105 squeezes (B,1,L): drops the batch dim too at B == 1
 
 
 class vqvae(BaseModel):

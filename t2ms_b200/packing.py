@@ -104,6 +104,8 @@ class PackedDit:
         self._keep = keep
         self.device = device
         self.latent_h = latent_h
+        from . import ops
+        self.handle = ops.register_handle(self)          # what the torch.library ops take instead of a pointer struct
 
 
 def _conv_w(w):      # Conv1d weight [oc][ic][k] -> [ic][k][oc]
@@ -134,6 +136,8 @@ class PackedVaeDecoder:
             t[f"w3{i}"], t[f"w1{i}"] = w3, w1
             st.res_w3[i], st.res_w1[i] = _ptr(w3), _ptr(w1)
         self.struct, self.ref, self._keep, self.device = st, C.byref(st), t, device
+        from . import ops
+        self.handle = ops.register_handle(self)
 
 
 class PackedVaeEncoder:
@@ -156,3 +160,5 @@ class PackedVaeEncoder:
             t[f"w3{i}"], t[f"w1{i}"] = w3, w1
             st.res_w3[i], st.res_w1[i] = _ptr(w3), _ptr(w1)
         self.struct, self.ref, self._keep, self.device = st, C.byref(st), t, device
+        from . import ops
+        self.handle = ops.register_handle(self)

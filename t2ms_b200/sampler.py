@@ -20,6 +20,11 @@ from .denoiser import Transformer, _aligned
 KIND = {"flowmatching": 0, "rf": 0, "rectified_flow": 0, "ddpm": 1}
 
 
+def _signed64(v: int) -> int:
+    """64-bit pattern as the signed int a custom-op `int` argument carries."""
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
 class T2SSampler:
     NOISE_WINDOW_BYTES = 1 << 30          # DDPM step noise drawn per window of steps when the caller supplies none
 
@@ -31,7 +36,7 @@ class T2SSampler:
         self._tables = {}
         self._graphs = {}
 
-    def _table(self, kind: int, steps: int, device) -> Tuple[torch.Tensor, C.Array]:
+    def _table(self, kind: int, steps: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
         key = (kind, steps, str(device))
         if key not in self._tables:
             if kind == 0:
@@ -41,8 +46,7 @@ class T2SSampler:
                 t = DDPM.timesteps(steps)
                 coef = DDPM.coefficients(steps)
             t100 = (t * 100.0).to(torch.float32).to(device)             # TimeEmbedding, transformer.py:31
-            flat = coef.reshape(-1).tolist()
-            self._tables[key] = (t100, (C.c_float * len(flat))(*flat))
+            self._tables[key] = (t100, coef.to(torch.float32).contiguous())      # coefficients stay on the host: launch parameters
         return self._tables[key]
 
     @torch.no_grad()
@@ -58,7 +62,7 @@ class T2SSampler:
         ``noise_source="torch"`` draws it with ``torch.randn`` per window of steps."""
         if not emb.is_cuda:
             raise RuntimeError("T2SSampler needs CUDA tensors (no CPU fallback); use sample_host for host buffers")
-        lib = _lib.load()
+        from . import ops
         kind = KIND[backbone]
         dev = emb.device
         B, H = emb.shape[0], self.dit.H
@@ -74,12 +78,9 @@ class T2SSampler:
             assert step_noise.shape == (steps, B, 64, H)
         tr = torch.empty(steps, B, 64, H, device=dev, dtype=torch.float32) if trace else None
         t100, coef = self._table(kind, steps, dev)
-        coef_p = C.cast(coef, C.c_void_p).value
         pk = self.dit.packed()
         chunk = B if not chunk else min(int(chunk), B)
         ws = self.dit.workspace(2 * chunk, dev)
-        nbytes = lib.t2s_dit_workspace_bytes_h(2 * chunk, H)
-        stream = torch.cuda.current_stream(dev).cuda_stream
         # DDPM draws fresh Gaussian noise inside every p_sample (DDPM.py:35).  When the caller does not supply it, it is drawn
         # here in windows of steps (<= NOISE_WINDOW_BYTES at a time) and the loop is enqueued window by window through the
         # same C entry (t100 / coef offset by the window start): no host synchronisation, bounded memory at any batch size.
@@ -107,20 +108,14 @@ class T2SSampler:
                         sn = sn_w[:, b0:b0 + nb].contiguous() if nb != B else sn_w
                     if trace:
                         tr_c = tr[j0:j0 + nj] if nb == B else torch.empty(nj, nb, 64, H, device=dev, dtype=torch.float32)
+                    # one custom-op call (t2s_b200::sample_loop -> t2s_sample / t2s_sample_ddpm_seeded) enqueues the whole window
                     if philox:
                         # every batch chunk gets its own key so that element indices (local to a call) never repeat a stream
-                        rc = lib.t2s_sample_ddpm_seeded(pk.ref, x[b0:b0 + nb].data_ptr(), emb[b0:b0 + nb].data_ptr(), t100.data_ptr(), coef,
-                                                        C.c_ulonglong((seed + 0x9E3779B97F4A7C15 * (b0 // chunk)) & (2 ** 64 - 1)),
-                                                        tr_c.data_ptr() if tr_c is not None else None, nb, steps, float(cfg_scale),
-                                                        _aligned(ws), nbytes, stream)
-                        _lib.check(rc, "t2s_sample_ddpm_seeded")
-                        if trace and nb != B:
-                            tr[:, b0:b0 + nb] = tr_c
-                        continue
-                    rc = lib.t2s_sample(pk.ref, kind, x[b0:b0 + nb].data_ptr(), emb[b0:b0 + nb].data_ptr(), t100.data_ptr() + 4 * j0,
-                                        C.cast(C.c_void_p(coef_p + 12 * j0), C.POINTER(C.c_float)), sn.data_ptr() if sn is not None else None,
-                                        tr_c.data_ptr() if tr_c is not None else None, nb, nj, float(cfg_scale), _aligned(ws), nbytes, stream)
-                    _lib.check(rc, "t2s_sample")
+                        ops.sample_loop(x[b0:b0 + nb], emb[b0:b0 + nb], t100, coef, None, tr_c, ws, 1, steps, float(cfg_scale),
+                                        _signed64((seed + 0x9E3779B97F4A7C15 * (b0 // chunk)) & (2 ** 64 - 1)), True, pk.handle, H)
+                    else:
+                        ops.sample_loop(x[b0:b0 + nb], emb[b0:b0 + nb], t100[j0:j0 + nj], coef[j0:j0 + nj], sn, tr_c, ws, kind, nj,
+                                        float(cfg_scale), 0, False, pk.handle, H)
                     if trace and nb != B:
                         tr[j0:j0 + nj, b0:b0 + nb] = tr_c
         return (x, tr) if trace else x

@@ -1,0 +1,61 @@
+"""The fused per-step kernel (csrc/dit_fused.cuh; off by default, t2s_set_fused switches it on): same results as the
+per-phase kernels and the reference golden vectors.  Covers an odd sequence count (the missing second sequence of the last
+pair), cond / uncond / int-t forwards, the guided RF and DDPM loops with the fused update, and a batch that spreads over
+every SM."""
+import pytest
+import torch
+
+from conftest import T, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def fused():
+    from t2ms_b200 import _lib
+    lib = _lib.load()
+    lib.t2s_set_fused(1, 0)
+    yield lib
+    lib.t2s_set_fused(-1, 0)
+
+
+def test_fused_forward_matches_reference_golden(fused):
+    from gpu_util import DEV, make_dit, rel_l2
+    g = load_golden("dit_forward.npz")
+    dit, _ = make_dit(int(g["dit_seed"]), bias_std=float(g["bias_std"]))
+    x, emb = T(g["x"]).to(DEV), T(g["emb"]).to(DEV)
+    with torch.no_grad():
+        for key, t, e in (("cond_float", T(g["t_float"]), emb), ("uncond_float", T(g["t_float"]), None), ("cond_int", T(g["t_int"]), emb)):
+            out = dit(input=x, t=t.to(DEV), text_input=e)
+            err = rel_l2(out, T(g[key]))
+            print("fused forward", key, "rel-L2 %.2e" % err)
+            assert err < 2e-3
+
+
+def test_fused_sampling_matches_reference_golden_and_per_phase_kernels(fused):
+    from gpu_util import DEV, make_dit, make_vae, max_abs, rel_l2
+    from t2ms_b200 import T2SSampler, synth
+    g = load_golden("sampling.npz")
+    dit, _ = make_dit(int(g["dit_seed"]), bias_std=float(g["bias_std"]))
+    vae, _ = make_vae(int(g["vae_seed"]))
+    smp = T2SSampler(dit, vae)
+    emb = T(g["emb"]).to(DEV)
+    k = "rf_5_96_"
+    lat, trace = smp.sample_latent(emb, steps=5, cfg_scale=float(g[k + "cfg"]), noise=T(g[k + "noise"]).to(DEV), trace=True)
+    assert max(rel_l2(trace[j], T(g[k + "vel"])[j]) for j in range(5)) < 2e-3
+    assert max_abs(lat, T(g[k + "latent"])) < 1e-2
+    steps = int(g["ddpm_steps"])
+    lat, trace = smp.sample_latent(emb, steps=steps, cfg_scale=float(g["ddpm_cfg"]), backbone="ddpm", noise=T(g["ddpm_noise"]).to(DEV),
+                                   step_noise=T(g["ddpm_step_noise"]).to(DEV), trace=True)
+    assert max(rel_l2(trace[j], T(g["ddpm_eps"])[j]) for j in range(steps)) < 2e-3
+    assert rel_l2(lat, T(g["ddpm_latent"])) < 2e-3
+    # a batch over every SM: bit-identical to the per-phase kernels (same tiles, same MMA shapes per output element,
+    # same attention chunking), run to run, and with the admission gate
+    B = 200
+    e2, x0 = synth.make_text_embeddings(B, seed=5).to(DEV), synth.make_noise(B, seed=6).to(DEV)
+    a = smp.sample(e2, 96, steps=3, noise=x0)
+    assert torch.equal(a, smp.sample(e2, 96, steps=3, noise=x0))
+    fused.t2s_set_fused(1, 24)
+    assert torch.equal(a, smp.sample(e2, 96, steps=3, noise=x0))
+    fused.t2s_set_fused(-1, 0)
+    assert torch.equal(a, smp.sample(e2, 96, steps=3, noise=x0))

@@ -64,3 +64,35 @@ def test_run_inference_writes_reference_formats(tmp_path):
     o, x = np.transpose(x_1, (0, 2, 1)), np.transpose(x_t, (0, 2, 1))               # evaluation.py:295-296
     assert abs(metrics["MSE"] - O.calculate_mse(o, x)) <= 1e-6 * O.calculate_mse(o, x)
     assert abs(metrics["WAPE"] - O.calculate_wape(o, x)) <= 1e-6 * O.calculate_wape(o, x)
+
+
+def test_backbone_classes_on_cuda_match_reference_golden():
+    """RectifiedFlow.euler / create_flow and DDPM.q_sample / p_sample (model/backbone/*.py) on CUDA tensors, through the custom
+    ops and the C-ABI kernels, against outputs of the reference classes (tests/golden/backbone.npz).  p_sample draws its
+    noise with torch.randn inside, like the reference: the golden draw is substituted to compare values."""
+    import unittest.mock as um
+    from conftest import T, load_golden
+    from gpu_util import DEV, max_abs
+    from oracle import t2s_oracle as O
+    from t2ms_b200 import DDPM, RectifiedFlow
+    g = load_golden("backbone.npz")
+    x1, t, eps, ti = (T(g[k]).to(DEV) for k in ("x1", "t", "eps", "ti"))
+    rf, dd = RectifiedFlow(), DDPM(1000, DEV)
+    assert max_abs(rf.euler(x1, eps, 0.01), T(g["euler"])) == 0.0
+    x_t, x_0 = rf.create_flow(x1, t)
+    assert x_0.shape == x1.shape and abs(float(x_0.mean())) < 0.05 and abs(float(x_0.std()) - 1) < 0.05
+    assert max_abs(x_t, O.rf_create_flow(x1.cpu(), t.cpu(), x_0.cpu())) < 1e-6
+    with um.patch.object(torch, "randn_like", lambda x: T(g["x0"]).to(DEV)):
+        x_t, x_0 = rf.create_flow(x1, t)
+    assert max_abs(x_0, T(g["x0"])) == 0.0 and max_abs(x_t, T(g["x_t"])) < 1e-6
+    q, e = dd.q_sample(x1, ti, eps)
+    assert e is eps and max_abs(q, T(g["q_sample"])) < 1e-6
+    mean, var = dd.q_xt_x0(x1, ti)
+    assert max_abs(mean + var ** 0.5 * eps, T(g["q_sample"])) < 1e-6
+    with um.patch.object(torch, "randn", lambda *a, **k: T(g["p_noise"]).to(DEV)):
+        p = dd.p_sample(x1, eps, ti)
+    assert max_abs(p, T(g["p_sample"])) < 1e-6
+    p2 = dd.p_sample(x1, eps, ti)                                  # its own draw: another sample of the same distribution
+    assert max_abs(p2, p) > 1e-3 and torch.isfinite(p2).all()
+    for bb in ("beta", "alpha", "alpha_bar"):
+        assert max_abs(getattr(dd, bb), T(g[bb])) < 1e-7

@@ -88,6 +88,26 @@ print("   starved share of the kernel: token %.1f %%, attention %.1f %%; kernel 
 res["token_starved"] = (s[:, 1].float() / tot).mean().item()
 res["attn_starved"] = (s[:, 3].float() / tot).mean().item()
 res["kernel_cycles"] = tot.mean().item()
-lib.t2s_set_fused(40, 0)
+# phase trace of the token epilogue (row 0, half 0): MID items of every CTA, items 4..15 (steady state)
+trace = torch.zeros(148 * 16 * 32, dtype=torch.int64, device=dev)
+lib.t2s_set_fused(1, a.inflight)
+lib.t2s_debug_set_fused_trace(trace.data_ptr())
+smp.sample(emb, 96, steps=1, noise=x0)
+torch.cuda.synchronize()
+lib.t2s_debug_set_fused_trace(None)
+t = trace.view(148, 16, 32).cpu()
+names = ["desc", "vec", "hq/acc0 wait", "resid+ln1 -> A2", "acc1 wait", "gelu a", "acc2 wait", "gelu b", "acc3 wait", "resid2+merge", "ln' -> A3",
+         "acc4 wait", "q store", "acc5 wait", "k store", "acc6 wait", "v store", "end barrier", "tok_done"]
+for mode, label in ((1, "MID"), (0, "EMBED"), (2, "FINAL")):
+    sel = [(c, i) for c in range(148) for i in range(3, 15) if t[c, i, 31] // 16 == mode and t[c, i, 31] > 0 and t[c, i + 1, 0] > 0]
+    if not sel:
+        continue
+    d = torch.stack([t[c, i, 1:20] - t[c, i, 0:19] for c, i in sel]).float()
+    d = torch.where((torch.stack([t[c, i, 1:20] for c, i in sel]) > 0) & (torch.stack([t[c, i, 0:19] for c, i in sel]) > 0), d, torch.zeros_like(d))
+    tot = torch.tensor([float(t[c, i + 1, 0] - t[c, i, 0]) for c, i in sel])
+    print(f"{label}: {len(sel)} items, {tot.mean():.0f} cycles per item (median {tot.median():.0f})")
+    print("   " + ", ".join(f"{n} {v:.0f}" for n, v in zip(names, d.mean(0).tolist()) if v > 0))
+    res[f"trace_{label}"] = {"cycles": tot.mean().item(), **{n: v for n, v in zip(names, d.mean(0).tolist())}}
+lib.t2s_set_fused(-1, 0)
 if a.out:
     json.dump(res, open(a.out, "w"), indent=1)
