@@ -81,6 +81,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=24, help="series in the bounded CPU-baseline sample (~10-15 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-PyTorch-eager-on-this-GPU baseline leg")
+    ap.add_argument("--fused", action="store_true", help="run the guided steps through the fused per-step kernel (csrc/dit_fused.cuh; off by default)")
+    ap.add_argument("--strong", action="store_true",
+                    help="also time the GLOBAL batch (batch x gpus) on rank 0 alone and add a strong_scaling object (BASELINE config 3)")
     ap.add_argument("--train-batch", type=int, default=256, help="latents per GPU per optimizer step of the training leg (0 = skip)")
     return ap.parse_args()
 
@@ -379,6 +382,9 @@ def main():
     vae.load_state_dict(synth.make_vae_state(1))
     vae = vae.to(dev).eval()
     smp = T2SSampler(dit, vae)
+    if a.fused:
+        from t2ms_b200 import _lib
+        _lib.load().t2s_set_fused(1, 0)
     B = a.batch
     gen = torch.Generator().manual_seed(1234 + rank)
     emb_host = torch.nn.functional.normalize(torch.randn(B, 128, generator=gen), dim=-1).pin_memory()
@@ -426,6 +432,27 @@ def main():
 
     value = world * B * a.steps / (ms / 1e3)
     e2e = world * B * a.steps / (ms_e2e / 1e3)
+    strong = None
+    if a.strong and world > 1:
+        # strong scaling (BASELINE config 3: a fixed global batch sharded over the GPUs): the same global batch on ONE GPU, timed
+        # on rank 0 while the other ranks wait; efficiency = rate_N / (N x rate_1) at equal global batch
+        if rank == 0:
+            Bg = B * world
+            emb_g = torch.nn.functional.normalize(torch.randn(Bg, 128, generator=gen), dim=-1).to(dev)
+            noise_g = torch.randn(Bg, 64, 30, device=dev)
+            smp.sample(emb_g, a.length, noise=noise_g, **kw)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            smp.sample(emb_g, a.length, noise=noise_g, **kw)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            one = Bg / (e0.elapsed_time(e1) / 1e3)
+            strong = {"global_batch": Bg, "batch_per_gpu": B, "n_gpus": world, "value": value, "unit": UNIT, "single_gpu_value": one,
+                      "efficiency": value / (world * one),
+                      "note": "same global batch on one GPU of the same box (rank 0, after the timed region); the loss is wave quantisation "
+                              "of small per-GPU batches on 148 SMs, not communication (no collective inside the loop)"}
+        dist.barrier()
     del flush
     train = train_leg(a, dev, rank, world, dist) if a.train_batch > 0 else None
     line = None
@@ -449,7 +476,7 @@ def main():
                        "l2": "256 MiB flush write between timed iterations; per-step working set (1.5 GB scratch) exceeds the 126 MB L2"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": emb_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
                     "ms_per_step": ms_e2e / a.steps},
-            "gpu_launches": a.steps * (a.rf_steps * 10 * n_chunks + 1),
+            "gpu_launches": a.steps * (a.rf_steps * (2 if a.fused else 10) * n_chunks + 1),
             "clocks": clocks,
             "tflops_algorithmic": world * B * a.steps * (2 * a.rf_steps * FLOP_FWD + FLOP_DECODE_96) / (ms / 1e3) / 1e12,
             "roofline": {"bound": "tensor", "kernel": "attn_kernel" if dom == "attention" else "token_kernel<MID>",
@@ -465,6 +492,15 @@ def main():
             "kernel_share_of_step": shares,
         }
         line["train"] = train
+        if strong is not None:
+            line["strong_scaling"] = strong
+        # the memory-bound tail of the path: LA-VAE decode (one launch per batch), reported against the measured HBM peak
+        dec_ms = kb["vae_decode"]
+        dec_bytes = (nseq // 2) * (64 * 30 * 4 + a.length * 4) + 319_937 * 4
+        line["vae_decode"] = {"ms": dec_ms, "series": nseq // 2, "algorithmic_bytes": dec_bytes, "achieved_gbs": dec_bytes / (dec_ms * 1e-3) / 1e9,
+                              "hbm_peak_gbs": pk["hbm"], "frac_of_hbm_peak": dec_bytes / (dec_ms * 1e-3) / 1e9 / pk["hbm"],
+                              "tflops_fp32": (nseq // 2) * 640_000 * (a.length // 4) / (dec_ms * 1e-3) / 1e12,
+                              "bound": "latency / L2 weight reads (1.28 MB of fp32 weights per group of series), 0.1 % of the workload's time"}
         if not a.no_cpu_baseline and world == 1:       # reported at N=1 only (host cores are shared by the ranks otherwise)
             v, dt, threads, kind = cpu_reference_run(a, a.cpu_sample)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,

@@ -151,22 +151,31 @@ int token_grid(int nseq, const Shape& sh, int ne) {
         else token_kernel<MODE_, HH_, 1><<<token_grid(nseq, sh, 1), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);             \
     }
 
-TokArgs base_args(const t2s_dit_weights* w, const Workspace& ws, int nseq) {
+// set by sample_impl for the launches of a guided loop whose cond kernel writes one shared unconditional modulation row
+thread_local bool g_uncond_shared = false;
+TokArgs base_args(const t2s_dit_weights* w, const Workspace& ws, int nseq, bool uncond_shared = g_uncond_shared) {
     TokArgs a;
     memset(&a, 0, sizeof(a));
     memcpy(&a.w, w, sizeof(DitWeights));
     a.h = ws.h; a.qkv = ws.qkv; a.o = ws.o; a.mod = ws.mod; a.nseq = nseq;
+    a.uncond_shared = uncond_shared ? 1 : 0;
     a.trace = g_trace;
     return a;
 }
 
+// uncond_shared (guided loops at throughput batch sizes): ONE unconditional modulation row per step (sequence 0) instead of one
+// per sample; the token kernels of the same loop read it for every pair (TokArgs / FusedArgs uncond_shared)
+bool cond_uncond_shared(int nseq, int cfg_pairs) { return cfg_pairs && nseq > 64; }
 int launch_cond(const t2s_dit_weights* w, const float* t100, int t_stride, const float* emb, int emb_shift, int cfg_pairs,
-                int nseq, const Workspace& ws, cudaStream_t st) {
+                int nseq, const Workspace& ws, cudaStream_t st, bool uncond_shared = false) {
     if (nseq <= 64)
         cond_split_kernel<<<dim3((nseq + 7) / 8, NLAYER * 3), 256, 0, st>>>(ws.mod, t100, t_stride, emb, emb_shift, cfg_pairs, w->freqs, w->w_ada_t,
                                                                            w->b_ada, nseq);
+    else if (uncond_shared)
+        cond_kernel<<<dim3((nseq / 2 + 7) / 8 + 1, NLAYER), 256, 0, st>>>(ws.mod, t100, t_stride, emb, emb_shift, cfg_pairs, w->freqs, w->w_ada_t,
+                                                                         w->b_ada, nseq, 1);
     else
-        cond_kernel<<<dim3((nseq + 7) / 8, NLAYER), 256, 0, st>>>(ws.mod, t100, t_stride, emb, emb_shift, cfg_pairs, w->freqs, w->w_ada_t, w->b_ada, nseq);
+        cond_kernel<<<dim3((nseq + 7) / 8, NLAYER), 256, 0, st>>>(ws.mod, t100, t_stride, emb, emb_shift, cfg_pairs, w->freqs, w->w_ada_t, w->b_ada, nseq, 0);
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
@@ -237,6 +246,7 @@ int launch_fused(const t2s_dit_weights* w, const float* x, int x_shift, int nseq
     a.out_mode = out_mode; a.out = out; a.x_upd = x_upd; a.noise = noise; a.seed = seed; a.step = step;
     a.cfg = cfg; a.c1 = c1; a.c2 = c2; a.c3 = c3;
     a.sched = ws.sched; a.inflight = g_fused_inflight; a.stats = g_fused_stats; a.trace = g_fused_trace;
+    a.uncond_shared = g_uncond_shared ? 1 : 0;
     CUDA_OK(cudaMemsetAsync(ws.sched, 0, fused_sched_ints((nseq + 1) / 2) * 4, st));
     // the CTAs wait on one another through the scheduler flags: a cooperative launch guarantees that all of them are resident
     cudaLaunchConfig_t cfgl;
@@ -355,8 +365,9 @@ int sample_impl(const t2s_dit_weights* w, int kind, float* x, const float* emb, 
     const Workspace ws = ws_view(workspace, nseq, sh);
     const size_t lat = (size_t)batch * sh.lat;
     const bool fused = use_fused(w, nseq, sh);
+    struct Scope { Scope(bool v) { g_uncond_shared = v; } ~Scope() { g_uncond_shared = false; } } scope(cond_uncond_shared(nseq, 1));
     for (int j = 0; j < steps; ++j) {
-        TRY(launch_cond(w, t100 + j, 0, emb, 1, 1, nseq, ws, st));
+        TRY(launch_cond(w, t100 + j, 0, emb, 1, 1, nseq, ws, st, g_uncond_shared));
         if (fused) {
             // one persistent launch per guided step: patch-embed, the four blocks (attention and token work of different
             // sequence pairs overlapped on every SM), final projection, guidance mix and the Euler / ancestral update

@@ -57,6 +57,7 @@ struct FusedArgs {
     float cfg, c1, c2, c3;
     int* sched;            // fused_sched_ints(npair) ints, zeroed before the launch
     int inflight;          // pairs admitted and not yet finished (0 = no limit)
+    int uncond_shared;     // guided loops: every pair's unconditional sequence reads modulation row 0 (cond_kernel writes it once)
     long long* stats;      // optional [grid][8]: token items, token starved cycles, attention units, attention starved cycles, total
     long long* trace;      // optional [grid][FS_TRACE_ITEMS][32]: clock64 stamps of the token epilogue's phases (row 0, half 0)
 };
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_step_kernel(const FusedAr
                         }
                         const int pair = tdesc[p_it & 3].z, tile = tdesc[p_it & 3].w;
                         fence_proxy_async_all();
-                        const int sq0 = min(2 * pair, p.nseq - 1), sq1 = min(2 * pair + 1, p.nseq - 1);
+                        const int sq0 = p.uncond_shared ? 0 : min(2 * pair, p.nseq - 1), sq1 = min(2 * pair + 1, p.nseq - 1);
                         const int ln = p_mode == TOK_EMBED ? 0 : p_l + 1;
                         const uint32_t vdst = sb + FS_SM_VEC + vb * (FV_FLOATS * 4), vbar = BAR(FB_VFULL + vb);
                         const uint32_t bytes = (p_mode != TOK_EMBED ? 2u * MOD * 4u : 0u) + (p_mode != TOK_FINAL ? 2u * 256u * 4u : 0u);

@@ -62,6 +62,9 @@ struct TokArgs {
     // materialise it.  EMBED skips its store (skip_h_store) and the MID kernel of block 0 recomputes its rows from x with the
     // same instruction sequence (recompute_h0; needs x, x_shift): 240 KB per sequence less written and read per step.
     int skip_h_store, recompute_h0;
+    // guided sampling loops: the unconditional branch's modulation depends on the step only, so cond_kernel writes ONE row
+    // (sequence 0) instead of one per sample and every pair reads that row for its even (unconditional) sequence
+    int uncond_shared;
 };
 
 // =================================================================================== cond
@@ -70,14 +73,21 @@ struct TokArgs {
 __device__ __forceinline__ bool mod_is_scale(int col) { return (col >> 7) == 1 || (col >> 7) == 4; }
 // mod[seq][l][:] = Linear_l( SiLU( temb(t) (+ text) ) )      transformer.py:30-40,106-109,115,174-178
 // grid (ceil(nseq/8), 4), block 256
+// uncond_shared (guided loops, cfg_pairs): the unconditional modulation row depends on the step only: CTA x = gridDim.x - 1
+// computes it once (sequence 0), the others 8 CONDITIONAL (odd) sequences each; grid (ceil(npair/8) + 1, 4).
+__device__ __forceinline__ int cond_seq_of(int slot, int uncond_shared) {
+    if (!uncond_shared) return blockIdx.x * 8 + slot;
+    if (blockIdx.x == gridDim.x - 1) return slot == 0 ? 0 : 0x3fffffff;
+    return 2 * (blockIdx.x * 8 + slot) + 1;
+}
 __global__ void __launch_bounds__(256) cond_kernel(float* __restrict__ mod, const float* __restrict__ t100, int t_stride,
                                                    const float* __restrict__ emb, int emb_shift, int cfg_pairs,
                                                    const float* __restrict__ freqs, const float* __restrict__ w_ada_t,
-                                                   const float* __restrict__ b_ada, int nseq) {
+                                                   const float* __restrict__ b_ada, int nseq, int uncond_shared) {
     __shared__ float sc[8][D];
-    const int s0 = blockIdx.x * 8, l = blockIdx.y, tid = threadIdx.x;
+    const int l = blockIdx.y, tid = threadIdx.x;
     for (int i = tid; i < 8 * D; i += 256) {
-        const int si = i >> 7, f = i & 127, seq = s0 + si;
+        const int si = i >> 7, f = i & 127, seq = cond_seq_of(si, uncond_shared);
         float v = 0.f;
         if (seq < nseq) {
             const float arg = __fdiv_rn(t100[(size_t)seq * t_stride], freqs[f & 63]);
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(256) cond_kernel(float* __restrict__ mod, cons
     }
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
-        const int seq = s0 + s;
+        const int seq = cond_seq_of(s, uncond_shared);
         if (seq < nseq) {
             float* dst = mod + ((size_t)seq * NLAYER + l) * MOD;
 #pragma unroll
@@ -446,7 +456,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
         auto fetch_inputs = [&](int it, int item) {
             const int pair = item / (TILES_PER_PAIR / NE), vb = it & 1;
             if (it >= 2) mbar_wait(BAR(B_VFREE + vb), ((it >> 1) - 1) & 1);     // the item two back has released this buffer
-            const int sq0 = min(2 * pair, p.nseq - 1), sq1 = min(2 * pair + 1, p.nseq - 1);
+            const int sq0 = p.uncond_shared ? 0 : min(2 * pair, p.nseq - 1), sq1 = min(2 * pair + 1, p.nseq - 1);
             const uint32_t vdst = sb + TC_SM_VEC + vb * (V_FLOATS * 4), vbar = BAR(B_VFULL + vb);
             uint32_t bytes = 0;
             auto cp = [&](int voff, const float* src, uint32_t n) {

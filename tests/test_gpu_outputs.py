@@ -86,12 +86,13 @@ def test_backbone_classes_on_cuda_match_reference_golden():
         x_t, x_0 = rf.create_flow(x1, t)
     assert max_abs(x_0, T(g["x0"])) == 0.0 and max_abs(x_t, T(g["x_t"])) < 1e-6
     q, e = dd.q_sample(x1, ti, eps)
-    assert e is eps and max_abs(q, T(g["q_sample"])) < 1e-6
+    # the coefficients sqrt(alpha_bar_t), sqrt(1 - alpha_bar_t) come from torch's CUDA pow here and its CPU pow in the golden run
+    assert e is eps and max_abs(q, T(g["q_sample"])) < 1e-5
     mean, var = dd.q_xt_x0(x1, ti)
-    assert max_abs(mean + var ** 0.5 * eps, T(g["q_sample"])) < 1e-6
+    assert max_abs(mean + var ** 0.5 * eps, T(g["q_sample"])) < 1e-5
     with um.patch.object(torch, "randn", lambda *a, **k: T(g["p_noise"]).to(DEV)):
         p = dd.p_sample(x1, eps, ti)
-    assert max_abs(p, T(g["p_sample"])) < 1e-6
+    assert max_abs(p, T(g["p_sample"])) < 1e-5
     p2 = dd.p_sample(x1, eps, ti)                                  # its own draw: another sample of the same distribution
     assert max_abs(p2, p) > 1e-3 and torch.isfinite(p2).all()
     for bb in ("beta", "alpha", "alpha_bar"):

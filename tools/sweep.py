@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE config 5: throughput sweep batch x length x denoising steps (x GPUs under torchrun) of the guided
 rectified-flow sampler through the host-buffer entry (`T2SSampler.sample_host`: pinned text embeddings in, series out),
-next to the oracle port of the reference loop (infer.py:75-95) on the host cores for the sizes it finishes in seconds.
+next to the reference loop (infer.py:75-95; the unmodified modules from baseline/_ref) on the host cores for the sizes it finishes in seconds.
 
     python tools/sweep.py [--out gpurun_out/sweep.json] [--batches 1,8,...] [--cpu-budget-s 40]
     python -m torch.distributed.run --nproc-per-node N ... tools/sweep.py     (weak scaling: every rank runs `batch`)
@@ -80,10 +80,10 @@ def main():
         for B, L, steps in ((1, 24, 10), (8, 24, 10), (8, 96, 10), (8, 24, 50), (8, 96, 100), (64, 96, 10)):
             if spent > a.cpu_budget_s:
                 break
-            v, dt, threads = bench.cpu_reference_run(Namespace(backbone=a.backbone, rf_steps=steps, cfg=a.cfg, length=L), B)
+            v, dt, threads, kind = bench.cpu_reference_run(Namespace(backbone=a.backbone, rf_steps=steps, cfg=a.cfg, length=L), B)
             spent += dt
             cpu.append({"batch": B, "length": L, "steps": steps, "s": round(dt, 3), "series_per_s": round(v, 3), "cores": threads,
-                        "kind": "port (bench.py cpu_baseline leg: oracle restatement of infer.py:75-95, torch fp32 CPU)"})
+                        "kind": kind + ": " + bench.BASELINE_WHAT[kind]})
     if rank == 0:
         out = {"workload": "BASELINE config 5: guided RF sampling sweep, host buffers in/out (e2e), CFG %g" % a.cfg, "n_gpus": world,
                "gpu": rows, "cpu_reference": cpu}
