@@ -96,4 +96,4 @@ def test_backbone_classes_on_cuda_match_reference_golden():
     p2 = dd.p_sample(x1, eps, ti)                                  # its own draw: another sample of the same distribution
     assert max_abs(p2, p) > 1e-3 and torch.isfinite(p2).all()
     for bb in ("beta", "alpha", "alpha_bar"):
-        assert max_abs(getattr(dd, bb), T(g[bb])) < 1e-7
+        assert max_abs(getattr(dd, bb), T(g[bb])) < 1e-6              # CUDA cumprod's summation order vs the CPU's
