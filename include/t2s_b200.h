@@ -97,6 +97,9 @@ int t2s_init(void);
  * §4.9).  `inflight` bounds the pairs admitted and not yet finished (0 = no limit).  Process-wide switches; results are
  * the same either way (tests/test_gpu_fused.py). */
 void t2s_set_fused(int min_pairs, int inflight);
+/* The kernels of a denoiser evaluation are launched with programmatic stream serialization (PDL): each kernel's set-up runs
+ * under the previous kernel's tail and waits (griddepcontrol.wait) before touching its data.  0 launches them plainly. */
+void t2s_set_pdl(int on);
 /* Profiling aid: when non-NULL, every CTA of the fused kernel writes device_buf[blockIdx.x*8 + {0: token items, 1: token
  * scheduler-starved cycles, 2: attention units, 3: attention starved cycles, 4: total cycles}]. */
 void t2s_debug_set_fused_stats(long long* device_buf);

@@ -10,10 +10,11 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libt2s_b200.so")
+# T2S_B200_LIB: another build of the same sources (A/B experiments: tools/build_variant.py); the default is the in-tree build
+LIB_PATH = os.environ.get("T2S_B200_LIB") or os.path.join(HERE, "lib", "libt2s_b200.so")
 
 EXPORTS = [
-    "t2s_version", "t2s_last_error", "t2s_init", "t2s_debug_set_phase_trace", "t2s_set_fused", "t2s_debug_set_fused_stats", "t2s_debug_set_fused_trace", "t2s_dit_workspace_bytes", "t2s_dit_workspace_offsets",
+    "t2s_version", "t2s_last_error", "t2s_init", "t2s_debug_set_phase_trace", "t2s_set_fused", "t2s_set_pdl", "t2s_debug_set_fused_stats", "t2s_debug_set_fused_trace", "t2s_dit_workspace_bytes", "t2s_dit_workspace_offsets",
     "t2s_dit_workspace_bytes_h", "t2s_dit_workspace_offsets_h", "t2s_dit_attention_h",
     "t2s_dit_forward", "t2s_sample", "t2s_sample_ddpm_seeded", "t2s_vae_decode", "t2s_vae_encode",
     "t2s_dit_cond", "t2s_dit_embed_qkv", "t2s_dit_attention", "t2s_dit_block_post", "t2s_dit_final",
@@ -80,6 +81,8 @@ def load() -> C.CDLL:
         lib.t2s_init.restype = i
         lib.t2s_debug_set_phase_trace.restype = None
         lib.t2s_debug_set_phase_trace.argtypes = [P]
+        lib.t2s_set_pdl.restype = None
+        lib.t2s_set_pdl.argtypes = [i]
         lib.t2s_set_fused.restype = None
         lib.t2s_set_fused.argtypes = [i, i]
         lib.t2s_debug_set_fused_stats.restype = None

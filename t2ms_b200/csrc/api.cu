@@ -81,6 +81,22 @@ int t2s_api::ensure_init() {
 
 namespace {
 
+// Launch with programmatic stream serialization (PDL, common.cuh: pdl_wait): the kernels of a step overlap their set-up with
+// the previous kernel's tail.  g_pdl = 0 launches plainly (A/B switch: t2s_set_pdl).
+int g_pdl = 1;
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 struct Workspace {
@@ -147,8 +163,8 @@ int token_grid(int nseq, const Shape& sh, int ne) {
 #define T2S_TOKEN_LAUNCH(MODE_, HH_)                                                                                  \
     {                                                                                                                 \
         const int ne = token_ne(nseq, sh);                                                                            \
-        if (ne == 2) token_kernel<MODE_, HH_, 2><<<token_grid(nseq, sh, 2), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);     \
-        else token_kernel<MODE_, HH_, 1><<<token_grid(nseq, sh, 1), TC_THREADS, TOK_SMEM_BYTES, st>>>(a);             \
+        if (ne == 2) CUDA_OK(launch_k(token_kernel<MODE_, HH_, 2>, token_grid(nseq, sh, 2), TC_THREADS, TOK_SMEM_BYTES, st, a)); \
+        else CUDA_OK(launch_k(token_kernel<MODE_, HH_, 1>, token_grid(nseq, sh, 1), TC_THREADS, TOK_SMEM_BYTES, st, a));         \
     }
 
 // set by sample_impl for the launches of a guided loop whose cond kernel writes one shared unconditional modulation row
@@ -169,13 +185,14 @@ bool cond_uncond_shared(int nseq, int cfg_pairs) { return cfg_pairs && nseq > 64
 int launch_cond(const t2s_dit_weights* w, const float* t100, int t_stride, const float* emb, int emb_shift, int cfg_pairs,
                 int nseq, const Workspace& ws, cudaStream_t st, bool uncond_shared = false) {
     if (nseq <= 64)
-        cond_split_kernel<<<dim3((nseq + 7) / 8, NLAYER * 3), 256, 0, st>>>(ws.mod, t100, t_stride, emb, emb_shift, cfg_pairs, w->freqs, w->w_ada_t,
-                                                                           w->b_ada, nseq);
+        CUDA_OK(launch_k(cond_split_kernel, dim3((nseq + 7) / 8, NLAYER * 3), 256, 0, st, ws.mod, t100, t_stride, emb, emb_shift, cfg_pairs, w->freqs,
+                         w->w_ada_t, w->b_ada, nseq));
     else if (uncond_shared)
-        cond_kernel<<<dim3((nseq / 2 + 7) / 8 + 1, NLAYER), 256, 0, st>>>(ws.mod, t100, t_stride, emb, emb_shift, cfg_pairs, w->freqs, w->w_ada_t,
-                                                                         w->b_ada, nseq, 1);
+        CUDA_OK(launch_k(cond_kernel, dim3((nseq / 2 + 7) / 8 + 1, NLAYER), 256, 0, st, ws.mod, t100, t_stride, emb, emb_shift, cfg_pairs, w->freqs,
+                         w->w_ada_t, w->b_ada, nseq, 1));
     else
-        cond_kernel<<<dim3((nseq + 7) / 8, NLAYER), 256, 0, st>>>(ws.mod, t100, t_stride, emb, emb_shift, cfg_pairs, w->freqs, w->w_ada_t, w->b_ada, nseq, 0);
+        CUDA_OK(launch_k(cond_kernel, dim3((nseq + 7) / 8, NLAYER), 256, 0, st, ws.mod, t100, t_stride, emb, emb_shift, cfg_pairs, w->freqs,
+                         w->w_ada_t, w->b_ada, nseq, 0));
     CUDA_OK(cudaGetLastError());
     return T2S_OK;
 }
@@ -199,9 +216,9 @@ int launch_attn(int nseq, const Shape& sh, const Workspace& ws, cudaStream_t st)
         using LS = AttShape<HH_, true>;                                                                                          \
         if (nseq * NHEAD < sms * LS::CTAS_PER_SM / 2) {                                                                          \
             const int npart = LS::NQT / LS::NWG;                                                                                 \
-            attn_kernel<HH_, true><<<nseq * NHEAD * npart, LS::THREADS, LS::SMEM_BYTES, st>>>(ws.qkv, ws.o, g_trace, npart);     \
+            CUDA_OK(launch_k(attn_kernel<HH_, true>, nseq * NHEAD * npart, LS::THREADS, LS::SMEM_BYTES, st, ws.qkv, ws.o, g_trace, npart));    \
         } else {                                                                                                                 \
-            attn_kernel<HH_><<<nseq * NHEAD, AttShape<HH_>::THREADS, AttShape<HH_>::SMEM_BYTES, st>>>(ws.qkv, ws.o, g_trace, 1); \
+            CUDA_OK(launch_k(attn_kernel<HH_, false>, nseq * NHEAD, AttShape<HH_>::THREADS, AttShape<HH_>::SMEM_BYTES, st, ws.qkv, ws.o, g_trace, 1)); \
         }                                                                                                                        \
     }
     T2S_DISPATCH_H(sh.H, T2S_ATTN_LAUNCH(HH));
@@ -270,6 +287,7 @@ extern "C" {
 
 int t2s_version(void) { return 200; }
 void t2s_set_fused(int min_pairs, int inflight) { g_fused_min_pairs = min_pairs; g_fused_inflight = inflight; }
+void t2s_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 void t2s_debug_set_fused_stats(long long* device_buf) { g_fused_stats = device_buf; }
 void t2s_debug_set_fused_trace(long long* device_buf) { g_fused_trace = device_buf; }
 const char* t2s_last_error(void) { return g_err; }

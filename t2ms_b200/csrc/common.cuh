@@ -165,6 +165,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
                      "selp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#ifdef T2S_WAIT_NS
+        if (!done) asm volatile("nanosleep.u32 %0;\n" :: "r"((uint32_t)T2S_WAIT_NS));   // A/B: back-off between polls
+#endif
         if (!done && (spins & 15) == 15) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
@@ -262,6 +265,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&u)[8])
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n"
                  :: "r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]) : "memory");
 }
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// The kernels of a sampling step are launched with programmatic stream serialization: a kernel's CTAs may start (barrier
+// set-up, TMEM allocation) while the previous kernel's last CTAs are still running.  pdl_launch_dependents() lets the next
+// grid start launching; pdl_wait() blocks until the previous grid has completed and its writes are visible — it must precede
+// the first read of anything the previous kernel produced.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 // ---------------------------------------------------------------- gpu-scope flags (dataflow between CTAs of one launch)
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;

@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(256) cond_kernel(float* __restrict__ mod, cons
                                                    const float* __restrict__ b_ada, int nseq, int uncond_shared) {
     __shared__ float sc[8][D];
     const int l = blockIdx.y, tid = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();                  // the previous step's kernels still read the modulation table this kernel overwrites
     for (int i = tid; i < 8 * D; i += 256) {
         const int si = i >> 7, f = i & 127, seq = cond_seq_of(si, uncond_shared);
         float v = 0.f;
@@ -138,6 +140,8 @@ __global__ void __launch_bounds__(256) cond_split_kernel(float* __restrict__ mod
                                                    const float* __restrict__ b_ada, int nseq) {
     __shared__ float sc[8][D];
     const int s0 = blockIdx.x * 8, l = blockIdx.y / 3, col = (blockIdx.y % 3) * 256 + threadIdx.x, tid = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     for (int i = tid; i < 8 * D; i += 256) {
         const int si = i >> 7, f = i & 127, seq = s0 + si;
         float v = 0.f;
@@ -440,10 +444,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
         float* semb = reinterpret_cast<float*>(smem + TC_SM_EMB);
         for (int i = tid; i < 5 * D; i += TC_THREADS) semb[i] = i < 4 * D ? p.w.w_embed[i] : p.w.b_embed[i - 4 * D];
     }
+    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + TC_SM_TMEM), 0);
+    pdl_wait();                  // set-up above overlapped the previous kernel's tail; everything below reads what it wrote
 
     if (warp == 16) {
         // ================================================================= producer (whole warp converged; lane 0 issues)
@@ -940,6 +946,8 @@ __global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::C
         // the CTA-wide synchronisation
         for (int i = 0; i < 3; ++i) mbar_init(bar0 + 8u * i, 1);
         mbar_fence_init();
+        pdl_launch_dependents();
+        pdl_wait();              // q|k|v come from the previous kernel
         const char* src = reinterpret_cast<const char*>(qkv + (size_t)sh * QKV_HEAD_HALVES);
         if (npart == 1) {
             mbar_expect_tx(bar0 + 8u * AB_QFULL, QKV_Q_HALVES * 2);
@@ -971,6 +979,7 @@ __global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::C
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                  // (the attention-output tiles this kernel overwrites were read by the previous kernel)
     const uint32_t tmem = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + ATT_SM_TMEM), 0) + wg * AS::TCOLS_WG;
     const int nql = ATT_NQT / NWG / npart;                              // q-tiles of this warpgroup in this CTA
     const int NG = nql * ATT_NCH;                                       // its score chunks: (local q-tile, key chunk)
