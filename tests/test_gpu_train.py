@@ -232,6 +232,43 @@ def test_micro_batches_accumulate_to_the_same_gradient():
     assert abs(a.loss_sum.item() - b.loss_sum.item()) / a.loss_sum.item() < 1e-5
 
 
+def test_graph_replayed_steps_equal_eagerly_enqueued_steps():
+    """DitTrainer.step replays the forward + backward of a whole batch from a CUDA graph from the second call of a shape on
+    (the step is ~130 short kernels); gradients and losses of every step, with and without text, equal the eager path's
+    (lr = 0 keeps both runs at the same parameters: AdamW's g / sqrt(v) would turn atomics-order noise into sign flips)."""
+    from t2ms_b200.training import DitTrainer
+    g, dsd, x1, x0, t, emb = _golden_case()
+    x_t, target = O.rf_create_flow(x1, t, x0).to(DEV), (x1 - x0).to(DEV)
+    finals = []
+    for graphs in (True, False):
+        _, tr = _trainer(dsd)
+        tr.GRAPHS = graphs
+        losses, grads = [], []
+        for k in range(5):
+            text = None if k == 2 else emb.to(DEV)
+            losses.append(tr.step(x_t * (1 + 0.1 * k), t.to(DEV), text, target, lr=0.0))
+            grads.append(tr.grads.flat.clone())
+        torch.cuda.synchronize()
+        assert (len(tr._graphs) == 2) == graphs
+        finals.append((torch.stack(grads), torch.stack(losses).cpu()))
+    # (the weight-gradient GEMMs accumulate their split-K partial sums with atomics: equal to summation order, not bit for bit)
+    assert rel(finals[0][0], finals[1][0]) < 1e-5 and rel(finals[0][1], finals[1][1]) < 1e-5
+
+
+def test_two_forwards_before_backward_are_detected():
+    """the autograd path keeps the activations of ONE forward per module; a second training-mode forward before
+    backward() must raise instead of silently differentiating the wrong activations."""
+    g, dsd, x1, x0, t, emb = _golden_case()
+    m, _ = _trainer(dsd)
+    x_t = O.rf_create_flow(x1, t, x0).to(DEV)
+    p1 = m(input=x_t, t=t.to(DEV), text_input=emb.to(DEV))
+    p2 = m(input=x_t * 0.5, t=t.to(DEV), text_input=None)
+    with pytest.raises(RuntimeError, match="ONE training-mode forward"):
+        (p1.sum() + p2.sum()).backward()
+    p3 = m(input=x_t, t=t.to(DEV), text_input=emb.to(DEV))      # one forward, one backward: fine
+    p3.sum().backward()
+
+
 def test_reference_style_loop_through_autograd():
     """train.py:79-87 verbatim on the drop-in module: zero_grad, forward, mse, backward, AdamW step."""
     from t2ms_b200 import RectifiedFlow, Transformer
