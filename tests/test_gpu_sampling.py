@@ -236,3 +236,33 @@ def test_ddpm_in_kernel_philox_noise_matches_its_restatement():
     assert max_abs(other, lat) > 1e-3                               # another seed, another trajectory
     default = smp.sample_latent(emb.to(DEV), steps=2, backbone="ddpm", noise=x0.to(DEV))   # seed drawn from torch's RNG
     assert torch.isfinite(default).all()
+
+
+def test_cached_graphs_survive_workspace_churn_and_weight_updates():
+    """a captured graph bakes in the workspace and packed-weight pointers.  The cache entry keeps those
+    objects alive, keys on pack generations (not id()), and drops graphs of replaced weights: six batch sizes + interleaved
+    forwards at other sizes (which evict the module's workspace cache) + an optimizer-style weight update, then every
+    cached graph still reproduces the eager result."""
+    from gpu_util import DEV, make_dit, make_vae, max_abs
+    from t2ms_b200 import T2SSampler, synth
+    (dit, _), (vae, _) = make_dit(3), make_vae(4)
+    smp = T2SSampler(dit, vae)
+    steps, L = 3, 24
+    cases = {}
+    for B in (1, 2, 3, 5, 6, 7):
+        emb, x0 = synth.make_text_embeddings(B, seed=10 + B).to(DEV), synth.make_noise(B, seed=20 + B).to(DEV)
+        cases[B] = (emb, x0, smp.sample(emb, L, steps=steps, noise=x0))
+        assert max_abs(smp.sample_graph(emb, L, steps=steps, noise=x0), cases[B][2]) == 0.0
+        with torch.no_grad():                                       # other sizes: the module's small workspace cache turns over
+            dit(input=synth.make_noise(B + 8, seed=1).to(DEV), t=torch.zeros(B + 8, device=DEV), text_input=None)
+    assert len(smp._graphs) == 6
+    junk = [torch.randn(1 << 20, device=DEV) for _ in range(8)]     # anything freed by mistake would be handed out again here
+    for B, (emb, x0, ref) in cases.items():
+        assert max_abs(smp.sample_graph(emb, L, steps=steps, noise=x0), ref) == 0.0
+    del junk
+    with torch.no_grad():
+        dit.ln.bias.add_(0.05)                                      # new weights: a new pack generation
+    emb, x0, old = cases[3]
+    new = smp.sample(emb, L, steps=steps, noise=x0)
+    assert max_abs(new, old) > 0 and max_abs(smp.sample_graph(emb, L, steps=steps, noise=x0), new) == 0.0
+    assert all(k[5] == dit.packed().generation for k in smp._graphs)   # graphs of the replaced weights are gone
