@@ -893,14 +893,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
 //   K: [d/8][key 0..479][8]             (B, K-major)         30720 B
 //   V: [key/8][d/8][key%8][8]           (B, MN-major)        30720 B
 constexpr int ATT_THREADS = 160;
-enum { AB_QFULL = 0, AB_KFULL = 1, AB_VFULL = 2, AB_SFULL = 3, AB_SFREE = 5, AB_PFULL = 7, AB_PVDONE = 9, AB_OFULL = 11, AB_OFREE = 12 };
+// barriers: Q / K / V loaded (shared), then per warpgroup a block of 3 NBUF + 2: S full [NBUF] | P full [NBUF] | P.V done [NBUF] | O full | O free
+enum { AB_QFULL = 0, AB_KFULL = 1, AB_VFULL = 2, AB_WG = 3 };
+#ifndef T2S_ATT_NBUF
+#define T2S_ATT_NBUF 2          // score buffers per warpgroup of the T2S shape: 2 x 48 keys (default) or 3 x 32 keys (A/B build)
+#endif
 // LAT: the small-batch form of the T2S shape (one CTA per q-tile, see attn_kernel): ONE warpgroup and 96-key chunks, the
 // shortest serial chain for a single q-tile when there is nothing to overlap it with
 template <int H, bool LAT = false>
 struct AttShape {
     using S = DitShape<H>;
     static constexpr bool ONE_WG = LAT && H == 30;
-    static constexpr int KC = ONE_WG ? 96 : S::KC, NCH = S::NTOK / KC, NQT = S::NQT;      // keys per chunk, chunks, q-tiles
+    static constexpr int NBUF = (!ONE_WG && H == 30) ? T2S_ATT_NBUF : 2;                   // S buffers per warpgroup (double / triple buffering)
+    static constexpr int KC = ONE_WG ? 96 : (NBUF == 3 ? 32 : S::KC), NCH = S::NTOK / KC, NQT = S::NQT;      // keys per chunk, chunks, q-tiles
+    static constexpr int AB_SFULL = 0, AB_PFULL = NBUF, AB_PVDONE = 2 * NBUF, AB_OFULL = 3 * NBUF, AB_OFREE = 3 * NBUF + 1, AB_BLOCK = 3 * NBUF + 2;
     static constexpr int SM_Q = 0, SM_K = S::Q_HALVES * 2, SM_V = SM_K + S::K_HALVES * 2;
     static constexpr int SM_BAR = SM_V + S::V_HALVES * 2;
     static constexpr int SM_TMEM = SM_BAR + 48 * 8;
@@ -911,10 +917,10 @@ struct AttShape {
     static constexpr int NWG = ONE_WG ? 1 : (CTAS_PER_SM == 2 ? 2 : 4);   // four softmax warpgroups per SM either way
     static constexpr int THREADS = NWG * ATT_THREADS;
     static constexpr uint32_t IDESC_S = umma_idesc_f16(128, KC);
-    static constexpr uint32_t TCOLS_WG = 2 * KC + HD <= 128 ? 128 : 256;   // per warpgroup: two S buffers (2 x KC) + O (32)
+    static constexpr uint32_t TCOLS_WG = NBUF * KC + HD <= 128 ? 128 : 256;   // per warpgroup: NBUF S buffers (NBUF x KC) + O (32)
     static constexpr uint32_t TCOLS = NWG * TCOLS_WG;
-    static constexpr uint32_t T_S = 0, T_O = 2 * KC;
-    static_assert(SMEM_BYTES <= 232448 && 2 * KC + HD <= 256 && NQT % NWG == 0, "attention kernel resources");
+    static constexpr uint32_t T_S = 0, T_O = NBUF * KC;
+    static_assert(SMEM_BYTES <= 232448 && NBUF * KC + HD <= 256 && NQT % NWG == 0 && AB_WG + NWG * AB_BLOCK <= 48, "attention kernel resources");
 };
 static_assert(AttShape<30>::CTAS_PER_SM == 2, "two attention CTAs must fit one SM for the T2S shape");
 constexpr uint32_t ATT_IDESC_PV = umma_idesc_f16(128, HD) | (1u << 16);   // B (V) is MN-major
@@ -929,7 +935,9 @@ __global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::C
     constexpr int ATT_KC = AS::KC, ATT_NCH = AS::NCH, ATT_NQT = AS::NQT;
     constexpr int ATT_SM_Q = AS::SM_Q, ATT_SM_K = AS::SM_K, ATT_SM_V = AS::SM_V, ATT_SM_BAR = AS::SM_BAR, ATT_SM_TMEM = AS::SM_TMEM;
     constexpr uint32_t ATT_IDESC_S = AS::IDESC_S, ATT_TCOLS = AS::TCOLS, ATT_T_S = AS::T_S, ATT_T_O = AS::T_O;
-    constexpr int NWG = AS::NWG;
+    constexpr int NWG = AS::NWG, NB = AS::NBUF;
+    constexpr int AB_SFULL = AB_WG + AS::AB_SFULL, AB_PFULL = AB_WG + AS::AB_PFULL, AB_PVDONE = AB_WG + AS::AB_PVDONE, AB_OFULL = AB_WG + AS::AB_OFULL,
+                  AB_OFREE = AB_WG + AS::AB_OFREE;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp_cta = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform
     const int wg = warp_cta / 5, warp = warp_cta % 5;                 // warpgroup; role inside it (0-3 softmax, 4 MMA)
@@ -940,7 +948,7 @@ __global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::C
     const uint32_t sb = smem_u32(smem);
     const uint32_t bar0 = sb + ATT_SM_BAR;
     // barriers 0-2 (Q / K / V loaded) are shared; every warpgroup owns a block of ten (AB_SFULL .. AB_OFREE)
-    auto BAR = [&](int i) { return bar0 + 8u * (i < 3 ? i : i + wg * 10); };
+    auto BAR = [&](int i) { return bar0 + 8u * (i < 3 ? i : i + wg * AS::AB_BLOCK); };
     if (warp_cta == 4 && lane == 0) {
         // the operand loads go out first: their latency overlaps the TMEM allocation, the remaining barrier set-up and
         // the CTA-wide synchronisation
@@ -963,10 +971,9 @@ __global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::C
     }
     if (tid == 0) {
         for (int g = 0; g < NWG; ++g) {
-            const uint32_t bg = bar0 + 8u * (g * 10);
-            for (int b = 0; b < 2; ++b) {
+            const uint32_t bg = bar0 + 8u * (g * AS::AB_BLOCK);
+            for (int b = 0; b < NB; ++b) {
                 mbar_init(bg + 8u * (AB_SFULL + b), 1);
-                mbar_init(bg + 8u * (AB_SFREE + b), 128);
                 mbar_init(bg + 8u * (AB_PFULL + b), 4);            // one arrival per softmax WARP (mbar_arrive_warp)
                 mbar_init(bg + 8u * (AB_PVDONE + b), 1);
             }
@@ -988,28 +995,27 @@ __global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::C
     if (warp == 4) {
         // ================================================================= loads + MMA issue; whole warp converged
         const bool lead = lane == 0;
-        // score chunk G: q-tile (G / NCH) * NWG + wg, key chunk G % NCH -> S buffer G & 1
+        // score chunk G: q-tile (G / NCH) * NWG + wg, key chunk G % NCH -> S buffer G % NB
         auto issue_s = [&](int G) {
             const int qt = q_tile(G / ATT_NCH), j = G % ATT_NCH;
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
                 const uint64_t ad = umma_desc(sb + ATT_SM_Q + qt * 8192 + kk * 2 * 2048, 2048, 128);
                 const uint64_t bd = umma_desc(sb + ATT_SM_K + j * (ATT_KC * 16) + kk * 2 * (NTOK * 16), NTOK * 16, 128);
-                if (lead) umma_f16(tmem + ATT_T_S + (G & 1) * ATT_KC, ad, bd, ATT_IDESC_S, kk > 0);
+                if (lead) umma_f16(tmem + ATT_T_S + (G % NB) * ATT_KC, ad, bd, ATT_IDESC_S, kk > 0);
             }
-            if (lead) umma_commit(BAR(AB_SFULL + (G & 1)));
+            if (lead) umma_commit(BAR(AB_SFULL + (G % NB)));
             __syncwarp();
         };
         mbar_wait(BAR(AB_QFULL), 0);
         mbar_wait(BAR(AB_KFULL), 0);
         tc_fence_after();
-        issue_s(0);
-        issue_s(1);
+        for (int g0 = 0; g0 < NB && g0 < NG; ++g0) issue_s(g0);
         mbar_wait(BAR(AB_VFULL), 0);
 #pragma unroll 1
         for (int G = 0; G < NG; ++G) {
-            const int b = G & 1, qt = G / ATT_NCH, j = G % ATT_NCH;
-            const uint32_t par = (G >> 1) & 1;
+            const int b = G % NB, qt = G / ATT_NCH, j = G % ATT_NCH;
+            const uint32_t par = (G / NB) & 1;
             mbar_wait(BAR(AB_PFULL + b), par);                   // P_j is in TMEM over S_j
             if (j == 0 && qt > 0) mbar_wait(BAR(AB_OFREE), (qt - 1) & 1);   // previous q-tile's O has been read
             tc_fence_after();
@@ -1023,10 +1029,10 @@ __global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::C
                 if (j == ATT_NCH - 1) umma_commit(BAR(AB_OFULL));
             }
             __syncwarp();
-            if (G + 2 < NG) {                                    // the next S into this buffer overwrites P_j
+            if (G + NB < NG) {                                   // the next S into this buffer overwrites P_j
                 mbar_wait(BAR(AB_PVDONE + b), par);
                 tc_fence_after();
-                issue_s(G + 2);
+                issue_s(G + NB);
             }
         }
         __syncwarp();
@@ -1068,8 +1074,8 @@ __global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::C
             float mref = 0.f, l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
             for (int j = 0; j < ATT_NCH; ++j) {
-                const int G = qt * ATT_NCH + j, b = G & 1;
-                mbar_wait(BAR(AB_SFULL + b), (G >> 1) & 1);
+                const int G = qt * ATT_NCH + j, b = G % NB;
+                mbar_wait(BAR(AB_SFULL + b), (G / NB) & 1);
                 tc_fence_after();
                 const uint32_t ts = trow + ATT_T_S + b * ATT_KC;
                 float v[ATT_KC];                                 // the score chunk: 32-column loads + a 16-column remainder
@@ -1089,7 +1095,7 @@ __global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::C
                         const float alpha = need ? ex2_approx((mref - cm) * sc) : 1.f;
                         if (need) mref = cm;
                         l0 *= alpha; l1 *= alpha;
-                        mbar_wait(BAR(AB_PVDONE + (b ^ 1)), ((G - 1) >> 1) & 1);      // every earlier P.V has landed in O
+                        mbar_wait(BAR(AB_PVDONE + (G - 1) % NB), ((G - 1) / NB) & 1);   // every earlier P.V has landed in O
                         tc_fence_after();
                         float a0[32];
                         tmem_ld32(trow + ATT_T_O, a0);
