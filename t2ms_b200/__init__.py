@@ -16,3 +16,4 @@ __all__ = ["Transformer", "Transformerlayer", "TimeEmbedding", "RectifiedFlow", 
            "T2SSampler", "gather_series", "shard_range", "DitTrainer",
            "series_metrics", "run_inference", "save_generation", "load_generation"]
 __version__ = "0.1.0"
+from . import ops  # noqa: E402,F401  registers the torch.library custom ops (namespace t2s_b200)

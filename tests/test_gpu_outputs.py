@@ -97,3 +97,27 @@ def test_backbone_classes_on_cuda_match_reference_golden():
     assert max_abs(p2, p) > 1e-3 and torch.isfinite(p2).all()
     for bb in ("beta", "alpha", "alpha_bar"):
         assert max_abs(getattr(dd, bb), T(g[bb])) < 1e-6              # CUDA cumprod's summation order vs the CPU's
+
+
+def test_custom_ops_trace_under_torch_compile():
+    """The module forwards go through torch.library custom ops with fake implementations, so a function that calls them can be
+    traced by torch.compile (fullgraph, the aot_eager backend: Dynamo + AOTAutograd with fake tensors, no code generation) and
+    returns what the eager call returns."""
+    from gpu_util import DEV, make_dit, make_vae, max_abs
+    from t2ms_b200 import synth
+    (dit, _), (vae, _) = make_dit(3), make_vae(4)
+    x, emb = synth.make_noise(4, seed=1).to(DEV), synth.make_text_embeddings(4, seed=2).to(DEV)
+    t = torch.tensor([0.1, 0.4, 0.7, 0.9], device=DEV)
+
+    ws, h_dit, h_dec = dit.workspace(4, x.device), dit.packed().handle, vae.decoder._packed_weights().handle   # host-side state: outside the graph
+
+    def step(x, t, emb):
+        u = torch.ops.t2s_b200.dit_forward(x, t * 100.0, None, ws, h_dit, 30)
+        c = torch.ops.t2s_b200.dit_forward(x, t * 100.0, emb, ws, h_dit, 30)
+        x1 = torch.ops.t2s_b200.rf_euler(x, u + 7.0 * (c - u), 0.01)
+        return torch.ops.t2s_b200.vae_decode(x1, 48, h_dec)[0]
+
+    with torch.no_grad():
+        eager = step(x, t, emb)
+        compiled = torch.compile(step, backend="aot_eager", fullgraph=True)(x, t, emb)
+    assert eager.shape == (4, 48) and max_abs(eager, compiled) == 0.0
