@@ -1030,8 +1030,10 @@ __global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::C
             }
             __syncwarp();
             if (G + NB < NG) {                                   // the next S into this buffer overwrites P_j
+#ifndef T2S_ATT_NO_PVWAIT
                 mbar_wait(BAR(AB_PVDONE + b), par);
                 tc_fence_after();
+#endif
                 issue_s(G + NB);
             }
         }
