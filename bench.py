@@ -489,6 +489,11 @@ def main():
                                      "(ncu: XU pipe 79 % busy, tensor pipe 19 %); this kernel is bound by the MUFU, not the tensor pipe"
                                      if dom == "attention" else "epilogue issue",
                          "peak_source": pk["src"], "flop_per_launch": flop, "launch_ms": kb[dom]},
+            # what actually bounds the dominant kernel: 480 x 480 exponentials per (sequence, head) on the 16 MUFU lanes per SM
+            "mufu_floor": ({"exp_per_launch": nseq * 4 * 480 * 480, "floor_ms": nseq * 4 * 480 * 480 / (16 * 148 * ((clocks or {}).get("sm_mhz") or 1837.0) * 1e3),
+                            "launch_ms": kb["attention"],
+                            "frac": nseq * 4 * 480 * 480 / (16 * 148 * ((clocks or {}).get("sm_mhz") or 1837.0) * 1e3) / kb["attention"],
+                            "note": "attention kernel: ex2 count / (16 per clock per SM x 148 SMs x the SM clock sampled during the timed region)"}),
             "kernel_ms": {k: round(v, 4) for k, v in kb.items()},
             "kernel_share_of_step": shares,
         }
