@@ -75,6 +75,18 @@ class _PackedMixin:
             self._pk.generation = self._pk_generation
         return self._pk
 
+    def _warn_if_grad_expected(self, inputs):
+        """The fused single-kernel encoder / decoder forwards carry no autograd graph (they serve inference and the frozen
+        encoder of train.py:30-33).  Say so once instead of silently returning detached tensors when the caller seems to
+        expect gradients; LA-VAE training goes through ``vqvae.shared_eval`` (t2s_lavae_train_step)."""
+        if torch.is_grad_enabled() and not getattr(self, "_warned_no_grad", False) and \
+                (inputs.requires_grad or any(p.requires_grad for p in self.parameters())):
+            import warnings
+            self._warned_no_grad = True
+            warnings.warn(f"t2ms_b200 {type(self).__name__}.forward returns tensors WITHOUT a grad_fn (fused inference kernel): freeze the "
+                          "module / use torch.no_grad() as train.py:31-33 and infer.py:65 do, or train the LA-VAE with vqvae.shared_eval.",
+                          stacklevel=3)
+
     def __getstate__(self):
         st = self.__dict__.copy()
         st.pop("_pk", None)
@@ -106,6 +118,7 @@ class Encoder(_PackedMixin, nn.Module):
     def forward(self, inputs):
         if not inputs.is_cuda:
             raise RuntimeError("t2ms_b200 Encoder.forward needs CUDA tensors (no CPU fallback)")
+        self._warn_if_grad_expected(inputs)
         B, L = inputs.shape[0], inputs.shape[-1]
         if L not in LENGTHS:
             raise ValueError(f"series length must be one of {LENGTHS}, got {L}")
@@ -135,6 +148,7 @@ class Decoder(_PackedMixin, nn.Module):
     def forward(self, inputs, length):
         if not inputs.is_cuda:
             raise RuntimeError("t2ms_b200 Decoder.forward needs CUDA tensors (no CPU fallback)")
+        self._warn_if_grad_expected(inputs)
         length = int(length)
         if length not in LENGTHS:
             raise ValueError(f"series length must be one of {LENGTHS}, got {length}")
