@@ -1071,58 +1071,99 @@ __global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::C
             }
         };
         float lprev = 1.f;
+        float v[ATT_KC];                                         // the score chunk: 32-column loads + a 16-column remainder
+        auto load_chunk = [&](int Gl) {                          // wait for S of chunk Gl and start its TMEM -> register load
+            const int bl = Gl % NB;
+            mbar_wait(BAR(AB_SFULL + bl), (Gl / NB) & 1);
+            tc_fence_after();
+            const uint32_t tl = trow + ATT_T_S + bl * ATT_KC;
+#pragma unroll
+            for (int c = 0; c + 32 <= ATT_KC; c += 32) tmem_ld32(tl + c, *reinterpret_cast<float (*)[32]>(&v[c]));
+            if constexpr (ATT_KC % 32 == 16) tmem_ld16(tl + ATT_KC - 16, *reinterpret_cast<float (*)[16]>(&v[ATT_KC - 16]));
+        };
 #pragma unroll 1
         for (int qt = 0; qt < nql; ++qt) {                       // local q-tile index (q-tile q_tile(qt))
             float mref = 0.f, l0 = 0.f, l1 = 0.f;
 #pragma unroll 1
             for (int j = 0; j < ATT_NCH; ++j) {
                 const int G = qt * ATT_NCH + j, b = G % NB;
-                mbar_wait(BAR(AB_SFULL + b), (G / NB) & 1);
-                tc_fence_after();
                 const uint32_t ts = trow + ATT_T_S + b * ATT_KC;
-                float v[ATT_KC];                                 // the score chunk: 32-column loads + a 16-column remainder
-#pragma unroll
-                for (int c = 0; c + 32 <= ATT_KC; c += 32) tmem_ld32(ts + c, *reinterpret_cast<float (*)[32]>(&v[c]));
-                if constexpr (ATT_KC % 32 == 16) tmem_ld16(ts + ATT_KC - 16, *reinterpret_cast<float (*)[16]>(&v[ATT_KC - 16]));
+#ifndef T2S_ATT_EARLY_LOAD
+                load_chunk(G);
+#else
+                if (G == 0) load_chunk(0);                       // later chunks were requested at the end of their predecessor
+#endif
                 tmem_wait_ld();
-                float c0 = -INFINITY, c1 = -INFINITY;
+                // exponentials of the chunk against the reference point `mr`: P packed to fp16 over the S buffer, row sums into l0 / l1
+                auto exps = [&](float mr) {
+                    const float nb = -mr * sc;
 #pragma unroll
-                for (int q = 0; q < ATT_KC; q += 4) { c0 = max3(c0, v[q], v[q + 1]); c1 = max3(c1, v[q + 2], v[q + 3]); }
-                const float cm = fmaxf(c0, c1);
+                    for (int hb = 0; hb < ATT_KC / 16; ++hb) {   // 16 scores -> 8 packed P columns
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {             // packed fp32 (FFMA2 / FADD2): one issue slot per pair
+                            float t0, t1;
+                            fma2(t0, t1, v[hb * 16 + 2 * q], v[hb * 16 + 2 * q + 1], sc, sc, nb, nb);
+                            const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+                            add2(l0, l1, l0, l1, e0, e1);
+                            pk[q] = pack_h2(e0, e1);
+                        }
+                        tmem_st8(ts + hb * 8, pk);
+                    }
+                };
+                auto chunk_max = [&]() {
+                    float c0 = -INFINITY, c1 = -INFINITY;
+#pragma unroll
+                    for (int q = 0; q < ATT_KC; q += 4) { c0 = max3(c0, v[q], v[q + 1]); c1 = max3(c1, v[q + 2], v[q + 3]); }
+                    return fmaxf(c0, c1);
+                };
+                // the reference point moves (rare): row sum and O row are rescaled once every earlier P.V has landed in O
+                auto move_reference = [&](float cm, bool need, float& la, float& lb) {
+                    const float alpha = need ? ex2_approx((mref - cm) * sc) : 1.f;
+                    if (need) mref = cm;
+                    la *= alpha; lb *= alpha;
+                    mbar_wait(BAR(AB_PVDONE + (G - 1) % NB), ((G - 1) / NB) & 1);
+                    tc_fence_after();
+                    float a0[32];
+                    tmem_ld32(trow + ATT_T_O, a0);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) a0[q] *= alpha;
+                    tmem_st16(trow + ATT_T_O, *reinterpret_cast<float (*)[16]>(&a0[0]));
+                    tmem_st16(trow + ATT_T_O + 16, *reinterpret_cast<float (*)[16]>(&a0[16]));
+                };
+#ifndef T2S_ATT_NO_SPECULATE
+                // Later chunks exponentiate against the CURRENT reference point straight away and take the chunk maximum beside the
+                // MUFU stream instead of in front of it; only if a row turns out to exceed the reference point by more than 2^8 (rare)
+                // are the row sums restored, the reference point moved and the chunk redone.
+                if (j == 0) {
+                    mref = chunk_max();
+                    exps(mref);
+                } else {
+                    const float s0 = l0, s1 = l1;
+                    exps(mref);
+                    const float cm = chunk_max();
+                    const bool need = (cm - mref) * sc > 8.f;
+                    if (__any_sync(0xffffffffu, need)) {
+                        l0 = s0; l1 = s1;
+                        move_reference(cm, need, l0, l1);
+                        exps(mref);
+                    }
+                }
+#else
+                const float cm = chunk_max();
                 if (j == 0) {
                     mref = cm;
                 } else {
                     const bool need = (cm - mref) * sc > 8.f;    // P would exceed 2^8: move the reference point
-                    if (__any_sync(0xffffffffu, need)) {
-                        const float alpha = need ? ex2_approx((mref - cm) * sc) : 1.f;
-                        if (need) mref = cm;
-                        l0 *= alpha; l1 *= alpha;
-                        mbar_wait(BAR(AB_PVDONE + (G - 1) % NB), ((G - 1) / NB) & 1);   // every earlier P.V has landed in O
-                        tc_fence_after();
-                        float a0[32];
-                        tmem_ld32(trow + ATT_T_O, a0);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) a0[q] *= alpha;
-                        tmem_st16(trow + ATT_T_O, *reinterpret_cast<float (*)[16]>(&a0[0]));
-                        tmem_st16(trow + ATT_T_O + 16, *reinterpret_cast<float (*)[16]>(&a0[16]));
-                    }
+                    if (__any_sync(0xffffffffu, need)) move_reference(cm, need, l0, l1);
                 }
-                const float nb = -mref * sc;
-#pragma unroll
-                for (int hb = 0; hb < ATT_KC / 16; ++hb) {       // 16 scores -> 8 packed P columns
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {                 // packed fp32 (FFMA2 / FADD2): one issue slot per pair
-                        float t0, t1;
-                        fma2(t0, t1, v[hb * 16 + 2 * q], v[hb * 16 + 2 * q + 1], sc, sc, nb, nb);
-                        const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
-                        add2(l0, l1, l0, l1, e0, e1);
-                        pk[q] = pack_h2(e0, e1);
-                    }
-                    tmem_st8(ts + hb * 8, pk);
-                }
+                exps(mref);
+#endif
                 if (j == 0 && qt > 0) finish(qt - 1, lprev);  // previous q-tile's O -> global before its accumulator is reused
+#ifdef T2S_ATT_EARLY_LOAD                                      // A/B build: measured slower (the chunk registers spill), off by default
+                if (G + 1 < NG) load_chunk(G + 1);            // the next chunk's TMEM load flies while this chunk's P store completes
+#endif
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive_warp(BAR(AB_PFULL + b));
