@@ -29,10 +29,14 @@ enum {
 /* DiT weights, packed by the host (t2ms_b200/packing.py) from the reference state dict
  * (model/denoiser/transformer.py:127-154; key names in SURVEY.md §8b).  All device pointers. */
 typedef struct {
-    /* fp16 weight stages, each a [128 n][128 k] operand image in the tcgen05 no-swizzle K-major canonical layout:
-     * element (n,k) at byte (k/8)*2048 + (n/8)*128 + (n%8)*16 + (k%8)*2 */
-    const void* w_qkv[4];   /* 3 stages: q | k | v rows of layers.{l}.attn.qkv.weight */
+    /* fp16 weight stages of 36,864 B each: a [128 n][128 k] operand image in the tcgen05 no-swizzle K-major canonical layout
+     * (element (n,k) at byte (k/8)*2048 + (n/8)*128 + (n%8)*16 + (k%8)*2; 32,768 B) followed by the Linear's bias as a
+     * [128 n][16 k] operand block in the same layout (4,096 B): k = 0 holds fp16(bias[n]), k = 1 holds
+     * fp16(bias[n] - fp16(bias[n])), k = 2..15 are zero (the GEMM adds the bias with one extra K = 16 MMA against a block
+     * of ones; mlp.fc2's second K half carries a zero block) */
+    const void* w_qkv[4];   /* 3 stages: q | k | v rows of layers.{l}.attn.qkv.weight (+ attn.qkv.bias) */
     const void* w_post[4];  /* 5 stages: attn.proj | mlp.fc1 rows 0..127 | rows 128..255 | mlp.fc2 cols 0..127 | cols 128..255 */
+    /* the same biases in fp32 (the fused step kernel and the stage-wise debugging entries read them) */
     const float* b_qkv[4];  /* [384] */
     const float* b_proj[4]; /* [128] */
     const float* b_fc1[4];  /* [256] */

@@ -16,8 +16,10 @@
 namespace t2s {
 
 struct DitWeights {                 // device pointers; mirrors t2s_dit_weights (include/t2s_b200.h)
-    const __half* w_qkv[NLAYER];    // 3 stages  [128 n][128 k] fp16, 16B-chunk XOR swizzle (q | k | v)
-    const __half* w_post[NLAYER];   // 5 stages: proj, then 4 x { fc1 rows c*64.. [64][128] | fc2 cols c*64.. [128][64] }
+    // weight stages of WSTAGE_BYTES: [128 n][128 k] fp16 tcgen05 operand image (32 KB) + the Linear's bias as a [128 n][16 k]
+    // operand block (4 KB: k = 0 / 1 hold the fp16 high / low parts of the fp32 bias, the rest is zero), see tc_gemm
+    const __half* w_qkv[NLAYER];    // 3 stages: q | k | v
+    const __half* w_post[NLAYER];   // 5 stages: proj | fc1 rows 0..127 | fc1 rows 128..255 | fc2 k 0..127 | fc2 k 128..255 (zero bias block)
     const float* b_qkv[NLAYER];     // [384]
     const float* b_proj[NLAYER];    // [128]
     const float* b_fc1[NLAYER];     // [256]
@@ -195,40 +197,56 @@ __global__ void __launch_bounds__(256) cond_split_kernel(float* __restrict__ mod
 // their own counters.  While an item is in its second half the producer already fetches the next item's vectors,
 // attention-output tiles (into the HA buffers, free once fc2's first K half has been consumed) and L2-prefetches its
 // residual tiles, so the next item starts with everything on the SM.
-constexpr int TC_THREADS = 576;                                   // 16 epilogue warps + producer + MMA issuer
+#ifndef T2S_TOK_MMA_WARPS
+#define T2S_TOK_MMA_WARPS 1      // MMA issuer warps of the token kernel: 1 = one in-order issuer for both tiles (default), 2 = one per tile (A/B build)
+#endif
+constexpr int TC_MMA_WARPS = T2S_TOK_MMA_WARPS;
+constexpr int TC_THREADS = 544 + 32 * TC_MMA_WARPS;               // 16 epilogue warps + producer + MMA issuer(s)
 constexpr int TC_NSTAGE = 2;
+constexpr int WBIAS_BYTES = 4096;                                // bias operand block [128 n][16 k] fp16 behind every weight image
+constexpr int WSTAGE_BYTES = STAGE_BYTES + WBIAS_BYTES;          // one weight stage in global memory and in the ring
 constexpr int TC_SM_A = 0;                                       // [2 tiles] 32 KB A operand: o tile / a2 / hidden-b / a'
 constexpr int TC_SM_HA = 2 * STAGE_BYTES;                        // [2 tiles] 32 KB A operand: hidden-a
 constexpr int TC_SM_W = 4 * STAGE_BYTES;                         // weight ring
-constexpr int TC_SM_VEC = TC_SM_W + TC_NSTAGE * STAGE_BYTES;     // [2 buffers] per-pair vectors (fp32), shared by both tiles
+constexpr int TC_SM_VEC = TC_SM_W + TC_NSTAGE * WSTAGE_BYTES;    // [2 buffers] per-pair vectors (fp32), shared by both tiles
 constexpr int V_MOD = 0;        // [2 branches][768]  adaLN chunk of block l
 constexpr int V_MODN = 1536;    // [2][256]           shift_msa | scale_msa of the next block
-constexpr int V_BPROJ = 2048, V_B1 = 2176, V_B2 = 2432, V_BQKV = 2560;
 constexpr int V_WEMB = 0;       // [4][128]   EMBED only: aliases the V_MOD area it does not use
 constexpr int V_BEMB = 512;     // [128]
 constexpr int V_WFIN = 1536;    // [4][128]   FINAL only: aliases the V_MODN area it does not use
-constexpr int V_BFIN = 2560;    // [4]        FINAL only: aliases V_BQKV
-constexpr int V_FLOATS = 2944;                                   // one vector buffer
-constexpr int TC_SM_VB = TC_SM_VEC + 2 * V_FLOATS * 4;           // [2 tiles][128][4] fp32 final-projection exchange
-constexpr int TC_SM_ST = TC_SM_VB + 2 * TILE_ROWS * 4 * 4;        // [2 tiles][2 halves][128] float2 LayerNorm statistics exchange
+constexpr int V_BFIN = 2048;    // [4]        FINAL only
+constexpr int V_FLOATS = 2064;                                   // one vector buffer (the Linear biases travel inside the weight stages)
+constexpr int TC_SM_ONES = TC_SM_VEC + 2 * V_FLOATS * 4;         // [128 rows][16 k] fp16 A operand block: k = 0, 1 are 1.0, the rest 0 (bias MMA)
+constexpr int TC_SM_ST = TC_SM_ONES + WBIAS_BYTES;               // [2 tiles][2 halves][128] float2 LayerNorm statistics exchange
 constexpr int TC_SM_BAR = TC_SM_ST + 2 * 2 * TILE_ROWS * 8;
-constexpr int TC_SM_TMEM = TC_SM_BAR + 48 * 8;
+constexpr int TC_SM_TMEM = TC_SM_BAR + 40 * 8;
 constexpr int TC_SM_EMB = TC_SM_TMEM + 16;                        // [4][128] folded patch-embed weight + [128] bias (recompute_h0)
 constexpr int TOK_SMEM_BYTES = TC_SM_EMB + 5 * D * 4;
+// FINAL's [2 tiles][128][4] fp32 projection exchange lives in the tile's A operand buffer: its last reader (fc2's second K
+// half) has completed before the final pass starts, and its next writer (the LN-modulate of the tile's next item) comes after
+// a 256-thread barrier (merge_stats) that every reader of the exchange has to reach first
 static_assert(TOK_SMEM_BYTES <= 232448, "token kernel shared memory exceeds 227 KB");
 // barrier ids
 enum { B_WFULL = 0, B_WEMPTY = 2, B_VFULL = 4, B_VFREE = 6, B_TILE = 8 };
 enum { T_OFULL = 0, T_A2 = 1, T_HA = 2, T_HB = 3, T_A3 = 4, T_XFREE = 5, T_DONE = 6, T_HAFREE = 7, T_ACC = 8 /* ..14 */, T_COUNT = 15 };
+static_assert(B_TILE + 2 * T_COUNT <= 40, "barrier slots");
 constexpr uint32_t TC_IDESC = umma_idesc_f16(128, 128);
 constexpr uint32_t KCH = 2048;   // byte stride between K chunks (16 row groups x 128 B) in a [128][128] operand image
 
 // one 128x128x128 GEMM chunk: 8 x tcgen05.mma (K = 16 each); operands in the canonical no-swizzle K-major image
 // Called by the whole (converged) MMA warp so that descriptors live in uniform registers; only `lead` issues.
-__device__ __forceinline__ void tc_gemm(uint32_t a_smem, uint32_t w_smem, uint32_t d_tmem, bool accumulate, bool lead) {
+// ones_smem != 0: a ninth MMA adds the Linear's bias: A = the constant block whose k = 0, 1 columns are 1.0 (every row), B =
+// the stage's bias block (k = 0 / 1: fp16 high / low part of the fp32 bias) — the epilogues then neither load nor add a bias
+// (the per-column constants every row thread has to load through the shared-memory crossbar are what paces the passes).
+__device__ __forceinline__ void tc_gemm(uint32_t a_smem, uint32_t w_smem, uint32_t d_tmem, bool accumulate, bool lead, uint32_t ones_smem = 0) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const uint64_t ad = umma_desc(a_smem + k * 2 * KCH, KCH, 128), bd = umma_desc(w_smem + k * 2 * KCH, KCH, 128);
         if (lead) umma_f16(d_tmem, ad, bd, TC_IDESC, (accumulate || k > 0) ? 1u : 0u);
+    }
+    if (ones_smem != 0) {
+        const uint64_t ad = umma_desc(ones_smem, KCH, 128), bd = umma_desc(w_smem + STAGE_BYTES, KCH, 128);
+        if (lead) umma_f16(d_tmem, ad, bd, TC_IDESC, 1u);
     }
 }
 
@@ -289,7 +307,8 @@ __device__ __forceinline__ HalfStats half_stats(float shift, float sum, float sq
     st.m2 = fmaxf(sq - sum * sum * (1.f / 64), 0.f);
     return st;
 }
-template <bool GB = false>
+// HASB = false: the GEMM already added the bias (token_kernel folds every Linear bias into its GEMM, see tc_gemm)
+template <bool GB = false, bool HASB = true>
 __device__ __forceinline__ HalfStats resid_pass_regs(uint32_t tacc, const float* __restrict__ gate, const float* __restrict__ bias,
                                                      const float4 (&hq)[16]) {
     float sum = 0.f, sq = 0.f, shift = 0.f;
@@ -301,10 +320,12 @@ __device__ __forceinline__ HalfStats resid_pass_regs(uint32_t tacc, const float*
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 g4 = *reinterpret_cast<const float4*>(gate + cb * 16 + q * 4);
-            const float4 b4 = ldv4<GB>(bias + cb * 16 + q * 4);
-            float t0, t1, t2, t3;
-            add2(t0, t1, a[q * 4 + 0], a[q * 4 + 1], b4.x, b4.y);
-            add2(t2, t3, a[q * 4 + 2], a[q * 4 + 3], b4.z, b4.w);
+            float t0 = a[q * 4 + 0], t1 = a[q * 4 + 1], t2 = a[q * 4 + 2], t3 = a[q * 4 + 3];
+            if constexpr (HASB) {
+                const float4 b4 = ldv4<GB>(bias + cb * 16 + q * 4);
+                add2(t0, t1, t0, t1, b4.x, b4.y);
+                add2(t2, t3, t2, t3, b4.z, b4.w);
+            }
             fma2(a[q * 4 + 0], a[q * 4 + 1], g4.x, g4.y, t0, t1, hq[cb * 4 + q].x, hq[cb * 4 + q].y);
             fma2(a[q * 4 + 2], a[q * 4 + 3], g4.z, g4.w, t2, t3, hq[cb * 4 + q].z, hq[cb * 4 + q].w);
         }
@@ -315,7 +336,7 @@ __device__ __forceinline__ HalfStats resid_pass_regs(uint32_t tacc, const float*
     tmem_wait_st();
     return half_stats(shift, sum, sq);
 }
-template <bool STORE, bool GB = false>
+template <bool STORE, bool GB = false, bool HASB = true>
 __device__ __forceinline__ HalfStats resid_pass_tmem(uint32_t tacc, uint32_t thin, const float* __restrict__ gate, const float* __restrict__ bias,
                                                      float* __restrict__ hdst, bool valid) {
     float sum = 0.f, sq = 0.f, shift = 0.f;
@@ -328,10 +349,12 @@ __device__ __forceinline__ HalfStats resid_pass_tmem(uint32_t tacc, uint32_t thi
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 g4 = *reinterpret_cast<const float4*>(gate + cb * 16 + q * 4);
-            const float4 b4 = ldv4<GB>(bias + cb * 16 + q * 4);
-            float t0, t1, t2, t3;
-            add2(t0, t1, a[q * 4 + 0], a[q * 4 + 1], b4.x, b4.y);
-            add2(t2, t3, a[q * 4 + 2], a[q * 4 + 3], b4.z, b4.w);
+            float t0 = a[q * 4 + 0], t1 = a[q * 4 + 1], t2 = a[q * 4 + 2], t3 = a[q * 4 + 3];
+            if constexpr (HASB) {
+                const float4 b4 = ldv4<GB>(bias + cb * 16 + q * 4);
+                add2(t0, t1, t0, t1, b4.x, b4.y);
+                add2(t2, t3, t2, t3, b4.z, b4.w);
+            }
             fma2(a[q * 4 + 0], a[q * 4 + 1], g4.x, g4.y, t0, t1, h[q * 4 + 0], h[q * 4 + 1]);
             fma2(a[q * 4 + 2], a[q * 4 + 3], g4.z, g4.w, t2, t3, h[q * 4 + 2], h[q * 4 + 3]);
         }
@@ -389,15 +412,17 @@ __device__ __forceinline__ void ln_mod_store(uint32_t trow, RowStats st, const f
 
 // hidden = GELU_tanh(acc + b1) over this thread's 64 columns, packed to fp16 into an A operand image (timm Mlp,
 // transformer.py:99,105)
-template <bool GB = false>
+template <bool GB = false, bool HASB = true>
 __device__ __forceinline__ void gelu_store(uint32_t taddr, const float* __restrict__ bias, uint8_t* abuf, int r, int kc0) {
     for_blocks16<4>(taddr, [&](int cb, float (&v)[16]) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float4 b4 = ldv4<GB>(bias + cb * 16 + q * 4);
-            float x0, x1, x2, x3;
-            add2(x0, x1, v[q * 4 + 0], v[q * 4 + 1], b4.x, b4.y);
-            add2(x2, x3, v[q * 4 + 2], v[q * 4 + 3], b4.z, b4.w);
+            float x0 = v[q * 4 + 0], x1 = v[q * 4 + 1], x2 = v[q * 4 + 2], x3 = v[q * 4 + 3];
+            if constexpr (HASB) {
+                const float4 b4 = ldv4<GB>(bias + cb * 16 + q * 4);
+                add2(x0, x1, x0, x1, b4.x, b4.y);
+                add2(x2, x3, x2, x3, b4.z, b4.w);
+            }
             gelu_tanh2(v[q * 4 + 0], v[q * 4 + 1], x0, x1);
             gelu_tanh2(v[q * 4 + 2], v[q * 4 + 3], x2, x3);
         }
@@ -406,6 +431,217 @@ __device__ __forceinline__ void gelu_store(uint32_t taddr, const float* __restri
             *reinterpret_cast<uint4*>(abuf + (kc0 + cb * 2 + c8) * KCH + r * 16) =
                 make_uint4(pack_h2(v[c8 * 8 + 0], v[c8 * 8 + 1]), pack_h2(v[c8 * 8 + 2], v[c8 * 8 + 3]),
                            pack_h2(v[c8 * 8 + 4], v[c8 * 8 + 5]), pack_h2(v[c8 * 8 + 6], v[c8 * 8 + 7]));
+    });
+}
+
+// ---- quad-layout epilogue (token_kernel).  The row-per-thread passes above make every thread load every per-column constant
+// of its 64 columns (scale, shift, gate, bias: warp-uniform 16-byte LDS, 3.3 KB per thread and work item): measured with
+// tools/probe_pass.cu, those broadcast loads alone cost 2.7-3.6 clk of the SM's shared-memory crossbar each and, together with
+// the tensor core's operand reads from the same crossbar, they — not issue slots, TMEM or HBM — paced every pass.  The passes
+// below read the accumulators through tcgen05.ld.16x256b instead (mapping verified by tools/probe_tmem_shapes.cu): thread T of
+// a warp then holds FOUR rows x 16 columns of its 32-lane x 64-column block,
+//   rows    R(rho) = 32 q + 8 rho + (T >> 2),  rho = 2 h + rr = 0..3      (q = warp & 3: TMEM lane quarter)
+//   columns c(g,e) = 64 hh + 8 g + 2 (T & 3) + e,  g = 0..7, e = 0..1     (hh: column half of the warp)
+// so a per-column constant is loaded once for four rows (a quarter of the bytes, 8-byte LDS), the packed fp32 operations pair
+// the two adjacent columns of a row, an fp16 pair of a row is one 4-byte store (a warp's store = 8 rows x 16 B contiguous, in
+// shared memory conflict-free) and row statistics take two xor-shuffles across the four threads of a row.
+// One tcgen05.ld.16x256b.x4 = block (b, h): lanes 16 h .. 16 h + 15 of the quarter, columns 32 b .. 32 b + 31 of the half;
+// register 4 g' + 2 rr + e <-> row rho = 2 h + rr, column group g = 4 b + g'.
+__device__ __forceinline__ void tmem_ld_q(uint32_t taddr, float (&v)[16]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                   "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_q(uint32_t taddr, const float (&v)[16]) {
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(v);
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+                 :: "r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]),
+                    "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]) : "memory");
+}
+__device__ __forceinline__ uint32_t q_blk(uint32_t tq, int b, int h) { return tq + ((uint32_t)(16 * h) << 16) + 32 * b; }
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+
+// pipelined walk over the four blocks of a region, (b, h) = (0,0) (0,1) (1,0) (1,1): prep(b) once per column block (loads
+// the column constants of its four groups), body(b, h, v) per block
+template <class P, class F>
+__device__ __forceinline__ void for_blocks_q(uint32_t tq, P&& prep, F&& body) {
+    float a[16], c[16];
+    tmem_ld_q(tq, a);
+#pragma unroll 1
+    for (int b = 0; b < 2; ++b) {
+        prep(b);
+        tmem_wait_ld();
+        tmem_ld_q(q_blk(tq, b, 1), c);
+        body(b, 0, a);
+        tmem_wait_ld();
+        if (b == 0) tmem_ld_q(q_blk(tq, 1, 0), a);
+        body(b, 1, c);
+    }
+}
+
+// per-thread accumulators of the shifted row sums of its four rows (packed over the two columns of a pair)
+struct QStats {
+    float shift[4], s0[4], s1[4], q0[4], q1[4];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) shift[i] = s0[i] = s1[i] = q0[i] = q1[i] = 0.f;
+    }
+    // one block (b, h): b == 0 also fixes the shift of rows 2 h, 2 h + 1 (the row's first column of this half, held by T & 3 == 0)
+    __device__ __forceinline__ void add(int b, int h, const float (&v)[16]) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int rho = 2 * h + rr;
+            if (b == 0) shift[rho] = __shfl_sync(0xffffffffu, v[2 * rr], (threadIdx.x & 31) & ~3);
+            const float ns = -shift[rho];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float d0, d1;
+                add2(d0, d1, v[4 * g + 2 * rr], v[4 * g + 2 * rr + 1], ns, ns);
+                add2(s0[rho], s1[rho], s0[rho], s1[rho], d0, d1);
+                fma2(q0[rho], q1[rho], d0, d1, d0, d1, q0[rho], q1[rho]);
+            }
+        }
+    }
+    // half-row statistics of row rho, identical in the four threads of the row
+    __device__ __forceinline__ HalfStats finish(int rho) const {
+        float sum = s0[rho] + s1[rho], sq = q0[rho] + q1[rho];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1); sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2); sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+        return half_stats(shift[rho], sum, sq);
+    }
+};
+// LayerNorm scalars of a thread's four rows: rs = rstd, nm = -mean * rstd
+struct QRows { float rs[4], nm[4]; };
+
+// merge the two half-row statistics of the thread's four rows (Chan's formula): thread T & 3 == rho publishes row rho
+// slot = exchange buffer [2 halves][128 rows] float2 of this tile; r0 = 32 q + (T >> 2), row rho = r0 + 8 rho
+__device__ __forceinline__ QRows merge_stats_q(const QStats& qs, float2* slot, int r0, int t, int hh, int bar_id, float eps) {
+    HalfStats hs[4];
+#pragma unroll
+    for (int rho = 0; rho < 4; ++rho) hs[rho] = qs.finish(rho);
+    {
+        const float m = t == 0 ? hs[0].mean : (t == 1 ? hs[1].mean : (t == 2 ? hs[2].mean : hs[3].mean));
+        const float v = t == 0 ? hs[0].m2 : (t == 1 ? hs[1].m2 : (t == 2 ? hs[2].m2 : hs[3].m2));
+        slot[hh * TILE_ROWS + r0 + 8 * t] = make_float2(m, v);
+    }
+    asm volatile("bar.sync %0, 256;\n" :: "r"(bar_id) : "memory");
+    QRows o;
+#pragma unroll
+    for (int rho = 0; rho < 4; ++rho) {
+        const float2 p = slot[(hh ^ 1) * TILE_ROWS + r0 + 8 * rho];
+        const float dm = hs[rho].mean - p.x;
+        const float mean = 0.5f * (hs[rho].mean + p.x);
+        o.rs[rho] = rsqrtf((hs[rho].m2 + p.y + 32.f * dm * dm) * (1.f / D) + eps);
+        o.nm[rho] = -mean * o.rs[rho];
+    }
+    return o;
+}
+
+// hn = hin + gate * (acc + bias) over the thread's 4 x 16 elements, written back over the accumulator; hin prefetched into
+// registers: hq[8 rho + g] = columns c(g, 0..1) of row rho.  gate / bias already offset to the column half + 2 (T & 3).
+__device__ __forceinline__ void resid_pass_regs_q(uint32_t tq, const float* __restrict__ gate, const float* __restrict__ bias,
+                                                  const float2 (&hq)[32], QStats& qs) {
+    qs.init();
+    float2 g2[4], b2[4];
+    for_blocks_q(tq, [&](int b) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { g2[g] = ld2(gate + 32 * b + 8 * g); b2[g] = ld2(bias + 32 * b + 8 * g); }
+    }, [&](int b, int h, float (&v)[16]) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                float t0, t1;
+                const float2 hin = hq[8 * (2 * h + rr) + 4 * b + g];
+                add2(t0, t1, v[4 * g + 2 * rr], v[4 * g + 2 * rr + 1], b2[g].x, b2[g].y);
+                fma2(v[4 * g + 2 * rr], v[4 * g + 2 * rr + 1], g2[g].x, g2[g].y, t0, t1, hin.x, hin.y);
+            }
+        qs.add(b, h, v);
+        tmem_st_q(q_blk(tq, b, h), v);
+    });
+    tmem_wait_st();
+}
+// the same with hin = the row parked in another TMEM region; STORE: hn also goes to the residual tile in global memory
+// (hdst = tile + 2 (T & 3) % 4 ... : element (row R, column c) at (c / 4) * TILE_ROWS * 4 + R * 4 + c % 4; see the caller)
+template <bool STORE>
+__device__ __forceinline__ void resid_pass_tmem_q(uint32_t tacc, uint32_t thin, const float* __restrict__ gate, const float* __restrict__ bias,
+                                                  float* __restrict__ hdst, const bool (&valid)[4], QStats& qs) {
+    qs.init();
+    float2 g2[4], b2[4];
+    float a[16], x[16];
+#pragma unroll 1
+    for (int b = 0; b < 2; ++b) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { g2[g] = ld2(gate + 32 * b + 8 * g); b2[g] = ld2(bias + 32 * b + 8 * g); }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            tmem_ld_q(q_blk(tacc, b, h), a);
+            tmem_ld_q(q_blk(thin, b, h), x);
+            tmem_wait_ld();
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    float t0, t1;
+                    add2(t0, t1, a[4 * g + 2 * rr], a[4 * g + 2 * rr + 1], b2[g].x, b2[g].y);
+                    fma2(a[4 * g + 2 * rr], a[4 * g + 2 * rr + 1], g2[g].x, g2[g].y, t0, t1, x[4 * g + 2 * rr], x[4 * g + 2 * rr + 1]);
+                }
+            qs.add(b, h, a);
+            tmem_st_q(q_blk(tacc, b, h), a);
+            if (STORE) {
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+                    if (valid[2 * h + rr]) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)       // column 32 b + 8 g (+ 2 (T & 3), in hdst): col chunk + 8 b + 2 g
+                            *reinterpret_cast<float2*>(hdst + (8 * b + 2 * g) * TILE_ROWS * 4 + (16 * h + 8 * rr) * 4) =
+                                make_float2(a[4 * g + 2 * rr], a[4 * g + 2 * rr + 1]);
+                    }
+            }
+        }
+    }
+    tmem_wait_st();
+}
+
+// LayerNorm (no affine) + modulate, packed to fp16 into the next GEMM's A operand image.  shift / scale1 offset to the
+// column half + 2 (T & 3); arow = abuf + kc0 * KCH + r0 * 16 + 4 (T & 3) (kc0 = first K chunk of the half)
+__device__ __forceinline__ void ln_mod_store_q(uint32_t tq, const QRows& st, const float* __restrict__ shift, const float* __restrict__ scale1, uint8_t* arow) {
+    float2 sc[4], sh[4];
+    for_blocks_q(tq, [&](int b) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { sc[g] = ld2(scale1 + 32 * b + 8 * g); sh[g] = ld2(shift + 32 * b + 8 * g); }
+    }, [&](int b, int h, float (&v)[16]) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int rho = 2 * h + rr;
+                float n0, n1, y0, y1;
+                fma2(n0, n1, v[4 * g + 2 * rr], v[4 * g + 2 * rr + 1], st.rs[rho], st.rs[rho], st.nm[rho], st.nm[rho]);
+                fma2(y0, y1, n0, n1, sc[g].x, sc[g].y, sh[g].x, sh[g].y);
+                *reinterpret_cast<uint32_t*>(arow + (4 * b + g) * KCH + (8 * rho) * 16) = pack_h2(y0, y1);
+            }
+    });
+}
+
+// hidden = GELU_tanh(acc + b1), packed to fp16 into an A operand image
+__device__ __forceinline__ void gelu_store_q(uint32_t tq, const float* __restrict__ bias, uint8_t* arow) {
+    float2 b2[4];
+    for_blocks_q(tq, [&](int b) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) b2[g] = ld2(bias + 32 * b + 8 * g);
+    }, [&](int b, int h, float (&v)[16]) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                float x0, x1, y0, y1;
+                add2(x0, x1, v[4 * g + 2 * rr], v[4 * g + 2 * rr + 1], b2[g].x, b2[g].y);
+                gelu_tanh2(y0, y1, x0, x1);
+                *reinterpret_cast<uint32_t*>(arow + (4 * b + g) * KCH + (8 * (2 * h + rr)) * 16) = pack_h2(y0, y1);
+            }
     });
 }
 
@@ -429,7 +665,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
     const int n_items = ((p.nseq + 1) / 2) * (TILES_PER_PAIR / NE);  // work item = NE consecutive pair tiles
 
     if (tid == 0) {
-        for (int i = 0; i < B_VFREE; ++i) mbar_init(BAR(i), 1);                  // WFULL, WEMPTY, VFULL
+        for (int i = 0; i < B_VFREE; ++i)                                         // WFULL, WEMPTY (one commit per issuer warp), VFULL
+            mbar_init(BAR(i), (i >= B_WEMPTY && i < B_VFULL && TC_MMA_WARPS == 2) ? NE : 1);
         for (int i = 0; i < 2; ++i) mbar_init(BAR(B_VFREE + i), 8 * NE);          // one arrival per epilogue WARP (mbar_arrive_warp)
         for (int e = 0; e < NE; ++e) {
             mbar_init(TBAR(e, T_OFULL), 1);
@@ -444,6 +681,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
         float* semb = reinterpret_cast<float*>(smem + TC_SM_EMB);
         for (int i = tid; i < 5 * D; i += TC_THREADS) semb[i] = i < 4 * D ? p.w.w_embed[i] : p.w.b_embed[i - 4 * D];
     }
+    // constant A block of the bias MMA: K chunk 0 = rows of {1, 1, 0, 0, 0, 0, 0, 0}, K chunk 1 = zeros
+    for (int i = tid; i < WBIAS_BYTES / 16; i += TC_THREADS)
+        reinterpret_cast<uint4*>(smem + TC_SM_ONES)[i] = make_uint4(i < KCH / 16 ? 0x3c003c00u : 0u, 0u, 0u, 0u);
+    fence_async_smem();
     pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
@@ -469,20 +710,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 if (lead) bulk_g2s(vdst + voff * 4, src, n * 4, vbar);
                 bytes += n * 4;
             };
-            constexpr uint32_t VBYTES = (MODE == TOK_EMBED ? 0u : (2 * MOD + 2 * D + DMLP) * 4u) + (MODE == TOK_FINAL ? 0u : (512 + 3 * D) * 4u) +
+            constexpr uint32_t VBYTES = (MODE == TOK_EMBED ? 0u : (2 * MOD) * 4u) + (MODE == TOK_FINAL ? 0u : 512 * 4u) +
                                         (MODE == TOK_EMBED ? (5 * D) * 4u : 0u) + (MODE == TOK_FINAL ? (4 * D + 4) * 4u : 0u);
             if (lead) mbar_expect_tx(vbar, VBYTES);
             if (MODE != TOK_EMBED) {
                 cp(V_MOD, p.mod + ((size_t)sq0 * NLAYER + l) * MOD, MOD);
                 cp(V_MOD + MOD, p.mod + ((size_t)sq1 * NLAYER + l) * MOD, MOD);
-                cp(V_BPROJ, p.w.b_proj[l], D);
-                cp(V_B1, p.w.b_fc1[l], DMLP);
-                cp(V_B2, p.w.b_fc2[l], D);
             }
             if (MODE != TOK_FINAL) {
                 cp(V_MODN, p.mod + ((size_t)sq0 * NLAYER + ln) * MOD, 256);
                 cp(V_MODN + 256, p.mod + ((size_t)sq1 * NLAYER + ln) * MOD, 256);
-                cp(V_BQKV, p.w.b_qkv[ln], 3 * D);
             }
             if (MODE == TOK_EMBED) { cp(V_WEMB, p.w.w_embed, 4 * D); cp(V_BEMB, p.w.b_embed, D); }
             if (MODE == TOK_FINAL) { cp(V_WFIN, p.w.w_final, 4 * D); cp(V_BFIN, p.w.b_final, 4); }
@@ -510,9 +747,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 const int slot = gs % TC_NSTAGE, use = gs / TC_NSTAGE;
                 if (use > 0) mbar_wait(BAR(B_WEMPTY + slot), (use - 1) & 1);
                 if (lead) {
-                    mbar_expect_tx(BAR(B_WFULL + slot), STAGE_BYTES);
-                    bulk_g2s(sb + TC_SM_W + slot * STAGE_BYTES, s < N_A ? src_a + (size_t)s * STAGE_BYTES : src_b + (size_t)(s - N_A) * STAGE_BYTES,
-                             STAGE_BYTES, BAR(B_WFULL + slot));
+                    mbar_expect_tx(BAR(B_WFULL + slot), WSTAGE_BYTES);
+                    bulk_g2s(sb + TC_SM_W + slot * WSTAGE_BYTES, s < N_A ? src_a + (size_t)s * WSTAGE_BYTES : src_b + (size_t)(s - N_A) * WSTAGE_BYTES,
+                             WSTAGE_BYTES, BAR(B_WFULL + slot));
                 }
                 __syncwarp();
                 // the next item's inputs: as early as its buffers can be free (MID / FINAL: after the fc2 stages have been queued)
@@ -520,15 +757,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             }
         }
         __syncwarp();
-    } else if (warp == 17) {
+    } else if (warp >= 17) {
         // ================================================================= MMA issuer (whole warp converged; lane 0 issues)
+        // -DT2S_TOK_MMA_WARPS=2 gives every tile its own issuer warp (17 + e; the ring slots are then released by one commit per
+        // issuer).  Measured (round 2): the leading tile no longer waits behind the other tile's pending event (its item 31.2 k ->
+        // 27.5 k cycles in the phase trace) but the step gets 2 % SLOWER (4.65 -> 4.75 ms): the tiles share the SM's load/store,
+        // FMA and MUFU throughput, which is what paces an item, so the single in-order issuer stays the default.
+        // E0 / E1 = range of tiles this warp serves.
         const bool lead = lane == 0;
+        const int E0 = TC_MMA_WARPS == 2 ? warp - 17 : 0, E1 = TC_MMA_WARPS == 2 ? min(warp - 16, NE) : NE;
         int gs = 0;                                                     // global weight-stage counter
         auto wfull = [&](int g) { mbar_wait(BAR(B_WFULL + g % TC_NSTAGE), (g / TC_NSTAGE) & 1); };
-        auto wslot = [&](int g) { return sb + TC_SM_W + (g % TC_NSTAGE) * STAGE_BYTES; };
+        auto wslot = [&](int g) { return sb + TC_SM_W + (g % TC_NSTAGE) * WSTAGE_BYTES; };
+        const uint32_t ones = sb + TC_SM_ONES;
         auto wdone = [&](int g) { if (lead) umma_commit(BAR(B_WEMPTY + g % TC_NSTAGE)); __syncwarp(); };
 #pragma unroll 1
-        for (int it = 0, item = blockIdx.x; item < n_items; ++it, item += gridDim.x) {
+        for (int it = 0, item = blockIdx.x; item < n_items && E0 < E1; ++it, item += gridDim.x) {
             const uint32_t par = it & 1;
             const uint32_t X = (it & 1) * 128, Y = 128 - X;             // the two TMEM regions swap roles every item
             // one weight stage feeds the same GEMM chunk of both tiles; chunks that wait on the same epilogue event
@@ -539,39 +783,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             auto acc = [&](int e, int i) { if (lead) umma_commit(TBAR(e, T_ACC + i)); };
             if (MODE != TOK_EMBED) {
                 wfull(gs);                                               // proj (o tile sits in HA) -> X
-#pragma unroll
-                for (int e = 0; e < NE; ++e) {
+#pragma unroll 1
+                for (int e = E0; e < E1; ++e) {
                     if (it > 0) mbar_wait(TBAR(e, T_DONE), (it - 1) & 1);   // the previous item has drained this region
                     mbar_wait(TBAR(e, T_OFULL), par);
                     tc_fence_after();
-                    tc_gemm(HA_(e), wslot(gs), D_(e, X), false, lead);
+                    tc_gemm(HA_(e), wslot(gs), D_(e, X), false, lead, ones);
                     acc(e, 0);
                 }
                 wdone(gs); ++gs;
                 wfull(gs);                                               // fc1 cols 0..127 -> Y
-#pragma unroll
-                for (int e = 0; e < NE; ++e) {
+#pragma unroll 1
+                for (int e = E0; e < E1; ++e) {
                     mbar_wait(TBAR(e, T_A2), par);
                     tc_fence_after();
-                    tc_gemm(A_(e), wslot(gs), D_(e, Y), false, lead);
+                    tc_gemm(A_(e), wslot(gs), D_(e, Y), false, lead, ones);
                     acc(e, 1);
                 }
                 wdone(gs); ++gs;
                 wfull(gs);                                               // fc1 cols 128..255 -> Y (hidden-a done: Y drained)
-#pragma unroll
-                for (int e = 0; e < NE; ++e) {
+#pragma unroll 1
+                for (int e = E0; e < E1; ++e) {
                     mbar_wait(TBAR(e, T_HA), par);
                     tc_fence_after();
-                    tc_gemm(A_(e), wslot(gs), D_(e, Y), false, lead);
+                    tc_gemm(A_(e), wslot(gs), D_(e, Y), false, lead, ones);
                     acc(e, 2);
                 }
                 wdone(gs); ++gs;
                 wfull(gs); wfull(gs + 1);                                // fc2, both K halves -> Y (hidden-b done: Y drained)
-#pragma unroll
-                for (int e = 0; e < NE; ++e) {
+#pragma unroll 1
+                for (int e = E0; e < E1; ++e) {
                     mbar_wait(TBAR(e, T_HB), par);
                     tc_fence_after();
-                    tc_gemm(HA_(e), wslot(gs), D_(e, Y), false, lead);
+                    tc_gemm(HA_(e), wslot(gs), D_(e, Y), false, lead, ones);
                     if (lead) umma_commit(TBAR(e, T_HAFREE));
                     tc_gemm(A_(e), wslot(gs + 1), D_(e, Y), true, lead);
                     acc(e, 3);
@@ -580,22 +824,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             }
             if (MODE != TOK_FINAL) {
                 wfull(gs); wfull(gs + 1);                                // q -> X, k -> Y
-#pragma unroll
-                for (int e = 0; e < NE; ++e) {
+#pragma unroll 1
+                for (int e = E0; e < E1; ++e) {
                     mbar_wait(TBAR(e, T_A3), par);
                     tc_fence_after();
-                    tc_gemm(A_(e), wslot(gs), D_(e, X), false, lead);
+                    tc_gemm(A_(e), wslot(gs), D_(e, X), false, lead, ones);
                     acc(e, 4);
-                    tc_gemm(A_(e), wslot(gs + 1), D_(e, Y), false, lead);
+                    tc_gemm(A_(e), wslot(gs + 1), D_(e, Y), false, lead, ones);
                     acc(e, 5);
                 }
                 wdone(gs); wdone(gs + 1); gs += 2;
                 wfull(gs);                                               // v -> X (after the q epilogue has drained X)
-#pragma unroll
-                for (int e = 0; e < NE; ++e) {
+#pragma unroll 1
+                for (int e = E0; e < E1; ++e) {
                     mbar_wait(TBAR(e, T_XFREE), par);
                     tc_fence_after();
-                    tc_gemm(A_(e), wslot(gs), D_(e, X), false, lead);
+                    tc_gemm(A_(e), wslot(gs), D_(e, X), false, lead, ones);
                     acc(e, 6);
                 }
                 wdone(gs); ++gs;
@@ -717,7 +961,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             mbar_wait(TBAR(e, T_ACC + 0), par);
             tc_fence_after();
             STAMP(3);
-            HalfStats hs = resid_pass_regs(trow + X, modb + 2 * D + c0, vec + V_BPROJ + c0, hq);
+            HalfStats hs = resid_pass_regs<false, false>(trow + X, modb + 2 * D + c0, nullptr, hq);
             st = merge_stats(hs, stx, r, hh, 1 + e, 1e-6f);
             ln_mod_store(trow + X, st, modb + 3 * D + c0, modb + 4 * D + c0, abuf, r, kc0);
             fence_async_smem();
@@ -728,7 +972,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             mbar_wait(TBAR(e, T_ACC + 1), par);
             tc_fence_after();
             STAMP(5);
-            gelu_store(trow + Y, vec + V_B1 + c0, habuf, r, kc0);
+            gelu_store<false, false>(trow + Y, nullptr, habuf, r, kc0);
             fence_async_smem();
             tc_fence_before();
             mbar_arrive_warp(TBAR(e, T_HA));
@@ -736,7 +980,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             mbar_wait(TBAR(e, T_ACC + 2), par);
             tc_fence_after();
             STAMP(7);
-            gelu_store(trow + Y, vec + V_B1 + D + c0, abuf, r, kc0);
+            gelu_store<false, false>(trow + Y, nullptr, abuf, r, kc0);
             fence_async_smem();
             tc_fence_before();
             mbar_arrive_warp(TBAR(e, T_HB));
@@ -745,7 +989,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             mbar_wait(TBAR(e, T_ACC + 3), par);
             tc_fence_after();
             STAMP(9);
-            hs = resid_pass_tmem<MODE == TOK_MID>(trow + Y, trow + X, modb + 5 * D + c0, vec + V_B2 + c0, hrow, valid);
+            hs = resid_pass_tmem<MODE == TOK_MID, false, false>(trow + Y, trow + X, modb + 5 * D + c0, nullptr, hrow, valid);
             st = merge_stats(hs, stx, r, hh, 1 + e, MODE == TOK_FINAL ? 1e-5f : 1e-6f);
             STAMP(10);
         }
@@ -765,7 +1009,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 tc_fence_after();
                 STAMP(12 + 2 * which);
                 const uint32_t tcol = which == 1 ? Y : X;
-                const float* bq = vec + V_BQKV + which * D + c0;
                 // tcgen05 operand images read by attn_kernel (a warp's 32 rows are contiguous): element offset of this
                 // token inside a (sequence, head) image and the stride between 8-wide d chunks
                 const int off = which == 0 ? (tok / QT_ROWS) * 4096 + (tok % QT_ROWS) * 8
@@ -777,14 +1020,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                     if (valid) {
                         __half* hb = hb0 + (cb >> 1) * QKV_HEAD_HALVES + (cb & 1) * 2 * dstride;
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const float4 b0 = *reinterpret_cast<const float4*>(bq + cb * 16 + c * 8);
-                            const float4 b1 = *reinterpret_cast<const float4*>(bq + cb * 16 + c * 8 + 4);
+                        for (int c = 0; c < 2; ++c) {                     // the bias is already in the accumulator (tc_gemm)
                             const float* x = v + c * 8;
-                            float y0, y1, y2, y3, y4, y5, y6, y7;
-                            add2(y0, y1, x[0], x[1], b0.x, b0.y); add2(y2, y3, x[2], x[3], b0.z, b0.w);
-                            add2(y4, y5, x[4], x[5], b1.x, b1.y); add2(y6, y7, x[6], x[7], b1.z, b1.w);
-                            *reinterpret_cast<uint4*>(hb + c * dstride) = make_uint4(pack_h2(y0, y1), pack_h2(y2, y3), pack_h2(y4, y5), pack_h2(y6, y7));
+                            *reinterpret_cast<uint4*>(hb + c * dstride) = make_uint4(pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[4], x[5]), pack_h2(x[6], x[7]));
                         }
                     }
                 });
@@ -815,7 +1053,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             });
             tc_fence_before();
             mbar_arrive_warp(TBAR(e, T_DONE));                                // Y drained: the next item's proj may overwrite it
-            float* vb = reinterpret_cast<float*>(smem + TC_SM_VB) + e * TILE_ROWS * 4;
+            float* vb = reinterpret_cast<float*>(abuf);                     // [128][4] projection exchange (see TC_SM_ONES comment)
             float4* px = reinterpret_cast<float4*>(stx);                 // the statistics exchange is idle now: partial sums of half 1
             asm volatile("bar.sync %0, 256;\n" :: "r"(1 + e) : "memory");  // ... once every thread has read its merge partner
             if (hh == 1) px[r] = make_float4(d4[0], d4[1], d4[2], d4[3]);

@@ -13,6 +13,7 @@ import torch
 from . import _lib
 
 D = 128
+WSTAGE_BYTES = 32768 + 4096      # token_kernel weight stage: operand image + bias block (csrc/dit_kernels.cuh)
 
 
 def umma_stage(w: torch.Tensor) -> torch.Tensor:
@@ -23,6 +24,25 @@ def umma_stage(w: torch.Tensor) -> torch.Tensor:
     assert tuple(w.shape) == (128, 128)
     w16 = w.detach().to(torch.float16).reshape(16, 8, 16, 8)            # [n//8][n%8][k//8][k%8]
     return w16.permute(2, 0, 1, 3).contiguous().reshape(-1)              # [k//8][n//8][n%8][k%8]
+
+
+def umma_bias_block(b: torch.Tensor | None) -> torch.Tensor:
+    """fp32 bias [128] -> the 4 KB fp16 operand block [128 n][16 k] that follows a weight image in a stage (same canonical
+    layout, two K chunks): k = 0 holds fp16(b), k = 1 holds fp16(b - fp16(b)), everything else is zero.  token_kernel multiplies
+    it with a constant A block whose k = 0, 1 columns are 1.0, so the GEMM's fp32 accumulator starts from the bias to 2^-22
+    relative (t2ms_b200/csrc/dit_kernels.cuh: tc_gemm).  None -> a zero block (fc2's second K half)."""
+    blk = torch.zeros(2, 16, 8, 8, dtype=torch.float16, device=b.device if b is not None else None)   # [k//8][n//8][n%8][k%8]
+    if b is not None:
+        b = b.detach().to(torch.float32).reshape(16, 8)
+        hi = b.to(torch.float16)
+        lo = (b - hi.to(torch.float32)).to(torch.float16)
+        blk[0, :, :, 0], blk[0, :, :, 1] = hi, lo
+    return blk.reshape(-1)
+
+
+def umma_wstage(w: torch.Tensor, b: torch.Tensor | None) -> torch.Tensor:
+    """One token_kernel weight stage (36 KB): the weight image followed by the bias block."""
+    return torch.cat([umma_stage(w), umma_bias_block(b).to(w.device)])
 
 
 def umma_half_stages(w: torch.Tensor) -> torch.Tensor:
@@ -62,12 +82,14 @@ class PackedDit:
         for l in range(4):
             p = f"layers.{l}."
             wq = g(p + "attn.qkv.weight")                                           # [384][128]
-            qkv = torch.cat([umma_stage(wq[i * D:(i + 1) * D]) for i in range(3)])
+            bq, bp = g(p + "attn.qkv.bias").contiguous(), g(p + "attn.proj.bias").contiguous()
+            b1, b2 = g(p + "mlp.fc1.bias").contiguous(), g(p + "mlp.fc2.bias").contiguous()
+            qkv = torch.cat([umma_wstage(wq[i * D:(i + 1) * D], bq[i * D:(i + 1) * D]) for i in range(3)])
             w1, w2 = g(p + "mlp.fc1.weight"), g(p + "mlp.fc2.weight")               # [256][128], [128][256]
-            post = [umma_stage(g(p + "attn.proj.weight")), umma_stage(w1[:D]), umma_stage(w1[D:]),
-                    umma_stage(w2[:, :D].contiguous()), umma_stage(w2[:, D:].contiguous())]
+            post = [umma_wstage(g(p + "attn.proj.weight"), bp), umma_wstage(w1[:D], b1[:D]), umma_wstage(w1[D:], b1[D:]),
+                    umma_wstage(w2[:, :D].contiguous(), b2), umma_wstage(w2[:, D:].contiguous(), None)]
             post = torch.cat(post)
-            assert qkv.numel() * 2 == 3 * 32768 and post.numel() * 2 == 5 * 32768
+            assert qkv.numel() * 2 == 3 * WSTAGE_BYTES and post.numel() * 2 == 5 * WSTAGE_BYTES
             if sd["pos_embed"].shape[-2] == 480:                                    # T2S shape: half stages for the fused step kernel
                 qkv_h = torch.cat([umma_half_stages(wq[i * D:(i + 1) * D]) for i in range(3)])
                 f2a, f2b = umma_half_stages(w2[:, :D].contiguous()).reshape(2, -1), umma_half_stages(w2[:, D:].contiguous()).reshape(2, -1)
@@ -76,8 +98,6 @@ class PackedDit:
                 assert qkv_h.numel() * 2 == 6 * 16384 and post_h.numel() * 2 == 10 * 16384
                 keep += [qkv_h, post_h]
                 st.w_qkv_half[l], st.w_post_half[l] = _ptr(qkv_h), _ptr(post_h)
-            bq, bp = g(p + "attn.qkv.bias").contiguous(), g(p + "attn.proj.bias").contiguous()
-            b1, b2 = g(p + "mlp.fc1.bias").contiguous(), g(p + "mlp.fc2.bias").contiguous()
             keep += [qkv, post, bq, bp, b1, b2]
             st.w_qkv[l], st.w_post[l] = _ptr(qkv), _ptr(post)
             st.b_qkv[l], st.b_proj[l], st.b_fc1[l], st.b_fc2[l] = _ptr(bq), _ptr(bp), _ptr(b1), _ptr(b2)
