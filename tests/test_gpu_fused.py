@@ -49,8 +49,9 @@ def test_fused_sampling_matches_reference_golden_and_per_phase_kernels(fused):
                                    step_noise=T(g["ddpm_step_noise"]).to(DEV), trace=True)
     assert max(rel_l2(trace[j], T(g["ddpm_eps"])[j]) for j in range(steps)) < 2e-3
     assert rel_l2(lat, T(g["ddpm_latent"])) < 2e-3
-    # a batch over every SM: bit-identical to the per-phase kernels (same tiles, same MMA shapes per output element,
-    # same attention chunking), run to run, and with the admission gate
+    # a batch over every SM: bit-identical run to run and with the admission gate; equal to the per-phase kernels to rounding
+    # (same tiles, MMA shapes and attention chunking, but the per-phase token kernel adds the Linear biases inside its GEMMs
+    # - as fp16 high + low parts, 2^-22 relative - and the fused kernel in its fp32 epilogues)
     B = 200
     e2, x0 = synth.make_text_embeddings(B, seed=5).to(DEV), synth.make_noise(B, seed=6).to(DEV)
     a = smp.sample(e2, 96, steps=3, noise=x0)
@@ -58,4 +59,8 @@ def test_fused_sampling_matches_reference_golden_and_per_phase_kernels(fused):
     fused.t2s_set_fused(1, 24)
     assert torch.equal(a, smp.sample(e2, 96, steps=3, noise=x0))
     fused.t2s_set_fused(-1, 0)
-    assert torch.equal(a, smp.sample(e2, 96, steps=3, noise=x0))
+    b = smp.sample(e2, 96, steps=3, noise=x0)
+    assert torch.equal(b, smp.sample(e2, 96, steps=3, noise=x0))
+    err = rel_l2(a, b)
+    print("fused vs per-phase kernels: rel-L2 %.2e, max-abs %.2e" % (err, max_abs(a, b)))
+    assert err < 2e-4
