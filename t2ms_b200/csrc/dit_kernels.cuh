@@ -228,7 +228,7 @@ constexpr int TOK_SMEM_BYTES = TC_SM_EMB + 5 * D * 4;
 static_assert(TOK_SMEM_BYTES <= 232448, "token kernel shared memory exceeds 227 KB");
 // barrier ids
 enum { B_WFULL = 0, B_WEMPTY = 2, B_VFULL = 4, B_VFREE = 6, B_TILE = 8 };
-enum { T_OFULL = 0, T_A2 = 1, T_HA = 2, T_HB = 3, T_A3 = 4, T_XFREE = 5, T_DONE = 6, T_HAFREE = 7, T_ACC = 8 /* ..14 */, T_COUNT = 15 };
+enum { T_OFULL = 0, T_A2 = 1, T_HA = 2, T_HB = 3, T_A3 = 4, T_XFREE = 5, T_DONE = 6, T_HAFREE = 7, T_ACC = 8 /* ..14 */, T_YFREE = 15, T_COUNT = 16 };
 static_assert(B_TILE + 2 * T_COUNT <= 40, "barrier slots");
 constexpr uint32_t TC_IDESC = umma_idesc_f16(128, 128);
 constexpr uint32_t KCH = 2048;   // byte stride between K chunks (16 row groups x 128 B) in a [128][128] operand image
@@ -671,8 +671,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
         for (int e = 0; e < NE; ++e) {
             mbar_init(TBAR(e, T_OFULL), 1);
             for (int i = T_A2; i <= T_DONE; ++i) mbar_init(TBAR(e, i), 8);
+            mbar_init(TBAR(e, T_YFREE), 8);
             mbar_init(TBAR(e, T_HAFREE), 1);
-            for (int i = T_ACC; i < T_COUNT; ++i) mbar_init(TBAR(e, i), 1);
+            for (int i = T_ACC; i < T_ACC + 7; ++i) mbar_init(TBAR(e, i), 1);
         }
         mbar_fence_init();
     }
@@ -747,9 +748,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 const int slot = gs % TC_NSTAGE, use = gs / TC_NSTAGE;
                 if (use > 0) mbar_wait(BAR(B_WEMPTY + slot), (use - 1) & 1);
                 if (lead) {
+#ifdef T2S_EXP_SKIP_WLOAD      // timing experiment only (wrong results): weight stages are fetched for a CTA's first item only
+                    if (it > 0) mbar_arrive(BAR(B_WFULL + slot)); else {
+#endif
                     mbar_expect_tx(BAR(B_WFULL + slot), WSTAGE_BYTES);
                     bulk_g2s(sb + TC_SM_W + slot * WSTAGE_BYTES, s < N_A ? src_a + (size_t)s * WSTAGE_BYTES : src_b + (size_t)(s - N_A) * WSTAGE_BYTES,
                              WSTAGE_BYTES, BAR(B_WFULL + slot));
+#ifdef T2S_EXP_SKIP_WLOAD
+                    }
+#endif
                 }
                 __syncwarp();
                 // the next item's inputs: as early as its buffers can be free (MID / FINAL: after the fc2 stages have been queued)
@@ -823,6 +830,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 wdone(gs); wdone(gs + 1); gs += 2;
             }
             if (MODE != TOK_FINAL) {
+#ifndef T2S_TOK_HSTORE_EARLY
+                // MID writes the residual tile to global memory AFTER the LN pass (see the epilogue): the k chunk may only
+                // overwrite region Y once that store pass has drained it, so q is issued for both tiles first and its ring slot
+                // is released before k: the v stage is then on its way while the q / k epilogues run
+                wfull(gs);                                               // q -> X
+#pragma unroll 1
+                for (int e = E0; e < E1; ++e) {
+                    mbar_wait(TBAR(e, T_A3), par);
+                    tc_fence_after();
+                    tc_gemm(A_(e), wslot(gs), D_(e, X), false, lead, ones);
+                    acc(e, 4);
+                }
+                wdone(gs); ++gs;
+                wfull(gs);                                               // k -> Y
+#pragma unroll 1
+                for (int e = E0; e < E1; ++e) {
+                    if (MODE == TOK_MID) { mbar_wait(TBAR(e, T_YFREE), par); tc_fence_after(); }
+                    tc_gemm(A_(e), wslot(gs), D_(e, Y), false, lead, ones);
+                    acc(e, 5);
+                }
+                wdone(gs); ++gs;
+#else
                 wfull(gs); wfull(gs + 1);                                // q -> X, k -> Y
 #pragma unroll 1
                 for (int e = E0; e < E1; ++e) {
@@ -834,6 +863,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                     acc(e, 5);
                 }
                 wdone(gs); wdone(gs + 1); gs += 2;
+#endif
                 wfull(gs);                                               // v -> X (after the q epilogue has drained X)
 #pragma unroll 1
                 for (int e = E0; e < E1; ++e) {
@@ -989,7 +1019,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             mbar_wait(TBAR(e, T_ACC + 3), par);
             tc_fence_after();
             STAMP(9);
+#ifndef T2S_TOK_HSTORE_EARLY
+            hs = resid_pass_tmem<false, false, false>(trow + Y, trow + X, modb + 5 * D + c0, nullptr, hrow, valid);
+#else
             hs = resid_pass_tmem<MODE == TOK_MID, false, false>(trow + Y, trow + X, modb + 5 * D + c0, nullptr, hrow, valid);
+#endif
             st = merge_stats(hs, stx, r, hh, 1 + e, MODE == TOK_FINAL ? 1e-5f : 1e-6f);
             STAMP(10);
         }
@@ -1002,6 +1036,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             tc_fence_before();
             mbar_arrive_warp(TBAR(e, T_A3));
             STAMP(11);
+#ifndef T2S_TOK_HSTORE_EARLY
+            if (MODE == TOK_MID) {
+                // the updated residual tile goes to global memory HERE, while the tensor pipe computes q: a store pass is paced by
+                // the SM's path to L2 (tools/probe_pass.cu: +1.7 k cycles per tile inside the residual pass), which this slot
+                // hides; region Y belongs to the k chunk afterwards
+                for_blocks16<4>(trow + Y, [&](int cb, float (&a)[16]) {
+                    if (valid) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<float4*>(hrow + (cb * 4 + q) * TILE_ROWS * 4) = make_float4(a[q * 4], a[q * 4 + 1], a[q * 4 + 2], a[q * 4 + 3]);
+                    }
+                });
+                tc_fence_before();
+                mbar_arrive_warp(TBAR(e, T_YFREE));
+            }
+#endif
             // q | k | v = a' W^T + b, stored fp16 in the attention kernel's smem image layout
 #pragma unroll 1
             for (int which = 0; which < 3; ++which) {

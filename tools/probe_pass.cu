@@ -221,6 +221,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pass_probe(int mode, int ntile,
                         }
                     }
                     acc += s4.x + s4.y + s4.z + s4.w;
+                } else if (mode >= 22) {                   // MLP residual pass: acc (region Y) + parked row (region X), write-back, statistics
+                    float* hrow = sink + 64 + ((size_t)(blockIdx.x * 2 + e) * TILE_ROWS * D) + (c0 / 4) * TILE_ROWS * 4 + r * 4;
+                    HalfStats hs;
+                    if (mode == 22) hs = resid_pass_tmem<true, false, false>(trow + 128, trow, vec + c0, nullptr, hrow, (r & 63) < 60);
+                    else hs = resid_pass_tmem<false, false, false>(trow + 128, trow, vec + c0, nullptr, hrow, (r & 63) < 60);
+                    if (mode == 24) {
+                        float2* stx = reinterpret_cast<float2*>(smem + TC_SM_ST) + e * (2 * TILE_ROWS);
+                        RowStats rs = merge_stats(hs, stx, r, hh, 3 + e, 1e-6f);
+                        acc += rs.mean + rs.rstd;
+                    } else acc += hs.mean + hs.m2;
                 } else if (mode >= 16) {                   // LSU instruction costs: 32 (16..19) or 8 (20, 21) instructions per thread
                     const uint32_t vb = smem_u32(vec) + c0 * 4, ab = smem_u32(abuf);
                     const int t = lane & 3;
@@ -281,15 +291,15 @@ int main() {
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     long long* cyc; __half* scratch; float* sink;
     CK(cudaMalloc(&cyc, sms * sizeof(long long)));
-    CK(cudaMalloc(&sink, 4));
+    CK(cudaMalloc(&sink, 256 + (size_t)(2 * sms + 2) * TILE_ROWS * D * 4));
     const size_t scratch_halves = (size_t)(2 * sms + 2) * NHEAD * DitShape<30>::HEAD_HALVES;
     CK(cudaMalloc(&scratch, scratch_halves * 2));
     CK(cudaFuncSetAttribute(pass_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK_SMEM_BYTES));
     const char* names[] = {"LN-modulate -> A image", "GELU -> A image", "k image global stores", "proj+gate+resid+stats (regs)", "bare TMEM read loop",
                            "LN-modulate, no smem stores", "LN-modulate, 2 x ld.x32", "k image stores, no bias loads", "GELU, no bias loads",
-                           "gate+resid+stats, no bias loads", "LN-modulate, constants in regs", "LN-mod, regs, no smem stores", "32 LDS.128 only", "quad: LN-modulate -> A image", "quad: GELU -> A image", "quad: proj+gate+resid+stats+merge", "32 LDS.128 broadcast", "32 LDS.64 quad pattern", "32 LDS.32 broadcast", "32 STS.32 (128 B per warp)", "8 STS.128 (512 B per warp)", "8 STSM.x4 (512 B per warp)"};
+                           "gate+resid+stats, no bias loads", "LN-modulate, constants in regs", "LN-mod, regs, no smem stores", "32 LDS.128 only", "quad: LN-modulate -> A image", "quad: GELU -> A image", "quad: proj+gate+resid+stats+merge", "32 LDS.128 broadcast", "32 LDS.64 quad pattern", "32 LDS.32 broadcast", "32 STS.32 (128 B per warp)", "8 STS.128 (512 B per warp)", "8 STSM.x4 (512 B per warp)", "MLP resid pass + h store", "MLP resid pass, no h store", "MLP resid pass, no store, + merge"};
     long long h[256];
-    for (int mode = (getenv("PROBE_FROM") ? atoi(getenv("PROBE_FROM")) : 0); mode < 22; ++mode)
+    for (int mode = (getenv("PROBE_FROM") ? atoi(getenv("PROBE_FROM")) : 0); mode < 25; ++mode)
         for (int ntile = 1; ntile <= 2; ++ntile)
             for (int mma = 0; mma <= 1; ++mma) {
                 for (int rep = 0; rep < 2; ++rep) {
