@@ -111,7 +111,11 @@ __device__ __forceinline__ void gelu_tanh2(float& y0, float& y1, float x0, float
 #ifdef T2S_PRECISE_GELU
     const float t0 = tanhf(u0), t1 = tanhf(u1);
 #else
+#ifdef T2S_KO_MUFU
+    const float t0 = u0, t1 = u1;                       // timing knock-out (wrong results)
+#else
     const float t0 = tanh_approx(u0), t1 = tanh_approx(u1);
+#endif
 #endif
     mul2(h0, h1, x0, x1, 0.5f, 0.5f);
     fma2(y0, y1, h0, h1, t0, t1, h0, h1);

@@ -233,6 +233,24 @@ static_assert(B_TILE + 2 * T_COUNT <= 40, "barrier slots");
 constexpr uint32_t TC_IDESC = umma_idesc_f16(128, 128);
 constexpr uint32_t KCH = 2048;   // byte stride between K chunks (16 row groups x 128 B) in a [128][128] operand image
 
+// ---- timing knock-outs (A/B builds only, WRONG results): which resource paces the token kernel?  (tools/build_variant.py,
+// tools/ab_tok.sh; measured in round 2, MID at 2048 sequences, base 0.489 ms: profiles/r02_token_knockouts.log)
+//   -DT2S_KO_LDS         the per-column constants (gate / scale / shift) come from a register instead of shared memory   -1.6 %
+//   -DT2S_KO_MUFU        GELU without the tanh                                                                           -1.6 %
+//   -DT2S_KO_STG         no global stores (q|k|v images, residual tile)                                                  -15 %
+//   -DT2S_KO_HLD         the residual tile is not loaded                                                                 -8 %
+//   -DT2S_EXP_SKIP_WLOAD weight stages fetched from L2 for a CTA's first item only                                       -4 %
+// i.e. what is left of the kernel's time is spread over everything; the path to L2 / HBM (2.2 GB per launch) is the largest share.
+// ko_never is false at run time but unknown to the compiler (g_ko_zero is never written), so the arithmetic feeding a knocked-out
+// store survives
+__device__ int g_ko_zero;
+__device__ __forceinline__ bool ko_never() { return *reinterpret_cast<volatile int*>(&g_ko_zero) != 0; }
+#ifdef T2S_KO_LDS
+#define KO_LD4(ptr) make_float4(__int_as_float(0x3f800000 + (int)(size_t)(ptr)), 1.f, 1.f, 1.f)
+#else
+#define KO_LD4(ptr) (*reinterpret_cast<const float4*>(ptr))
+#endif
+
 // one 128x128x128 GEMM chunk: 8 x tcgen05.mma (K = 16 each); operands in the canonical no-swizzle K-major image
 // Called by the whole (converged) MMA warp so that descriptors live in uniform registers; only `lead` issues.
 // ones_smem != 0: a ninth MMA adds the Linear's bias: A = the constant block whose k = 0, 1 columns are 1.0 (every row), B =
@@ -319,7 +337,7 @@ __device__ __forceinline__ HalfStats resid_pass_regs(uint32_t tacc, const float*
         tmem_wait_ld();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float4 g4 = *reinterpret_cast<const float4*>(gate + cb * 16 + q * 4);
+            const float4 g4 = KO_LD4(gate + cb * 16 + q * 4);
             float t0 = a[q * 4 + 0], t1 = a[q * 4 + 1], t2 = a[q * 4 + 2], t3 = a[q * 4 + 3];
             if constexpr (HASB) {
                 const float4 b4 = ldv4<GB>(bias + cb * 16 + q * 4);
@@ -348,7 +366,7 @@ __device__ __forceinline__ HalfStats resid_pass_tmem(uint32_t tacc, uint32_t thi
         tmem_wait_ld();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float4 g4 = *reinterpret_cast<const float4*>(gate + cb * 16 + q * 4);
+            const float4 g4 = KO_LD4(gate + cb * 16 + q * 4);
             float t0 = a[q * 4 + 0], t1 = a[q * 4 + 1], t2 = a[q * 4 + 2], t3 = a[q * 4 + 3];
             if constexpr (HASB) {
                 const float4 b4 = ldv4<GB>(bias + cb * 16 + q * 4);
@@ -393,8 +411,8 @@ __device__ __forceinline__ void ln_mod_store(uint32_t trow, RowStats st, const f
     for_blocks16<4>(trow, [&](int cb, float (&a)[16]) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float4 sc = *reinterpret_cast<const float4*>(scale1 + cb * 16 + q * 4);   // 1 + scale
-            const float4 sh = *reinterpret_cast<const float4*>(shift + cb * 16 + q * 4);
+            const float4 sc = KO_LD4(scale1 + cb * 16 + q * 4);   // 1 + scale
+            const float4 sh = KO_LD4(shift + cb * 16 + q * 4);
             // ((a - mean) * rstd) * (1 + scale) + shift as two packed fused multiply-adds per pair
             float n0, n1, n2, n3;
             fma2(n0, n1, a[q * 4 + 0], a[q * 4 + 1], rs, rs, nm, nm);
@@ -984,7 +1002,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                         hq[c4] = make_float4(y0, y1, y2, y3);
                     }
                 }
+#ifdef T2S_KO_HLD
+            } else if (valid && ko_never()) {
+#else
             } else if (valid) {
+#endif
 #pragma unroll
                 for (int c4 = 0; c4 < 16; ++c4) hq[c4] = *reinterpret_cast<const float4*>(hrow_c + c4 * TILE_ROWS * 4);
             }
@@ -1042,7 +1064,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 // the SM's path to L2 (tools/probe_pass.cu: +1.7 k cycles per tile inside the residual pass), which this slot
                 // hides; region Y belongs to the k chunk afterwards
                 for_blocks16<4>(trow + Y, [&](int cb, float (&a)[16]) {
+#ifdef T2S_KO_STG
+                    if (valid && ko_never()) {
+#else
                     if (valid) {
+#endif
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
                             *reinterpret_cast<float4*>(hrow + (cb * 4 + q) * TILE_ROWS * 4) = make_float4(a[q * 4], a[q * 4 + 1], a[q * 4 + 2], a[q * 4 + 3]);
@@ -1067,7 +1093,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
                 const int dstride = which == 0 ? 1024 : (which == 1 ? NTOK * 8 : 64);
                 __half* hb0 = p.qkv + ((size_t)seq * NHEAD + hh * 2) * QKV_HEAD_HALVES + off;
                 for_blocks16<4>(trow + tcol, [&](int cb, float (&v)[16]) {
+#ifdef T2S_KO_STG
+                    if (valid && ko_never()) {
+#else
                     if (valid) {
+#endif
                         __half* hb = hb0 + (cb >> 1) * QKV_HEAD_HALVES + (cb & 1) * 2 * dstride;
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {                     // the bias is already in the accumulator (tc_gemm)
