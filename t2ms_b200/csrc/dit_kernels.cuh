@@ -251,6 +251,29 @@ __device__ __forceinline__ bool ko_never() { return *reinterpret_cast<volatile i
 #define KO_LD4(ptr) (*reinterpret_cast<const float4*>(ptr))
 #endif
 
+// global accesses of the epilogues: plain, or (-DT2S_TOK_CS, A/B build) with the streaming cache hint
+__device__ __forceinline__ void stg16(void* p, uint4 v) {
+#ifdef T2S_TOK_CS
+    __stcs(reinterpret_cast<uint4*>(p), v);
+#else
+    *reinterpret_cast<uint4*>(p) = v;
+#endif
+}
+__device__ __forceinline__ void stg16f(float* p, float4 v) {
+#ifdef T2S_TOK_CS
+    __stcs(reinterpret_cast<float4*>(p), v);
+#else
+    *reinterpret_cast<float4*>(p) = v;
+#endif
+}
+__device__ __forceinline__ float4 ldg16f(const float* p) {
+#ifdef T2S_TOK_CS
+    return __ldcs(reinterpret_cast<const float4*>(p));
+#else
+    return *reinterpret_cast<const float4*>(p);
+#endif
+}
+
 // one 128x128x128 GEMM chunk: 8 x tcgen05.mma (K = 16 each); operands in the canonical no-swizzle K-major image
 // Called by the whole (converged) MMA warp so that descriptors live in uniform registers; only `lead` issues.
 // ones_smem != 0: a ninth MMA adds the Linear's bias: A = the constant block whose k = 0, 1 columns are 1.0 (every row), B =
@@ -1008,7 +1031,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             } else if (valid) {
 #endif
 #pragma unroll
-                for (int c4 = 0; c4 < 16; ++c4) hq[c4] = *reinterpret_cast<const float4*>(hrow_c + c4 * TILE_ROWS * 4);
+                for (int c4 = 0; c4 < 16; ++c4) hq[c4] = ldg16f(hrow_c + c4 * TILE_ROWS * 4);
             }
             mbar_wait(TBAR(e, T_ACC + 0), par);
             tc_fence_after();
@@ -1071,7 +1094,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
 #endif
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<float4*>(hrow + (cb * 4 + q) * TILE_ROWS * 4) = make_float4(a[q * 4], a[q * 4 + 1], a[q * 4 + 2], a[q * 4 + 3]);
+                            stg16f(hrow + (cb * 4 + q) * TILE_ROWS * 4, make_float4(a[q * 4], a[q * 4 + 1], a[q * 4 + 2], a[q * 4 + 3]));
                     }
                 });
                 tc_fence_before();
@@ -1102,7 +1125,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {                     // the bias is already in the accumulator (tc_gemm)
                             const float* x = v + c * 8;
-                            *reinterpret_cast<uint4*>(hb + c * dstride) = make_uint4(pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[4], x[5]), pack_h2(x[6], x[7]));
+                            stg16(hb + c * dstride, make_uint4(pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[4], x[5]), pack_h2(x[6], x[7])));
                         }
                     }
                 });
