@@ -61,9 +61,9 @@ FLOP_DECODE_96 = 15_360_000
 # fp16 attention output (480 x 128 x 2); the MID token kernel reads the residual (fp32) and the attention output,
 # writes the residual and the next block's q|k|v images
 ALGO_BYTES_PER_SEQ = {"attention": 4 * 94_208 + 480 * 128 * 2, "token_mid": 2 * 480 * 128 * 4 + 480 * 128 * 2 + 4 * 94_208}
-# DRAM bytes per launch measured by ncu at nseq = 2048 (attention: profiles/r02_ncu_full_v3_attention_summary.json,
-# token MID: profiles/r01_ncu_full_v23_summary.json)
-NCU_DRAM_BYTES_PER_LAUNCH = {"attention": 771_777_280 + 228_897_024, "token_mid": 916_387_584 + 1_273_898_000}
+# DRAM bytes per launch measured by ncu at nseq = 2048 (final build of round 2: profiles/r02_ncu_full_v8_attention_summary.json,
+# profiles/r02_ncu_full_v8_token_summary.json)
+NCU_DRAM_BYTES_PER_LAUNCH = {"attention": 772_288_768 + 229_882_624, "token_mid": 889_779_456 + 1_202_538_000}
 
 
 def parse():
@@ -483,7 +483,7 @@ def main():
                          "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dom) if nseq == 2048 else None,
                          "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum at this workload size "
-                                           "(profiles/r02_ncu_full_v3_attention_summary.json, r01_ncu_full_v23_summary.json)",
+                                           "(profiles/r02_ncu_full_v8_attention_summary.json, r02_ncu_full_v8_token_summary.json)",
                          "algorithmic_bytes": ALGO_BYTES_PER_SEQ[dom] * nseq,
                          "co_bound": "MUFU ex2: 0.9216 M exp per sequence-block at 16/clk/SM = 0.41 ms per 2048-sequence launch "
                                      "(ncu: XU pipe 79 % busy, tensor pipe 19 %); this kernel is bound by the MUFU, not the tensor pipe"
