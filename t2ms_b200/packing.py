@@ -34,6 +34,8 @@ def umma_bias_block(b: torch.Tensor | None) -> torch.Tensor:
     blk = torch.zeros(2, 16, 8, 8, dtype=torch.float16, device=b.device if b is not None else None)   # [k//8][n//8][n%8][k%8]
     if b is not None:
         b = b.detach().to(torch.float32).reshape(16, 8)
+        if not bool((b.abs() < 6.0e4).all()):
+            raise RuntimeError("t2ms_b200: a Linear bias is outside the fp16 operand range (|b| < 6e4) of the sampling kernels")
         hi = b.to(torch.float16)
         lo = (b - hi.to(torch.float32)).to(torch.float16)
         blk[0, :, :, 0], blk[0, :, :, 1] = hi, lo

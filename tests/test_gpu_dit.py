@@ -127,6 +127,32 @@ def test_forward_matches_oracle(B):
     assert e_m < TOL_FWD
 
 
+def test_large_linear_biases_enter_the_gemms_exactly():
+    """token_kernel adds every Linear bias inside its GEMM as fp16 high + low parts (csrc/dit_kernels.cuh: tc_gemm,
+    packing.umma_bias_block).  With biases of order 1 (50x the other tests) a single fp16 rounding of the bias would be 2e-4
+    absolute per Linear; the split keeps the forward inside the usual tolerance against the fp32 oracle."""
+    from gpu_util import DEV, make_dit, rel_l2
+    from t2ms_b200 import synth
+    from t2ms_b200.packing import umma_bias_block
+    b = torch.randn(128) * 3.0
+    blk = umma_bias_block(b).reshape(2, 16, 8, 8).float()
+    assert (blk[0, :, :, 0] + blk[0, :, :, 1]).reshape(-1).sub(b).abs().max() < 3.0 * 2.0 ** -20 and blk[1].abs().max() == 0
+    model, sd = make_dit(7, bias_std=0.02)
+    g = torch.Generator().manual_seed(11)
+    for l in range(4):
+        for k in ("attn.qkv.bias", "attn.proj.bias", "mlp.fc1.bias", "mlp.fc2.bias"):
+            sd[f"layers.{l}.{k}"] = torch.randn(sd[f"layers.{l}.{k}"].shape, generator=g)
+    model.load_state_dict(sd, strict=True)
+    B = 3
+    x, emb, t = synth.make_noise(B, seed=42), synth.make_text_embeddings(B, seed=43), torch.tensor([0.1, 0.5, 0.9])
+    with torch.no_grad():
+        ref = O.dit_forward(sd, x, t, emb)
+        out = model(input=x.to(DEV), t=t.to(DEV), text_input=emb.to(DEV))
+    err = rel_l2(out, ref)
+    print(f"biases ~ N(0, 1): forward rel-L2 {err:.2e}")
+    assert err < TOL_FWD
+
+
 def test_forward_matches_reference_golden():
     from gpu_util import DEV, make_dit, rel_l2
     g = load_golden("dit_forward.npz")
