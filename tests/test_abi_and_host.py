@@ -15,7 +15,7 @@ from conftest import ROOT, T, load_golden
 from oracle import t2s_oracle as O
 from t2ms_b200 import DDPM, RectifiedFlow, Transformer, _lib, synth, vqvae
 from t2ms_b200.compat import VAE_ARGS
-from t2ms_b200.packing import tile_rows, umma_stage
+from t2ms_b200.packing import WSTAGE_BYTES, tile_rows, umma_bias_block, umma_stage, umma_wstage
 from t2ms_b200.sampler import gather_series, shard_range
 
 
@@ -85,6 +85,26 @@ def test_umma_stage_layout():
     tiled = tile_rows(pos)
     assert tiled.shape == (8, 32, 64, 4)
     assert torch.equal(tiled[3, 5, 17], pos[3 * 60 + 17, 20:24]) and float(tiled[:, :, 60:].abs().sum()) == 0.0
+
+
+def test_weight_stage_carries_the_bias_block():
+    """A token_kernel weight stage = the 32 KB operand image + a [128 n][16 k] bias block in the same layout: k = 0 / 1 hold the
+    fp16 high / low parts of the fp32 bias (their sum is the bias to 2^-22), everything else is zero; fc2's second K half and
+    out-of-range biases are handled (include/t2s_b200.h: t2s_dit_weights.w_qkv / w_post)."""
+    g = torch.Generator().manual_seed(3)
+    w, b = torch.randn(128, 128, generator=g), torch.randn(128, generator=g) * 2.0
+    st = umma_wstage(w, b)
+    assert st.dtype == torch.float16 and st.numel() * 2 == WSTAGE_BYTES
+    assert torch.equal(st[:128 * 128], umma_stage(w))
+    blk = st[128 * 128:].float()
+    for n in (0, 1, 7, 8, 77, 127):
+        base = ((n // 8) * 128 + (n % 8) * 16) // 2                       # K chunk 0
+        assert abs(float(blk[base] + blk[base + 1]) - float(b[n])) <= abs(float(b[n])) * 2.0 ** -21 + 1e-9
+        assert float(blk[base]) == float(b[n].to(torch.float16)) and float(blk[base + 2:base + 8].abs().sum()) == 0.0
+    assert float(blk[1024:].abs().sum()) == 0.0                           # K chunk 1 (k = 8..15) is zero
+    assert float(umma_bias_block(None).abs().sum()) == 0.0 and umma_bias_block(None).numel() == 2048
+    with pytest.raises(RuntimeError):
+        umma_bias_block(torch.full((128,), 1.0e5))
 
 
 def test_module_interfaces_match_reference_state_dict():
