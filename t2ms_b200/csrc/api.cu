@@ -181,10 +181,16 @@ TokArgs base_args(const t2s_dit_weights* w, const Workspace& ws, int nseq, bool 
 
 // uncond_shared (guided loops at throughput batch sizes): ONE unconditional modulation row per step (sequence 0) instead of one
 // per sample; the token kernels of the same loop read it for every pair (TokArgs / FusedArgs uncond_shared)
+#ifndef T2S_COND_SPLIT_MAX
+// up to this many sequences the conditioning runs as cond_split_kernel (three CTAs per block and 8 sequences): the one-CTA form
+// has too few CTAs to fill the GPU there.  Same-box A/B of 64 vs 256 (profiles/r02_ab_cond_split.log): batch 64 0.397 -> 0.386 ms per
+// guided step, batch 128 0.677 -> 0.667; at batch 256 (512 sequences) the one-CTA form is the faster one (1.240 vs 1.252 ms)
+#define T2S_COND_SPLIT_MAX 256
+#endif
 bool cond_uncond_shared(int nseq, int cfg_pairs) { return cfg_pairs && nseq > 64; }
 int launch_cond(const t2s_dit_weights* w, const float* t100, int t_stride, const float* emb, int emb_shift, int cfg_pairs,
                 int nseq, const Workspace& ws, cudaStream_t st, bool uncond_shared = false) {
-    if (nseq <= 64)
+    if (nseq <= T2S_COND_SPLIT_MAX)
         CUDA_OK(launch_k(cond_split_kernel, dim3((nseq + 7) / 8, NLAYER * 3), 256, 0, st, ws.mod, t100, t_stride, emb, emb_shift, cfg_pairs, w->freqs,
                          w->w_ada_t, w->b_ada, nseq));
     else if (uncond_shared)
