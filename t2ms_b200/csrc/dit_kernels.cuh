@@ -1445,7 +1445,30 @@ __global__ void __launch_bounds__(AttShape<H, LAT>::THREADS, AttShape<H, LAT>::C
                         for (int q = 0; q < 8; ++q) {             // packed fp32 (FFMA2 / FADD2): one issue slot per pair
                             float t0, t1;
                             fma2(t0, t1, v[hb * 16 + 2 * q], v[hb * 16 + 2 * q + 1], sc, sc, nb, nb);
+#ifdef T2S_ATT_POLY
+                            // A/B build: T2S_ATT_POLY of every 8 pairs take their exponentials on the FMA / ALU pipes instead of the MUFU:
+                            // 2^t = 2^n p(f), n = round(t) by the magic-number add, f = t - n in [-0.5, 0.5], p = degree-3 minimax polynomial
+                            // (7.5e-5 relative; P is rounded to fp16 afterwards), the exponent added to the bits of p.  t is clamped at -30
+                            // (2^-30 of a row sum >= 1)
+                            float e0, e1;
+                            if (q >= 8 - T2S_ATT_POLY) {
+                                const float MAGIC = 12582912.f;
+                                const float c0 = fmaxf(t0, -30.f), c1 = fmaxf(t1, -30.f);
+                                float z0, z1, n0, n1, f0, f1, p0, p1;
+                                add2(z0, z1, c0, c1, MAGIC, MAGIC);
+                                add2(n0, n1, z0, z1, -MAGIC, -MAGIC);
+                                fma2(f0, f1, n0, n1, -1.f, -1.f, c0, c1);
+                                fma2(p0, p1, f0, f1, 0.05517164617776871f, 0.05517164617776871f, 0.2426111251115799f, 0.2426111251115799f);
+                                fma2(p0, p1, p0, p1, f0, f1, 0.6932609677314758f, 0.6932609677314758f);
+                                fma2(p0, p1, p0, p1, f0, f1, 0.9999280571937561f, 0.9999280571937561f);
+                                e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(z0) << 23));
+                                e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(z1) << 23));
+                            } else {
+                                e0 = ex2_approx(t0); e1 = ex2_approx(t1);
+                            }
+#else
                             const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+#endif
                             add2(l0, l1, l0, l1, e0, e1);
                             pk[q] = pack_h2(e0, e1);
                         }
