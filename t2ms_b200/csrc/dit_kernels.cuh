@@ -240,6 +240,7 @@ constexpr uint32_t KCH = 2048;   // byte stride between K chunks (16 row groups 
 //   -DT2S_KO_STG         no global stores (q|k|v images, residual tile)                                                  -15 %
 //   -DT2S_KO_HLD         the residual tile is not loaded                                                                 -8 %
 //   -DT2S_EXP_SKIP_WLOAD weight stages fetched from L2 for a CTA's first item only                                       -4 %
+//   -DT2S_KO_MMA         one of the eight MMAs of a chunk (sustained-clock / power experiment, tools/power_by_kernel.py)
 // i.e. what is left of the kernel's time is spread over everything; the path to L2 / HBM (2.2 GB per launch) is the largest share.
 // ko_never is false at run time but unknown to the compiler (g_ko_zero is never written), so the arithmetic feeding a knocked-out
 // store survives
@@ -283,7 +284,11 @@ __device__ __forceinline__ void tc_gemm(uint32_t a_smem, uint32_t w_smem, uint32
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const uint64_t ad = umma_desc(a_smem + k * 2 * KCH, KCH, 128), bd = umma_desc(w_smem + k * 2 * KCH, KCH, 128);
+#ifdef T2S_KO_MMA              // timing / power knock-out: only the first of the eight MMAs of a chunk is issued
+        if (lead && k == 0) umma_f16(d_tmem, ad, bd, TC_IDESC, accumulate ? 1u : 0u);
+#else
         if (lead) umma_f16(d_tmem, ad, bd, TC_IDESC, (accumulate || k > 0) ? 1u : 0u);
+#endif
     }
     if (ones_smem != 0) {
         const uint64_t ad = umma_desc(ones_smem, KCH, 128), bd = umma_desc(w_smem + STAGE_BYTES, KCH, 128);
