@@ -297,3 +297,16 @@ def test_fork_module_aliases_and_state_dicts():
     assert v.encoder._conv_1.weight.shape == (64, 7, 4) and v.decoder._conv_trans_2.weight.shape == (64, 7, 4)
     with pytest.raises(RuntimeError):
         v.encoder(torch.rand(2, 7, 100))                       # CPU tensors: no fallback
+
+
+def test_tools_compile():
+    """The measurement tools the profiles were produced with stay syntactically valid, and the probes that include the product
+    kernels (tools/probe_pass.cu) still compile against them."""
+    import py_compile
+    tools = os.path.join(ROOT, "tools")
+    for f in sorted(os.listdir(tools)):
+        if f.endswith(".py"):
+            py_compile.compile(os.path.join(tools, f), doraise=True)
+    r = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-I", os.path.join(ROOT, "t2ms_b200", "csrc"),
+                        "-c", "-o", os.devnull, os.path.join(tools, "probe_pass.cu")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
