@@ -480,11 +480,15 @@ __device__ __forceinline__ void gelu_store(uint32_t taddr, const float* __restri
     });
 }
 
-// ---- quad-layout epilogue (token_kernel).  The row-per-thread passes above make every thread load every per-column constant
+// ---- quad-layout epilogue passes: MEASURED, NOT ADOPTED (run by tools/probe_pass.cu only; token_kernel uses the row-per-thread
+// passes above).  LN pass 1729 -> 1573 clk for both tiles (2478 -> 1838 beside a tensor-core stream): the 4-byte stores and 8-byte
+// loads cost as many crossbar slots as the 16-byte ones they replace, and once the biases had moved into the GEMMs the constant
+// loads were 1.6 % of the kernel (knock-out map above).  Kept as the reference for the 16x256b TMEM shape.
+// The row-per-thread passes make every thread load every per-column constant
 // of its 64 columns (scale, shift, gate, bias: warp-uniform 16-byte LDS, 3.3 KB per thread and work item): measured with
 // tools/probe_pass.cu, those broadcast loads alone cost 2.7-3.6 clk of the SM's shared-memory crossbar each and, together with
-// the tensor core's operand reads from the same crossbar, they — not issue slots, TMEM or HBM — paced every pass.  The passes
-// below read the accumulators through tcgen05.ld.16x256b instead (mapping verified by tools/probe_tmem_shapes.cu): thread T of
+// the tensor core's operand reads from the same crossbar, they — not issue slots, TMEM or HBM — paced every pass.  These passes
+// read the accumulators through tcgen05.ld.16x256b instead (mapping verified by tools/probe_tmem_shapes.cu): thread T of
 // a warp then holds FOUR rows x 16 columns of its 32-lane x 64-column block,
 //   rows    R(rho) = 32 q + 8 rho + (T >> 2),  rho = 2 h + rr = 0..3      (q = warp & 3: TMEM lane quarter)
 //   columns c(g,e) = 64 hh + 8 g + 2 (T & 3) + e,  g = 0..7, e = 0..1     (hh: column half of the warp)
@@ -1161,7 +1165,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) token_kernel(const TokArgs p) {
             });
             tc_fence_before();
             mbar_arrive_warp(TBAR(e, T_DONE));                                // Y drained: the next item's proj may overwrite it
-            float* vb = reinterpret_cast<float*>(abuf);                     // [128][4] projection exchange (see TC_SM_ONES comment)
+            float* vb = reinterpret_cast<float*>(abuf);                     // [128][4] projection exchange (lives in the A buffer: see the note at TOK_SMEM_BYTES)
             float4* px = reinterpret_cast<float4*>(stx);                 // the statistics exchange is idle now: partial sums of half 1
             asm volatile("bar.sync %0, 256;\n" :: "r"(1 + e) : "memory");  // ... once every thread has read its merge partner
             if (hh == 1) px[r] = make_float4(d4[0], d4[1], d4[2], d4[3]);
